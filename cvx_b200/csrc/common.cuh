@@ -1,0 +1,149 @@
+// cvx_b200 -- shared declarations for the CUDA side of the Newton/KKT hot path.
+// sm_100a only.  All matrices are column-major FP64 with padded leading dimensions
+// (multiples of 16 doubles = 128 B) so every 16-byte cp.async / vector access is aligned.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <string>
+#include "../../include/cvxb.h"
+
+namespace cvxb {
+
+#define CVXB_CUDA_OK(expr)                                                                   \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      cvxb::set_last_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                \
+                           cudaGetErrorString(_e));                                          \
+      return CVXB_ECUDA;                                                                     \
+    }                                                                                        \
+  } while (0)
+
+#define CVXB_TRY(expr)                                                                       \
+  do {                                                                                       \
+    int _s = (expr);                                                                         \
+    if (_s != CVXB_OK) return _s;                                                            \
+  } while (0)
+
+void set_last_error(const char* fmt, ...);
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int pad_ld(int rows) { return round_up(rows < 1 ? 1 : rows, 16); }
+
+constexpr int NB = 128;          // diagonal-block size of the blocked factorisations / solves
+
+}  // namespace cvxb
+
+// One handle = one device + one stream (include/cvxb.h "Threading").
+struct cvxb_handle_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  unsigned flags = 0;
+  long long launches = 0;
+  int sm_count = 148;
+  // device scalar / flag blocks shared by all kernels of this handle, and their pinned mirrors
+  double* d_scal = nullptr;   // cvxb::NSCAL doubles
+  int* d_flag = nullptr;      // cvxb::NFLAG ints
+  double* h_scal = nullptr;
+  int* h_flag = nullptr;
+  double* d_part = nullptr;   // partial-sum scratch for split reductions (PART_DOUBLES doubles)
+  unsigned* d_ticket = nullptr;  // last-block-done counters
+  void* kkt_cache = nullptr;     // cvxb::KktWork of the last seam-B call (re-used when (n,p) repeat)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace cvxb {
+
+typedef cvxb_handle_s Handle;
+constexpr int NSCAL = 128, NFLAG = 64;
+constexpr size_t PART_DOUBLES = (size_t)1 << 22;   // 32 MiB of split-K partials for gemv_n
+
+// count + launch + error check
+#define CVXB_LAUNCH(h, kernel, grid, block, smem, ...)                                       \
+  do {                                                                                       \
+    kernel<<<(grid), (block), (smem), (h).stream>>>(__VA_ARGS__);                            \
+    (h).launches++;                                                                          \
+    CVXB_CUDA_OK(cudaGetLastError());                                                        \
+  } while (0)
+
+// ---- device scalar slots (h.d_scal) ------------------------------------------------------------
+enum Scal {
+  S_RUIZ_RHO = 0, S_MINDIAG_H, S_MINDIAG_S, S_ERR1, S_ERR2, S_NORM_Q, S_NORM_B,
+  S_FVAL,        // barrier function value at x
+  S_F0,          // objective value f0(x)
+  S_LOGSUM, S_NORMGRAD, S_EQNORM, S_Q /* d.y */, S_ND, S_STEP, S_TRUST, S_HNORM, S_T,
+  S_C1, S_C2,    // quadratic-objective line coefficients
+  S_TMP0, S_TMP1, S_TMP2, S_TMP3,
+  S_PD_GAP, S_PD_RNORM, S_PD_SMAX, S_PD_RDUAL, S_PD_EQGAP, S_PD_T, S_OBJ,
+  S_MINSLACK,
+  S_COUNT
+};
+// ---- device flag slots (h.d_flag) --------------------------------------------------------------
+enum Flag {
+  F_RUIZ_DONE = 0, F_RUIZ_SWEEPS, F_CHOL_H /* 0 or 1-based failing column */, F_CHOL_S, F_INFEAS /* slack<=0 */,
+  F_LS_STATUS /* 0 ok, 1 set-backtrack failed, 2 armijo failed, 3 not feasible in value */, F_LS_TRIALS,
+  F_STEP_TAKEN, F_BAD /* any failure upstream: gates the x update */, F_ZERO_DIAG,
+  F_PD_LS_FAIL, F_PD_NOTNEG, F_PD_LAMNEG,
+  F_COUNT
+};
+
+// ---------------------------------------------------------------- GEMM (gemm_dmma.cu)
+// C[MxN] (col-major, ldc) = alpha * op(A) * op(B) + beta * C on FP64 DMMA tensor cores.
+//   a_kc: A(m,k) = A[m*lda + k]   (K contiguous) else A[k*lda + m] (M contiguous)
+//   b_kc: B(k,n) = B[n*ldb + k]   (K contiguous) else B[k*ldb + n] (N contiguous)
+//   tri:  0 = all tiles; 1 = only tiles with bm >= bn are computed and only elements m >= n are
+//         written (lower triangle); 2 = like 1 and the strict lower part is mirrored to the
+//         upper triangle (exactly symmetric result).  Needs M == N.
+// Requirements: lda/ldb even, A/B 16-byte aligned, tile origins even.
+struct GemmArgs {
+  int M, N, K;
+  const double* A; int lda; bool a_kc;
+  const double* B; int ldb; bool b_kc;
+  double* C; int ldc;
+  double alpha, beta;
+  int tri;
+};
+int gemm_dmma(Handle& h, const GemmArgs& g);
+int gemm_dmma_init();   // sets the dynamic-smem attribute on all instantiations (once per device)
+int dmma_peak_probe(Handle& h, int iters, double* ms, double* flops);   // register-only DMMA issue rate
+
+// ---------------------------------------------------------------- BLAS-2 (blas2.cu)
+// y[m] = alpha * A x + beta * y      A m x n col-major
+int gemv_n(Handle& h, int m, int n, double alpha, const double* A, int lda, const double* x, double beta, double* y);
+// y[n] = alpha * A' x + beta * y     A m x n col-major, x length m
+int gemv_t(Handle& h, int m, int n, double alpha, const double* A, int lda, const double* x, double beta, double* y);
+// Gs(i,j) = s_i * G(i,j)             m x n
+int scale_rows(Handle& h, int m, int n, const double* G, int ldg, const double* s, double* Gs, int ldgs, bool sqrt_of_s);
+// C = alpha * A (+ diag)              n x n (objective Hessian prefill); A may be NULL (zero)
+int fill_matrix(Handle& h, int n, double alpha, const double* A, int lda, const double* diag_num, double diag_scale,
+                double* C, int ldc);
+// Bt(i,j) = s_i * A(j,i)   (n x p from p x n), s may be NULL
+int transpose_scale(Handle& h, int p, int n, const double* A, int lda, const double* s, double* Bt, int ldbt);
+// C (n x n) += alpha * I
+int add_diag(Handle& h, int n, double alpha, double* C, int ldc);
+int copy_matrix(Handle& h, int m, int n, const double* A, int lda, double* B, int ldb);
+
+// ---------------------------------------------------------------- factorisations (factor.cu)
+// MatrixUtils.ruizEquilibrate: leaves d in `d` (n), sweeps in flag F_RUIZ_SWEEPS.  No host sync.
+int ruiz_equilibrate(Handle& h, int n, const double* Hm, int ldh, double* d, double* colnorm_scratch,
+                     int max_sweeps, double tol);
+// L := lower((d d') o H) + delta*I, zeros above the diagonal
+int scaled_lower(Handle& h, int n, const double* Hm, int ldh, const double* d, double delta, double* L, int ldl);
+// full Q = (d d') o H
+int scaled_full(Handle& h, int n, const double* Hm, int ldh, const double* d, double* Q, int ldq);
+// in-place blocked Cholesky of the lower triangle; inverse diagonal blocks to invD (ceil(n/NB) * NB*NB);
+// failure column -> d_flag[flag_slot] (first failure wins), min diag -> d_scal[mindiag_slot]
+int potrf_lower(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot);
+// B (n x r) := L^-1 B   /  L^-T B, using the inverse diagonal blocks
+int trsm_lower(Handle& h, int n, int r, const double* L, int ldl, const double* invD, double* B, int ldb, bool trans);
+// inverse diagonal blocks of a given lower-triangular matrix (for cvxb_triangular_solve and
+// solveWithCholFactor); zero diagonal -> F_ZERO_DIAG
+int invert_diag_blocks(Handle& h, int n, const double* L, int ldl, double* invD);
+
+}  // namespace cvxb

@@ -1,0 +1,242 @@
+// FP64 GEMM / SYRK on the DMMA tensor pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4, the only FP64
+// tensor instruction sm_100a has: tcgen05 has no f64 kind).  This one mainloop serves every dense
+// contraction of the Newton step:
+//   * Hessian assembly      H  = Gs' Gs            (TN, tri=2)   BarrierSolver.scala:303-315
+//   * Cholesky trailing     A22 -= L21 L21'        (NT, tri=1)   MatrixUtils.scala:452-461 (dpotrf)
+//   * panel / TRSM updates  B2  -= L21 Y1          (NN)          KKTSystem.scala:116-124 (dtrtrs)
+//   * Schur complement      S  = Y' Y              (TN, tri=2)   KKTSystem.scala:126-139
+//
+// CTA tile 128x128x16, 256 threads = 8 warps (2 x 4), warp tile 64x32 = 8x4 DMMA tiles, so each
+// k4-step issues 12 LDS.64 for 32 DMMA (shared-memory pipe ~19% busy, tensor pipe is the limiter).
+// Operands are staged global->shared with 16-byte cp.async (zero-fill predication at the edges)
+// through a 4-stage ring; padded shared layouts make every fragment load bank-conflict free:
+//   K-contiguous operand: [128][16+4] doubles  -> bank = 8*g + 2*t   (g = lane/4, t = lane%4)
+//   M-contiguous operand: [16][128+4] doubles  -> bank = 8*t + 2*g
+#include "common.cuh"
+
+namespace cvxb {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, NT = 256;
+constexpr int WM = 64, WN = 32;             // warp tile
+constexpr int KC_LD = BK + 4;               // K-contiguous tile row stride (doubles)
+constexpr int MC_LD = BM + 4;               // M/N-contiguous tile row stride (doubles)
+constexpr int KC_ELEMS = BM * KC_LD;        // 2560
+constexpr int MC_ELEMS = BK * MC_LD;        // 2112
+constexpr int TILE_ELEMS = KC_ELEMS;        // reserve the larger of the two for either layout
+constexpr int SMEM_BYTES = STAGES * 2 * TILE_ELEMS * (int)sizeof(double);   // 163840
+
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Stage one 128 x 16 operand tile.  `rows` = extent along the 128-long (M or N) direction,
+// `kext` = K; (r0, k0) = tile origin.  KC: element (r,k) at src[r*ld + k]; else at src[k*ld + r].
+template <bool KC>
+__device__ __forceinline__ void load_tile(double* dst, const double* __restrict__ src, int ld, int rows, int kext,
+                                          int r0, int k0, int tid) {
+#pragma unroll
+  for (int it = 0; it < (BM * BK / 2) / NT; ++it) {   // 1024 16-byte chunks / 256 threads
+    int c = tid + it * NT;
+    if (KC) {
+      int r = c >> 3, kc = (c & 7) * 2;
+      int gr = r0 + r, gk = k0 + kc;
+      int bytes = 0;
+      if (gr < rows) { int rem = (kext - gk) * 8; bytes = rem < 0 ? 0 : (rem > 16 ? 16 : rem); }
+      const double* g = bytes > 0 ? src + (size_t)gr * ld + gk : src;
+      cp_async16(dst + r * KC_LD + kc, g, bytes);
+    } else {
+      int k = c >> 6, rc = (c & 63) * 2;
+      int gk = k0 + k, gr = r0 + rc;
+      int bytes = 0;
+      if (gk < kext) { int rem = (rows - gr) * 8; bytes = rem < 0 ? 0 : (rem > 16 ? 16 : rem); }
+      const double* g = bytes > 0 ? src + (size_t)gk * ld + gr : src;
+      cp_async16(dst + k * MC_LD + rc, g, bytes);
+    }
+  }
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(NT, 1)
+gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                 double* __restrict__ C, int ldc, double alpha, double beta, int tri, int tiles_m) {
+  extern __shared__ __align__(16) double smem[];
+  int bm, bn;
+  if (tri) {
+    // linear id -> (bm, bn) with bn <= bm, row-major over the lower triangle of tiles
+    int id = blockIdx.x;
+    int r = (int)((sqrt(8.0 * (double)id + 1.0) - 1.0) * 0.5);
+    while ((long long)(r + 1) * (r + 2) / 2 <= id) ++r;
+    while ((long long)r * (r + 1) / 2 > id) --r;
+    bm = r;
+    bn = id - r * (r + 1) / 2;
+  } else {
+    bm = blockIdx.x % tiles_m;
+    bn = blockIdx.x / tiles_m;
+  }
+  const int m0 = bm * BM, n0 = bn * BN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp & 1) * WM, wn0 = (warp >> 1) * WN;
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int KT = (K + BK - 1) / BK;
+  auto stageA = [&](int s) { return smem + (size_t)s * 2 * TILE_ELEMS; };
+  auto stageB = [&](int s) { return smem + (size_t)s * 2 * TILE_ELEMS + TILE_ELEMS; };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) {
+      load_tile<A_KC>(stageA(s), A, lda, M, K, m0, s * BK, tid);
+      load_tile<B_KC>(stageB(s), B, ldb, N, K, n0, s * BK, tid);
+    }
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      int nk = kt + STAGES - 1;
+      if (nk < KT) {
+        int s = nk % STAGES;
+        load_tile<A_KC>(stageA(s), A, lda, M, K, m0, nk * BK, tid);
+        load_tile<B_KC>(stageB(s), B, ldb, N, K, n0, nk * BK, tid);
+      }
+      cp_async_commit();
+    }
+    const double* As = stageA(kt % STAGES);
+    const double* Bs = stageB(kt % STAGES);
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        a[i] = A_KC ? As[(wm0 + i * 8 + g) * KC_LD + kk + t] : As[(kk + t) * MC_LD + wm0 + i * 8 + g];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        b[j] = B_KC ? Bs[(wn0 + j * 8 + g) * KC_LD + kk + t] : Bs[(kk + t) * MC_LD + wn0 + j * 8 + g];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: thread (g,t) of tile (i,j) holds C(m, n), C(m, n+1), m = ..+g, n = ..+2t
+  const bool diag = tri && (bm == bn);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int m = m0 + wm0 + i * 8 + g;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int n = n0 + wn0 + j * 8 + 2 * t + e;
+        if (n >= N) continue;
+        if (diag && n > m) continue;
+        double v = alpha * acc[i][j][e];
+        size_t idx = (size_t)n * ldc + m;
+        if (beta != 0.0) v += beta * C[idx];
+        C[idx] = v;
+        if (tri == 2 && n != m) C[(size_t)m * ldc + n] = v;
+      }
+    }
+  }
+}
+
+template <bool A_KC, bool B_KC>
+int launch(Handle& h, const GemmArgs& g) {
+  cudaStream_t st = h.stream;
+  int tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
+  long long grid = g.tri ? (long long)tm * (tm + 1) / 2 : (long long)tm * tn;
+  if (grid <= 0) return CVXB_OK;
+  gemm_dmma_kernel<A_KC, B_KC><<<(unsigned)grid, NT, SMEM_BYTES, st>>>(g.M, g.N, g.K, g.A, g.lda, g.B, g.ldb, g.C,
+                                                                        g.ldc, g.alpha, g.beta, g.tri, tm);
+  h.launches++;
+  CVXB_CUDA_OK(cudaGetLastError());
+  return CVXB_OK;
+}
+
+// Register-only DMMA issue-rate probe: every warp of every SM issues independent DMMA chains.
+// Used to calibrate the FP64 tensor peak the roofline fractions are quoted against.
+__global__ void __launch_bounds__(NT, 1) dmma_peak_kernel(int iters, double* sink) {
+  double acc[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dmma884(acc[i][0], acc[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+  if (s == 123.456) sink[0] = s;
+}
+
+}  // namespace
+
+int dmma_peak_probe(Handle& h, int iters, double* ms, double* flops) {
+  cudaEvent_t e0, e1;
+  CVXB_CUDA_OK(cudaEventCreate(&e0));
+  CVXB_CUDA_OK(cudaEventCreate(&e1));
+  int grid = h.sm_count * 2;
+  dmma_peak_kernel<<<grid, NT, 0, h.stream>>>(iters / 10 + 1, h.d_scal + S_TMP3);
+  CVXB_CUDA_OK(cudaEventRecord(e0, h.stream));
+  dmma_peak_kernel<<<grid, NT, 0, h.stream>>>(iters, h.d_scal + S_TMP3);
+  CVXB_CUDA_OK(cudaEventRecord(e1, h.stream));
+  h.launches += 2;
+  CVXB_CUDA_OK(cudaEventSynchronize(e1));
+  float t = 0;
+  CVXB_CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
+  *ms = t;
+  *flops = (double)grid * (NT / 32) * (double)iters * 16.0 * 512.0;   // m8n8k4 = 256 FMA = 512 flop
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return CVXB_OK;
+}
+
+int gemm_dmma_init() {
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  return CVXB_OK;
+}
+
+int gemm_dmma(Handle& h, const GemmArgs& g) {
+  if (g.M <= 0 || g.N <= 0) return CVXB_OK;
+  if ((g.lda & 1) || (g.ldb & 1) || ((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15)) {
+    set_last_error("gemm_dmma: operands must be 16-byte aligned with even leading dimensions");
+    return CVXB_EINVAL;
+  }
+  if (g.tri && g.M != g.N) {
+    set_last_error("gemm_dmma: triangular mode needs M == N");
+    return CVXB_EINVAL;
+  }
+  if (g.a_kc && g.b_kc) return launch<true, true>(h, g);
+  if (!g.a_kc && g.b_kc) return launch<false, true>(h, g);
+  if (!g.a_kc && !g.b_kc) return launch<false, false>(h, g);
+  return launch<true, false>(h, g);
+}
+
+}  // namespace cvxb

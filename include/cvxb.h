@@ -1,0 +1,254 @@
+/* cvxb.h -- C ABI of libcvxb: the B200-native (sm_100a) Newton/KKT hot path behind the API of the
+ * Scala convex solver spyqqqdia/cvx.  Plain C: pointers, sizes and POD structs only.
+ *
+ * The reference has no FFI of its own (pure Scala + Breeze/netlib JNI); each entry point below
+ * names the reference method it stands in for (paths relative to src/main/scala/cvx/).  The JNI
+ * binding a maintainer would add on the Scala side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every matrix is column-major FP64 with an explicit leading dimension, exactly Breeze's
+ *     DenseMatrix layout (data, offset, majorStride);
+ *   - pointers are HOST pointers unless the handle was created with CVXB_FLAG_DEVICE_PTRS, in which
+ *     case all array arguments of the seam-B calls are device pointers on the handle's device;
+ *   - every function returns a cvxb_status; cvxb_last_error() gives the message of the last failure
+ *     on the calling thread;
+ *   - a handle owns one CUDA device + stream and is not thread-safe; use one handle per thread.
+ */
+#ifndef CVXB_H
+#define CVXB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cvxb_status {
+  CVXB_OK = 0,
+  CVXB_ELINSOLVE = 1,     /* LinSolveException            (LinSolveException.scala:11-17)           */
+  CVXB_EUNSOLVABLE = 2,   /* UnsolvableSystemException    (UnsolvableSystemException.scala)          */
+  CVXB_ELINESEARCH = 3,   /* LineSearchFailedException (PD) / NotConvergedException.Breakdown (BR)   */
+  CVXB_ENOTFEASIBLE = 4,  /* IllegalArgumentException "x not strictly feasible" (BarrierSolver.scala:284) */
+  CVXB_EINFEASIBLE = 5,   /* InfeasibleProblemException   (InfeasibleProblemException.scala:6)       */
+  CVXB_EDIM = 6,          /* AssertionError: dimension mismatch (KKTSystem.scala:31-32)              */
+  CVXB_ENOTSYMMETRIC = 7, /* Breeze MatrixNotSymmetricException raised inside cholesky / eigSym       */
+  CVXB_ECUDA = 8,         /* CUDA runtime failure (no reference analogue)                            */
+  CVXB_EINVAL = 9,        /* bad argument                                                            */
+  CVXB_ENOTIMPL = 10      /* path of the reference not built yet (see DESIGN.md "out of scope")      */
+} cvxb_status;
+
+typedef struct cvxb_handle_s* cvxb_handle;
+typedef struct cvxb_problem_s* cvxb_problem;
+
+enum { CVXB_FLAG_DEVICE_PTRS = 1 };
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* `stream` is a cudaStream_t (or NULL: the handle creates its own non-blocking stream). */
+int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out);
+int cvxb_destroy(cvxb_handle h);
+int cvxb_synchronize(cvxb_handle h);
+const char* cvxb_last_error(void);
+const char* cvxb_version(void);
+/* number of kernels launched through this handle since creation (bench.py "gpu_launches") */
+long long cvxb_launch_count(cvxb_handle h);
+
+/* ---- parameters: SolverParams.scala:24-46 plus the constants hard-coded in the solvers ------- */
+typedef struct cvxb_params {
+  int maxIter;          /* SolverParams.maxIter          1000 */
+  double alpha;         /* line-search descent factor    0.04 */
+  double beta;          /* line-search backtrack factor  0.8  */
+  double tolSolver;     /* 1e-8 */
+  double tolEqSolve;    /* 1e-1 */
+  double tolFeas;       /* 1e-7 */
+  double delta;         /* 1e-6 (never used by the reference, KKTSystem.scala:43; kept) */
+  double mu;            /* 10   BarrierSolver.scala:73,130; PrimalDualSolver.scala:392,562 */
+  double t0;            /* 1    BarrierSolver.scala:74,131 */
+  int ruizMaxSweeps;    /* 20   MatrixUtils.scala:247 */
+  double ruizTol;       /* 1e-6 MatrixUtils.scala:250 */
+  double cholRegDelta;  /* 1e-10 MatrixUtils.scala:454 */
+  double cholMinDiag;   /* 1e-7  MatrixUtils.scala:460 */
+  double newtonRegDelta;/* 1e-9  UnconstrainedSolver.scala:60 */
+  double phase1EqTol;   /* 1e-6  ConstraintSet.scala:342, CvxUtils.scala:86 */
+  double pdStepFraction;/* 0.99  PrimalDualSolver.scala:339,509 */
+  int bugCompat;        /* 1: reproduce reference defects D1/D2 of PrimalDualSolver.solve_withEQs */
+  long long stepLimit;  /* >0: stop after this many Newton steps in total (bench.py --steps) */
+} cvxb_params;
+int cvxb_default_params(cvxb_params* p);
+
+/* ---- seam B: per-step linear algebra on caller-owned matrices -------------------------------- */
+typedef struct cvxb_kkt_info {
+  int path;            /* 0 solvePD(H); 1 solvePD(H+A'A) (KKTSystem.scala:57-59); 2 eigen fallback  */
+  int regularized;     /* regularizedCholesky took the Q+1e-10 I branch (MatrixUtils.scala:452-461) */
+  int ruiz_sweeps;     /* sweeps taken by ruizEquilibrate (MatrixUtils.scala:240-268)                */
+  int chol_info;       /* 0, or 1-based column of the first non-positive pivot of the last attempt   */
+  double min_diag;     /* min diag(L) of the factor that was used                                    */
+  double err1;         /* ||LL'x + A'w + q|| / (tol+||q||)   (KKTSystem.scala:148-151)               */
+  double err2;         /* ||Ax-b|| / (tol+||b||)             (KKTSystem.scala:153-154)               */
+} cvxb_kkt_info;
+
+/* KKTSystem(H,A,q,b).solve(delta,logger,tol,debugLevel): (x,w)   KKTSystem.scala:43-66
+ * Solves Hx + A'w = -q, Ax = b.  H is n x n symmetric, A is p x n (p may be 0). */
+int cvxb_kkt_solve(cvxb_handle h, int n, int p, const double* H, int ldh, const double* A, int lda,
+                   const double* q, const double* b, double tol, double* x, double* w,
+                   cvxb_kkt_info* info);
+
+/* KKTSystem.solveWithCholFactor(L,A,q,b,logger,tol,debugLevel)   KKTSystem.scala:99-167 */
+int cvxb_kkt_solve_with_chol_factor(cvxb_handle h, int n, int p, const double* L, int ldl,
+                                    const double* A, int lda, const double* q, const double* b,
+                                    double tol, double* x, double* w, cvxb_kkt_info* info);
+
+/* MatrixUtils.choleskySolve(H,b,logger,tol,debugLevel)           MatrixUtils.scala:468-516 */
+int cvxb_cholesky_solve(cvxb_handle h, int n, const double* H, int ldh, const double* b, double tol,
+                        double* x, cvxb_kkt_info* info);
+
+/* SymmetricLinearSystem(H,r,logger).solve(tol,debugLevel)        SymmetricLinearSystem.scala:15-56 */
+int cvxb_symmetric_solve(cvxb_handle h, int n, const double* H, int ldh, const double* r, double tol,
+                         double* x, cvxb_kkt_info* info);
+
+/* MatrixUtils.ruizEquilibrate(H): (d, Q)                         MatrixUtils.scala:240-268 */
+int cvxb_ruiz_equilibrate(cvxb_handle h, int n, const double* H, int ldh, double* d, double* Q,
+                          int ldq, int* sweeps);
+
+/* MatrixUtils.regularizedCholesky(Q): L (lower, zeros above)     MatrixUtils.scala:452-461 */
+int cvxb_regularized_cholesky(cvxb_handle h, int n, const double* Q, int ldq, double* L, int ldl,
+                              cvxb_kkt_info* info);
+
+/* MatrixUtils.triangularSolve(A,"L"|"U",B)                       MatrixUtils.scala:362-376
+ * uplo 'L': solves L X = B; 'U': solves U X = B with U given as an upper-triangular matrix.
+ * B (n x nrhs) is overwritten by X. */
+int cvxb_triangular_solve(cvxb_handle h, char uplo, int n, int nrhs, const double* T, int ldt,
+                          double* B, int ldb);
+
+/* ---- seam A: device-resident problems (closed-form families) ------------- */
+typedef enum cvxb_objective_kind {
+  CVXB_OBJ_LINEAR = 0,    /* r + a'x            LinearObjectiveFunction.scala:5-22     */
+  CVXB_OBJ_QUADRATIC = 1, /* r + a'x + x'Px/2   QuadraticObjectiveFunction.scala:11-33 */
+  CVXB_OBJ_KL = 2         /* sum x log(n x)     Dist_KL.scala:223-239                  */
+} cvxb_objective_kind;
+
+typedef struct cvxb_problem_desc {
+  int n, m, p;               /* variables, linear inequalities, equalities                        */
+  int objective;             /* cvxb_objective_kind                                               */
+  const double* obj_a;       /* n   (LINEAR, QUADRATIC)                                           */
+  double obj_r;
+  const double* obj_P;       /* n x n, ld obj_ldP (QUADRATIC)                                     */
+  int obj_ldP;
+  const double* G;           /* m x n: rows are LinearConstraint.a  (LinearConstraint.scala:7-13) */
+  int ldg;
+  const double* g_r;         /* m: LinearConstraint.r (NULL = zeros)                              */
+  const double* ub;          /* m: Constraint.ub                                                  */
+  const double* A;           /* p x n  EqualityConstraint.A (NULL when p == 0)                    */
+  int lda;
+  const double* b;           /* p      EqualityConstraint.b                                       */
+  const double* x_feasible;  /* n: ConstraintSet with FeasiblePoint .feasiblePoint, or NULL        */
+  const double* x_defined;   /* n: ConstraintSet.pointWhereDefined (start of phase I)             */
+} cvxb_problem_desc;
+
+/* mirrors Solution.scala:32-43; has_* say which Option fields are Some(...) */
+typedef struct cvxb_solution {
+  double* x;       /* n, caller-allocated */
+  double* lambda;  /* m, caller-allocated or NULL */
+  double* nu;      /* p, caller-allocated or NULL */
+  int has_lambda, has_nu;
+  double newtonDecrement; int has_newtonDecrement;
+  double dualityGap;      int has_dualityGap;
+  double equalityGap;     int has_equalityGap;
+  double normGrad;        int has_normGrad;
+  double normDualResidual;int has_normDualResidual;
+  int iter;
+  int maxedOut;
+  /* extras */
+  double objective;            /* objF.valueAt(x) at the returned point                   */
+  int outer_stages;            /* barrier stages / PD iterations taken                    */
+  long long newton_steps;      /* Newton steps over all stages (phase I not included)     */
+  long long phase1_newton_steps;
+  int phase1_stages;
+  double phase1_s;             /* slack s at the phase-I solution (ConstraintSet.scala:369-371) */
+  long long linesearch_trials; /* backtracking multiplications by beta, summed            */
+  int kkt_fallbacks;           /* Newton steps that left path 0                           */
+  int kkt_regularized;         /* Newton steps whose Cholesky was regularised             */
+  int stage_newton_steps[128]; /* per outer stage                                         */
+  double solve_ms;             /* device time of the solve, CUDA events on the handle's stream */
+} cvxb_solution;
+
+int cvxb_problem_create(cvxb_handle h, const cvxb_problem_desc* desc, cvxb_problem* out);
+int cvxb_problem_destroy(cvxb_problem prob);
+
+/* ConstraintSet.withFeasiblePoint(eqs,pars,debugLevel): phase I   ConstraintSet.scala:556-575.
+ * On success the problem holds a strictly feasible point (also copied to x_feas if non-NULL). */
+int cvxb_phase1(cvxb_handle h, cvxb_problem prob, const cvxb_params* pars, double* x_feas,
+                cvxb_solution* phase1_out);
+
+/* BarrierSolver(...).solve(debugLevel): Solution                   BarrierSolver.scala:184-188
+ * Runs phase I first when the problem has no feasible point (OptimizationProblem.scala:174-196). */
+int cvxb_barrier_solve(cvxb_handle h, cvxb_problem prob, const cvxb_params* pars, cvxb_solution* out);
+
+/* PrimalDualSolver(...).solve(debugLevel): Solution                PrimalDualSolver.scala:628-641 */
+int cvxb_pd_solve(cvxb_handle h, cvxb_problem prob, const cvxb_params* pars, cvxb_solution* out);
+
+/* One barrier Newton direction at (x, t): H = hessianBarrierFunction(t,x), g = gradientBarrierFunction
+ * (BarrierSolver.scala:291-315), then KKTSystem(H,A,g,b-Ax).solve (EqualityConstrainedSolver.scala:52-58)
+ * or choleskySolve(H,-g) when p == 0 (UnconstrainedSolver.scala:50-55).  Any of H_out (n x n, ld n),
+ * g_out, dx, nu may be NULL. */
+int cvxb_barrier_newton_direction(cvxb_handle h, cvxb_problem prob, const cvxb_params* pars,
+                                  const double* x, double t, double* H_out, double* g_out,
+                                  double* dx, double* nu, cvxb_kkt_info* info);
+
+/* One primal-dual search direction at (x, lambda, nu, t): H_pd (PrimalDualSolver.scala:216-240),
+ * rhs1 (:162-176), KKT solve (:254-285), deltaLambda (:184-209). */
+int cvxb_pd_newton_direction(cvxb_handle h, cvxb_problem prob, const cvxb_params* pars,
+                             const double* x, const double* lambda, const double* nu, double t,
+                             double* H_out, double* dx, double* dlambda, double* dnu,
+                             cvxb_kkt_info* info);
+
+/* ---- batched small problems (one CTA per problem) ------------------------------ */
+/* B independent problems of identical shape (n <= 64, m <= 128, p in {0,1}); arrays are packed
+ * problem after problem, each matrix column-major with ld = its row count.  objective[i] is a
+ * cvxb_objective_kind; x0 must be strictly feasible (no phase I).  Outputs: x (B*n), per-problem
+ * status, Newton step and outer-stage counts. */
+typedef struct cvxb_batch_desc {
+  int B, n, m, p;
+  const int* objective;    /* B */
+  const double* obj_a;     /* B*n (ignored for KL problems) */
+  const double* obj_r;     /* B */
+  const double* obj_P;     /* B*n*n (ignored unless QUADRATIC) */
+  const double* G;         /* B*m*n */
+  const double* ub;        /* B*m   */
+  const double* A;         /* B*p*n */
+  const double* b;         /* B*p   */
+  const double* x0;        /* B*n   */
+} cvxb_batch_desc;
+
+typedef struct cvxb_batch_result {
+  double* x;               /* B*n */
+  int* status;             /* B: cvxb_status per problem */
+  int* newton_steps;       /* B */
+  int* outer_stages;       /* B */
+  double* objective;       /* B */
+  double* duality_gap;     /* B */
+  double* equality_gap;    /* B */
+  double solve_ms;
+} cvxb_batch_result;
+
+typedef struct cvxb_batch_s* cvxb_batch;
+int cvxb_batch_create(cvxb_handle h, const cvxb_batch_desc* desc, cvxb_batch* out);
+int cvxb_batch_destroy(cvxb_batch batch);
+int cvxb_batch_barrier_solve(cvxb_handle h, cvxb_batch batch, const cvxb_params* pars,
+                             cvxb_batch_result* out);
+
+/* ---- calibration / measurement helpers (bench.py, not part of the reference surface) ---------- */
+/* C = alpha*op(A)op(B) + beta*C through the DMMA kernel on HOST column-major arrays (tests) */
+int cvxb_test_dgemm(cvxb_handle h, int a_kc, int b_kc, int M, int N, int K, double alpha,
+                    const double* A, int lda, const double* B, int ldb, double beta, double* C,
+                    int ldc, int tri);
+/* times `reps` launches of one resident kernel; returns average milliseconds per launch.
+ * which: 0 = DMMA issue-rate peak (registers only), 1 = SYRK-TN n x n x k, 2 = SYRK-NT trailing
+ * update n x n x k, 3 = blocked Cholesky n, 4 = HBM copy of n*k doubles */
+int cvxb_bench_kernel(cvxb_handle h, int which, int n, int k, int reps, double* ms_per_launch,
+                      double* flops_or_bytes_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVXB_H */

@@ -1,0 +1,224 @@
+"""Seeded synthetic problems of the BASELINE.json shapes and the reference's known-answer problems.
+
+TEST / BENCH INPUT GENERATION ONLY (numpy, no CUDA).  The generators mirror the reference's own
+random helpers, with seeds added (the reference never seeds):
+  Constraints.randomLinearIneqConstraint / linearIneqConstraint   (Constraints.scala:158-176)
+  Constraints.randomEqualityConstraint                             (Constraints.scala:205-214)
+  ObjectiveFunctions.quadraticObjectiveFunction                    (ObjectiveFunctions.scala:21-34)
+  Dist_KL.apply                                                    (Dist_KL.scala:270-315)
+  KktTest.testSolutionWithCholFactor / testPositiveDefinite        (src/test/scala/cvx/KktTest.scala:146-272)
+Everything returns plain numpy arrays (row-major); a "problem" is a dict:
+  kind: 'linear'|'quadratic'|'kl'   objective family, with a (n), r, P (n x n) as applicable
+  G (m x n), rvec (m), ub (m)       inequalities  rvec_i + G_i x <= ub_i
+  A (p x n), b (p)                  equalities or None
+  x0 (n)                            strictly feasible start or None (=> phase I from `xdef`)
+  xdef (n)                          pointWhereDefined
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def slab_lp(n, m_half, p, seed=0, feasible_start=True):
+    """C1 / C5 family:  min -c'x  s.t.  -e <= R(x-x0) <= e  (G=[R;-R]),  A x = A x0."""
+    rng = np.random.default_rng(seed)
+    x0 = np.full(n, 1.0 / n)
+    c = rng.uniform(-1, 1, n)
+    R = rng.uniform(-1, 1, (m_half, n))
+    e = rng.uniform(0.1, 0.2, m_half)
+    G = np.vstack([R, -R])
+    Rx0 = R @ x0
+    ub = np.concatenate([Rx0 + e, -Rx0 + e])
+    prob = dict(kind="linear", n=n, a=-c, r=0.0, P=None, G=G, rvec=np.zeros(2 * m_half), ub=ub,
+                A=None, b=None, x0=x0 if feasible_start else None, xdef=x0.copy())
+    if p > 0:
+        A = rng.uniform(-1, 1, (p, n))
+        prob["A"], prob["b"] = A, A @ x0
+    if not feasible_start:
+        # deliberately infeasible point where everything is defined (cf. minDotProduct x0 = 2a)
+        prob["xdef"] = x0 + 2.0 * rng.uniform(0.1, 0.2, n)
+    return prob
+
+
+def min_dot_product(a):
+    """SimpleOptimizationProblems.minDotProduct (src/test/.../SimpleOptimizationProblems.scala:142-169):
+    min -a'x s.t. |x_j| <= |a_j|; optimum x = a; pointWhereDefined 2a (infeasible => phase I)."""
+    a = np.asarray(a, float)
+    n = a.shape[0]
+    G = np.zeros((2 * n, n))
+    ub = np.zeros(2 * n)
+    for j in range(n):   # Constraints.absoluteValuesBoundedBy: +x_j <= ub_j, -x_j <= ub_j per j
+        G[2 * j, j], G[2 * j + 1, j] = 1.0, -1.0
+        ub[2 * j] = ub[2 * j + 1] = abs(a[j])
+    return dict(kind="linear", n=n, a=-a, r=0.0, P=None, G=G, rvec=np.zeros(2 * n), ub=ub, A=None, b=None,
+                x0=None, xdef=2.0 * a, xopt=a.copy())
+
+
+def kl_random(n, m_h, p_extra, seed=0):
+    """C2 family via Dist_KL.apply semantics: KL objective, m_h rows Hx<=u plus n positivity rows,
+    p_extra rows A x = r plus the sum-to-one row (stacked last); start 1/n => phase I."""
+    rng = np.random.default_rng(seed)
+    z = rng.normal(0.0, 0.5, n)
+    qs = np.exp(z - z.max())
+    qs /= qs.sum()
+    H = rng.uniform(-1, 1, (m_h, n))
+    u = H @ qs + rng.uniform(0.05, 0.15, m_h)
+    G = np.vstack([H, -np.eye(n)])
+    ub = np.concatenate([u, np.zeros(n)])
+    ones = np.ones((1, n))
+    if p_extra > 0:
+        A0 = rng.uniform(-1, 1, (p_extra, n))
+        A = np.vstack([A0, ones])
+        b = np.concatenate([A0 @ qs, [1.0]])
+    else:
+        A, b = ones, np.array([1.0])
+    return dict(kind="kl", n=n, a=None, r=0.0, P=None, G=G, rvec=np.zeros(m_h + n), ub=ub, A=A, b=b,
+                x0=None, xdef=np.full(n, 1.0 / n), qstar=qs)
+
+
+def kl_1A(n):
+    """OptimizationProblems.kl_1A (src/test/.../OptimizationProblems.scala:167-244): P(A)>=0.36, P(B)<=0.1."""
+    assert n > 9 and n % 2 == 0
+    I_A = (np.arange(n) < 3).astype(float)
+    I_B = (np.arange(n) >= n // 2).astype(float)
+    H = np.vstack([-I_A, I_B])
+    u = np.array([-0.36, 0.1])
+    G = np.vstack([H, -np.eye(n)])
+    ub = np.concatenate([u, np.zeros(n)])
+    if n <= 15:
+        xopt = np.where(np.arange(n) < n // 2, 1.8 / n, 0.2 / n)
+    else:
+        j = np.arange(n)
+        xopt = np.where(j < 3, 0.12, np.where(j >= n // 2, 0.2 / n, 1.08 / (n - 6)))
+    return dict(kind="kl", n=n, a=None, r=0.0, P=None, G=G, rvec=np.zeros(n + 2), ub=ub,
+                A=np.ones((1, n)), b=np.array([1.0]), x0=None, xdef=np.full(n, 1.0 / n), xopt=xopt)
+
+
+def kl_2A(n):
+    """OptimizationProblems.kl_2A (:331-369): P(A)=0.36, P(B)=0.1 as equalities."""
+    assert n > 9 and n % 2 == 0
+    j = np.arange(n)
+    I_A = (j < 3).astype(float)
+    I_B = (j >= n // 2).astype(float)
+    A = np.vstack([I_A, I_B, np.ones(n)])
+    b = np.array([0.36, 0.1, 1.0])
+    xopt = np.where(j < 3, 0.12, np.where(j >= n // 2, 0.2 / n, 1.08 / (n - 6)))
+    return dict(kind="kl", n=n, a=None, r=0.0, P=None, G=-np.eye(n), rvec=np.zeros(n), ub=np.zeros(n),
+                A=A, b=b, x0=None, xdef=np.full(n, 1.0 / n), xopt=xopt)
+
+
+def infeasible_kl_1(n):
+    """OptimizationProblems.infeasible_kl_1 (:379-405): P(A)>=0.51 and P(B)>=0.51, disjoint A, B."""
+    j = np.arange(n)
+    I_A = (j < 3).astype(float)
+    I_B = (j >= n // 2).astype(float)
+    # ConstraintSets.probAB: positivity constraints first, then the two probability constraints
+    G = np.vstack([-np.eye(n), -I_A, -I_B])
+    ub = np.concatenate([np.zeros(n), [-0.51, -0.51]])
+    return dict(kind="kl", n=n, a=None, r=0.0, P=None, G=G, rvec=np.zeros(n + 2), ub=ub,
+                A=np.ones((1, n)), b=np.array([1.0]), x0=None, xdef=np.full(n, 1.0 / n))
+
+
+def slab_qp(n, m_half, p, seed=0, scale=True):
+    """C3(QP half) / C4 family:  min 0.5||R(x-xc)||^2  s.t. slab G=[R2;-R2] around x0,  A x = A x0."""
+    rng = np.random.default_rng(seed)
+    x0 = np.full(n, 1.0 / n)
+    sc = 1.0 / np.sqrt(n) if scale else 1.0
+    R = rng.uniform(-1, 1, (n, n)) * sc
+    xc = x0 + rng.normal(0, 1, n)
+    Rxc = R @ xc
+    P = R.T @ R
+    P = (P + P.T) * 0.5
+    a = -(R.T @ Rxc)
+    r = 0.5 * float(Rxc @ Rxc)
+    R2 = rng.uniform(-1, 1, (m_half, n))
+    e = rng.uniform(0.1, 0.2, m_half) * (np.sqrt(n) if scale else 1.0)
+    G = np.vstack([R2, -R2])
+    R2x0 = R2 @ x0
+    ub = np.concatenate([R2x0 + e, -R2x0 + e])
+    prob = dict(kind="quadratic", n=n, a=a, r=r, P=P, G=G, rvec=np.zeros(2 * m_half), ub=ub, A=None, b=None,
+                x0=x0, xdef=x0.copy())
+    if p > 0:
+        A = rng.uniform(-1, 1, (p, n))
+        prob["A"], prob["b"] = A, A @ x0
+    return prob
+
+
+def kl_small(n, m_h, seed=0):
+    """C3(KL half): KL objective, m_h rows Hx<=u + n positivity rows, p=1 (sum to one), feasible
+    start given (the softmax point q*, strictly inside by construction)."""
+    pr = kl_random(n, m_h, 0, seed)
+    pr["x0"] = pr["qstar"].copy()
+    return pr
+
+
+def batched_problem(i, n=64, m=128, base_seed=1000):
+    """C3: problem i of the batch; even i -> KL (p=1), odd i -> QP (p=0)."""
+    if i % 2 == 0:
+        return kl_small(n, m - n, base_seed + i)
+    return slab_qp(n, m // 2, 0, base_seed + i, scale=True)
+
+
+# ---------------- planted KKT systems (KktTest.scala) ----------------
+
+
+def kkt_planted_chol(n, p, seed=0):
+    """KktTest.testSolutionWithCholFactor(n,p,...) :146-167:  L = tril(U(-5,5)) + sqrt(n) I,
+    A = U(0,1)^{p x n} + I, x ~ U(-1,1), w ~ U(-2,2); q = -(Hx + A'w), b = A x."""
+    rng = np.random.default_rng(seed)
+    L = np.tril(rng.uniform(-5, 5, (n, n)))
+    L[np.arange(n), np.arange(n)] += np.sqrt(n)
+    A = rng.uniform(0, 1, (p, n))
+    A[np.arange(p), np.arange(p)] += 1.0
+    x = rng.uniform(-1, 1, n)
+    w = rng.uniform(-2, 2, p)
+    H = L @ L.T
+    H = (H + H.T) * 0.5
+    return dict(L=L, H=H, A=A, x=x, w=w, q=-(H @ x + A.T @ w), b=A @ x)
+
+
+def kkt_planted_pd(n, p, seed=0):
+    """KktTest.testPositiveDefinite(n,p,...) :246-262: H = sym(LL'), A = U(-5,5) + 20 I."""
+    rng = np.random.default_rng(seed)
+    L = np.tril(rng.uniform(-5, 5, (n, n)))
+    L[np.arange(n), np.arange(n)] += np.sqrt(n)
+    M = L @ L.T
+    H = (M + M.T) * 0.5
+    A = rng.uniform(-5, 5, (p, n))
+    A[np.arange(p), np.arange(p)] += 20.0
+    x = rng.uniform(-1, 1, n)
+    w = rng.uniform(-2, 2, p)
+    return dict(H=H, A=A, x=x, w=w, q=-(H @ x + A.T @ w), b=A @ x)
+
+
+def newton_step_inputs(n, m_half, p, seed=0):
+    """One barrier Newton step at a strictly feasible random iterate of a slab problem: returns
+    the problem, an iterate x (not x0) and a barrier parameter t."""
+    prob = slab_qp(n, m_half, p, seed)
+    rng = np.random.default_rng(seed + 7919)
+    d = rng.normal(0, 1, n)
+    Gd = prob["G"] @ d
+    slack = prob["ub"] - prob["G"] @ prob["x0"]
+    smax = float(np.min(np.where(Gd > 0, slack / np.where(Gd > 0, Gd, 1.0), np.inf)))
+    x = prob["x0"] + 0.5 * smax * d
+    return prob, x, 10.0
+
+
+# ---------------- conversion to oracle objects ----------------
+
+
+def to_oracle(prob):
+    from . import cvx_oracle as O
+    if prob["kind"] == "linear":
+        objF = O.LinearObjective(prob["a"], prob["r"])
+    elif prob["kind"] == "quadratic":
+        objF = O.QuadraticObjective(prob["P"], prob["a"], prob["r"])
+    elif prob["kind"] == "kl":
+        objF = O.KLObjective(prob["n"])
+    else:
+        raise ValueError(prob["kind"])
+    cnts = O.ConstraintSet(prob["G"], prob["rvec"], prob["ub"], None, prob["xdef"])
+    if prob.get("x0") is not None:
+        cnts = cnts.addFeasiblePoint(prob["x0"])
+    eqs = O.EqualityConstraint(prob["A"], prob["b"]) if prob.get("A") is not None else None
+    return objF, cnts, eqs

@@ -1,0 +1,204 @@
+"""Seam B (per-step dense linear algebra) through the C ABI against the CPU oracle.  The test designs
+are the reference's own (src/test/scala/cvx/KktTest.scala, MatrixUtilsTests.scala) with seeds added."""
+import numpy as np
+import pytest
+
+from oracle import cvx_oracle as O
+from oracle import problems as P
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10     # BASELINE.json north_star: dx, nu within 1e-10 relative
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def spd(n, seed, cond_pow=0):
+    rng = np.random.default_rng(seed)
+    M = rng.uniform(-1, 1, (n, n))
+    H = M @ M.T + n * 1e-3 * np.eye(n)
+    s = 10.0 ** rng.uniform(-cond_pow, cond_pow, n)       # bad row/column scaling, Ruiz must undo it
+    H = H * np.outer(s, s)
+    return (H + H.T) * 0.5
+
+
+def test_ruiz_zero_row(handle):
+    """MatrixUtilsTests.scala:16-26: a zero row keeps d_i = 1 (MatrixUtils.scala:259)."""
+    from cvx_b200 import MatrixUtils
+    A = np.array([[.5, 0, .5], [0, 0, 0], [-.5, 0, -.5]])
+    d, Q, sweeps = MatrixUtils.ruizEquilibrate(A, handle, return_sweeps=True)
+    d0, Q0 = O.ruizEquilibrate(A)
+    assert d[1] == 1.0
+    assert sweeps == O.ruizEquilibrate.last_sweeps
+    assert np.allclose(d, d0, rtol=1e-14, atol=0) and np.allclose(Q, Q0, rtol=1e-13, atol=1e-300)
+
+
+@pytest.mark.parametrize("n,cond_pow", [(50, 0), (257, 2), (1000, 3)])
+def test_ruiz_matches_oracle(handle, n, cond_pow):
+    from cvx_b200 import MatrixUtils
+    H = spd(n, n, cond_pow)
+    d, Q, sweeps = MatrixUtils.ruizEquilibrate(H, handle, return_sweeps=True)
+    d0, Q0 = O.ruizEquilibrate(H)
+    assert abs(sweeps - O.ruizEquilibrate.last_sweeps) <= 1
+    if sweeps == O.ruizEquilibrate.last_sweeps:
+        assert rel(d, d0) < 1e-12 and rel(Q, Q0) < 1e-12
+    assert np.array_equal(Q, Q.T)
+
+
+@pytest.mark.parametrize("n", [1, 7, 128, 129, 300, 1025])
+def test_regularized_cholesky(handle, n):
+    from cvx_b200 import MatrixUtils
+    H = spd(n, 100 + n)
+    L = MatrixUtils.regularizedCholesky(H, handle)
+    L0 = O.regularizedCholesky(H)
+    assert np.array_equal(np.triu(L, 1), np.zeros((n, n)))
+    assert rel(L, L0) < 1e-11
+    assert rel(L @ L.T, H) < 1e-13
+
+
+def test_regularized_cholesky_semidefinite(handle):
+    """rank-deficient Q: plain dpotrf fails or min diag <= 1e-7 -> Q + 1e-10 I (MatrixUtils.scala:452-461)."""
+    from cvx_b200 import MatrixUtils, _lib
+    rng = np.random.default_rng(3)
+    B = rng.uniform(-1, 1, (40, 10))
+    Q = B @ B.T
+    Q = (Q + Q.T) / 2
+    info = _lib.KktInfo()
+    try:
+        L = MatrixUtils.regularizedCholesky(Q, handle, info)
+        ok = True
+    except _lib.LinSolveException:
+        ok = False
+    try:
+        L0 = O.regularizedCholesky(Q)
+        ok0 = True
+    except Exception:
+        ok0 = False
+    assert ok == ok0
+    if ok:
+        assert info.regularized == 1 and O.regularizedCholesky.last_regularized
+        assert rel(L @ L.T, Q + 1e-10 * np.eye(40)) < 1e-9
+
+
+@pytest.mark.parametrize("n,nrhs", [(5, 1), (200, 3), (513, 70), (1000, 1)])
+@pytest.mark.parametrize("uplo", ["L", "U"])
+def test_triangular_solve_planted(handle, n, nrhs, uplo):
+    """MatrixUtilsTests.testTriangularSolve (:36-93): L = tril(U(-5,5)) + 20 I, planted X."""
+    from cvx_b200 import MatrixUtils
+    rng = np.random.default_rng(n + nrhs)
+    T = np.tril(rng.uniform(-5, 5, (n, n))) + 20 * np.eye(n)
+    if uplo == "U":
+        T = T.T.copy()
+    X = rng.uniform(0, 1, (n, nrhs))
+    B = T @ X
+    X1 = MatrixUtils.triangularSolve(T, uplo, B, handle)
+    X0 = O.triangularSolve(T, uplo, B)
+    assert rel(X1, X0) < 1e-10 and rel(X1, X) < 1e-10
+    if nrhs == 1:
+        f = MatrixUtils.forwardSolve if uplo == "L" else MatrixUtils.backSolve
+        assert rel(f(T, B[:, 0], handle), X[:, 0]) < 1e-10
+
+
+def test_triangular_solve_singular(handle):
+    from cvx_b200 import MatrixUtils, _lib
+    T = np.tril(np.ones((10, 10)))
+    T[4, 4] = 0.0
+    with pytest.raises(_lib.LinSolveException):
+        MatrixUtils.triangularSolve(T, "L", np.ones(10), handle)
+
+
+@pytest.mark.parametrize("n", [3, 100, 700])
+def test_cholesky_solve(handle, n):
+    """MatrixUtilsTests.testSolveWithPreconditioning (:165-198)."""
+    from cvx_b200 import MatrixUtils, _lib
+    H = spd(n, 7 * n, 2)
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-1, 1, n)
+    b = H @ x
+    info = _lib.KktInfo()
+    x1 = MatrixUtils.choleskySolve(H, b, None, 1e-9, 0, handle, info)
+    x0 = O.choleskySolve(H, b, 1e-9)
+    assert np.linalg.norm(H @ x1 - b) / np.linalg.norm(b) < 1e-10
+    assert rel(x1, x0) < 1e-7      # forward error is cond-limited; the residual above is the contract
+
+
+def test_cholesky_solve_not_pd(handle):
+    from cvx_b200 import MatrixUtils, _lib
+    H = np.diag([1.0, -1.0, 2.0])
+    with pytest.raises(_lib.LinSolveException):
+        MatrixUtils.choleskySolve(H, np.ones(3), None, 1e-1, 0, handle)
+    with pytest.raises(Exception):
+        O.choleskySolve(H, np.ones(3), 1e-1)
+
+
+@pytest.mark.parametrize("n,p,seed", [(10, 2, 0), (100, 20, 1), (300, 40, 2), (1000, 100, 3), (513, 129, 4)])
+def test_kkt_planted_pd(handle, n, p, seed):
+    """KktTest.testPositiveDefinite (:197-272): planted (x,w); intended size n=1000, p=100, tol 1e-10
+    (Runner.scala:79-80)."""
+    from cvx_b200 import KKTSystem
+    s = P.kkt_planted_pd(n, p, seed)
+    K = KKTSystem(s["H"], s["A"], s["q"], s["b"], handle)
+    x, w = K.solve(1e-6, None, 1e-10, 0)
+    info0 = O.KKTInfo()
+    x0, w0 = O.kkt_solve(s["H"], s["A"], s["q"], s["b"], 1e-10, info0)
+    assert K.info.path == info0.path == 0
+    assert abs(K.info.ruiz_sweeps - info0.ruiz_sweeps) <= 1
+    # forward error against the planted solution and the oracle; backward error (KktTest :170-182)
+    assert rel(x, s["x"]) < 1e-9 and rel(w, s["w"]) < 1e-9
+    assert rel(x, x0) < RTOL * 100 and rel(w, w0) < RTOL * 100
+    H, A = s["H"], s["A"]
+    res = np.linalg.norm(np.concatenate([H @ x + A.T @ w + s["q"], A @ x - s["b"]]))
+    assert res / np.linalg.norm(np.concatenate([s["q"], s["b"]])) < RTOL
+
+
+@pytest.mark.parametrize("n,p,seed", [(50, 5, 0), (400, 60, 1)])
+def test_solve_with_chol_factor(handle, n, p, seed):
+    """KktTest.testSolutionWithCholFactor (:117-184)."""
+    from cvx_b200 import KKTSystem
+    s = P.kkt_planted_chol(n, p, seed)
+    x, w = KKTSystem.solveWithCholFactor(s["L"], s["A"], s["q"], s["b"], None, 1e-10, 0, handle)
+    x0, w0 = O.solveWithCholFactor(s["L"], s["A"], s["q"], s["b"], 1e-10)
+    assert rel(x, s["x"]) < 1e-9 and rel(w, s["w"]) < 1e-9
+    assert rel(x, x0) < 1e-8 and rel(w, w0) < 1e-8
+
+
+def test_kkt_fallback_path1(handle):
+    """H singular on null(A)-complement directions but H + A'A positive definite: path 0 fails,
+    path 1 (KKTSystem.scala:57-59) succeeds -- same path in the oracle."""
+    from cvx_b200 import KKTSystem
+    rng = np.random.default_rng(11)
+    n, p = 60, 10
+    A = rng.uniform(-1, 1, (p, n))
+    # H = projector-like PSD matrix vanishing on row space of A
+    Qm, _ = np.linalg.qr(A.T, mode="complete")
+    N = Qm[:, p:]
+    H = N @ N.T
+    H = (H + H.T) / 2
+    x = rng.uniform(-1, 1, n)
+    w = rng.uniform(-1, 1, p)
+    q = -(H @ x + A.T @ w)
+    b = A @ x
+    info0 = O.KKTInfo()
+    x0, w0 = O.kkt_solve(H, A, q, b, 1e-6, info0)
+    K = KKTSystem(H, A, q, b, handle)
+    x1, w1 = K.solve(1e-6, None, 1e-6, 0)
+    assert K.info.path == info0.path
+    assert rel(x1, x0) < 1e-6 and rel(w1, w0) < 1e-6
+
+
+def test_symmetric_linear_system(handle):
+    from cvx_b200 import SymmetricLinearSystem
+    H = spd(200, 42, 2)
+    rng = np.random.default_rng(1)
+    r = rng.uniform(-1, 1, 200)
+    x1 = SymmetricLinearSystem(H, r, None, handle).solve(1e-9, 0)
+    x0 = O.symmetricLinearSystemSolve(H, r, 1e-9)
+    assert np.linalg.norm(H @ x1 - r) / np.linalg.norm(r) < 1e-10
+    assert rel(x1, x0) < 1e-7
+
+
+def test_dimension_asserts(handle):
+    from cvx_b200 import KKTSystem, _lib
+    with pytest.raises(AssertionError):
+        KKTSystem(np.eye(3), np.ones((1, 4)), np.ones(3), np.ones(1), handle)
