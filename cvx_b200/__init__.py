@@ -8,3 +8,6 @@ from ._lib import (CvxbError, LinSolveException, UnsolvableSystemException, Line
 from .linalg import KKTSystem, SymmetricLinearSystem, MatrixUtils  # noqa: F401
 
 __version__ = "0.1.0"
+from .solvers import (SolverParams, Solution, LinearObjectiveFunction, QuadraticObjectiveFunction,  # noqa: F401,E402
+                      KLObjectiveFunction, ConstraintSet, EqualityConstraint, BarrierSolver, PrimalDualSolver,
+                      OptimizationProblem, Dist_KL, from_dict)

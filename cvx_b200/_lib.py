@@ -101,7 +101,8 @@ class SolutionC(C.Structure):
                 ("normGrad", C.c_double), ("has_normGrad", C.c_int),
                 ("normDualResidual", C.c_double), ("has_normDualResidual", C.c_int),
                 ("iter", C.c_int), ("maxedOut", C.c_int), ("objective", C.c_double), ("outer_stages", C.c_int),
-                ("newton_steps", C.c_longlong), ("phase1_newton_steps", C.c_longlong), ("phase1_stages", C.c_int),
+                ("newton_steps", C.c_longlong), ("executed_newton_steps", C.c_longlong),
+                ("phase1_newton_steps", C.c_longlong), ("phase1_executed_steps", C.c_longlong), ("phase1_stages", C.c_int),
                 ("phase1_s", C.c_double), ("linesearch_trials", C.c_longlong), ("kkt_fallbacks", C.c_int),
                 ("kkt_regularized", C.c_int), ("stage_newton_steps", C.c_int * 128), ("solve_ms", C.c_double)]
 
@@ -126,6 +127,8 @@ SYMBOLS = {
     "cvxb_version": (C.c_char_p, []),
     "cvxb_launch_count": (C.c_longlong, [_vp]),
     "cvxb_default_params": (C.c_int, [C.POINTER(Params)]),
+    "cvxb_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "cvxb_profile_read": (C.c_int, [_vp, C.POINTER(C.c_longlong), _dp, _dp]),
     "cvxb_kkt_solve": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_double, _vp, _vp,
                                  C.POINTER(KktInfo)]),
     "cvxb_kkt_solve_with_chol_factor": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp,
@@ -229,6 +232,15 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+    def profile_enable(self, on: bool = True):
+        check(self.lib.cvxb_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        """(launches, total ms, total algorithmic flops) of the timed Hessian-assembly SYRK launches."""
+        n, ms, fl = C.c_longlong(), C.c_double(), C.c_double()
+        check(self.lib.cvxb_profile_read(self._h, C.byref(n), C.byref(ms), C.byref(fl)))
+        return n.value, ms.value, fl.value
 
     # measurement helper (bench.py)
     def bench_kernel(self, which: int, n: int, k: int, reps: int):

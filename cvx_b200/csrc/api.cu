@@ -165,6 +165,7 @@ int cvxb_destroy(cvxb_handle h) {
   cudaFree(h->d_scal); cudaFree(h->d_flag); cudaFree(h->d_part); cudaFree(h->d_ticket);
   cudaFreeHost(h->h_scal); cudaFreeHost(h->h_flag);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return CVXB_OK;
@@ -177,6 +178,30 @@ int cvxb_synchronize(cvxb_handle h) {
 }
 
 long long cvxb_launch_count(cvxb_handle h) { return h ? h->launches : 0; }
+
+int cvxb_profile_enable(cvxb_handle h, int on) {
+  CHECK_HANDLE(h);
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->prof_on = on;
+  h->prof_used = 0;
+  h->prof_flops = 0.0;
+  return CVXB_OK;
+}
+
+int cvxb_profile_read(cvxb_handle h, long long* launches, double* ms_total, double* flops_total) {
+  CHECK_HANDLE(h);
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  double ms = 0;
+  for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+    float t = 0;
+    CVXB_CUDA_OK(cudaEventElapsedTime(&t, h->prof_events[i], h->prof_events[i + 1]));
+    ms += t;
+  }
+  if (launches) *launches = (long long)(h->prof_used / 2);
+  if (ms_total) *ms_total = ms;
+  if (flops_total) *flops_total = h->prof_flops;
+  return CVXB_OK;
+}
 
 // ------------------------------------------------------------------------------------ seam B
 int cvxb_kkt_solve(cvxb_handle h, int n, int p, const double* H, int ldh, const double* A, int lda, const double* q,

@@ -56,6 +56,11 @@ struct cvxb_handle_s {
   unsigned* d_ticket = nullptr;  // last-block-done counters
   void* kkt_cache = nullptr;     // cvxb::KktWork of the last seam-B call (re-used when (n,p) repeat)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // optional per-launch timing of the dominant kernel (Hessian-assembly SYRK), bench.py roofline
+  int prof_on = 0;
+  std::vector<cudaEvent_t> prof_events;   // start/stop pairs
+  size_t prof_used = 0;
+  double prof_flops = 0.0;
 };
 
 namespace cvxb {
@@ -110,6 +115,8 @@ struct GemmArgs {
   int tri;
 };
 int gemm_dmma(Handle& h, const GemmArgs& g);
+// gemm_dmma bracketed by CUDA events when the handle's profiling is on (flops = algorithmic flops)
+int gemm_dmma_timed(Handle& h, const GemmArgs& g, double flops);
 int gemm_dmma_init();   // sets the dynamic-smem attribute on all instantiations (once per device)
 int dmma_peak_probe(Handle& h, int iters, double* ms, double* flops);   // register-only DMMA issue rate
 

@@ -223,6 +223,23 @@ int gemm_dmma_init() {
   return CVXB_OK;
 }
 
+int gemm_dmma_timed(Handle& h, const GemmArgs& g, double flops) {
+  if (!h.prof_on) return gemm_dmma(h, g);
+  if (h.prof_used + 2 > h.prof_events.size()) {
+    for (int i = 0; i < 64; ++i) {
+      cudaEvent_t e;
+      CVXB_CUDA_OK(cudaEventCreate(&e));
+      h.prof_events.push_back(e);
+    }
+  }
+  CVXB_CUDA_OK(cudaEventRecord(h.prof_events[h.prof_used], h.stream));
+  int st = gemm_dmma(h, g);
+  CVXB_CUDA_OK(cudaEventRecord(h.prof_events[h.prof_used + 1], h.stream));
+  h.prof_used += 2;
+  h.prof_flops += flops;
+  return st;
+}
+
 int gemm_dmma(Handle& h, const GemmArgs& g) {
   if (g.M <= 0 || g.N <= 0) return CVXB_OK;
   if ((g.lda & 1) || (g.ldb & 1) || ((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15)) {

@@ -1,16 +1,758 @@
-// seam A (device-resident problems): placeholder until the solver loops land
-#include "kkt.cuh"
+// Seam A: device-resident barrier solves.
+//   barrier function family     BarrierSolver.scala:280-315   (value, gradient, Hessian)
+//   EqualityConstrainedSolver   EqualityConstrainedSolver.scala:37-107
+//   UnconstrainedSolver         UnconstrainedSolver.scala:34-125   (with defect D4 reproduced)
+//   BarrierSolver outer loop    BarrierSolver.scala:70-188
+//   phase I                     ConstraintSet.scala:131-168,310-395,556-575, Constraint.scala:64-89,
+//                               EqualityConstraint.scala:84-100, CvxUtils.scala:61-87
+// The iterate never leaves the device.  One Newton step is a fixed kernel sequence (assembly, KKT
+// solve, line search, re-evaluation); the host reads one block of status words per step.
+//
+// Line search in O(m+n) per trial: the reference re-evaluates every constraint object at every trial
+// point (O(mn) each); along the ray x + s*d the constraint values are g(x) + s*(G d), so after ONE
+// extra GEMV (G d) a whole backtracking search is a loop inside a single CTA.
+#include "solver.cuh"
+#include "vecops.cuh"
+
 using namespace cvxb;
-#define NOTIMPL(name) cvxb::set_last_error(name ": not built yet"); return CVXB_ENOTIMPL
-extern "C" {
-int cvxb_problem_create(cvxb_handle, const cvxb_problem_desc*, cvxb_problem*) { NOTIMPL("cvxb_problem_create"); }
-int cvxb_problem_destroy(cvxb_problem) { return CVXB_OK; }
-int cvxb_phase1(cvxb_handle, cvxb_problem, const cvxb_params*, double*, cvxb_solution*) { NOTIMPL("cvxb_phase1"); }
-int cvxb_barrier_solve(cvxb_handle, cvxb_problem, const cvxb_params*, cvxb_solution*) { NOTIMPL("cvxb_barrier_solve"); }
-int cvxb_pd_solve(cvxb_handle, cvxb_problem, const cvxb_params*, cvxb_solution*) { NOTIMPL("cvxb_pd_solve"); }
-int cvxb_barrier_newton_direction(cvxb_handle, cvxb_problem, const cvxb_params*, const double*, double, double*, double*, double*, double*, cvxb_kkt_info*) { NOTIMPL("cvxb_barrier_newton_direction"); }
-int cvxb_pd_newton_direction(cvxb_handle, cvxb_problem, const cvxb_params*, const double*, const double*, const double*, double, double*, double*, double*, double*, cvxb_kkt_info*) { NOTIMPL("cvxb_pd_newton_direction"); }
-int cvxb_batch_create(cvxb_handle, const cvxb_batch_desc*, cvxb_batch*) { NOTIMPL("cvxb_batch_create"); }
-int cvxb_batch_destroy(cvxb_batch) { return CVXB_OK; }
-int cvxb_batch_barrier_solve(cvxb_handle, cvxb_batch, const cvxb_params*, cvxb_batch_result*) { NOTIMPL("cvxb_batch_barrier_solve"); }
+
+namespace cvxb {
+namespace {
+
+constexpr double IN_SET_FACTOR = 1.0 + 3e-16;   // Constraint.isSatisfiedStrictly, Constraint.scala:23
+
+// ---- objective families (device) -------------------------------------------------------------------
+// value needs a.x / x.Px/2 / sum x log(n x): partial term of entry j
+__device__ __forceinline__ double obj_term(int kind, int n, int j, double xj, const double* a, const double* Px) {
+  if (kind == CVXB_OBJ_LINEAR) return a[j] * xj;
+  if (kind == CVXB_OBJ_QUADRATIC) return a[j] * xj + 0.5 * xj * Px[j];
+  return xj * log(xj * (double)n);   // Dist_KL.scala:225-227
 }
+__device__ __forceinline__ double obj_grad(int kind, int n, int j, double xj, const double* a, const double* Px) {
+  if (kind == CVXB_OBJ_LINEAR) return a[j];
+  if (kind == CVXB_OBJ_QUADRATIC) return a[j] + Px[j];
+  return 1.0 + log(xj) + log((double)n);   // Dist_KL.scala:229-233
+}
+
+// E3: gx = r + Gx ; slack, 1/slack, log-sum, feasibility ; objective value f0 and barrier value
+__global__ void __launch_bounds__(VT) eval_cnt_kernel(int m, int n, int kind, double obj_r, double t,
+                                                      const double* __restrict__ gr, const double* __restrict__ ub,
+                                                      double* __restrict__ gx, double* __restrict__ inv,
+                                                      const double* __restrict__ x, const double* __restrict__ a,
+                                                      const double* __restrict__ Px, double* scal, int* flag) {
+  __shared__ double buf[33];
+  __shared__ int ibuf[33];
+  double ls = 0.0, mn = 1e308;
+  int bad = 0;
+  for (int i = threadIdx.x; i < m; i += VT) {
+    double g = (gr ? gr[i] : 0.0) + gx[i];
+    gx[i] = g;
+    double d = ub[i] - g;
+    if (!(d > 0.0)) bad = 1;
+    inv[i] = 1.0 / d;
+    ls += log(d);
+    mn = fmin(mn, d);
+  }
+  ls = block_sum(ls, buf);
+  mn = block_min(mn, buf);
+  bad = block_or(bad, ibuf);
+  double f0 = 0.0;
+  for (int j = threadIdx.x; j < n; j += VT) f0 += obj_term(kind, n, j, x[j], a, Px);
+  f0 = block_sum(f0, buf) + obj_r;
+  if (threadIdx.x == 0) {
+    scal[S_LOGSUM] = ls;
+    scal[S_F0] = f0;
+    scal[S_FVAL] = t * f0 - ls;      // BarrierSolver.scala:280-289
+    scal[S_MINSLACK] = mn;
+    scal[S_T] = t;
+    flag[F_INFEAS] = bad;
+  }
+}
+
+// E6: y = t*grad f0 + G'(1/d) ; ||y|| ; eqdiff = b - Ax ; ||eqdiff||     BarrierSolver.scala:291-301
+__global__ void __launch_bounds__(VT) eval_grad_kernel(int n, int p, int kind, double t, const double* __restrict__ x,
+                                                       const double* __restrict__ a, const double* __restrict__ Px,
+                                                       const double* __restrict__ gt, double* __restrict__ y,
+                                                       const double* __restrict__ b, const double* __restrict__ ax,
+                                                       double* __restrict__ eqdiff, double* scal) {
+  __shared__ double buf[33];
+  double s = 0.0;
+  for (int j = threadIdx.x; j < n; j += VT) {
+    double v = t * obj_grad(kind, n, j, x[j], a, Px) + gt[j];
+    y[j] = v;
+    s = fma(v, v, s);
+  }
+  s = block_sum(s, buf);
+  double e = 0.0;
+  for (int i = threadIdx.x; i < p; i += VT) {
+    double v = b[i] - ax[i];
+    eqdiff[i] = v;
+    e = fma(v, v, e);
+  }
+  e = block_sum(e, buf);
+  if (threadIdx.x == 0) {
+    scal[S_NORMGRAD] = sqrt(s);
+    scal[S_EQNORM] = sqrt(e);
+  }
+}
+
+// ---- line search ---------------------------------------------------------------------------------
+struct LsArgs {
+  int m, n, kind, mode /*0 equality-constrained, 1 unconstrained*/, iter0;
+  double t, alpha, beta, tol;
+  const double *gx, *ub, *Gd, *a, *Px, *Pd, *y;
+  double *x, *dir;
+};
+
+__device__ bool ls_in_set(const LsArgs& A, double s, int* ibuf) {
+  int out = 0;
+  for (int i = threadIdx.x; i < A.m; i += VT) {
+    double g = A.gx[i] + s * A.Gd[i];
+    if (!(g * IN_SET_FACTOR < A.ub[i])) out = 1;
+  }
+  return block_or(out, ibuf) == 0;
+}
+
+// barrier value at x + s*dir; *throws = 1 when some slack <= 0 (IllegalArgumentException in the reference)
+__device__ double ls_value(const LsArgs& A, double s, double f0, double c1, double c2, double* buf, int* ibuf,
+                           int* throws) {
+  double ls = 0.0;
+  int bad = 0;
+  for (int i = threadIdx.x; i < A.m; i += VT) {
+    double d = A.ub[i] - (A.gx[i] + s * A.Gd[i]);
+    if (!(d > 0.0)) bad = 1;
+    ls += log(d);
+  }
+  ls = block_sum(ls, buf);
+  bad = block_or(bad, ibuf);
+  *throws = bad;
+  double f0s;
+  if (A.kind == CVXB_OBJ_KL) {
+    double v = 0.0;
+    for (int j = threadIdx.x; j < A.n; j += VT) {
+      double xj = A.x[j] + s * A.dir[j];
+      v += xj * log(xj * (double)A.n);
+    }
+    f0s = block_sum(v, buf);
+  } else {
+    f0s = f0 + s * c1 + 0.5 * s * s * c2;   // exact along the ray for linear / quadratic objectives
+  }
+  return A.t * f0s - ls;
+}
+
+__global__ void __launch_bounds__(VT) linesearch_kernel(LsArgs A, double* scal, int* flag) {
+  __shared__ double buf[33];
+  __shared__ int ibuf[33];
+  // q = d . grad ;  objective line coefficients
+  double q = 0.0, c1 = 0.0, c2 = 0.0;
+  for (int j = threadIdx.x; j < A.n; j += VT) {
+    double dj = A.dir[j];
+    q = fma(dj, A.y[j], q);
+    if (A.kind == CVXB_OBJ_LINEAR) c1 = fma(A.a[j], dj, c1);
+    else if (A.kind == CVXB_OBJ_QUADRATIC) { c1 = fma(A.a[j] + A.Px[j], dj, c1); c2 = fma(dj, A.Pd[j], c2); }
+  }
+  q = block_sum(q, buf);
+  c1 = block_sum(c1, buf);
+  c2 = block_sum(c2, buf);
+  const double nd = -q / 2;
+  const double f = scal[S_FVAL], f0 = scal[S_F0];
+  const int upstream_bad = flag[F_BAD] | flag[F_INFEAS];
+  int status = 0, it = 0, taken = 0;
+  double step = 0.0;
+  if (!upstream_bad && nd > A.tol) {
+    if (A.mode == 0) {
+      // EqualityConstrainedSolver.scala:79-92 (one counter shared by both loops, defect D7)
+      double s = 1.0;
+      while (!ls_in_set(A, s, ibuf) && it < 100) { s *= A.beta; ++it; }
+      if (it == 100) status = 1;
+      else {
+        int thr = 0;
+        while (it < 100) {
+          double v = ls_value(A, s, f0, c1, c2, buf, ibuf, &thr);
+          if (thr) { status = 3; break; }
+          if (!(v > f + A.alpha * s * q)) break;
+          s *= A.beta; ++it;
+        }
+        if (!status && it == 100) status = 2;
+      }
+      step = s;
+    } else {
+      // UnconstrainedSolver.scala:85-115; rho = 1+1/4 == 1 in integer arithmetic (defect D4), so the
+      // trust radius stays at its first value; loops bounded by 200 but the failure test is it == 100.
+      const double hnorm = sqrt(-q);
+      double trust = A.iter0 ? hnorm : scal[S_TRUST];
+      const double sc = (A.iter0 || hnorm <= trust) ? 1.0 : trust / hnorm;
+      double tt = 1.0;
+      while (!ls_in_set(A, sc * tt, ibuf) && it < 200) { tt *= A.beta; ++it; }
+      if (it == 100) status = 1;
+      else {
+        int thr = 0;
+        if (ls_in_set(A, sc, ibuf)) {   // else-branch of :100-105 evaluates objF.valueAt(x + s*t)
+          (void)ls_value(A, sc * tt, f0, c1, c2, buf, ibuf, &thr);
+          if (thr) status = 3;
+        }
+        while (!status && it < 200) {
+          double v = ls_value(A, sc * tt, f0, c1, c2, buf, ibuf, &thr);
+          if (thr) { status = 3; break; }
+          if (!(v > f + A.alpha * tt * q)) break;
+          tt *= A.beta; ++it;
+        }
+        if (!status && it == 100) status = 2;
+      }
+      step = sc * tt;
+      if (threadIdx.x == 0) { scal[S_TRUST] = trust; scal[S_HNORM] = hnorm; }
+    }
+    if (!status) {
+      for (int j = threadIdx.x; j < A.n; j += VT) A.x[j] = A.x[j] + A.dir[j] * step;
+      taken = 1;
+    }
+  }
+  if (threadIdx.x == 0) {
+    scal[S_Q] = q;
+    scal[S_ND] = nd;
+    scal[S_STEP] = step;
+    flag[F_LS_STATUS] = status;
+    flag[F_LS_TRIALS] = it;
+    flag[F_STEP_TAKEN] = taken;
+  }
+}
+
+// ---- phase I construction -----------------------------------------------------------------------
+// G1 = [G, -1 ; Ae, -1] with Ae rows interleaved (a_i, -a_i), ub1 = [ub ; b_i + tol, -b_i + tol], r1 = [r ; 0]
+__global__ void phase1_build_kernel(int n, int m, int p, const double* __restrict__ G, int ldg,
+                                    const double* __restrict__ gr, const double* __restrict__ ub,
+                                    const double* __restrict__ A, int lda, const double* __restrict__ b, double eqtol,
+                                    double* __restrict__ G1, int ldg1, double* __restrict__ gr1,
+                                    double* __restrict__ ub1) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int m1 = m + 2 * p;
+  if (i >= m1) return;
+  for (int j = blockIdx.y; j <= n; j += gridDim.y) {
+    double v;
+    if (j == n) v = -1.0;
+    else if (i < m) v = G[(size_t)j * ldg + i];
+    else {
+      int k = (i - m) >> 1;
+      double a = A[(size_t)j * lda + k];
+      v = ((i - m) & 1) ? -a : a;
+    }
+    G1[(size_t)j * ldg1 + i] = v;
+  }
+  if (blockIdx.y == 0) {
+    if (i < m) { gr1[i] = gr ? gr[i] : 0.0; ub1[i] = ub[i]; }
+    else {
+      int k = (i - m) >> 1;
+      gr1[i] = 0.0;
+      ub1[i] = ((i - m) & 1) ? (-b[k] + eqtol) : (b[k] + eqtol);
+    }
+  }
+}
+
+// start of phase I: (x0, 1 + max_i (g_i(x0) - ub_i))   ConstraintSet.scala:161-163 ; gx holds G1[:, :n] x0 (s column = 0)
+__global__ void __launch_bounds__(VT) phase1_start_kernel(int m1, int n, const double* __restrict__ gx,
+                                                          const double* __restrict__ gr1, const double* __restrict__ ub1,
+                                                          double* __restrict__ x1) {
+  __shared__ double buf[33];
+  double mx = -1e308;
+  for (int i = threadIdx.x; i < m1; i += VT) mx = fmax(mx, (gr1[i] + gx[i]) - ub1[i]);
+  mx = -block_min(-mx, buf);
+  if (threadIdx.x == 0) x1[n] = 1.0 + mx;
+}
+
+__global__ void set_unit_kernel(int n, int k, double* a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (i == k) ? 1.0 : 0.0;
+}
+
+template <typename T>
+int palloc(cvxb_problem_s* P, T** ptr, size_t count) {
+  void* q = nullptr;
+  CVXB_CUDA_OK(cudaMalloc(&q, (count ? count : 1) * sizeof(T)));
+  CVXB_CUDA_OK(cudaMemsetAsync(q, 0, (count ? count : 1) * sizeof(T), P->h->stream));
+  P->owned.push_back(q);
+  *ptr = (T*)q;
+  return CVXB_OK;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------- problem objects
+int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s** out) {
+  cvxb_problem_s* P = new cvxb_problem_s();
+  P->h = &h;
+  P->n = n; P->m = m; P->p = p; P->objective = objective;
+  P->ldm = pad_ld(m); P->ldn = pad_ld(n); P->ldp = pad_ld(p);
+  int st = CVXB_OK;
+  auto A = [&](double** ptr, size_t c) { if (st == CVXB_OK) st = palloc(P, ptr, c); };
+  A(&P->G, (size_t)P->ldm * n); A(&P->gr, P->ldm); A(&P->ub, P->ldm);
+  A(&P->A, (size_t)P->ldp * n); A(&P->b, P->ldp);
+  A(&P->obj_a, P->ldn);
+  if (objective == CVXB_OBJ_QUADRATIC) A(&P->obj_P, (size_t)P->ldn * n);
+  A(&P->x_feas, P->ldn); A(&P->x_def, P->ldn);
+  A(&P->x, P->ldn); A(&P->gx, P->ldm); A(&P->inv, P->ldm); A(&P->Gd, P->ldm); A(&P->y, P->ldn); A(&P->gt, P->ldn);
+  A(&P->dir, P->ldn); A(&P->nu, P->ldp); A(&P->eqdiff, P->ldp); A(&P->Px, P->ldn); A(&P->Pd, P->ldn); A(&P->axv, P->ldp);
+  A(&P->Gs, (size_t)P->ldm * n); A(&P->H, (size_t)P->ldn * n);
+  if (st == CVXB_OK) st = kkt_work_alloc(h, P->kw, n, p);
+  if (st != CVXB_OK) {
+    for (void* q : P->owned) cudaFree(q);
+    kkt_work_free(P->kw);
+    delete P;
+    return st;
+  }
+  *out = P;
+  return CVXB_OK;
+}
+
+void problem_free(cvxb_problem_s* P) {
+  if (!P) return;
+  if (P->phase1) problem_free(P->phase1);
+  for (void* q : P->owned) cudaFree(q);
+  kkt_work_free(P->kw);
+  delete P;
+}
+
+// ------------------------------------------------------------------------------- barrier function
+// value / gradient / constraint state at P->x for barrier parameter t (E1-E6); no host sync
+int barrier_eval(cvxb_problem_s* P, double t) {
+  Handle& h = *P->h;
+  const int n = P->n, m = P->m, p = P->p;
+  CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->x, 0.0, P->gx));
+  if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->Px));
+  CVXB_LAUNCH(h, eval_cnt_kernel, 1, VT, 0, m, n, P->objective, P->obj_r, t, P->gr, P->ub, P->gx, P->inv, P->x,
+              P->obj_a, P->Px, h.d_scal, h.d_flag);
+  CVXB_TRY(gemv_t(h, m, n, 1.0, P->G, P->ldm, P->inv, 0.0, P->gt));
+  if (p > 0) CVXB_TRY(gemv_n(h, p, n, 1.0, P->A, P->ldp, P->x, 0.0, P->axv));
+  CVXB_LAUNCH(h, eval_grad_kernel, 1, VT, 0, n, p, P->objective, t, P->x, P->obj_a, P->Px, P->gt, P->y, P->b, P->axv,
+              P->eqdiff, h.d_scal);
+  return CVXB_OK;
+}
+
+// H = t*hess f0 + G' diag(1/d^2) G     BarrierSolver.scala:303-315 (weighted outer-product sum as one SYRK)
+int barrier_hessian(cvxb_problem_s* P, double t) {
+  Handle& h = *P->h;
+  const int n = P->n, m = P->m;
+  CVXB_TRY(scale_rows(h, m, n, P->G, P->ldm, P->inv, P->Gs, P->ldm, false));
+  if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(fill_matrix(h, n, t, P->obj_P, P->ldn, nullptr, 0.0, P->H, P->ldn));
+  else if (P->objective == CVXB_OBJ_KL) CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, t, P->H, P->ldn));
+  else CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, nullptr, 0.0, P->H, P->ldn));
+  GemmArgs g{n, n, m, P->Gs, P->ldm, true, P->Gs, P->ldm, true, P->H, P->ldn, 1.0, 1.0, 2};
+  return gemm_dmma_timed(h, g, (double)m * n * ((double)n + 1.0));   // lower triangle, mul + add
+}
+
+int enqueue_linesearch(cvxb_problem_s* P, const cvxb_params& pars, double t, int mode, int iter0) {
+  Handle& h = *P->h;
+  const int n = P->n, m = P->m;
+  CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->dir, 0.0, P->Gd));
+  if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->dir, 0.0, P->Pd));
+  LsArgs A;
+  A.m = m; A.n = n; A.kind = P->objective; A.mode = mode; A.iter0 = iter0;
+  A.t = t; A.alpha = pars.alpha; A.beta = pars.beta; A.tol = pars.tolSolver;
+  A.gx = P->gx; A.ub = P->ub; A.Gd = P->Gd; A.a = P->obj_a; A.Px = P->Px; A.Pd = P->Pd; A.y = P->y;
+  A.x = P->x; A.dir = P->dir;
+  CVXB_LAUNCH(h, linesearch_kernel, 1, VT, 0, A, h.d_scal, h.d_flag);
+  return CVXB_OK;
+}
+
+struct InnerResult {
+  double nd = 0, normGrad = 0, eqGap = 0;
+  int iter = 0;
+  bool maxedOut = false;
+  long long executed = 0, trials = 0;
+  int fallbacks = 0, regularized = 0;
+};
+
+struct RunStats {
+  long long budget = 0;       // remaining Newton steps when stepLimit > 0
+  bool limited = false;
+};
+
+static int ls_status_to_error(Handle& h, const char* who) {
+  int s = h.h_flag[F_LS_STATUS];
+  if (s == 0) return CVXB_OK;
+  if (s == 3) {
+    set_last_error("%s: barrierFunction: x not strictly feasible at a line-search trial point "
+                   "(IllegalArgumentException, BarrierSolver.scala:284)", who);
+    return CVXB_ENOTFEASIBLE;
+  }
+  set_last_error("%s: Line search: %s", who, s == 1 ? "backtracking into the set C failed."
+                                                    : "sufficient decrease not reached after 100 iterations.");
+  return CVXB_ELINESEARCH;
+}
+
+// EqualityConstrainedSolver.solve (EqualityConstrainedSolver.scala:37-107) at barrier parameter t, from P->x
+int inner_solve_eq(cvxb_problem_s* P, const cvxb_params& pars, double t, RunStats& rs, InnerResult& R) {
+  Handle& h = *P->h;
+  const double tol = pars.tolSolver;
+  R = InnerResult();
+  R.nd = tol + 1;
+  CVXB_TRY(barrier_eval(P, t));
+  CVXB_TRY(fetch_status(h));
+  if (h.h_flag[F_INFEAS]) { set_last_error("gradientBarrierFunction: x not strictly feasible"); return CVXB_ENOTFEASIBLE; }
+  R.normGrad = h.h_scal[S_NORMGRAD];
+  R.eqGap = h.h_scal[S_EQNORM];
+  while (R.iter < pars.maxIter && ((R.nd > tol && R.normGrad > tol) || R.eqGap > tol)) {
+    if (rs.limited && rs.budget <= 0) break;
+    CVXB_TRY(barrier_hessian(P, t));
+    CVXB_TRY(kkt_enqueue(h, P->kw, pars, P->H, P->ldn, P->A, P->ldp, P->y, P->eqdiff, pars.tolEqSolve, false, false,
+                         P->dir, P->nu));
+    CVXB_TRY(enqueue_linesearch(P, pars, t, 0, 0));
+    CVXB_TRY(barrier_eval(P, t));
+    CVXB_TRY(fetch_status(h));
+    if (h.h_flag[F_BAD]) {
+      // optimistic attempt refused on the device (x untouched): walk the reference's fallback chain
+      cvxb_kkt_info info;
+      CVXB_TRY(kkt_solve_fallbacks(h, P->kw, pars, P->H, P->ldn, P->A, P->ldp, P->y, P->eqdiff, pars.tolEqSolve,
+                                   P->dir, P->nu, &info));
+      if (info.path) R.fallbacks++;
+      if (info.regularized) R.regularized++;
+      CVXB_TRY(enqueue_linesearch(P, pars, t, 0, 0));
+      CVXB_TRY(barrier_eval(P, t));
+      CVXB_TRY(fetch_status(h));
+    }
+    CVXB_TRY(ls_status_to_error(h, "EqualityConstrainedSolver"));
+    if (h.h_flag[F_INFEAS]) { set_last_error("gradientBarrierFunction: x not strictly feasible"); return CVXB_ENOTFEASIBLE; }
+    R.nd = h.h_scal[S_ND];
+    R.executed++;
+    if (rs.limited) rs.budget--;
+    R.iter++;
+    if (h.h_flag[F_STEP_TAKEN]) {
+      R.trials += h.h_flag[F_LS_TRIALS];
+      R.normGrad = h.h_scal[S_NORMGRAD];
+      R.eqGap = h.h_scal[S_EQNORM];
+    } else if ((R.nd > tol && R.normGrad > tol) || R.eqGap > tol) {
+      // No step was taken, so x, H and d repeat exactly: the reference spins here until maxIter
+      // (its loop condition keeps ||b-Ax|| > tol alive).  Same result, without re-running identical steps.
+      if (!(R.nd > tol)) { R.iter = pars.maxIter; break; }
+    }
+  }
+  R.maxedOut = R.iter >= pars.maxIter;
+  return CVXB_OK;
+}
+
+// UnconstrainedSolver.solve (UnconstrainedSolver.scala:34-125)
+int inner_solve_uncon(cvxb_problem_s* P, const cvxb_params& pars, double t, RunStats& rs, InnerResult& R) {
+  Handle& h = *P->h;
+  const double tol = pars.tolSolver;
+  const int n = P->n;
+  R = InnerResult();
+  R.nd = tol + 1;
+  CVXB_TRY(barrier_eval(P, t));
+  CVXB_TRY(fetch_status(h));
+  if (h.h_flag[F_INFEAS]) { set_last_error("gradientBarrierFunction: x not strictly feasible"); return CVXB_ENOTFEASIBLE; }
+  R.normGrad = h.h_scal[S_NORMGRAD];
+  while (R.iter < pars.maxIter && R.nd > tol && R.normGrad > tol) {
+    if (rs.limited && rs.budget <= 0) break;
+    CVXB_TRY(barrier_hessian(P, t));
+    CVXB_TRY(chol_enqueue(h, P->kw, pars, P->H, P->ldn, P->y, -1.0, pars.tolEqSolve, false, false, P->dir));
+    CVXB_TRY(enqueue_linesearch(P, pars, t, 1, R.iter == 0));
+    CVXB_TRY(barrier_eval(P, t));
+    CVXB_TRY(fetch_status(h));
+    if (h.h_flag[F_BAD]) {
+      cvxb_kkt_info info;
+      int st = chol_solve_retry(h, P->kw, pars, P->H, P->ldn, P->y, -1.0, pars.tolEqSolve, P->dir, &info);
+      if (st == CVXB_ELINSOLVE) {
+        // choleskySolve(H + 1e-9 I, -y)    UnconstrainedSolver.scala:58-61
+        if (!P->Hreg) CVXB_TRY(palloc(P, &P->Hreg, (size_t)P->ldn * n));
+        CVXB_TRY(copy_matrix(h, n, n, P->H, P->ldn, P->Hreg, P->ldn));
+        CVXB_TRY(add_diag(h, n, pars.newtonRegDelta, P->Hreg, P->ldn));
+        st = chol_solve_device(h, P->kw, pars, P->Hreg, P->ldn, P->y, -1.0, pars.tolEqSolve, P->dir, &info);
+        R.fallbacks++;
+        if (st == CVXB_ELINSOLVE) {
+          set_last_error("UnconstrainedSolver: choleskySolve failed on H and on H + 1e-9 I; the symSolve "
+                         "(eigendecomposition) fallback (UnconstrainedSolver.scala:65) is not implemented on the device");
+          return CVXB_ELINSOLVE;
+        }
+      }
+      if (st != CVXB_OK) return st;
+      if (info.regularized) R.regularized++;
+      CVXB_TRY(enqueue_linesearch(P, pars, t, 1, R.iter == 0));
+      CVXB_TRY(barrier_eval(P, t));
+      CVXB_TRY(fetch_status(h));
+    }
+    CVXB_TRY(ls_status_to_error(h, "UnconstrainedSolver"));
+    if (h.h_flag[F_INFEAS]) { set_last_error("gradientBarrierFunction: x not strictly feasible"); return CVXB_ENOTFEASIBLE; }
+    R.nd = h.h_scal[S_ND];
+    R.executed++;
+    if (rs.limited) rs.budget--;
+    R.iter++;
+    if (h.h_flag[F_STEP_TAKEN]) {
+      R.trials += h.h_flag[F_LS_TRIALS];
+      R.normGrad = h.h_scal[S_NORMGRAD];
+    }
+  }
+  R.maxedOut = R.iter >= pars.maxIter;
+  return CVXB_OK;
+}
+
+enum Termination { TERM_STANDARD = 0, TERM_PHASE1 = 1 };
+
+// BarrierSolver.solveWithEQs / solveWithoutEQs (BarrierSolver.scala:70-177), from P->x
+int barrier_loop(cvxb_problem_s* P, const cvxb_params& pars, int term, RunStats& rs, cvxb_solution* out) {
+  Handle& h = *P->h;
+  const double mu = pars.mu;
+  double t = pars.t0;
+  double dualityGap = 1.7976931348623157e308, equalityGap = 1.7976931348623157e308, objValue = 1.7976931348623157e308;
+  const bool withEqs = P->p > 0;
+  const double maxIter = 1000.0 / mu;
+  int it = 0;
+  InnerResult R;
+  long long steps = 0, executed = 0, trials = 0;
+  int fallbacks = 0, regularized = 0;
+  auto terminated = [&]() {
+    if (term == TERM_STANDARD) return dualityGap < pars.tolSolver && equalityGap < pars.tolSolver;
+    return objValue < 0.0 && equalityGap < pars.phase1EqTol;    // CvxUtils.scala:78-87
+  };
+  // first check uses the MaxValue state, never true
+  while (!terminated() && it < maxIter) {
+    int st = withEqs ? inner_solve_eq(P, pars, t, rs, R) : inner_solve_uncon(P, pars, t, rs, R);
+    if (st != CVXB_OK) return st;
+    if (it < 128) out->stage_newton_steps[it] = R.iter;
+    steps += R.iter; executed += R.executed; trials += R.trials;
+    fallbacks += R.fallbacks; regularized += R.regularized;
+    objValue = h.h_scal[S_F0];             // objF.valueAt(x) at the stage's final iterate
+    dualityGap = (double)P->m / t;
+    equalityGap = withEqs ? R.eqGap : 0.0;
+    t = mu * t;
+    it++;
+    if (rs.limited && rs.budget <= 0) break;
+  }
+  out->newtonDecrement = R.nd; out->has_newtonDecrement = 1;
+  out->dualityGap = dualityGap; out->has_dualityGap = 1;
+  out->equalityGap = withEqs ? equalityGap : 0.0; out->has_equalityGap = withEqs ? 1 : 0;
+  out->normGrad = R.normGrad; out->has_normGrad = 1;
+  out->has_normDualResidual = 0; out->normDualResidual = 0;
+  out->has_lambda = out->has_nu = 0;
+  out->iter = R.iter;
+  out->maxedOut = R.maxedOut ? 1 : 0;
+  out->objective = objValue;
+  out->outer_stages = it;
+  out->newton_steps = steps;
+  out->executed_newton_steps = executed;
+  out->linesearch_trials = trials;
+  out->kkt_fallbacks = fallbacks;
+  out->kkt_regularized = regularized;
+  return CVXB_OK;
+}
+
+// ConstraintSet.withFeasiblePoint -> phase_I_Analysis (ConstraintSet.scala:326-395, 556-575)
+int run_phase1(cvxb_problem_s* P, const cvxb_params& pars, RunStats& rs, cvxb_solution* ph_out) {
+  Handle& h = *P->h;
+  const int n = P->n, m = P->m, p = P->p;
+  const int m1 = m + 2 * p;
+  if (!P->phase1) {
+    CVXB_TRY(problem_alloc(h, n + 1, m1, 0, CVXB_OBJ_LINEAR, &P->phase1));
+    cvxb_problem_s* Q = P->phase1;
+    dim3 grid((m1 + 127) / 128, n + 1 > 1024 ? 1024 : n + 1);
+    CVXB_LAUNCH(h, phase1_build_kernel, grid, 128, 0, n, m, p, P->G, P->ldm, P->gr, P->ub, P->A, P->ldp, P->b,
+                pars.phase1EqTol, Q->G, Q->ldm, Q->gr, Q->ub);
+    CVXB_LAUNCH(h, set_unit_kernel, (n + 1 + 255) / 256, 256, 0, n + 1, n, Q->obj_a);   // f(x,s) = s  (:131-144)
+    Q->obj_r = 0.0;
+  }
+  cvxb_problem_s* Q = P->phase1;
+  // start (pointWhereDefined, 1 + max(g - ub))
+  CVXB_CUDA_OK(cudaMemsetAsync(Q->x, 0, (size_t)Q->ldn * sizeof(double), h.stream));
+  CVXB_CUDA_OK(cudaMemcpyAsync(Q->x, P->x_def, n * sizeof(double), cudaMemcpyDeviceToDevice, h.stream));
+  CVXB_TRY(gemv_n(h, m1, n + 1, 1.0, Q->G, Q->ldm, Q->x, 0.0, Q->gx));
+  CVXB_LAUNCH(h, phase1_start_kernel, 1, VT, 0, m1, n, Q->gx, Q->gr, Q->ub, Q->x);
+  cvxb_solution sol;
+  memset(&sol, 0, sizeof(sol));
+  int st = barrier_loop(Q, pars, TERM_PHASE1, rs, &sol);
+  if (ph_out) {
+    double *x = ph_out->x, *l = ph_out->lambda, *nu = ph_out->nu;
+    *ph_out = sol;
+    ph_out->x = x; ph_out->lambda = l; ph_out->nu = nu;
+  }
+  if (st != CVXB_OK) return st;
+  double s_feas = 0;
+  CVXB_CUDA_OK(cudaMemcpyAsync(&s_feas, Q->x + n, sizeof(double), cudaMemcpyDeviceToHost, h.stream));
+  CVXB_CUDA_OK(cudaStreamSynchronize(h.stream));
+  if (ph_out) ph_out->phase1_s = s_feas;
+  if (rs.limited && rs.budget <= 0) return CVXB_OK;     // step-limited benchmark run: stop here
+  if (!(s_feas < pars.tolSolver)) {   // FeasibilityReport.isFeasible(tol)
+    set_last_error("Problem not feasible within tolerance %g: phase I slack s = %g (InfeasibleProblemException)",
+                   pars.tolSolver, s_feas);
+    return CVXB_EINFEASIBLE;
+  }
+  CVXB_CUDA_OK(cudaMemcpyAsync(P->x_feas, Q->x, n * sizeof(double), cudaMemcpyDeviceToDevice, h.stream));
+  P->has_feasible = true;
+  return CVXB_OK;
+}
+
+int upload_vec(Handle& h, double* dst, const double* src, int n) {
+  if (!src || n <= 0) return CVXB_OK;
+  bool dev = (h.flags & CVXB_FLAG_DEVICE_PTRS) != 0;
+  CVXB_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                               h.stream));
+  return CVXB_OK;
+}
+int upload_mat(Handle& h, double* dst, int ldd, const double* src, int lds, int rows, int cols) {
+  if (!src || rows <= 0 || cols <= 0) return CVXB_OK;
+  bool dev = (h.flags & CVXB_FLAG_DEVICE_PTRS) != 0;
+  CVXB_CUDA_OK(cudaMemcpy2DAsync(dst, (size_t)ldd * sizeof(double), src, (size_t)lds * sizeof(double),
+                                 (size_t)rows * sizeof(double), cols, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                 h.stream));
+  return CVXB_OK;
+}
+int download_vec(Handle& h, double* dst, const double* src, int n) {
+  if (!dst || n <= 0) return CVXB_OK;
+  bool dev = (h.flags & CVXB_FLAG_DEVICE_PTRS) != 0;
+  CVXB_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                               h.stream));
+  return CVXB_OK;
+}
+
+}  // namespace cvxb
+
+#define CHECK_HP(h, prob)                                                                        \
+  if (!(h) || !(prob)) { cvxb::set_last_error("null handle or problem"); return CVXB_EINVAL; }  \
+  if ((prob)->h != (h)) { cvxb::set_last_error("problem belongs to another handle"); return CVXB_EINVAL; } \
+  int _prev_dev = 0; cudaGetDevice(&_prev_dev); cudaSetDevice((h)->device)
+
+extern "C" {
+
+int cvxb_problem_create(cvxb_handle h, const cvxb_problem_desc* d, cvxb_problem* out) {
+  if (!h || !d || !out) { cvxb::set_last_error("cvxb_problem_create: null argument"); return CVXB_EINVAL; }
+  if (d->n < 1 || d->m < 1 || d->p < 0) {
+    cvxb::set_last_error("cvxb_problem_create: need n >= 1, m >= 1, p >= 0 (got %d, %d, %d)", d->n, d->m, d->p);
+    return CVXB_EDIM;
+  }
+  if (d->objective < CVXB_OBJ_LINEAR || d->objective > CVXB_OBJ_KL) { cvxb::set_last_error("unknown objective kind"); return CVXB_EINVAL; }
+  if (!d->G || !d->ub || (d->p > 0 && (!d->A || !d->b)) || (!d->x_feasible && !d->x_defined) ||
+      (d->objective != CVXB_OBJ_KL && !d->obj_a) || (d->objective == CVXB_OBJ_QUADRATIC && !d->obj_P)) {
+    cvxb::set_last_error("cvxb_problem_create: missing array for this problem family");
+    return CVXB_EINVAL;
+  }
+  if (d->ldg < d->m || (d->p > 0 && d->lda < d->p) || (d->objective == CVXB_OBJ_QUADRATIC && d->obj_ldP < d->n)) {
+    cvxb::set_last_error("cvxb_problem_create: leading dimension too small");
+    return CVXB_EDIM;
+  }
+  cudaSetDevice(h->device);
+  cvxb_problem_s* P = nullptr;
+  CVXB_TRY(problem_alloc(*h, d->n, d->m, d->p, d->objective, &P));
+  int st = CVXB_OK;
+  auto T = [&](int s) { if (st == CVXB_OK) st = s; };
+  T(upload_mat(*h, P->G, P->ldm, d->G, d->ldg, d->m, d->n));
+  T(upload_vec(*h, P->gr, d->g_r, d->m));
+  T(upload_vec(*h, P->ub, d->ub, d->m));
+  T(upload_mat(*h, P->A, P->ldp, d->A, d->lda, d->p, d->n));
+  T(upload_vec(*h, P->b, d->b, d->p));
+  T(upload_vec(*h, P->obj_a, d->obj_a, d->n));
+  if (d->objective == CVXB_OBJ_QUADRATIC) T(upload_mat(*h, P->obj_P, P->ldn, d->obj_P, d->obj_ldP, d->n, d->n));
+  P->obj_r = d->obj_r;
+  if (d->x_feasible) { T(upload_vec(*h, P->x_feas, d->x_feasible, d->n)); P->has_feasible = true; }
+  T(upload_vec(*h, P->x_def, d->x_defined ? d->x_defined : d->x_feasible, d->n));
+  if (st == CVXB_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) { cvxb::set_last_error("upload failed"); st = CVXB_ECUDA; }
+  if (st != CVXB_OK) { problem_free(P); return st; }
+  *out = P;
+  return CVXB_OK;
+}
+
+int cvxb_problem_destroy(cvxb_problem prob) {
+  if (!prob) return CVXB_OK;
+  cudaSetDevice(prob->h->device);
+  cudaStreamSynchronize(prob->h->stream);
+  problem_free(prob);
+  return CVXB_OK;
+}
+
+static void init_run(const cvxb_params* pars, RunStats& rs) {
+  rs.limited = pars->stepLimit > 0;
+  rs.budget = pars->stepLimit;
+}
+
+int cvxb_phase1(cvxb_handle h, cvxb_problem prob, const cvxb_params* pars, double* x_feas, cvxb_solution* ph) {
+  CHECK_HP(h, prob);
+  cvxb_params dp;
+  if (!pars) { cvxb_default_params(&dp); pars = &dp; }
+  RunStats rs;
+  init_run(pars, rs);
+  CVXB_CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+  int st = run_phase1(prob, *pars, rs, ph);
+  cudaEventRecord(h->ev1, h->stream);
+  cudaEventSynchronize(h->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  if (ph) {
+    ph->solve_ms = ms;
+    if (prob->phase1) download_vec(*h, ph->x, prob->phase1->x, prob->n + 1);
+  }
+  if (st == CVXB_OK && x_feas) CVXB_TRY(download_vec(*h, x_feas, prob->x_feas, prob->n));
+  cudaStreamSynchronize(h->stream);
+  return st;
+}
+
+int cvxb_barrier_solve(cvxb_handle h, cvxb_problem prob, const cvxb_params* pars, cvxb_solution* out) {
+  CHECK_HP(h, prob);
+  if (!out) { cvxb::set_last_error("cvxb_barrier_solve: null solution"); return CVXB_EINVAL; }
+  cvxb_params dp;
+  if (!pars) { cvxb_default_params(&dp); pars = &dp; }
+  RunStats rs;
+  init_run(pars, rs);
+  double *ox = out->x, *ol = out->lambda, *onu = out->nu;
+  memset(out, 0, sizeof(*out));
+  out->x = ox; out->lambda = ol; out->nu = onu;
+  CVXB_CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+  long long ph_steps = 0, ph_exec = 0;
+  int ph_stages = 0;
+  double ph_s = 0;
+  if (!prob->has_feasible) {   // OptimizationProblem.withoutFeasiblePoint: phase I first (OptimizationProblem.scala:174-196)
+    cvxb_solution ph;
+    memset(&ph, 0, sizeof(ph));
+    int st = run_phase1(prob, *pars, rs, &ph);
+    ph_steps = ph.newton_steps; ph_exec = ph.executed_newton_steps; ph_stages = ph.outer_stages; ph_s = ph.phase1_s;
+    if (st != CVXB_OK || (rs.limited && rs.budget <= 0)) {
+      out->phase1_newton_steps = ph_steps; out->phase1_executed_steps = ph_exec; out->phase1_stages = ph_stages;
+      out->phase1_s = ph_s;
+      cudaEventRecord(h->ev1, h->stream); cudaEventSynchronize(h->ev1);
+      float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); out->solve_ms = ms;
+      return st;
+    }
+  }
+  CVXB_CUDA_OK(cudaMemcpyAsync(prob->x, prob->x_feas, prob->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  int st = barrier_loop(prob, *pars, TERM_STANDARD, rs, out);
+  out->phase1_newton_steps = ph_steps; out->phase1_executed_steps = ph_exec; out->phase1_stages = ph_stages;
+  out->phase1_s = ph_s;
+  cudaEventRecord(h->ev1, h->stream);
+  cudaEventSynchronize(h->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  out->solve_ms = ms;
+  if (st != CVXB_OK) return st;
+  CVXB_TRY(download_vec(*h, out->x, prob->x, prob->n));
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CVXB_OK;
+}
+
+int cvxb_barrier_newton_direction(cvxb_handle h, cvxb_problem prob, const cvxb_params* pars, const double* x, double t,
+                                  double* H_out, double* g_out, double* dx, double* nu, cvxb_kkt_info* info) {
+  CHECK_HP(h, prob);
+  if (!x) { cvxb::set_last_error("null x"); return CVXB_EINVAL; }
+  cvxb_params dp;
+  if (!pars) { cvxb_default_params(&dp); pars = &dp; }
+  cvxb_problem_s* P = prob;
+  CVXB_TRY(upload_vec(*h, P->x, x, P->n));
+  CVXB_TRY(barrier_eval(P, t));
+  CVXB_TRY(barrier_hessian(P, t));
+  CVXB_TRY(fetch_status(*h));
+  if (h->h_flag[F_INFEAS]) { cvxb::set_last_error("hessianBarrierFunction: x not strictly feasible"); return CVXB_ENOTFEASIBLE; }
+  int st;
+  if (P->p > 0)
+    st = kkt_solve_device(*h, P->kw, *pars, P->H, P->ldn, P->A, P->ldp, P->y, P->eqdiff, pars->tolEqSolve, P->dir, P->nu, info);
+  else
+    st = chol_solve_device(*h, P->kw, *pars, P->H, P->ldn, P->y, -1.0, pars->tolEqSolve, P->dir, info);
+  if (H_out) {
+    bool dev = (h->flags & CVXB_FLAG_DEVICE_PTRS) != 0;
+    CVXB_CUDA_OK(cudaMemcpy2DAsync(H_out, (size_t)P->n * sizeof(double), P->H, (size_t)P->ldn * sizeof(double),
+                                   (size_t)P->n * sizeof(double), P->n, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                   h->stream));
+  }
+  CVXB_TRY(download_vec(*h, g_out, P->y, P->n));
+  if (st == CVXB_OK) {
+    CVXB_TRY(download_vec(*h, dx, P->dir, P->n));
+    if (P->p > 0) CVXB_TRY(download_vec(*h, nu, P->nu, P->p));
+  }
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return st;
+}
+
+}  // extern "C"

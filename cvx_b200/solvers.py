@@ -1,0 +1,329 @@
+"""Host-side mirror of the reference's problem / solver API (seam A), the closed-form families only:
+
+  SolverParams                       SolverParams.scala:24-46
+  Solution                           Solution.scala:32-43
+  LinearObjectiveFunction(dim,r,a)   LinearObjectiveFunction.scala:5-22
+  QuadraticObjectiveFunction(dim,r,a,P)   QuadraticObjectiveFunction.scala:11-33
+  Dist_KL objective                  Dist_KL.scala:223-239
+  ConstraintSet(H, u)                ConstraintSet.apply(H,u,C), ConstraintSet.scala:621-638 (rows are LinearConstraints)
+  EqualityConstraint(A, b)           EqualityConstraint.scala:16-23
+  BarrierSolver(objF, cnts, eqs, pars).solve()          BarrierSolver.scala:184-188, 269-278
+  PrimalDualSolver(objF, cnts, eqs, pars).solve()       PrimalDualSolver.scala:628-641, 718-728
+  OptimizationProblem(id, objF, ineqs, eqs, solverType, pars).solve()   OptimizationProblem.scala:19,133-196
+  Dist_KL(n, H, u, A, r, solverType, pars)              Dist_KL.scala:270-315
+
+The objects only describe the problem; `solve` uploads the descriptor once (cvxb_problem_create) and
+the whole solve -- phase I included -- runs device-resident in libcvxb (cvxb_barrier_solve /
+cvxb_pd_solve).  numpy arrays stand in for Breeze DenseMatrix / DenseVector.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import (KktInfo, Params, ProblemDesc, SolutionC, check, dptr, fmat, fvec, ptr,
+                   OBJ_KL, OBJ_LINEAR, OBJ_QUADRATIC)
+
+
+@dataclass
+class SolverParams:
+    maxIter: int = 1000
+    alpha: float = 0.04
+    beta: float = 0.8
+    tolSolver: float = 1e-8
+    tolEqSolve: float = 1e-1
+    tolFeas: float = 1e-7
+    delta: float = 1e-6
+    # not in the reference record: PrimalDualSolver.solve_withEQs defects D1/D2 reproduced when True
+    bugCompat: bool = False
+    # benchmark aid: stop after this many Newton steps in total (0 = run to termination)
+    stepLimit: int = 0
+
+    @staticmethod
+    def standardParams(dim: int = 0) -> "SolverParams":
+        return SolverParams()
+
+    def to_c(self, handle) -> Params:
+        p = handle.default_params()
+        for k in ("maxIter", "alpha", "beta", "tolSolver", "tolEqSolve", "tolFeas", "delta"):
+            setattr(p, k, getattr(self, k))
+        p.bugCompat = int(self.bugCompat)
+        p.stepLimit = int(self.stepLimit)
+        return p
+
+
+@dataclass
+class Solution:
+    """Solution.scala:32-43 (Option fields are None when the reference has None) + bookkeeping."""
+    x: np.ndarray
+    lam: Optional[np.ndarray] = None
+    nu: Optional[np.ndarray] = None
+    newtonDecrement: Optional[float] = None
+    dualityGap: Optional[float] = None
+    equalityGap: Optional[float] = None
+    normGrad: Optional[float] = None
+    normDualResidual: Optional[float] = None
+    iter: int = 0
+    maxedOut: bool = False
+    objective: float = float("nan")
+    outer_stages: int = 0
+    newton_steps: int = 0
+    executed_newton_steps: int = 0
+    stage_newton_steps: List[int] = field(default_factory=list)
+    phase1_newton_steps: int = 0
+    phase1_executed_steps: int = 0
+    phase1_stages: int = 0
+    phase1_s: float = float("nan")
+    linesearch_trials: int = 0
+    kkt_fallbacks: int = 0
+    kkt_regularized: int = 0
+    solve_ms: float = 0.0
+
+
+class ObjectiveFunction:
+    dim: int
+    kind: int
+
+
+class LinearObjectiveFunction(ObjectiveFunction):
+    kind = OBJ_LINEAR
+
+    def __init__(self, dim, r, a):
+        self.dim, self.r, self.a = int(dim), float(r), fvec(a)
+        assert self.a.shape[0] == self.dim
+
+
+class QuadraticObjectiveFunction(ObjectiveFunction):
+    kind = OBJ_QUADRATIC
+
+    def __init__(self, dim, r, a, P):
+        self.dim, self.r, self.a, self.P = int(dim), float(r), fvec(a), fmat(P)
+        assert self.a.shape[0] == self.dim and self.P.shape == (self.dim, self.dim)
+
+
+class KLObjectiveFunction(ObjectiveFunction):
+    """Dist_KL.objectiveFunction: sum_j x_j log(n x_j)."""
+    kind = OBJ_KL
+
+    def __init__(self, dim):
+        self.dim, self.r, self.a = int(dim), 0.0, None
+
+
+class ConstraintSet:
+    """Linear inequality block  r + Hx <= u  (one LinearConstraint per row)."""
+
+    def __init__(self, H, u, pointWhereDefined=None, r=None):
+        self.H = fmat(H)
+        self.u = fvec(u)
+        self.r = None if r is None else fvec(r)
+        self.dim = self.H.shape[1]
+        assert self.u.shape[0] == self.H.shape[0]
+        self.pointWhereDefined = None if pointWhereDefined is None else fvec(pointWhereDefined)
+        self.feasiblePoint = None
+
+    @property
+    def numConstraints(self):
+        return self.H.shape[0]
+
+    def addFeasiblePoint(self, x0):
+        """ConstraintSet.addFeasiblePoint (ConstraintSet.scala:43-54)."""
+        c = ConstraintSet(self.H, self.u, self.pointWhereDefined if self.pointWhereDefined is not None else x0, self.r)
+        c.feasiblePoint = fvec(x0)
+        return c
+
+
+class EqualityConstraint:
+    def __init__(self, A, b):
+        self.A, self.b = fmat(A), fvec(b)
+        assert self.A.shape[0] == self.b.shape[0]
+
+
+class _DeviceProblem:
+    """cvxb_problem: the uploaded descriptor.  Keeps the host arrays alive during the upload."""
+
+    def __init__(self, objF, cnts: ConstraintSet, eqs: Optional[EqualityConstraint], handle):
+        self.handle = handle if handle is not None else _lib.default_handle()
+        n, m = cnts.dim, cnts.numConstraints
+        assert objF.dim == n, "objective / constraint dimension mismatch"
+        d = ProblemDesc()
+        d.n, d.m, d.p = n, m, 0 if eqs is None else eqs.A.shape[0]
+        d.objective = objF.kind
+        d.obj_a = dptr(objF.a) if objF.a is not None else None
+        d.obj_r = objF.r
+        if objF.kind == OBJ_QUADRATIC:
+            d.obj_P, d.obj_ldP = dptr(objF.P), n
+        d.G, d.ldg = dptr(cnts.H), m
+        d.g_r = dptr(cnts.r) if cnts.r is not None else None
+        d.ub = dptr(cnts.u)
+        if eqs is not None:
+            assert eqs.A.shape[1] == n
+            d.A, d.lda, d.b = dptr(eqs.A), eqs.A.shape[0], dptr(eqs.b)
+        d.x_feasible = dptr(cnts.feasiblePoint) if cnts.feasiblePoint is not None else None
+        d.x_defined = dptr(cnts.pointWhereDefined) if cnts.pointWhereDefined is not None else None
+        self.n, self.m, self.p = d.n, d.m, d.p
+        self._keep = (objF, cnts, eqs)
+        self._p = C.c_void_p()
+        check(self.handle.lib.cvxb_problem_create(self.handle._h, C.byref(d), C.byref(self._p)))
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self.handle.lib.cvxb_problem_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _solution_from_c(s: SolutionC, x, lam, nu) -> Solution:
+    opt = lambda has, v: float(v) if has else None
+    stages = int(s.outer_stages)
+    return Solution(
+        x=x, lam=lam if s.has_lambda else None, nu=nu if s.has_nu else None,
+        newtonDecrement=opt(s.has_newtonDecrement, s.newtonDecrement), dualityGap=opt(s.has_dualityGap, s.dualityGap),
+        equalityGap=opt(s.has_equalityGap, s.equalityGap), normGrad=opt(s.has_normGrad, s.normGrad),
+        normDualResidual=opt(s.has_normDualResidual, s.normDualResidual), iter=int(s.iter), maxedOut=bool(s.maxedOut),
+        objective=float(s.objective), outer_stages=stages, newton_steps=int(s.newton_steps),
+        executed_newton_steps=int(s.executed_newton_steps),
+        stage_newton_steps=[int(s.stage_newton_steps[i]) for i in range(min(stages, 128))],
+        phase1_newton_steps=int(s.phase1_newton_steps), phase1_executed_steps=int(s.phase1_executed_steps),
+        phase1_stages=int(s.phase1_stages), phase1_s=float(s.phase1_s), linesearch_trials=int(s.linesearch_trials),
+        kkt_fallbacks=int(s.kkt_fallbacks), kkt_regularized=int(s.kkt_regularized), solve_ms=float(s.solve_ms))
+
+
+class Solver:
+    """Solver trait (Solver.scala:29-33)."""
+
+    solverType = "BR"
+
+    def __init__(self, objF, cnts, eqs=None, pars=None, logger=None, handle=None):
+        self.objF, self.cnts, self.eqs = objF, cnts, eqs
+        self.pars = pars if pars is not None else SolverParams.standardParams()
+        self.problem = _DeviceProblem(objF, cnts, eqs, handle)
+        self.handle = self.problem.handle
+
+    def _run(self, fn):
+        pr = self.problem
+        x = np.zeros(pr.n)
+        lam = np.zeros(max(pr.m, 1))
+        nu = np.zeros(max(pr.p, 1))
+        s = SolutionC()
+        s.x, s.lam, s.nu = dptr(x), dptr(lam), dptr(nu)
+        cp = self.pars.to_c(self.handle)
+        check(fn(self.handle._h, pr._p, C.byref(cp), C.byref(s)))
+        return _solution_from_c(s, x, lam[:pr.m], nu[:pr.p])
+
+    def solve(self, debugLevel: int = 0) -> Solution:
+        raise NotImplementedError
+
+
+class BarrierSolver(Solver):
+    """BarrierSolver(objF, cnts, eqs, pars, logger).solve(debugLevel); phase I runs first when the
+    constraint set has no feasible point (what OptimizationProblem.withoutFeasiblePoint does)."""
+    solverType = "BR"
+
+    def solve(self, debugLevel: int = 0) -> Solution:
+        return self._run(self.handle.lib.cvxb_barrier_solve)
+
+    def phase_I(self):
+        """ConstraintSet.withFeasiblePoint: returns (x_feasible, phase-I Solution whose x is (x, s))."""
+        pr = self.problem
+        xf = np.zeros(pr.n)
+        w = np.zeros(pr.n + 1)
+        s = SolutionC()
+        s.x = dptr(w)
+        cp = self.pars.to_c(self.handle)
+        check(self.handle.lib.cvxb_phase1(self.handle._h, pr._p, C.byref(cp), ptr(xf), C.byref(s)))
+        return xf, _solution_from_c(s, w, None, None)
+
+    def newton_direction(self, x, t):
+        """One barrier Newton direction at (x, t): (H, grad, dx, nu, info)  -- per-step parity hook."""
+        pr = self.problem
+        x = fvec(x)
+        H = np.empty((pr.n, pr.n), order="F")
+        g = np.empty(pr.n)
+        dx = np.empty(pr.n)
+        nu = np.empty(max(pr.p, 1))
+        info = KktInfo()
+        cp = self.pars.to_c(self.handle)
+        check(self.handle.lib.cvxb_barrier_newton_direction(self.handle._h, pr._p, C.byref(cp), ptr(x), float(t), ptr(H),
+                                                            ptr(g), ptr(dx), ptr(nu), C.byref(info)))
+        return H, g, dx, (nu[:pr.p] if pr.p else None), info
+
+
+class PrimalDualSolver(Solver):
+    solverType = "PD"
+
+    def solve(self, debugLevel: int = 0) -> Solution:
+        return self._run(self.handle.lib.cvxb_pd_solve)
+
+    def newton_direction(self, x, lam, nu, t):
+        pr = self.problem
+        x, lam = fvec(x), fvec(lam)
+        nu = fvec(nu) if nu is not None else None
+        H = np.empty((pr.n, pr.n), order="F")
+        dx = np.empty(pr.n)
+        dlam = np.empty(pr.m)
+        dnu = np.empty(max(pr.p, 1))
+        info = KktInfo()
+        cp = self.pars.to_c(self.handle)
+        check(self.handle.lib.cvxb_pd_newton_direction(self.handle._h, pr._p, C.byref(cp), ptr(x), ptr(lam), ptr(nu),
+                                                       float(t), ptr(H), ptr(dx), ptr(dlam), ptr(dnu), C.byref(info)))
+        return H, dx, dlam, (dnu[:pr.p] if pr.p else None), info
+
+
+class OptimizationProblem:
+    """OptimizationProblem.apply / withoutFeasiblePoint (OptimizationProblem.scala:133-196)."""
+
+    def __init__(self, id, objF, ineqs: ConstraintSet, eqs: Optional[EqualityConstraint] = None, solverType="BR",
+                 pars: Optional[SolverParams] = None, logger=None, debugLevel=0, handle=None):
+        assert solverType in ("BR", "PD"), "solverType must be 'BR' or 'PD'"
+        self.id, self.objectiveFunction = id, objF
+        cls = BarrierSolver if solverType == "BR" else PrimalDualSolver
+        self.solver = cls(objF, ineqs, eqs, pars, logger, handle)
+
+    withoutFeasiblePoint = classmethod(lambda cls, *a, **k: cls(*a, **k))
+
+    def solve(self, debugLevel: int = 0) -> Solution:
+        return self.solver.solve(debugLevel)
+
+
+def Dist_KL(n, H=None, u=None, A=None, r=None, solverType="BR", pars=None, logger=None, debugLevel=0, handle=None):
+    """Dist_KL.apply (Dist_KL.scala:270-315): min d_KL(x, uniform) s.t. Hx <= u, x >= 0 (positivity rows
+    after the H rows), A x = r and sum x = 1 (stacked last); pointWhereDefined = 1/n, phase I first."""
+    Gpos = -np.eye(n)
+    if H is not None:
+        G = np.vstack([np.asarray(H, float), Gpos])
+        ub = np.concatenate([np.asarray(u, float), np.zeros(n)])
+    else:
+        G, ub = Gpos, np.zeros(n)
+    ones = np.ones((1, n))
+    if A is not None:
+        Aeq, beq = np.vstack([np.asarray(A, float), ones]), np.concatenate([np.asarray(r, float), [1.0]])
+    else:
+        Aeq, beq = ones, np.array([1.0])
+    cnts = ConstraintSet(G, ub, np.full(n, 1.0 / n))
+    return OptimizationProblem("Dist_KL", KLObjectiveFunction(n), cnts, EqualityConstraint(Aeq, beq), solverType, pars,
+                               logger, debugLevel, handle)
+
+
+def from_dict(prob: dict, solverType="BR", pars=None, handle=None) -> OptimizationProblem:
+    """Problem dictionaries of oracle/problems.py (tests and bench) -> OptimizationProblem."""
+    n = prob["n"]
+    if prob["kind"] == "linear":
+        objF = LinearObjectiveFunction(n, prob["r"], prob["a"])
+    elif prob["kind"] == "quadratic":
+        objF = QuadraticObjectiveFunction(n, prob["r"], prob["a"], prob["P"])
+    else:
+        objF = KLObjectiveFunction(n)
+    cnts = ConstraintSet(prob["G"], prob["ub"], prob["xdef"], prob.get("rvec"))
+    if prob.get("x0") is not None:
+        cnts = cnts.addFeasiblePoint(prob["x0"])
+    eqs = EqualityConstraint(prob["A"], prob["b"]) if prob.get("A") is not None else None
+    return OptimizationProblem(prob.get("id", "problem"), objF, cnts, eqs, solverType, pars, None, 0, handle)

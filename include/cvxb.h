@@ -53,6 +53,11 @@ const char* cvxb_version(void);
 /* number of kernels launched through this handle since creation (bench.py "gpu_launches") */
 long long cvxb_launch_count(cvxb_handle h);
 
+/* Per-launch timing of the dominant kernel (the Hessian-assembly SYRK) with CUDA events on the handle's
+ * stream: enable, run solves, then read {launches, total milliseconds, total algorithmic flops}. */
+int cvxb_profile_enable(cvxb_handle h, int on);
+int cvxb_profile_read(cvxb_handle h, long long* launches, double* ms_total, double* flops_total);
+
 /* ---- parameters: SolverParams.scala:24-46 plus the constants hard-coded in the solvers ------- */
 typedef struct cvxb_params {
   int maxIter;          /* SolverParams.maxIter          1000 */
@@ -161,8 +166,12 @@ typedef struct cvxb_solution {
   /* extras */
   double objective;            /* objF.valueAt(x) at the returned point                   */
   int outer_stages;            /* barrier stages / PD iterations taken                    */
-  long long newton_steps;      /* Newton steps over all stages (phase I not included)     */
+  long long newton_steps;      /* Newton iterations over all stages as the reference counts them (phase I not included) */
+  long long executed_newton_steps; /* of those, the ones computed on the device: a stage that can no longer move
+                                  (newton decrement <= tol but ||b-Ax|| > tol) makes the reference repeat the same
+                                  step until maxIter; those repeats are counted above and skipped here */
   long long phase1_newton_steps;
+  long long phase1_executed_steps;
   int phase1_stages;
   double phase1_s;             /* slack s at the phase-I solution (ConstraintSet.scala:369-371) */
   long long linesearch_trials; /* backtracking multiplications by beta, summed            */
