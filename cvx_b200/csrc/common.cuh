@@ -113,6 +113,7 @@ struct GemmArgs {
   double* C; int ldc;
   double alpha, beta;
   int tri;
+  int tile = 0;   // 0 = choose 128 / 64 / 32 by grid size; in-place callers (C aliases A or B) must pin 128
 };
 int gemm_dmma(Handle& h, const GemmArgs& g);
 // gemm_dmma bracketed by CUDA events when the handle's profiling is on (flops = algorithmic flops)

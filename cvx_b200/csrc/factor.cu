@@ -107,22 +107,94 @@ __global__ void scaled_lower_kernel(int n, const double* __restrict__ Hm, int ld
 // ------------------------------------------------------------------------------------------- leaf
 constexpr int LDW = NB + 1;                                   // odd stride: conflict-free rows and columns
 constexpr int LEAF_SMEM = (NB + 1) * LDW * (int)sizeof(double);   // L (lower) + inverse (transposed, upper, shifted)
-constexpr int LEAF_THREADS = 1024;
+constexpr int LEAF_THREADS = 512;
+constexpr int LEAF_WARPS = LEAF_THREADS / 32;
 
 // W holds L(i,j), i >= j, at W[i + j*LDW]; the inverse X(i,j), i >= j, at W[j + (i+1)*LDW].
 #define LW(i, j) W[(i) + (j) * LDW]
 #define XW(i, j) W[(j) + ((i) + 1) * LDW]
 
+constexpr int SUB = 16;      // diagonal sub-block factored inside one warp
+constexpr int NACC = 8;      // outputs per thread in the widest inverse-assembly level (128*64/2 / 512)
+
+// In-warp Cholesky of one SUB x SUB diagonal sub-block at offset o (bs valid rows): lane i < SUB holds
+// row i in registers, pivots travel by shuffle, no block barrier inside.  The pivot uses rsqrt plus one
+// Newton correction instead of IEEE sqrt + divide (each a ~400-cycle dependent chain, and there are 128
+// pivots on the critical path of a leaf); reciprocal pivots go to rdiag for every later solve.
+__device__ __forceinline__ void warp_diag_factor(double* W, double* rdiag, int o, int bs, int col0, int* s_fail,
+                                                 double* s_mind) {
+  const int lane = threadIdx.x & 31;
+  double a[SUB];
+#pragma unroll
+  for (int c = 0; c < SUB; ++c)
+    a[c] = (lane < bs && c < bs && c <= lane) ? LW(o + lane, o + c) : ((c == lane) ? 1.0 : 0.0);
+  double mind = 1e300;
+  int fail = 0;
+#pragma unroll
+  for (int j = 0; j < SUB; ++j) {
+    double d = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(d > 0.0) || d > 1e300) {            // dpotrf: ajj <= 0 or NaN (inf would poison rsqrt)
+      if (!fail && j < bs) fail = col0 + o + j + 1;
+      d = 1.0;
+    }
+    double r = rsqrt(d);
+    double l = d * r;
+    l = fma(0.5 * r, fma(-l, l, d), l);        // l = sqrt(d) to the last bit or two
+    r = fma(r, fma(-l, r, 1.0), r);            // r = 1/l
+    if (j < bs && l < mind) mind = l;
+    if (lane == j) { a[j] = l; rdiag[o + j] = r; }
+    else if (lane > j) a[j] *= r;
+#pragma unroll
+    for (int c = j + 1; c < SUB; ++c) {
+      const double t = __shfl_sync(0xffffffffu, a[j], c);
+      if (lane >= c) a[c] = fma(-a[j], t, a[c]);
+    }
+  }
+  if (lane == 0) {
+    if (fail && !*s_fail) *s_fail = fail;
+    if (mind < *s_mind) *s_mind = mind;
+  }
+#pragma unroll
+  for (int c = 0; c < SUB; ++c)
+    if (lane < bs && c <= lane) LW(o + lane, o + c) = a[c];
+}
+
+// inverse of the diagonal sub-block at o: lane j holds column j of X = L^-1 (forward substitution,
+// L(i,k) broadcast from shared memory, reciprocal pivots from rdiag)
+__device__ __forceinline__ void warp_diag_inverse(double* W, const double* rdiag, int o, int bs) {
+  const int lane = threadIdx.x & 31;
+  double x[SUB];
+#pragma unroll
+  for (int i = 0; i < SUB; ++i) {
+    double acc = (i == lane) ? 1.0 : 0.0;
+    double ri = 1.0;
+    if (i < bs) {
+#pragma unroll
+      for (int k = 0; k < i; ++k) acc = fma(-LW(o + i, o + k), x[k], acc);
+      ri = rdiag[o + i];
+    }
+    x[i] = (i >= lane) ? acc * ri : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < SUB; ++i)
+    if (i < bs && lane < bs && i >= lane) XW(o + i, o + lane) = x[i];
+}
+
 // blockIdx.x selects the diagonal block when only inverting (FACTOR == false).
+// 128 x 128 leaf as 8 x 8 sub-blocks of 16.  Per sub-block column: in-warp diagonal factorisation, panel
+// solve by per-row forward substitution, rank-16 trailing update -- three block barriers.  The
+// triangular inverse is assembled afterwards: the 8 diagonal inverses concurrently (one warp each), then
+// three doubling levels X21 = -X22 (L21 X11).
 template <bool FACTOR>
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
 leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* flag, double* scal, int flag_slot,
             int mindiag_slot, int col0) {
   extern __shared__ double W[];
-  __shared__ double s_piv;
+  __shared__ double rdiag[NB];
+  __shared__ double s_mind;
   __shared__ int s_fail;
   const int tid = threadIdx.x;
-  const int tx = tid & 31, ty = tid >> 5;        // 32 x 32
+  const int tx = tid & 31, ty = tid >> 5;        // 32 x LEAF_WARPS
   int nb, off;
   if (FACTOR) { nb = nb_first; off = 0; }
   else {
@@ -132,67 +204,135 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
   }
   double* Ab = A + (size_t)off * lda + off;
   double* Xg = invD + (size_t)(FACTOR ? 0 : blockIdx.x) * NB * NB;
-  for (int j = ty; j < nb; j += 32)
+  for (int j = ty; j < nb; j += LEAF_WARPS)
     for (int i = tx; i < nb; i += 32)
       if (i >= j) LW(i, j) = Ab[(size_t)j * lda + i];
-  if (tid == 0) s_fail = 0;
+  if (tid == 0) { s_fail = 0; s_mind = 1e300; }
   __syncthreads();
 
+  const int nblk = (nb + SUB - 1) / SUB;
   if (FACTOR) {
-    double mind = 1e300;
-    for (int j = 0; j < nb; ++j) {
-      if (tid == 0) {
-        double pv = LW(j, j);
-        if (!(pv > 0.0)) {       // also catches NaN, as dpotrf's  ajj <= 0 || isnan(ajj)
-          if (!s_fail) s_fail = col0 + j + 1;
-          pv = 1.0;
+    for (int kb = 0; kb < nblk; ++kb) {
+      const int o = kb * SUB;
+      const int bs = (nb - o) < SUB ? (nb - o) : SUB;
+      if (ty == 0) warp_diag_factor(W, rdiag, o, bs, col0, &s_fail, &s_mind);
+      __syncthreads();
+      const int r0 = o + SUB;
+      const int nrows = nb - r0;
+      if (nrows <= 0) continue;
+      // panel: row r of A(r0.., o..o+15) := row * L_d^-T by forward substitution, one thread per row
+      if (tid < nrows) {
+        const int r = r0 + tid;
+        double x[SUB];
+#pragma unroll
+        for (int c = 0; c < SUB; ++c) {
+          double v = LW(r, o + c);
+#pragma unroll
+          for (int k = 0; k < c; ++k) v = fma(-x[k], LW(o + c, o + k), v);
+          x[c] = v * rdiag[o + c];
         }
-        double l = sqrt(pv);
-        LW(j, j) = l;
-        s_piv = 1.0 / l;
-        if (l < mind) mind = l;
+#pragma unroll
+        for (int c = 0; c < SUB; ++c) LW(r, o + c) = x[c];
       }
       __syncthreads();
-      const double r = s_piv;
-      for (int i = j + 1 + tid; i < nb; i += LEAF_THREADS) LW(i, j) *= r;
-      __syncthreads();
-      // trailing update of the lower triangle: (i,c), c > j, i >= c
-      for (int c = j + 1 + ty; c < nb; c += 32) {
-        const double lc = LW(c, j);
-        for (int i = c + tx; i < nb; i += 32) LW(i, c) = fma(-LW(i, j), lc, LW(i, c));
+      // trailing update: A(r,c) -= sum_k L(r,o+k) L(c,o+k),  r >= c >= r0 ; warp per column, lanes down the rows
+      for (int c = r0 + ty; c < nb; c += LEAF_WARPS) {
+        double lc[SUB];
+#pragma unroll
+        for (int k = 0; k < SUB; ++k) lc[k] = LW(c, o + k);
+        for (int r = c - ((c - r0) & 31) + tx; r < nb; r += 32) {
+          if (r < c) continue;
+          double v = LW(r, c);
+#pragma unroll
+          for (int k = 0; k < SUB; ++k) v = fma(-LW(r, o + k), lc[k], v);
+          LW(r, c) = v;
+        }
       }
       __syncthreads();
     }
-    __syncthreads();
     if (tid == 0) {
       if (s_fail && flag[flag_slot] == 0) flag[flag_slot] = s_fail;
-      if (mind < scal[mindiag_slot]) scal[mindiag_slot] = mind;
+      if (s_mind < scal[mindiag_slot]) scal[mindiag_slot] = s_mind;
     }
+  } else {
+    if (tid < nb) {
+      double pv = LW(tid, tid);
+      if (pv == 0.0) { flag[F_ZERO_DIAG] = 1; pv = 1.0; }
+      rdiag[tid] = 1.0 / pv;
+    }
+    __syncthreads();
   }
 
-  // ---- triangular inverse: right-looking forward substitution on R = I
-  for (int j = ty; j < nb; j += 32)
+  // ---- triangular inverse.  Zero-fill the strictly-lower X blocks first (the doubling reads them).
+  for (int j = ty; j < nb; j += LEAF_WARPS)
     for (int i = tx; i < nb; i += 32)
-      if (i >= j) XW(i, j) = (i == j) ? 1.0 : 0.0;
+      if (i >= j) XW(i, j) = 0.0;
   __syncthreads();
-  for (int k = 0; k < nb; ++k) {
-    if (tid == 0) {
-      double pv = LW(k, k);
-      if (pv == 0.0) { flag[F_ZERO_DIAG] = 1; pv = 1.0; }
-      s_piv = 1.0 / pv;
+  if (ty < nblk) {
+    const int o = ty * SUB;
+    warp_diag_inverse(W, rdiag, o, (nb - o) < SUB ? (nb - o) : SUB);
+  }
+  __syncthreads();
+  for (int sh = 4; (1 << sh) < nb; ++sh) {           // s = 16, 32, 64
+    const int s2 = 1 << sh;
+    const int npairs = (nb + 2 * s2 - 1) / (2 * s2);
+    const int total = npairs << (2 * sh);
+    double acc[NACC];
+    // T = L21 * X11  (rows of the second half, columns of the first half of each pair)
+#pragma unroll
+    for (int u = 0; u < NACC; ++u) {
+      const int idx = tid + u * LEAF_THREADS;
+      acc[u] = 0.0;
+      if (idx < total) {
+        const int cc = idx & (s2 - 1), rr = (idx >> sh) & (s2 - 1), pr = idx >> (2 * sh);
+        const int base = pr * 2 * s2;
+        const int c = base + cc, r = base + s2 + rr;
+        if (r < nb) {
+          double v = 0.0;
+          for (int k = c; k < base + s2; ++k) v = fma(LW(r, k), XW(k, c), v);   // X(k,c) = 0 for k < c
+          acc[u] = v;
+        }
+      }
     }
     __syncthreads();
-    const double r = s_piv;
-    for (int j = tid; j <= k; j += LEAF_THREADS) XW(k, j) *= r;
+#pragma unroll
+    for (int u = 0; u < NACC; ++u) {
+      const int idx = tid + u * LEAF_THREADS;
+      if (idx < total) {
+        const int cc = idx & (s2 - 1), rr = (idx >> sh) & (s2 - 1), pr = idx >> (2 * sh);
+        const int base = pr * 2 * s2;
+        if (base + s2 + rr < nb) XW(base + s2 + rr, base + cc) = acc[u];
+      }
+    }
     __syncthreads();
-    for (int i = k + 1 + ty; i < nb; i += 32) {
-      const double lik = LW(i, k);
-      for (int j = tx; j <= k; j += 32) XW(i, j) = fma(-lik, XW(k, j), XW(i, j));
+    // X21 = -X22 * T
+#pragma unroll
+    for (int u = 0; u < NACC; ++u) {
+      const int idx = tid + u * LEAF_THREADS;
+      if (idx < total) {
+        const int cc = idx & (s2 - 1), rr = (idx >> sh) & (s2 - 1), pr = idx >> (2 * sh);
+        const int base = pr * 2 * s2;
+        const int c = base + cc, r = base + s2 + rr;
+        if (r < nb) {
+          double v = 0.0;
+          for (int k = base + s2; k <= r; ++k) v = fma(XW(r, k), XW(k, c), v);
+          acc[u] = -v;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < NACC; ++u) {
+      const int idx = tid + u * LEAF_THREADS;
+      if (idx < total) {
+        const int cc = idx & (s2 - 1), rr = (idx >> sh) & (s2 - 1), pr = idx >> (2 * sh);
+        const int base = pr * 2 * s2;
+        if (base + s2 + rr < nb) XW(base + s2 + rr, base + cc) = acc[u];
+      }
     }
     __syncthreads();
   }
-  __syncthreads();
-  for (int j = ty; j < NB; j += 32)
+  for (int j = ty; j < NB; j += LEAF_WARPS)
     for (int i = tx; i < NB; i += 32) {
       double x = (i < nb && j < nb && i >= j) ? XW(i, j) : 0.0;
       Xg[(size_t)j * NB + i] = x;
@@ -216,7 +356,7 @@ int trsm_right_lt(Handle& h, int M, int n1, const double* L, int ldl, const doub
   if (M <= 0 || n1 <= 0) return CVXB_OK;
   if (n1 <= NB) {
     // in place: the tile grid has a single column (N = n1 <= 128), so a CTA reads only the rows it writes
-    GemmArgs g{M, n1, n1, A21, lda, false, invD, NB, false, A21, lda, 1.0, 0.0, 0};
+    GemmArgs g{M, n1, n1, A21, lda, false, invD, NB, false, A21, lda, 1.0, 0.0, 0, 128};
     return gemm_dmma(h, g);
   }
   int a = split_point(n1), b = n1 - a;
@@ -248,7 +388,7 @@ int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot,
 int trsm_rec(Handle& h, int n, int r, const double* L, int ldl, const double* invD, double* B, int ldb, bool trans) {
   if (n <= NB) {
     // in place: single tile row (M = n <= 128): a CTA reads only the columns it writes
-    GemmArgs g{n, r, n, invD, NB, trans, B, ldb, true, B, ldb, 1.0, 0.0, 0};
+    GemmArgs g{n, r, n, invD, NB, trans, B, ldb, true, B, ldb, 1.0, 0.0, 0, 128};
     return gemm_dmma(h, g);
   }
   int a = split_point(n), b = n - a;
@@ -266,6 +406,130 @@ int trsm_rec(Handle& h, int n, int r, const double* L, int ldl, const double* in
   GemmArgs g{a, r, b, L + a, ldl, true, B + a, ldb, true, B, ldb, -1.0, 1.0, 0};
   CVXB_TRY(gemm_dmma(h, g));
   return trsm_rec(h, a, r, L, ldl, invD, B, ldb, true);
+}
+
+// ------------------------------------------------------------------------------- single-RHS solves
+// One launch per 128-column block: every CTA recomputes y_k = invD_k b_k (16k FMA, the
+// block inverse comes from L2), CTA 0 publishes it, and each CTA folds L[rows, block] y_k into its own
+// 256 rows of b.  HBM-bound: L is read exactly once, coalesced down the columns.
+constexpr int TRSV_ROWS = 64;
+
+__global__ void __launch_bounds__(256) trsv_fwd_step_kernel(int n, int k0, int kb, const double* __restrict__ L, int ldl,
+                                                            const double* __restrict__ invDk, double* __restrict__ b,
+                                                            double* __restrict__ out) {
+  __shared__ double ys[NB];
+  __shared__ double bs[NB];
+  __shared__ double red[4][NB];
+  const int tid = threadIdx.x;
+  if (tid < NB) bs[tid] = tid < kb ? b[k0 + tid] : 0.0;
+  __syncthreads();
+  {   // y = invD_k b_k : row i = tid & 127, two column halves (invD is lower: zeros above the diagonal)
+    const int i = tid & (NB - 1), half = tid >> 7;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const double* col = invDk + i + (size_t)(half * 64) * NB;
+    const double* bb = bs + half * 64;
+#pragma unroll 4
+    for (int j = 0; j < 64; j += 4) {
+      a0 = fma(col[(size_t)j * NB], bb[j], a0);
+      a1 = fma(col[(size_t)(j + 1) * NB], bb[j + 1], a1);
+      a2 = fma(col[(size_t)(j + 2) * NB], bb[j + 2], a2);
+      a3 = fma(col[(size_t)(j + 3) * NB], bb[j + 3], a3);
+    }
+    red[half][i] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  if (tid < NB) {
+    const double y = red[0][tid] + red[1][tid];
+    ys[tid] = y;
+    if (blockIdx.x == 0 && tid < kb) out[k0 + tid] = y;
+  }
+  __syncthreads();
+  // b[r] -= L[r, block] . y : 64 rows per CTA, 4 column groups of 32
+  const int rl = tid & 63, grp = tid >> 6;
+  const int r = k0 + kb + blockIdx.x * TRSV_ROWS + rl;
+  double part = 0.0;
+  if (r < n) {
+    const double* Lr = L + (size_t)(k0 + grp * 32) * ldl + r;
+    const double* yy = ys + grp * 32;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (grp * 32 + j + 3 < kb) {
+        a0 = fma(Lr[(size_t)j * ldl], yy[j], a0);
+        a1 = fma(Lr[(size_t)(j + 1) * ldl], yy[j + 1], a1);
+        a2 = fma(Lr[(size_t)(j + 2) * ldl], yy[j + 2], a2);
+        a3 = fma(Lr[(size_t)(j + 3) * ldl], yy[j + 3], a3);
+      } else {
+        for (int q = 0; q < 4; ++q)
+          if (grp * 32 + j + q < kb) a0 = fma(Lr[(size_t)(j + q) * ldl], yy[j + q], a0);
+      }
+    }
+    part = (a0 + a1) + (a2 + a3);
+  }
+  red[grp][rl] = part;
+  __syncthreads();
+  if (tid < 64 && r < n) b[r] -= (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+}
+
+// backward (L' x = y): block k from the last to the first; x_k = invD_k' y_k, then
+// y[c] -= L[block rows, c] . x_k for every column c < k0 (one warp per column, 64 columns per CTA)
+__global__ void __launch_bounds__(256) trsv_bwd_step_kernel(int k0, int kb, const double* __restrict__ L, int ldl,
+                                                            const double* __restrict__ invDk, double* __restrict__ y,
+                                                            double* __restrict__ out) {
+  __shared__ double xs[NB];
+  __shared__ double ysb[NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < NB) ysb[tid] = tid < kb ? y[k0 + tid] : 0.0;
+  __syncthreads();
+  for (int i = warp; i < kb; i += 8) {        // x_i = sum_{j >= i} invD(j,i) y_j
+    double a = 0.0;
+    for (int j = i + lane; j < kb; j += 32) a = fma(invDk[j + (size_t)i * NB], ysb[j], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      xs[i] = a;
+      if (blockIdx.x == 0) out[k0 + i] = a;
+    }
+  }
+  __syncthreads();
+  const int cbase = blockIdx.x * 64;
+  for (int cc = warp; cc < 64; cc += 8) {
+    const int c = cbase + cc;
+    if (c >= k0) break;
+    const double* col = L + (size_t)c * ldl + k0;
+    double a = 0.0;
+    for (int i = lane; i < kb; i += 32) a = fma(col[i], xs[i], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) y[c] -= a;
+  }
+}
+
+__global__ void copy_vec_kernel(int n, const double* __restrict__ a, double* __restrict__ b) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) b[i] = a[i];
+}
+
+int trsv_lower(Handle& h, int n, const double* L, int ldl, const double* invD, double* b, bool trans) {
+  double* out = h.d_part + (PART_DOUBLES - 32768);     // tail of the scratch block (n <= 32768)
+  if (n > 32768) { set_last_error("trsv_lower: n = %d exceeds the single-RHS scratch", n); return CVXB_EINVAL; }
+  const int nblk = (n + NB - 1) / NB;
+  if (!trans) {
+    for (int k = 0; k < nblk; ++k) {
+      int k0 = k * NB, kb = n - k0 < NB ? n - k0 : NB;
+      int rem = n - k0 - kb;
+      int grid = rem > 0 ? (rem + TRSV_ROWS - 1) / TRSV_ROWS : 1;
+      CVXB_LAUNCH(h, trsv_fwd_step_kernel, grid, 256, 0, n, k0, kb, L, ldl, invD + (size_t)k * NB * NB, b, out);
+    }
+  } else {
+    for (int k = nblk - 1; k >= 0; --k) {
+      int k0 = k * NB, kb = n - k0 < NB ? n - k0 : NB;
+      int grid = k0 > 0 ? (k0 + 63) / 64 : 1;
+      CVXB_LAUNCH(h, trsv_bwd_step_kernel, grid, 256, 0, k0, kb, L, ldl, invD + (size_t)k * NB * NB, b, out);
+    }
+  }
+  CVXB_LAUNCH(h, copy_vec_kernel, (n + 255) / 256, 256, 0, n, out, b);
+  return CVXB_OK;
 }
 
 bool leaf_attr_set = false;
@@ -311,6 +575,7 @@ int potrf_lower(Handle& h, int n, double* A, int lda, double* invD, int flag_slo
 
 int trsm_lower(Handle& h, int n, int r, const double* L, int ldl, const double* invD, double* B, int ldb, bool trans) {
   if (n <= 0 || r <= 0) return CVXB_OK;
+  if (r == 1 && n > NB) return trsv_lower(h, n, L, ldl, invD, B, trans);
   return trsm_rec(h, n, r, L, ldl, invD, B, ldb, trans);
 }
 

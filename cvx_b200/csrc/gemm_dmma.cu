@@ -6,26 +6,26 @@
 //   * panel / TRSM updates  B2  -= L21 Y1          (NN)          KKTSystem.scala:116-124 (dtrtrs)
 //   * Schur complement      S  = Y' Y              (TN, tri=2)   KKTSystem.scala:126-139
 //
-// CTA tile 128x128x16, 256 threads = 8 warps (2 x 4), warp tile 64x32 = 8x4 DMMA tiles, so each
-// k4-step issues 12 LDS.64 for 32 DMMA (shared-memory pipe ~19% busy, tensor pipe is the limiter).
-// Operands are staged global->shared with 16-byte cp.async (zero-fill predication at the edges)
-// through a 4-stage ring; padded shared layouts make every fragment load bank-conflict free:
-//   K-contiguous operand: [128][16+4] doubles  -> bank = 8*g + 2*t   (g = lane/4, t = lane%4)
-//   M-contiguous operand: [16][128+4] doubles  -> bank = 8*t + 2*g
+// Three CTA tile shapes share one templated mainloop (k-slab 16, 4-stage cp.async ring):
+//   128x128, 8 warps (2x4), warp tile 64x32 = 8x4 DMMA tiles: each k4-step issues 12 LDS.64 for 32 DMMA
+//            (shared-memory pipe ~19% busy, the tensor pipe is the limiter) -- the big contractions;
+//    64x64,  4 warps (2x2), warp tile 32x32;   32x32, 4 warps (2x2), warp tile 16x16 -- the small GEMMs
+//            of the recursive Cholesky / TRSM levels, where a 128x128 grid would leave most of the 148
+//            SMs idle and a single CTA would walk the whole K range alone.
+// Operands are staged global->shared with 16-byte cp.async (zero-fill predication at the edges);
+// padded shared layouts make every fragment load bank-conflict free:
+//   K-contiguous operand: [R][16+4] doubles  -> bank = 8*g + 2*t   (g = lane/4, t = lane%4)
+//   M-contiguous operand: [16][R+4] doubles  -> bank = 8*t + 2*g
 #include "common.cuh"
 
 namespace cvxb {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, NT = 256;
-constexpr int WM = 64, WN = 32;             // warp tile
+constexpr int BK = 16, STAGES = 4;
 constexpr int KC_LD = BK + 4;               // K-contiguous tile row stride (doubles)
-constexpr int MC_LD = BM + 4;               // M/N-contiguous tile row stride (doubles)
-constexpr int KC_ELEMS = BM * KC_LD;        // 2560
-constexpr int MC_ELEMS = BK * MC_LD;        // 2112
-constexpr int TILE_ELEMS = KC_ELEMS;        // reserve the larger of the two for either layout
-constexpr int SMEM_BYTES = STAGES * 2 * TILE_ELEMS * (int)sizeof(double);   // 163840
+
+template <int R> struct TileElems { static constexpr int value = (R * KC_LD > BK * (R + 4)) ? R * KC_LD : BK * (R + 4); };
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -41,14 +41,15 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// Stage one 128 x 16 operand tile.  `rows` = extent along the 128-long (M or N) direction,
+// Stage one R x 16 operand tile.  `rows` = extent along the R-long (M or N) direction,
 // `kext` = K; (r0, k0) = tile origin.  KC: element (r,k) at src[r*ld + k]; else at src[k*ld + r].
-template <bool KC>
+template <bool KC, int R, int NTHR>
 __device__ __forceinline__ void load_tile(double* dst, const double* __restrict__ src, int ld, int rows, int kext,
                                           int r0, int k0, int tid) {
+  constexpr int MC_LD = R + 4;
 #pragma unroll
-  for (int it = 0; it < (BM * BK / 2) / NT; ++it) {   // 1024 16-byte chunks / 256 threads
-    int c = tid + it * NT;
+  for (int it = 0; it < (R * BK / 2) / NTHR; ++it) {
+    int c = tid + it * NTHR;
     if (KC) {
       int r = c >> 3, kc = (c & 7) * 2;
       int gr = r0 + r, gk = k0 + kc;
@@ -57,7 +58,7 @@ __device__ __forceinline__ void load_tile(double* dst, const double* __restrict_
       const double* g = bytes > 0 ? src + (size_t)gr * ld + gk : src;
       cp_async16(dst + r * KC_LD + kc, g, bytes);
     } else {
-      int k = c >> 6, rc = (c & 63) * 2;
+      int k = c / (R / 2), rc = (c % (R / 2)) * 2;
       int gk = k0 + k, gr = r0 + rc;
       int bytes = 0;
       if (gk < kext) { int rem = (rows - gr) * 8; bytes = rem < 0 ? 0 : (rem > 16 ? 16 : rem); }
@@ -67,10 +68,15 @@ __device__ __forceinline__ void load_tile(double* dst, const double* __restrict_
   }
 }
 
-template <bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(NT, 1)
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (BM >= 128 ? 1 : 2))
 gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
                  double* __restrict__ C, int ldc, double alpha, double beta, int tri, int tiles_m) {
+  constexpr int NTHR = WARPS_M * WARPS_N * 32;
+  constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+  constexpr int MT = WM / 8, NTL = WN / 8;
+  constexpr int A_ELEMS = TileElems<BM>::value, B_ELEMS = TileElems<BN>::value;
+  constexpr int A_MC_LD = BM + 4, B_MC_LD = BN + 4;
   extern __shared__ __align__(16) double smem[];
   int bm, bn;
   if (tri) {
@@ -88,23 +94,23 @@ gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, con
   const int m0 = bm * BM, n0 = bn * BN;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp & 1) * WM, wn0 = (warp >> 1) * WN;
+  const int wm0 = (warp % WARPS_M) * WM, wn0 = (warp / WARPS_M) * WN;
 
-  double acc[8][4][2];
+  double acc[MT][NTL][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NTL; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int KT = (K + BK - 1) / BK;
-  auto stageA = [&](int s) { return smem + (size_t)s * 2 * TILE_ELEMS; };
-  auto stageB = [&](int s) { return smem + (size_t)s * 2 * TILE_ELEMS + TILE_ELEMS; };
+  auto stageA = [&](int s) { return smem + (size_t)s * (A_ELEMS + B_ELEMS); };
+  auto stageB = [&](int s) { return smem + (size_t)s * (A_ELEMS + B_ELEMS) + A_ELEMS; };
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < KT) {
-      load_tile<A_KC>(stageA(s), A, lda, M, K, m0, s * BK, tid);
-      load_tile<B_KC>(stageB(s), B, ldb, N, K, n0, s * BK, tid);
+      load_tile<A_KC, BM, NTHR>(stageA(s), A, lda, M, K, m0, s * BK, tid);
+      load_tile<B_KC, BN, NTHR>(stageB(s), B, ldb, N, K, n0, s * BK, tid);
     }
     cp_async_commit();
   }
@@ -116,8 +122,8 @@ gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, con
       int nk = kt + STAGES - 1;
       if (nk < KT) {
         int s = nk % STAGES;
-        load_tile<A_KC>(stageA(s), A, lda, M, K, m0, nk * BK, tid);
-        load_tile<B_KC>(stageB(s), B, ldb, N, K, n0, nk * BK, tid);
+        load_tile<A_KC, BM, NTHR>(stageA(s), A, lda, M, K, m0, nk * BK, tid);
+        load_tile<B_KC, BN, NTHR>(stageB(s), B, ldb, N, K, n0, nk * BK, tid);
       }
       cp_async_commit();
     }
@@ -125,17 +131,17 @@ gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, con
     const double* Bs = stageB(kt % STAGES);
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
-      double a[8], b[4];
+      double a[MT], b[NTL];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        a[i] = A_KC ? As[(wm0 + i * 8 + g) * KC_LD + kk + t] : As[(kk + t) * MC_LD + wm0 + i * 8 + g];
+      for (int i = 0; i < MT; ++i)
+        a[i] = A_KC ? As[(wm0 + i * 8 + g) * KC_LD + kk + t] : As[(kk + t) * A_MC_LD + wm0 + i * 8 + g];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        b[j] = B_KC ? Bs[(wn0 + j * 8 + g) * KC_LD + kk + t] : Bs[(kk + t) * MC_LD + wn0 + j * 8 + g];
+      for (int j = 0; j < NTL; ++j)
+        b[j] = B_KC ? Bs[(wn0 + j * 8 + g) * KC_LD + kk + t] : Bs[(kk + t) * B_MC_LD + wn0 + j * 8 + g];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < NTL; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
   }
   cp_async_wait<0>();
@@ -143,11 +149,11 @@ gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, con
   // epilogue: thread (g,t) of tile (i,j) holds C(m, n), C(m, n+1), m = ..+g, n = ..+2t
   const bool diag = tri && (bm == bn);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < MT; ++i) {
     int m = m0 + wm0 + i * 8 + g;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NTL; ++j) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         int n = n0 + wn0 + j * 8 + 2 * t + e;
@@ -163,18 +169,42 @@ gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, con
   }
 }
 
-template <bool A_KC, bool B_KC>
+template <int BM, int WARPS_M, int WARPS_N>
+constexpr int smem_bytes() { return STAGES * 2 * TileElems<BM>::value * (int)sizeof(double); }
+
+template <int BM, int WARPS_M, int WARPS_N, bool A_KC, bool B_KC>
 int launch(Handle& h, const GemmArgs& g) {
   cudaStream_t st = h.stream;
-  int tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
+  int tm = (g.M + BM - 1) / BM, tn = (g.N + BM - 1) / BM;
   long long grid = g.tri ? (long long)tm * (tm + 1) / 2 : (long long)tm * tn;
   if (grid <= 0) return CVXB_OK;
-  gemm_dmma_kernel<A_KC, B_KC><<<(unsigned)grid, NT, SMEM_BYTES, st>>>(g.M, g.N, g.K, g.A, g.lda, g.B, g.ldb, g.C,
-                                                                        g.ldc, g.alpha, g.beta, g.tri, tm);
+  gemm_dmma_kernel<BM, BM, WARPS_M, WARPS_N, A_KC, B_KC>
+      <<<(unsigned)grid, WARPS_M * WARPS_N * 32, smem_bytes<BM, WARPS_M, WARPS_N>(), st>>>(
+          g.M, g.N, g.K, g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.alpha, g.beta, g.tri, tm);
   h.launches++;
   CVXB_CUDA_OK(cudaGetLastError());
   return CVXB_OK;
 }
+
+template <int BM, int WARPS_M, int WARPS_N>
+int launch_layout(Handle& h, const GemmArgs& g) {
+  if (g.a_kc && g.b_kc) return launch<BM, WARPS_M, WARPS_N, true, true>(h, g);
+  if (!g.a_kc && g.b_kc) return launch<BM, WARPS_M, WARPS_N, false, true>(h, g);
+  if (!g.a_kc && !g.b_kc) return launch<BM, WARPS_M, WARPS_N, false, false>(h, g);
+  return launch<BM, WARPS_M, WARPS_N, true, false>(h, g);
+}
+
+template <int BM, int WARPS_M, int WARPS_N>
+int set_attr() {
+  const int b = smem_bytes<BM, WARPS_M, WARPS_N>();
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<BM, BM, WARPS_M, WARPS_N, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<BM, BM, WARPS_M, WARPS_N, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<BM, BM, WARPS_M, WARPS_N, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<BM, BM, WARPS_M, WARPS_N, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+  return CVXB_OK;
+}
+
+constexpr int NT = 256;
 
 // Register-only DMMA issue-rate probe: every warp of every SM issues independent DMMA chains.
 // Used to calibrate the FP64 tensor peak the roofline fractions are quoted against.
@@ -216,10 +246,9 @@ int dmma_peak_probe(Handle& h, int iters, double* ms, double* flops) {
 }
 
 int gemm_dmma_init() {
-  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CVXB_TRY((set_attr<128, 2, 4>()));
+  CVXB_TRY((set_attr<64, 2, 2>()));
+  CVXB_TRY((set_attr<32, 2, 2>()));
   return CVXB_OK;
 }
 
@@ -250,10 +279,17 @@ int gemm_dmma(Handle& h, const GemmArgs& g) {
     set_last_error("gemm_dmma: triangular mode needs M == N");
     return CVXB_EINVAL;
   }
-  if (g.a_kc && g.b_kc) return launch<true, true>(h, g);
-  if (!g.a_kc && g.b_kc) return launch<false, true>(h, g);
-  if (!g.a_kc && !g.b_kc) return launch<false, false>(h, g);
-  return launch<true, false>(h, g);
+  // tile shape: the largest one that still fills the machine (in-place callers pin 128x128)
+  auto ntiles = [&](int b) {
+    long long tm = (g.M + b - 1) / b, tn = (g.N + b - 1) / b;
+    return g.tri ? tm * (tm + 1) / 2 : tm * tn;
+  };
+  const long long want = (long long)h.sm_count * 3 / 4;
+  int tile = g.tile;
+  if (tile == 0) tile = ntiles(128) >= want ? 128 : (ntiles(64) >= want ? 64 : 32);
+  if (tile == 128) return launch_layout<128, 2, 4>(h, g);
+  if (tile == 64) return launch_layout<64, 2, 2>(h, g);
+  return launch_layout<32, 2, 2>(h, g);
 }
 
 }  // namespace cvxb

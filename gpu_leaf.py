@@ -1,0 +1,3 @@
+from cvx_b200 import _lib
+h = _lib.default_handle()
+print(h.bench_kernel(3, 128, 0, 3))
