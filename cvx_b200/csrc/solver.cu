@@ -578,6 +578,15 @@ int run_phase1(cvxb_problem_s* P, const cvxb_params& pars, RunStats& rs, cvxb_so
   return CVXB_OK;
 }
 
+int run_phase1_public(cvxb_problem_s* P, const cvxb_params& pars, long long* budget, bool* limited, cvxb_solution* ph) {
+  RunStats rs;
+  rs.budget = *budget;
+  rs.limited = *limited;
+  int st = run_phase1(P, pars, rs, ph);
+  *budget = rs.budget;
+  return st;
+}
+
 int upload_vec(Handle& h, double* dst, const double* src, int n) {
   if (!src || n <= 0) return CVXB_OK;
   bool dev = (h.flags & CVXB_FLAG_DEVICE_PTRS) != 0;

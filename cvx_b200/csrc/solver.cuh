@@ -16,7 +16,9 @@ struct cvxb_problem_s {
          *nu = nullptr, *eqdiff = nullptr, *Px = nullptr, *Pd = nullptr, *axv = nullptr;
   // primal-dual work (allocated on first use)
   double *lam = nullptr, *dlam = nullptr, *dnu = nullptr, *wts = nullptr, *rd0 = nullptr, *rd1 = nullptr,
-         *Adx = nullptr, *pres = nullptr, *x0s = nullptr, *lam0s = nullptr, *nu0s = nullptr, *tmpm = nullptr;
+         *Adx = nullptr, *pres = nullptr, *x0s = nullptr, *lam0s = nullptr, *nu0s = nullptr, *tmpm = nullptr,
+         *gx0s = nullptr, *rd00s = nullptr, *Px0s = nullptr, *vvec = nullptr, *qvec = nullptr, *atnu = nullptr,
+         *pres0s = nullptr, *negpres = nullptr;
   // matrices
   double *Gs = nullptr, *H = nullptr, *Hreg = nullptr;
   cvxb::KktWork kw;
