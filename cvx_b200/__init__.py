@@ -11,3 +11,4 @@ __version__ = "0.1.0"
 from .solvers import (SolverParams, Solution, LinearObjectiveFunction, QuadraticObjectiveFunction,  # noqa: F401,E402
                       KLObjectiveFunction, ConstraintSet, EqualityConstraint, BarrierSolver, PrimalDualSolver,
                       OptimizationProblem, Dist_KL, from_dict)
+from .batched import BatchedBarrierSolver, BatchSolution, pack_problems, shard_range, gather_solutions  # noqa: F401,E402

@@ -108,8 +108,8 @@ class SolutionC(C.Structure):
 
 
 class BatchDesc(C.Structure):
-    _fields_ = [("B", C.c_int), ("n", C.c_int), ("m", C.c_int), ("p", C.c_int), ("objective", _ip), ("obj_a", _dp),
-                ("obj_r", _dp), ("obj_P", _dp), ("G", _dp), ("ub", _dp), ("A", _dp), ("b", _dp), ("x0", _dp)]
+    _fields_ = [("B", C.c_int), ("n", C.c_int), ("m", C.c_int), ("p", C.c_int), ("objective", _ip), ("pcount", _ip),
+                ("obj_a", _dp), ("obj_r", _dp), ("obj_P", _dp), ("G", _dp), ("ub", _dp), ("A", _dp), ("b", _dp), ("x0", _dp)]
 
 
 class BatchResult(C.Structure):

@@ -1,0 +1,748 @@
+// Batched small-problem barrier solver: B independent problems with
+// n <= 64 variables, m <= 128 linear inequalities and p in {0,1} equalities, ONE CTA PER PROBLEM.
+// The whole barrier solve of a problem -- every Newton step's Hessian assembly (FP64 DMMA out of shared
+// memory), Ruiz equilibration, Cholesky, triangular solves, Schur complement (a scalar for p = 1),
+// residual checks, line search and the outer t *= mu loop -- runs on-chip: G (66 KB) and the n x n work
+// matrix (33 KB) live in shared memory for the life of the problem; HBM sees one read of the problem
+// and one write of x.  CTAs are persistent and pull problem indices from an atomic counter, so the
+// different iteration counts of different problems balance themselves.
+//
+// Semantics are those of the large path (solver.cu / kkt.cu), i.e. of BarrierSolver.scala:70-188,
+// EqualityConstrainedSolver.scala:37-107, UnconstrainedSolver.scala:34-125 (incl. D4, D7),
+// KKTSystem.scala:43-246 (path 0, regularised retry, path 1 = H + A'A) and MatrixUtils.scala:240-516.
+// The eigendecomposition last resorts (kktSymSolve / symSolve) are reported as CVXB_ELINSOLVE.
+#include "kkt.cuh"
+#include "vecops.cuh"
+
+using namespace cvxb;
+
+struct cvxb_batch_s {
+  cvxb_handle_s* h = nullptr;
+  int B = 0, n = 0, m = 0, p = 0;
+  int* objective = nullptr;
+  int* pcount = nullptr;
+  double *obj_a = nullptr, *obj_r = nullptr, *obj_P = nullptr, *G = nullptr, *ub = nullptr, *A = nullptr, *b = nullptr,
+         *x0 = nullptr;
+  // outputs (device)
+  double *x = nullptr, *objval = nullptr, *gap = nullptr, *eqgap = nullptr;
+  int *status = nullptr, *steps = nullptr, *stages = nullptr;
+  double* scratch = nullptr;     // per-CTA copy of H (n x n)
+  unsigned* counter = nullptr;
+  int grid = 0;
+  std::vector<void*> owned;
+};
+
+namespace cvxb {
+namespace {
+
+constexpr int BN = 64, BM_ = 128;          // capacity
+constexpr int LDG = BM_ + 4;               // G col-major in shared memory; LDG mod 16 == 4 -> conflict-free DMMA fragments
+constexpr int LDH = BN + 1;                // H / L col-major, odd stride
+constexpr int BT = 256;                    // threads per CTA
+constexpr int BSUB = 16;
+constexpr double IN_SET = 1.0 + 3e-16;
+
+struct BatchArgs {
+  int B, n, m, p;
+  const int* objective;
+  const int* pcount;
+  const double *obj_a, *obj_r, *obj_P, *G, *ub, *A, *b, *x0;
+  double *x, *objval, *gap, *eqgap;
+  int *status, *steps, *stages;
+  double* scratch;
+  unsigned* counter;
+  cvxb_params P;
+};
+
+struct Smem {
+  double G[BN * LDG];
+  double L[BN * LDH];
+  double x[BN], y[BN], dir[BN], dr[BN], qs[BN], ya[BN], yq[BN], aeq[BN], oa[BN], Px[BN], Pd[BN], rdiag[BN], zrhs[BN];
+  double work[4 * BN];      // t1 | t2 | xtry | spare during a solve; Ruiz column partial sums before it
+  double gx[BM_], ub[BM_], inv[BM_], Gd[BM_];
+  double red[40];
+  int ired[40];
+  double sc[16];
+  int fl[8];
+  int pcur;                 // equalities of the current problem (0 or 1)
+};
+#define S_T1 (S.work)
+#define S_T2 (S.work + BN)
+#define S_XTRY (S.work + 2 * BN)
+#define S_COLSQ (S.work)
+
+__device__ __forceinline__ void dmma884b(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+#define HL(i, j) S.L[(i) + (j) * LDH]
+#define GG(i, j) S.G[(i) + (j) * LDG]
+
+// ---- evaluation at S.x for parameter t: gx, 1/slack, barrier value, gradient, eq residual -----------------
+// returns false when x is not strictly feasible (slack <= 0)
+__device__ bool b_eval(Smem& S, const BatchArgs& A, int kind, double obj_r, const double* Pg, double beq, double t,
+                       double* fval, double* f0out, double* normGrad, double* eqdiff) {
+  const int tid = threadIdx.x, n = A.n, m = A.m;
+  if (tid < m) {
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) s = fma(GG(tid, j), S.x[j], s);
+    S.gx[tid] = s;
+  }
+  if (kind == CVXB_OBJ_QUADRATIC && tid >= 128 && tid < 128 + n) {
+    const int i = tid - 128;
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) s = fma(Pg[i + (size_t)j * n], S.x[j], s);
+    S.Px[i] = s;
+  }
+  __syncthreads();
+  double ls = 0.0;
+  int bad = 0;
+  if (tid < m) {
+    double d = S.ub[tid] - S.gx[tid];
+    if (!(d > 0.0)) bad = 1;
+    S.inv[tid] = 1.0 / d;
+    ls = log(d);
+  }
+  ls = block_sum(ls, S.red);
+  bad = block_or(bad, S.ired);
+  double f0 = 0.0;
+  if (tid < n) {
+    double xj = S.x[tid];
+    if (kind == CVXB_OBJ_LINEAR) f0 = S.oa[tid] * xj;
+    else if (kind == CVXB_OBJ_QUADRATIC) f0 = S.oa[tid] * xj + 0.5 * xj * S.Px[tid];
+    else f0 = xj * log(xj * (double)n);
+  }
+  f0 = block_sum(f0, S.red) + obj_r;
+  // gradient: y_j = t grad f0_j + sum_i G(i,j)/d_i ; 4 threads per column
+  {
+    const int j = tid >> 2, part = tid & 3;
+    double s = 0.0;
+    if (j < n)
+      for (int i = part; i < m; i += 4) s = fma(GG(i, j), S.inv[i], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (j < n && part == 0) {
+      double xj = S.x[j], gf;
+      if (kind == CVXB_OBJ_LINEAR) gf = S.oa[j];
+      else if (kind == CVXB_OBJ_QUADRATIC) gf = S.oa[j] + S.Px[j];
+      else gf = 1.0 + log(xj) + log((double)n);
+      S.y[j] = t * gf + s;
+    }
+  }
+  __syncthreads();
+  double g2 = 0.0, ax = 0.0;
+  if (tid < n) {
+    g2 = S.y[tid] * S.y[tid];
+    if (S.pcur) ax = S.aeq[tid] * S.x[tid];
+  }
+  g2 = block_sum(g2, S.red);
+  ax = block_sum(ax, S.red);
+  *fval = t * f0 - ls;
+  *f0out = f0;
+  *normGrad = sqrt(g2);
+  *eqdiff = S.pcur ? (beq - ax) : 0.0;
+  return bad == 0;
+}
+
+// ---- H = t hess f0 + G' diag(inv^2) G, full symmetric in S.L, via DMMA out of shared memory --------------
+__device__ void b_hessian(Smem& S, const BatchArgs& A, int kind, const double* Pg, double t) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = A.n, m = A.m;
+  const int g = lane >> 2, tq = lane & 3;
+  const int nt = (n + 7) >> 3;
+  const int ntiles = nt * (nt + 1) / 2;
+  const int m4 = (m + 3) & ~3;
+  for (int tl = warp; tl < ntiles; tl += BT / 32) {
+    int r = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
+    while ((r + 1) * (r + 2) / 2 <= tl) ++r;
+    while (r * (r + 1) / 2 > tl) --r;
+    const int ti = r, tj = tl - r * (r + 1) / 2;
+    const int i0 = ti * 8, j0 = tj * 8;
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+    for (int kk = 0; kk < m4; kk += 8) {
+      const double w0 = (kk + tq < m) ? S.inv[kk + tq] : 0.0;
+      double a = GG(kk + tq, i0 + g) * (w0 * w0);
+      double b = GG(kk + tq, j0 + g);
+      dmma884b(c0, c1, a, b);
+      if (kk + 4 < m4) {
+        const double w1 = (kk + 4 + tq < m) ? S.inv[kk + 4 + tq] : 0.0;
+        double a2 = GG(kk + 4 + tq, i0 + g) * (w1 * w1);
+        double b2 = GG(kk + 4 + tq, j0 + g);
+        dmma884b(e0, e1, a2, b2);
+      }
+    }
+    c0 += e0; c1 += e1;
+    const int i = i0 + g;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = j0 + 2 * tq + e;
+      if (i < n && j < n && j <= i) {
+        double v = e ? c1 : c0;
+        if (kind == CVXB_OBJ_QUADRATIC) v += t * Pg[i + (size_t)j * n];
+        else if (kind == CVXB_OBJ_KL && i == j) v += t / S.x[i];
+        HL(i, j) = v;
+        HL(j, i) = v;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---- Ruiz equilibration of the full symmetric H in S.L -> S.dr  (MatrixUtils.scala:240-268) ---------------
+__device__ void b_ruiz(Smem& S, const BatchArgs& A) {
+  const int tid = threadIdx.x, n = A.n;
+  if (tid < n) S.dr[tid] = 1.0;
+  __syncthreads();
+  for (int sweep = 0; sweep < A.P.ruizMaxSweeps; ++sweep) {
+    const int j = tid & 63, part = tid >> 6;
+    double s = 0.0;
+    if (j < n) {
+      const double dj = S.dr[j];
+      for (int i = part; i < n; i += 4) {
+        double q = (S.dr[i] * dj) * HL(i, j);
+        s = fma(q, q, s);
+      }
+    }
+    S_COLSQ[part * BN + j] = s;
+    __syncthreads();
+    double dev = 0.0;
+    if (tid < n) {
+      double tot = (S_COLSQ[tid] + S_COLSQ[BN + tid]) + (S_COLSQ[2 * BN + tid] + S_COLSQ[3 * BN + tid]);
+      double u = sqrt(sqrt(tot));
+      if (u > 0) S.dr[tid] = S.dr[tid] * (1.0 / u);
+      dev = fabs(1.0 - u);
+      if (dev != dev) dev = 1e308;
+    }
+    double rho = -block_min(-dev, S.red);
+    if (!(rho > A.P.ruizTol)) break;      // uniform: every thread sees the same rho
+  }
+  __syncthreads();
+}
+
+// ---- in-place Cholesky of the lower triangle of S.L (n <= 64); returns 0 or the failing column ------------
+__device__ int b_potrf(Smem& S, int n, double* mind_out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { S.fl[0] = 0; S.sc[0] = 1e300; }
+  __syncthreads();
+  const int nblk = (n + BSUB - 1) / BSUB;
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int o = kb * BSUB;
+    const int bs = (n - o) < BSUB ? (n - o) : BSUB;
+    if (warp == 0) {
+      double a[BSUB];
+#pragma unroll
+      for (int c = 0; c < BSUB; ++c)
+        a[c] = (lane < bs && c < bs && c <= lane) ? HL(o + lane, o + c) : ((c == lane) ? 1.0 : 0.0);
+      double mind = 1e300;
+      int fail = 0;
+#pragma unroll
+      for (int j = 0; j < BSUB; ++j) {
+        double d = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(d > 0.0) || d > 1e300) {
+          if (!fail && j < bs) fail = o + j + 1;
+          d = 1.0;
+        }
+        double r = rsqrt(d);
+        double l = d * r;
+        l = fma(0.5 * r, fma(-l, l, d), l);
+        r = fma(r, fma(-l, r, 1.0), r);
+        if (j < bs && l < mind) mind = l;
+        if (lane == j) { a[j] = l; S.rdiag[o + j] = r; }
+        else if (lane > j) a[j] *= r;
+#pragma unroll
+        for (int c = j + 1; c < BSUB; ++c) {
+          const double tt = __shfl_sync(0xffffffffu, a[j], c);
+          if (lane >= c) a[c] = fma(-a[j], tt, a[c]);
+        }
+      }
+      if (lane == 0) {
+        if (fail && !S.fl[0]) S.fl[0] = fail;
+        if (mind < S.sc[0]) S.sc[0] = mind;
+      }
+#pragma unroll
+      for (int c = 0; c < BSUB; ++c)
+        if (lane < bs && c <= lane) HL(o + lane, o + c) = a[c];
+    }
+    __syncthreads();
+    const int r0 = o + BSUB;
+    const int nrows = n - r0;
+    if (nrows <= 0) continue;
+    if (tid < nrows) {
+      const int r = r0 + tid;
+      double xr[BSUB];
+#pragma unroll
+      for (int c = 0; c < BSUB; ++c) {
+        double v = HL(r, o + c);
+#pragma unroll
+        for (int k = 0; k < c; ++k) v = fma(-xr[k], HL(o + c, o + k), v);
+        xr[c] = v * S.rdiag[o + c];
+      }
+#pragma unroll
+      for (int c = 0; c < BSUB; ++c) HL(r, o + c) = xr[c];
+    }
+    __syncthreads();
+    for (int c = r0 + warp; c < n; c += BT / 32) {
+      for (int r = c - ((c - r0) & 31) + lane; r < n; r += 32) {
+        if (r < c) continue;
+        double v = HL(r, c);
+#pragma unroll
+        for (int k = 0; k < BSUB; ++k) v = fma(-HL(r, o + k), HL(c, o + k), v);
+        HL(r, c) = v;
+      }
+    }
+    __syncthreads();
+  }
+  *mind_out = S.sc[0];
+  return S.fl[0];
+}
+
+// ---- triangular solves with the factor in S.L, by warp 0 (and warp 1 for a second right-hand side) -------
+// forward: v := L^-1 v ; backward: v := L^-T v.  Rows lane and lane + 32.
+__device__ __forceinline__ void b_trsv_warp(Smem& S, int n, double* v, bool trans) {
+  const int lane = threadIdx.x & 31;
+  double b0 = lane < n ? v[lane] : 0.0, b1 = lane + 32 < n ? v[lane + 32] : 0.0;
+  if (!trans) {
+    for (int j = 0; j < n; ++j) {
+      double src = (j < 32) ? b0 : b1;
+      double yj = __shfl_sync(0xffffffffu, src, j & 31) * S.rdiag[j];
+      if (lane == (j & 31)) { if (j < 32) b0 = yj; else b1 = yj; }
+      if (lane > j && lane < n) b0 = fma(-HL(lane, j), yj, b0);
+      if (lane + 32 > j && lane + 32 < n) b1 = fma(-HL(lane + 32, j), yj, b1);
+    }
+  } else {
+    for (int j = n - 1; j >= 0; --j) {
+      double src = (j < 32) ? b0 : b1;
+      double xj = __shfl_sync(0xffffffffu, src, j & 31) * S.rdiag[j];
+      if (lane == (j & 31)) { if (j < 32) b0 = xj; else b1 = xj; }
+      if (lane < j) b0 = fma(-HL(j, lane), xj, b0);
+      if (lane + 32 < j) b1 = fma(-HL(j, lane + 32), xj, b1);
+    }
+  }
+  if (lane < n) v[lane] = b0;
+  if (lane + 32 < n) v[lane + 32] = b1;
+}
+
+// t2 = L (L' v)   (for the residual with L L' in place of Q)
+__device__ void b_llt_apply(Smem& S, int n, const double* v, double* out) {
+  const int tid = threadIdx.x;
+  if (tid < n) {
+    double s = 0.0;
+    for (int i = tid; i < n; ++i) s = fma(HL(i, tid), v[i], s);      // (L'v)_tid
+    S_T1[tid] = s;
+  }
+  __syncthreads();
+  if (tid < n) {
+    double s = 0.0;
+    for (int k = 0; k <= tid; ++k) s = fma(HL(tid, k), S_T1[k], s);
+    out[tid] = s;
+  }
+  __syncthreads();
+}
+
+// restore H (full) from the per-CTA scratch, optionally adding delta*I and a rank-one term aa'
+__device__ void b_load_H(Smem& S, int n, const double* Hs, double diag_add, bool rank1) {
+  for (int idx = threadIdx.x; idx < n * n; idx += BT) {
+    int i = idx % n, j = idx / n;
+    double v = Hs[idx];
+    if (i == j) v += diag_add;
+    if (rank1) v += S.aeq[i] * S.aeq[j];
+    HL(i, j) = v;
+  }
+  __syncthreads();
+}
+__device__ void b_store_H(Smem& S, int n, double* Hs) {
+  for (int idx = threadIdx.x; idx < n * n; idx += BT) Hs[idx] = HL(idx % n, idx / n);
+  __syncthreads();
+}
+
+// (d d') o H in place, + delta on the diagonal
+__device__ void b_scale_H(Smem& S, int n, double delta) {
+  for (int idx = threadIdx.x; idx < n * n; idx += BT) {
+    int i = idx % n, j = idx / n;
+    double v = (S.dr[i] * S.dr[j]) * HL(i, j);
+    if (i == j) v += delta;
+    HL(i, j) = v;
+  }
+  __syncthreads();
+}
+
+// One solvePD / choleskySolve attempt chain on the matrix currently in the scratch copy Hs (+ modifiers).
+//   p == 0: dir = choleskySolve(Hmod, -y)          (rhs = -y)
+//   p == 1: KKT  Hmod dir + a' w = -q, a.dir = beq_rhs
+// returns true when the attempt chain (plain, then regularised) produced an accepted solution.
+__device__ bool b_linear_solve(Smem& S, const BatchArgs& A, const double* Hs, double diag_add, bool rank1,
+                               const double* q, double brhs, double tol, int* regularized) {
+  const int tid = threadIdx.x, n = A.n;
+  bool have_dr = false;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    b_load_H(S, n, Hs, diag_add, rank1);
+    if (!have_dr) { b_ruiz(S, A); have_dr = true; }
+    b_scale_H(S, n, attempt ? A.P.cholRegDelta : 0.0);
+    double mind;
+    int fail = b_potrf(S, n, &mind);
+    if (attempt == 0 && (fail || !(mind > A.P.cholMinDiag))) { *regularized = 1; continue; }
+    if (fail) return false;
+    if (S.pcur == 0) {
+      // w = L^-1 (d o (-q)) ; u = L^-T w ; dir = d o u ; residual || Hmod dir + q || / relsize(q)
+      if (tid < n) S.qs[tid] = S.dr[tid] * (-q[tid]);
+      __syncthreads();
+      if (tid < 32) { b_trsv_warp(S, n, S.qs, false); __syncwarp(); b_trsv_warp(S, n, S.qs, true); }
+      __syncthreads();
+      if (tid < n) S.dir[tid] = S.dr[tid] * S.qs[tid];
+      __syncthreads();
+      double r2 = 0.0, q2 = 0.0;
+      if (tid < n) {
+        double s = 0.0;
+        for (int j = 0; j < n; ++j) {
+          double hij = Hs[tid + (size_t)j * n];
+          if (tid == j) hij += diag_add;
+          s = fma(hij, S.dir[j], s);
+        }
+        double r = s + q[tid];
+        r2 = r * r;
+        q2 = q[tid] * q[tid];
+      }
+      r2 = block_sum(r2, S.red);
+      q2 = block_sum(q2, S.red);
+      double e1 = relative_size(sqrt(r2), sqrt(q2), tol);
+      return e1 <= tol;
+    }
+    // ---- p == 1 block elimination (KKTSystem.scala:99-167 on the equilibrated system)
+    if (tid < n) { S.ya[tid] = S.dr[tid] * S.aeq[tid]; S.qs[tid] = S.dr[tid] * q[tid]; S.yq[tid] = S.qs[tid]; }
+    __syncthreads();
+    if (tid < 32) b_trsv_warp(S, n, S.ya, false);
+    else if (tid < 64) b_trsv_warp(S, n, S.yq, false);
+    __syncthreads();
+    double sa = 0.0, saq = 0.0, nq = 0.0;
+    if (tid < n) { sa = S.ya[tid] * S.ya[tid]; saq = S.ya[tid] * S.yq[tid]; nq = S.qs[tid] * S.qs[tid]; }
+    sa = block_sum(sa, S.red);
+    saq = block_sum(saq, S.red);
+    nq = block_sum(nq, S.red);
+    if (!(sa > 0.0)) return false;               // cholesky(S) of the 1 x 1 Schur complement fails
+    const double K = sqrt(sa);
+    const double z = -(brhs + saq);
+    const double w = (z / K) / K;
+    if (tid < n) S.yq[tid] = S.yq[tid] + S.ya[tid] * w;
+    __syncthreads();
+    if (tid < 32) b_trsv_warp(S, n, S.yq, true);
+    __syncthreads();
+    if (tid < n) { S_T2[tid] = -S.yq[tid]; }        // xs
+    __syncthreads();
+    b_llt_apply(S, n, S_T2, S_XTRY);               // L L' xs
+    double r2 = 0.0, axs = 0.0;
+    if (tid < n) {
+      double r = S_XTRY[tid] + S.dr[tid] * S.aeq[tid] * w + S.qs[tid];
+      r2 = r * r;
+      S.dir[tid] = S.dr[tid] * S_T2[tid];
+      axs = S.aeq[tid] * S.dir[tid];
+    }
+    r2 = block_sum(r2, S.red);
+    axs = block_sum(axs, S.red);
+    double e1 = relative_size(sqrt(r2), sqrt(nq), tol);
+    double e2 = relative_size(fabs(axs - brhs), fabs(brhs), tol);
+    if (tid == 0) S.sc[1] = w;
+    __syncthreads();
+    return (e1 <= tol) && (e2 <= tol);
+  }
+  return false;
+}
+
+__device__ bool b_in_set(Smem& S, int m, double s) {
+  int out = 0;
+  if (threadIdx.x < m) {
+    double g = S.gx[threadIdx.x] + s * S.Gd[threadIdx.x];
+    if (!(g * IN_SET < S.ub[threadIdx.x])) out = 1;
+  }
+  return block_or(out, S.ired) == 0;
+}
+
+__device__ double b_value(Smem& S, const BatchArgs& A, int kind, double t, double s, double f0, double c1, double c2,
+                          int* throws) {
+  const int tid = threadIdx.x;
+  double ls = 0.0;
+  int bad = 0;
+  if (tid < A.m) {
+    double d = S.ub[tid] - (S.gx[tid] + s * S.Gd[tid]);
+    if (!(d > 0.0)) bad = 1;
+    ls = log(d);
+  }
+  ls = block_sum(ls, S.red);
+  bad = block_or(bad, S.ired);
+  *throws = bad;
+  double f0s;
+  if (kind == CVXB_OBJ_KL) {
+    double v = 0.0;
+    if (tid < A.n) {
+      double xj = S.x[tid] + s * S.dir[tid];
+      v = xj * log(xj * (double)A.n);
+    }
+    f0s = block_sum(v, S.red);
+  } else {
+    f0s = f0 + s * c1 + 0.5 * s * s * c2;
+  }
+  return t * f0s - ls;
+}
+
+__global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  __shared__ int s_pid;
+  const int tid = threadIdx.x, n = A.n, m = A.m;
+  double* Hs = A.scratch + (size_t)blockIdx.x * BN * BN;
+  const double tol = A.P.tolSolver, tolEq = A.P.tolEqSolve;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_pid = (int)atomicAdd(A.counter, 1u);
+    __syncthreads();
+    const int pid = s_pid;
+    if (pid >= A.B) break;
+    // ---- load the problem
+    const int kind = A.objective[pid];
+    const int p = A.pcount ? A.pcount[pid] : A.p;
+    if (tid == 0) S.pcur = p;
+    const double obj_r = A.obj_r ? A.obj_r[pid] : 0.0;
+    const double* Pg = A.obj_P ? A.obj_P + (size_t)pid * n * n : nullptr;
+    const double* Gg = A.G + (size_t)pid * m * n;
+    for (int idx = tid; idx < BN * LDG; idx += BT) S.G[idx] = 0.0;
+    __syncthreads();
+    for (int idx = tid; idx < m * n; idx += BT) GG(idx % m, idx / m) = Gg[idx];
+    if (tid < BM_) S.ub[tid] = tid < m ? A.ub[(size_t)pid * m + tid] : 1.0;
+    if (tid < n) {
+      S.x[tid] = A.x0[(size_t)pid * n + tid];
+      S.oa[tid] = (kind != CVXB_OBJ_KL && A.obj_a) ? A.obj_a[(size_t)pid * n + tid] : 0.0;
+      S.aeq[tid] = p ? A.A[(size_t)pid * n + tid] : 0.0;
+      S.Px[tid] = 0.0; S.Pd[tid] = 0.0;
+    }
+    const double beq = p ? A.b[pid] : 0.0;
+    __syncthreads();
+
+    int status = CVXB_OK, stage = 0, total_steps = 0;
+    double t = A.P.t0, gap = 1.7976931348623157e308, eqgap = 1.7976931348623157e308, objv = 0.0;
+    const double maxStage = 1000.0 / A.P.mu;
+    while (!(gap < tol && eqgap < tol) && stage < maxStage && status == CVXB_OK) {
+      // ---------------- inner Newton solve at parameter t
+      int iter = 0;
+      double nd = tol + 1, fval, f0, normGrad, eqd, trust = 0.0;
+      if (!b_eval(S, A, kind, obj_r, Pg, beq, t, &fval, &f0, &normGrad, &eqd)) { status = CVXB_ENOTFEASIBLE; break; }
+      double eqnorm = fabs(eqd);
+      while (iter < A.P.maxIter && (p ? ((nd > tol && normGrad > tol) || eqnorm > tol) : (nd > tol && normGrad > tol))) {
+        b_hessian(S, A, kind, Pg, t);
+        b_store_H(S, n, Hs);
+        int reg = 0;
+        bool ok = b_linear_solve(S, A, Hs, 0.0, false, S.y, eqd, tolEq, &reg);
+        if (!ok) {
+          if (p) {
+            // path 1: K = H + a a', z = q - a' b   (KKTSystem.scala:57-59)
+            if (tid < n) S.zrhs[tid] = S.y[tid] - S.aeq[tid] * eqd;
+            __syncthreads();
+            ok = b_linear_solve(S, A, Hs, 0.0, true, S.zrhs, eqd, tolEq, &reg);
+          } else {
+            ok = b_linear_solve(S, A, Hs, A.P.newtonRegDelta, false, S.y, 0.0, tolEq, &reg);   // H + 1e-9 I
+          }
+          if (!ok) { status = CVXB_ELINSOLVE; break; }
+        }
+        // q = d . grad
+        double q = 0.0, c1 = 0.0, c2 = 0.0;
+        if (kind == CVXB_OBJ_QUADRATIC && tid >= 128 && tid < 128 + n) {
+          const int i = tid - 128;
+          double s = 0.0;
+          for (int j = 0; j < n; ++j) s = fma(Pg[i + (size_t)j * n], S.dir[j], s);
+          S.Pd[i] = s;
+        }
+        if (tid < m) {
+          double s = 0.0;
+          for (int j = 0; j < n; ++j) s = fma(GG(tid, j), S.dir[j], s);
+          S.Gd[tid] = s;
+        }
+        __syncthreads();
+        if (tid < n) {
+          double dj = S.dir[tid];
+          q = dj * S.y[tid];
+          if (kind == CVXB_OBJ_LINEAR) c1 = S.oa[tid] * dj;
+          else if (kind == CVXB_OBJ_QUADRATIC) { c1 = (S.oa[tid] + S.Px[tid]) * dj; c2 = dj * S.Pd[tid]; }
+        }
+        q = block_sum(q, S.red);
+        c1 = block_sum(c1, S.red);
+        c2 = block_sum(c2, S.red);
+        nd = -q / 2;
+        bool moved = false;
+        if (nd > tol) {
+          int it = 0, thr = 0;
+          double step;
+          if (p) {
+            double s = 1.0;
+            while (!b_in_set(S, m, s) && it < 100) { s *= A.P.beta; ++it; }
+            if (it == 100) { status = CVXB_ELINESEARCH; break; }
+            while (it < 100) {
+              double v = b_value(S, A, kind, t, s, f0, c1, c2, &thr);
+              if (thr) break;
+              if (!(v > fval + A.P.alpha * s * q)) break;
+              s *= A.P.beta; ++it;
+            }
+            if (thr) { status = CVXB_ENOTFEASIBLE; break; }
+            if (it == 100) { status = CVXB_ELINESEARCH; break; }
+            step = s;
+          } else {
+            const double hnorm = sqrt(-q);
+            if (iter == 0) trust = hnorm;
+            const double scl = (iter == 0 || hnorm <= trust) ? 1.0 : trust / hnorm;
+            double tt = 1.0;
+            while (!b_in_set(S, m, scl * tt) && it < 200) { tt *= A.P.beta; ++it; }
+            if (it == 100) { status = CVXB_ELINESEARCH; break; }
+            if (b_in_set(S, m, scl)) {
+              (void)b_value(S, A, kind, t, scl * tt, f0, c1, c2, &thr);
+              if (thr) { status = CVXB_ENOTFEASIBLE; break; }
+            }
+            while (it < 200) {
+              double v = b_value(S, A, kind, t, scl * tt, f0, c1, c2, &thr);
+              if (thr) break;
+              if (!(v > fval + A.P.alpha * tt * q)) break;
+              tt *= A.P.beta; ++it;
+            }
+            if (thr) { status = CVXB_ENOTFEASIBLE; break; }
+            if (it == 100) { status = CVXB_ELINESEARCH; break; }
+            step = scl * tt;
+          }
+          if (tid < n) S.x[tid] = S.x[tid] + S.dir[tid] * step;
+          __syncthreads();
+          if (!b_eval(S, A, kind, obj_r, Pg, beq, t, &fval, &f0, &normGrad, &eqd)) { status = CVXB_ENOTFEASIBLE; break; }
+          eqnorm = fabs(eqd);
+          moved = true;
+        }
+        ++iter;
+        if (!moved && p && ((nd > tol && normGrad > tol) || eqnorm > tol)) { iter = A.P.maxIter; break; }   // identical repeats
+      }
+      if (status != CVXB_OK) break;
+      total_steps += iter;
+      objv = f0;
+      gap = (double)m / t;
+      eqgap = p ? eqnorm : 0.0;
+      t *= A.P.mu;
+      ++stage;
+    }
+    if (tid < n) A.x[(size_t)pid * n + tid] = S.x[tid];
+    if (tid == 0) {
+      A.status[pid] = status;
+      A.steps[pid] = total_steps;
+      A.stages[pid] = stage;
+      A.objval[pid] = objv;
+      A.gap[pid] = gap;
+      A.eqgap[pid] = p ? eqgap : 0.0;
+    }
+  }
+}
+
+template <typename T>
+int balloc(cvxb_batch_s* Bt, T** ptr, size_t count) {
+  void* q = nullptr;
+  CVXB_CUDA_OK(cudaMalloc(&q, (count ? count : 1) * sizeof(T)));
+  Bt->owned.push_back(q);
+  *ptr = (T*)q;
+  return CVXB_OK;
+}
+
+template <typename T>
+int bupload(cvxb_batch_s* Bt, T** dst, const T* src, size_t count) {
+  if (!src) { *dst = nullptr; return CVXB_OK; }
+  CVXB_TRY(balloc(Bt, dst, count));
+  bool dev = (Bt->h->flags & CVXB_FLAG_DEVICE_PTRS) != 0;
+  CVXB_CUDA_OK(cudaMemcpyAsync(*dst, src, count * sizeof(T), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                               Bt->h->stream));
+  return CVXB_OK;
+}
+
+}  // namespace
+}  // namespace cvxb
+
+extern "C" {
+
+int cvxb_batch_create(cvxb_handle h, const cvxb_batch_desc* d, cvxb_batch* out) {
+  if (!h || !d || !out) { cvxb::set_last_error("cvxb_batch_create: null argument"); return CVXB_EINVAL; }
+  if (d->B < 1 || d->n < 1 || d->n > BN || d->m < 1 || d->m > BM_ || d->p < 0 || d->p > 1) {
+    cvxb::set_last_error("cvxb_batch_create: need B >= 1, 1 <= n <= 64, 1 <= m <= 128, p in {0,1} (got %d, %d, %d, %d)", d->B,
+                         d->n, d->m, d->p);
+    return CVXB_EDIM;
+  }
+  if (!d->objective || !d->G || !d->ub || !d->x0 || (d->p && (!d->A || !d->b))) {
+    cvxb::set_last_error("cvxb_batch_create: missing array");
+    return CVXB_EINVAL;
+  }
+  cudaSetDevice(h->device);
+  cvxb_batch_s* Bt = new cvxb_batch_s();
+  Bt->h = h; Bt->B = d->B; Bt->n = d->n; Bt->m = d->m; Bt->p = d->p;
+  const size_t B = d->B, n = d->n, m = d->m;
+  int st = CVXB_OK;
+  auto T = [&](int s) { if (st == CVXB_OK) st = s; };
+  T(bupload(Bt, &Bt->objective, d->objective, B));
+  T(bupload(Bt, &Bt->pcount, d->pcount, B));
+  T(bupload(Bt, &Bt->obj_a, d->obj_a, B * n));
+  T(bupload(Bt, &Bt->obj_r, d->obj_r, B));
+  T(bupload(Bt, &Bt->obj_P, d->obj_P, B * n * n));
+  T(bupload(Bt, &Bt->G, d->G, B * m * n));
+  T(bupload(Bt, &Bt->ub, d->ub, B * m));
+  if (d->p) { T(bupload(Bt, &Bt->A, d->A, B * n)); T(bupload(Bt, &Bt->b, d->b, B)); }
+  T(bupload(Bt, &Bt->x0, d->x0, B * n));
+  T(balloc(Bt, &Bt->x, B * n)); T(balloc(Bt, &Bt->objval, B)); T(balloc(Bt, &Bt->gap, B)); T(balloc(Bt, &Bt->eqgap, B));
+  T(balloc(Bt, &Bt->status, B)); T(balloc(Bt, &Bt->steps, B)); T(balloc(Bt, &Bt->stages, B));
+  Bt->grid = h->sm_count * 2;
+  if (Bt->grid > d->B) Bt->grid = d->B;
+  T(balloc(Bt, &Bt->scratch, (size_t)Bt->grid * BN * BN));
+  T(balloc(Bt, &Bt->counter, 1));
+  if (st == CVXB_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) st = CVXB_ECUDA;
+  if (st != CVXB_OK) { for (void* q : Bt->owned) cudaFree(q); delete Bt; return st; }
+  *out = Bt;
+  return CVXB_OK;
+}
+
+int cvxb_batch_destroy(cvxb_batch Bt) {
+  if (!Bt) return CVXB_OK;
+  cudaSetDevice(Bt->h->device);
+  cudaStreamSynchronize(Bt->h->stream);
+  for (void* q : Bt->owned) cudaFree(q);
+  delete Bt;
+  return CVXB_OK;
+}
+
+int cvxb_batch_barrier_solve(cvxb_handle h, cvxb_batch Bt, const cvxb_params* pars, cvxb_batch_result* out) {
+  if (!h || !Bt || !out) { cvxb::set_last_error("cvxb_batch_barrier_solve: null argument"); return CVXB_EINVAL; }
+  if (Bt->h != h) { cvxb::set_last_error("batch belongs to another handle"); return CVXB_EINVAL; }
+  cudaSetDevice(h->device);
+  cvxb_params dp;
+  if (!pars) { cvxb_default_params(&dp); pars = &dp; }
+  static bool attr = false;
+  if (!attr) {
+    CVXB_CUDA_OK(cudaFuncSetAttribute(batched_barrier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    attr = true;
+  }
+  BatchArgs A;
+  A.B = Bt->B; A.n = Bt->n; A.m = Bt->m; A.p = Bt->p;
+  A.objective = Bt->objective; A.pcount = Bt->pcount; A.obj_a = Bt->obj_a; A.obj_r = Bt->obj_r; A.obj_P = Bt->obj_P; A.G = Bt->G; A.ub = Bt->ub;
+  A.A = Bt->A; A.b = Bt->b; A.x0 = Bt->x0;
+  A.x = Bt->x; A.objval = Bt->objval; A.gap = Bt->gap; A.eqgap = Bt->eqgap;
+  A.status = Bt->status; A.steps = Bt->steps; A.stages = Bt->stages;
+  A.scratch = Bt->scratch; A.counter = Bt->counter; A.P = *pars;
+  CVXB_CUDA_OK(cudaMemsetAsync(Bt->counter, 0, sizeof(unsigned), h->stream));
+  CVXB_CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+  batched_barrier_kernel<<<Bt->grid, BT, sizeof(Smem), h->stream>>>(A);
+  h->launches++;
+  CVXB_CUDA_OK(cudaGetLastError());
+  CVXB_CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+  bool dev = (h->flags & CVXB_FLAG_DEVICE_PTRS) != 0;
+  cudaMemcpyKind k = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  const size_t B = Bt->B, n = Bt->n;
+  if (out->x) CVXB_CUDA_OK(cudaMemcpyAsync(out->x, Bt->x, B * n * sizeof(double), k, h->stream));
+  if (out->status) CVXB_CUDA_OK(cudaMemcpyAsync(out->status, Bt->status, B * sizeof(int), k, h->stream));
+  if (out->newton_steps) CVXB_CUDA_OK(cudaMemcpyAsync(out->newton_steps, Bt->steps, B * sizeof(int), k, h->stream));
+  if (out->outer_stages) CVXB_CUDA_OK(cudaMemcpyAsync(out->outer_stages, Bt->stages, B * sizeof(int), k, h->stream));
+  if (out->objective) CVXB_CUDA_OK(cudaMemcpyAsync(out->objective, Bt->objval, B * sizeof(double), k, h->stream));
+  if (out->duality_gap) CVXB_CUDA_OK(cudaMemcpyAsync(out->duality_gap, Bt->gap, B * sizeof(double), k, h->stream));
+  if (out->equality_gap) CVXB_CUDA_OK(cudaMemcpyAsync(out->equality_gap, Bt->eqgap, B * sizeof(double), k, h->stream));
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CVXB_CUDA_OK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  out->solve_ms = ms;
+  return CVXB_OK;
+}
+
+}  // extern "C"

@@ -219,6 +219,7 @@ int cvxb_pd_newton_direction(cvxb_handle h, cvxb_problem prob, const cvxb_params
 typedef struct cvxb_batch_desc {
   int B, n, m, p;
   const int* objective;    /* B */
+  const int* pcount;       /* B or NULL: equalities of each problem (0 or 1 <= p); NULL = p for all */
   const double* obj_a;     /* B*n (ignored for KL problems) */
   const double* obj_r;     /* B */
   const double* obj_P;     /* B*n*n (ignored unless QUADRATIC) */
