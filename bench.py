@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="cvxb", choices=["cvxb", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--batch", type=int, default=8192, help="problems in the batched leg (configs[2])")
     ap.add_argument("--cpu-steps", type=int, default=0, help="Newton steps of the CPU-baseline sample (0 = auto)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -289,6 +291,38 @@ def main():
         dist.all_reduce(e2e_n, op=dist.ReduceOp.SUM)
     e2e_value = e2e_n.item() / e2e_t.item()
 
+    # ---- batched leg (BASELINE.json configs[2]): B = 8192 independent n=64, m=128 problems (half KL with
+    # p=1, half QP with p=0), contiguous shards over the ranks, one CTA per problem, then the NCCL gather
+    # of the solutions + convergence all-reduce.  Strong scaling: B is fixed as N grows.
+    batched = None
+    if not args.no_batched:
+        from oracle import problems as P
+        Bt = args.batch
+        lo, hi = cb.shard_range(Bt, rank, world)
+        bprobs = [P.batched_problem(i, 64, 128, 1000) for i in range(lo, hi)]
+        solver = cb.BatchedBarrierSolver(cb.pack_problems(bprobs), cb.SolverParams(), h)
+        solver.solve()                                    # warm-up (same shapes)
+        barrier()
+        t0 = time.perf_counter()
+        bsol = solver.solve()
+        if world > 1:
+            g = cb.gather_solutions(bsol, Bt, 64)
+            conv, mxs = g["converged"], g["max_newton_steps"]
+        else:
+            conv, mxs = int((bsol.status == 0).sum()), int(bsol.newton_steps.max())
+        torch.cuda.synchronize()
+        bt = torch.tensor([time.perf_counter() - t0, bsol.solve_ms / 1e3], dtype=torch.float64, device="cuda")
+        bn = torch.tensor([float(bsol.newton_steps.sum())], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(bn, op=dist.ReduceOp.SUM)
+        wall_s, dev_s = bt.tolist()
+        batched = {"metric": "batched_barrier_solves_per_sec", "value": Bt / wall_s, "unit": "solves/s", "B": Bt, "n": 64,
+                   "m": 128, "scaling": "strong", "device_only_value": Bt / dev_s, "converged": conv,
+                   "max_newton_steps": mxs, "newton_steps_per_sec": bn.item() / wall_s,
+                   "includes": "kernel + device-to-host of the shard + NCCL all-gather of x and status + all-reduce"
+                               if world > 1 else "kernel + device-to-host of the results"}
+
     if rank == 0:
         # ---- roofline of the dominant kernel ---------------------------------------------------------------
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -327,7 +361,7 @@ def main():
                 "flops_per_step": f_step(n, m, p), "tflops": f_step(n, m, p) * value / world / 1e12,
                 "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d / max(e2e_steps, 1),
                         "d2h_bytes_per_step": d2h / max(e2e_steps, 1), "steps": e2e_steps, "seconds": e2e_s, "checksum": xsum},
-                "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu,
+                "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu, "batched": batched,
                 "last_solution": {"objective": last.objective, "outer_stages": last.outer_stages,
                                   "newton_steps": last.newton_steps, "phase1_newton_steps": last.phase1_newton_steps}}
         print(json.dumps(line))

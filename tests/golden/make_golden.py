@@ -1,0 +1,57 @@
+"""Generates tests/golden/oracle_golden.json.
+
+The reference (Scala 2.11 + Breeze) cannot run in the build container (no JVM), and its own tests hold no
+golden vectors or seeds, so these fixtures pin the CPU oracle against (a) the analytic optima of the
+reference's known-answer problems and (b) its own outputs on seeded inputs (regression guard for the
+oracle, which in turn is the checker of the CUDA path).  Run from the repo root:
+    python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import cvx_oracle as O  # noqa: E402
+from oracle import problems as P  # noqa: E402
+
+CASES = {
+    "min_dot_product_10": lambda: P.min_dot_product(np.linspace(0.5, 2, 10)),
+    "kl_1A_20": lambda: P.kl_1A(20),
+    "kl_2A_20": lambda: P.kl_2A(20),
+    "slab_qp_64": lambda: P.slab_qp(64, 64, 0, 1),
+    "kl_small_64": lambda: P.kl_small(64, 64, 2),
+    "slab_lp_phase1_40": lambda: P.slab_lp(40, 60, 0, 7, feasible_start=False),
+    "kl_random_60": lambda: P.kl_random(60, 60, 9, 1),
+}
+
+
+def main():
+    out = {}
+    for name, mk in CASES.items():
+        prob = mk()
+        objF, cnts, eqs = P.to_oracle(prob)
+        for solver in ("BR", "PD"):
+            sol, ph1 = O.solveProblem(objF, cnts, eqs, solver)
+            rec = dict(objective=objF.valueAt(sol.x), x=sol.x.tolist(), newton_steps=int(sol.newton_steps),
+                       outer_stages=int(sol.outer_stages), stage_newton_steps=[int(v) for v in sol.stage_newton_steps],
+                       dualityGap=float(sol.dualityGap),
+                       phase1_stage_newton_steps=None if ph1 is None else [int(v) for v in ph1.stage_newton_steps])
+            if "xopt" in prob:
+                rec["analytic_objective"] = objF.valueAt(prob["xopt"])
+            out[name + ":" + solver] = rec
+    # planted KKT systems (KktTest.scala designs)
+    for n, p, seed in [(10, 2, 0), (100, 20, 1)]:
+        s = P.kkt_planted_pd(n, p, seed)
+        info = O.KKTInfo()
+        x, w = O.kkt_solve(s["H"], s["A"], s["q"], s["b"], 1e-7, info)
+        out["kkt_planted_pd_%d_%d" % (n, p)] = dict(x=x.tolist(), w=w.tolist(), path=info.path, ruiz_sweeps=info.ruiz_sweeps)
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_golden.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print("wrote %d records" % len(out))
+
+
+if __name__ == "__main__":
+    main()
