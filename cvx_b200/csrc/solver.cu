@@ -714,6 +714,10 @@ int cvxb_barrier_solve(cvxb_handle h, cvxb_problem prob, const cvxb_params* pars
       out->phase1_s = ph_s;
       cudaEventRecord(h->ev1, h->stream); cudaEventSynchronize(h->ev1);
       float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); out->solve_ms = ms;
+      if (st == CVXB_OK && prob->phase1) {   // step-limited run that ended inside phase I: hand back the current iterate
+        download_vec(*h, out->x, prob->phase1->x, prob->n);
+        cudaStreamSynchronize(h->stream);
+      }
       return st;
     }
   }
