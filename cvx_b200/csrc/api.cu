@@ -457,6 +457,8 @@ __global__ void copy_kernel(size_t count, const double2* __restrict__ a, double2
   for (; i < count; i += stride) b[i] = a[i];
 }
 
+int cvxb_debug_leaf_clocks(long long* out, int reset) { return cvxb::leaf_clocks(out, reset != 0); }
+
 int cvxb_bench_kernel(cvxb_handle h, int which, int n, int k, int reps, double* ms_per_launch,
                       double* flops_or_bytes_per_launch) {
   CHECK_HANDLE(h);

@@ -243,10 +243,14 @@ __device__ int b_potrf(Smem& S, int n, double* mind_out) {
           if (!fail && j < bs) fail = o + j + 1;
           d = 1.0;
         }
-        double r = rsqrt(d);
-        double l = d * r;
-        l = fma(0.5 * r, fma(-l, l, d), l);
-        r = fma(r, fma(-l, r, 1.0), r);
+        double r;
+        if (d < 1e-30 || d > 1e30) r = rsqrt(d);
+        else {                                   // float seed + one cubic correction (factor.cu: pivot_rsqrt)
+          const double y0 = (double)rsqrtf((float)d);
+          const double e = fma(-(d * y0), y0, 1.0);
+          r = fma(y0, fma(e, 0.375, 0.5) * e, y0);
+        }
+        const double l = d * r;
         if (j < bs && l < mind) mind = l;
         if (lane == j) { a[j] = l; S.rdiag[o + j] = r; }
         else if (lane > j) a[j] *= r;

@@ -152,6 +152,7 @@ int potrf_lower(Handle& h, int n, double* A, int lda, double* invD, int flag_slo
 int trsm_lower(Handle& h, int n, int r, const double* L, int ldl, const double* invD, double* B, int ldb, bool trans);
 // inverse diagonal blocks of a given lower-triangular matrix (for cvxb_triangular_solve and
 // solveWithCholFactor); zero diagonal -> F_ZERO_DIAG
+int leaf_clocks(long long* out, bool reset);   // per-phase clock64 sums of the leaf kernel (debug builds)
 int invert_diag_blocks(Handle& h, int n, const double* L, int ldl, double* invD);
 
 }  // namespace cvxb

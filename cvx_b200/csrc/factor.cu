@@ -115,7 +115,27 @@ constexpr int LEAF_WARPS = LEAF_THREADS / 32;
 #define XW(i, j) W[(j) + ((i) + 1) * LDW]
 
 constexpr int SUB = 16;      // diagonal sub-block factored inside one warp
+
+__device__ __forceinline__ void dmma_leaf(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
 constexpr int NACC = 8;      // outputs per thread in the widest inverse-assembly level (128*64/2 / 512)
+
+// 1/sqrt(d) for a pivot: single-precision MUFU.RSQ seed (2^-22) + ONE third-order correction
+//   y = y0 (1 + e/2 + 3e^2/8),  e = 1 - d y0^2      (error ~ e^3 < 1e-19)
+// Five dependent FP64 operations instead of the ~13 of rsqrt() + refinement: the 128 pivots of a leaf
+// are a serial chain of FP64-latency-bound operations, so this is the critical path of the factorisation.
+__device__ __forceinline__ double pivot_rsqrt(double d) {
+  if (d < 1e-30 || d > 1e30) return rsqrt(d);          // outside float range: library path (rare, warp-uniform)
+  const double y0 = (double)rsqrtf((float)d);
+  const double t = d * y0;
+  const double e = fma(-t, y0, 1.0);
+  double p = fma(e, 0.375, 0.5);
+  p = p * e;
+  return fma(y0, p, y0);
+}
 
 // In-warp Cholesky of one SUB x SUB diagonal sub-block at offset o (bs valid rows): lane i < SUB holds
 // row i in registers, pivots travel by shuffle, no block barrier inside.  The pivot uses rsqrt plus one
@@ -124,30 +144,30 @@ constexpr int NACC = 8;      // outputs per thread in the widest inverse-assembl
 __device__ __forceinline__ void warp_diag_factor(double* W, double* rdiag, int o, int bs, int col0, int* s_fail,
                                                  double* s_mind) {
   const int lane = threadIdx.x & 31;
-  double a[SUB];
+  double a[SUB], rr[SUB];
 #pragma unroll
   for (int c = 0; c < SUB; ++c)
     a[c] = (lane < bs && c < bs && c <= lane) ? LW(o + lane, o + c) : ((c == lane) ? 1.0 : 0.0);
   double mind = 1e300;
   int fail = 0;
+  // Straight-line, branch-free sweep (selects only): a divergent branch next to a full-mask shuffle costs a
+  // reconvergence barrier per shuffle.  Entries above the diagonal (lane < c) are never read, so the
+  // updates run unpredicated.
 #pragma unroll
   for (int j = 0; j < SUB; ++j) {
     double d = __shfl_sync(0xffffffffu, a[j], j);
-    if (!(d > 0.0) || d > 1e300) {            // dpotrf: ajj <= 0 or NaN (inf would poison rsqrt)
-      if (!fail && j < bs) fail = col0 + o + j + 1;
-      d = 1.0;
-    }
-    double r = rsqrt(d);
-    double l = d * r;
-    l = fma(0.5 * r, fma(-l, l, d), l);        // l = sqrt(d) to the last bit or two
-    r = fma(r, fma(-l, r, 1.0), r);            // r = 1/l
-    if (j < bs && l < mind) mind = l;
-    if (lane == j) { a[j] = l; rdiag[o + j] = r; }
-    else if (lane > j) a[j] *= r;
+    const bool bad = !(d > 0.0) || d > 1e300;        // dpotrf: ajj <= 0 or NaN (inf would poison rsqrt)
+    fail = (bad && !fail && j < bs) ? (col0 + o + j + 1) : fail;
+    d = bad ? 1.0 : d;
+    const double r = pivot_rsqrt(d);                 // 1/sqrt(d), full double accuracy, 5 dependent FP64 ops
+    const double l = d * r;                          // sqrt(d) to ~1 ulp
+    mind = (j < bs && l < mind) ? l : mind;
+    rr[j] = r;
+    a[j] = (lane == j) ? l : a[j] * r;
 #pragma unroll
     for (int c = j + 1; c < SUB; ++c) {
       const double t = __shfl_sync(0xffffffffu, a[j], c);
-      if (lane >= c) a[c] = fma(-a[j], t, a[c]);
+      a[c] = fma(-a[j], t, a[c]);
     }
   }
   if (lane == 0) {
@@ -155,8 +175,10 @@ __device__ __forceinline__ void warp_diag_factor(double* W, double* rdiag, int o
     if (mind < *s_mind) *s_mind = mind;
   }
 #pragma unroll
-  for (int c = 0; c < SUB; ++c)
+  for (int c = 0; c < SUB; ++c) {
     if (lane < bs && c <= lane) LW(o + lane, o + c) = a[c];
+    if (lane == c) rdiag[o + c] = rr[c];
+  }
 }
 
 // inverse of the diagonal sub-block at o: lane j holds column j of X = L^-1 (forward substitution,
@@ -179,6 +201,19 @@ __device__ __forceinline__ void warp_diag_inverse(double* W, const double* rdiag
   for (int i = 0; i < SUB; ++i)
     if (i < bs && lane < bs && i >= lane) XW(o + i, o + lane) = x[i];
 }
+
+__device__ long long g_leaf_clk[8];
+#define LEAF_CLK(slot)                                            \
+  do {                                                            \
+    if (CVXB_LEAF_TIMING && threadIdx.x == 0) {                   \
+      long long _c = clock64();                                   \
+      g_leaf_clk[slot] += _c - _t0;                               \
+      _t0 = _c;                                                   \
+    }                                                             \
+  } while (0)
+#ifndef CVXB_LEAF_TIMING
+#define CVXB_LEAF_TIMING 0
+#endif
 
 // blockIdx.x selects the diagonal block when only inverting (FACTOR == false).
 // 128 x 128 leaf as 8 x 8 sub-blocks of 16.  Per sub-block column: in-warp diagonal factorisation, panel
@@ -204,11 +239,13 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
   }
   double* Ab = A + (size_t)off * lda + off;
   double* Xg = invD + (size_t)(FACTOR ? 0 : blockIdx.x) * NB * NB;
+  long long _t0 = CVXB_LEAF_TIMING ? clock64() : 0;
   for (int j = ty; j < nb; j += LEAF_WARPS)
     for (int i = tx; i < nb; i += 32)
       if (i >= j) LW(i, j) = Ab[(size_t)j * lda + i];
   if (tid == 0) { s_fail = 0; s_mind = 1e300; }
   __syncthreads();
+  LEAF_CLK(0);
 
   const int nblk = (nb + SUB - 1) / SUB;
   if (FACTOR) {
@@ -217,6 +254,7 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
       const int bs = (nb - o) < SUB ? (nb - o) : SUB;
       if (ty == 0) warp_diag_factor(W, rdiag, o, bs, col0, &s_fail, &s_mind);
       __syncthreads();
+      LEAF_CLK(1);
       const int r0 = o + SUB;
       const int nrows = nb - r0;
       if (nrows <= 0) continue;
@@ -235,20 +273,32 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
         for (int c = 0; c < SUB; ++c) LW(r, o + c) = x[c];
       }
       __syncthreads();
+      LEAF_CLK(2);
       // trailing update: A(r,c) -= sum_k L(r,o+k) L(c,o+k),  r >= c >= r0 ; warp per column, lanes down the rows
-      for (int c = r0 + ty; c < nb; c += LEAF_WARPS) {
-        double lc[SUB];
+      {
+        // rank-16 update of the lower triangle of A(r0.., r0..) on the DMMA pipe: 8 x 8 output tiles, one
+        // warp per tile, A(m,k) = L(row, o+k), B(k,n) = L(col, o+k); out-of-range rows only feed discarded outputs
+        const int g = tx >> 2, tq = tx & 3;
+        const int T = (nrows + 7) >> 3;
+        const int ntile = T * (T + 1) / 2;
+        for (int tl = ty; tl < ntile; tl += LEAF_WARPS) {
+          int ti = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
+          while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+          while (ti * (ti + 1) / 2 > tl) --ti;
+          const int tj = tl - ti * (ti + 1) / 2;
+          const int rr = r0 + 8 * ti + g, cr = r0 + 8 * tj + g;
+          double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-        for (int k = 0; k < SUB; ++k) lc[k] = LW(c, o + k);
-        for (int r = c - ((c - r0) & 31) + tx; r < nb; r += 32) {
-          if (r < c) continue;
-          double v = LW(r, c);
-#pragma unroll
-          for (int k = 0; k < SUB; ++k) v = fma(-LW(r, o + k), lc[k], v);
-          LW(r, c) = v;
+          for (int kk = 0; kk < SUB; kk += 4) dmma_leaf(c0, c1, LW(rr, o + kk + tq), LW(cr, o + kk + tq));
+          const int cc = r0 + 8 * tj + 2 * tq;
+          if (rr < nb) {
+            if (cc <= rr) LW(rr, cc) -= c0;
+            if (cc + 1 <= rr) LW(rr, cc + 1) -= c1;
+          }
         }
       }
       __syncthreads();
+      LEAF_CLK(3);
     }
     if (tid == 0) {
       if (s_fail && flag[flag_slot] == 0) flag[flag_slot] = s_fail;
@@ -273,71 +323,79 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
     warp_diag_inverse(W, rdiag, o, (nb - o) < SUB ? (nb - o) : SUB);
   }
   __syncthreads();
+  LEAF_CLK(4);
   for (int sh = 4; (1 << sh) < nb; ++sh) {           // s = 16, 32, 64
     const int s2 = 1 << sh;
     const int npairs = (nb + 2 * s2 - 1) / (2 * s2);
-    const int total = npairs << (2 * sh);
-    double acc[NACC];
-    // T = L21 * X11  (rows of the second half, columns of the first half of each pair)
+    // Both products of the level on the DMMA pipe, 8 x 8 output tiles spread over the 16 warps:
+    //   T   = L21 * X11      A(m,k) = L(r,k),            B(k,n) = X(k,c) (zero for k < c)
+    //   X21 = -X22 * T       A(m,k) = X(r,k) (k <= r),   B(k,n) = T(k,c)
+    const int g = tx >> 2, tq = tx & 3;
+    const int tps = s2 >> 3;                         // tiles per side of one block
+    const int ntile = npairs * tps * tps;
+    constexpr int MAXT = 4;                          // 64 tiles at the widest level / 16 warps
+    double c0[MAXT], c1[MAXT];
+    int rT[MAXT], cT[MAXT], bT[MAXT];
+    bool onT[MAXT];
 #pragma unroll
-    for (int u = 0; u < NACC; ++u) {
-      const int idx = tid + u * LEAF_THREADS;
-      acc[u] = 0.0;
-      if (idx < total) {
-        const int cc = idx & (s2 - 1), rr = (idx >> sh) & (s2 - 1), pr = idx >> (2 * sh);
-        const int base = pr * 2 * s2;
-        const int c = base + cc, r = base + s2 + rr;
-        if (r < nb) {
-          double v = 0.0;
-          for (int k = c; k < base + s2; ++k) v = fma(LW(r, k), XW(k, c), v);   // X(k,c) = 0 for k < c
-          acc[u] = v;
+    for (int u = 0; u < MAXT; ++u) {
+      c0[u] = c1[u] = 0.0;
+      int tl = ty + u * LEAF_WARPS;
+      onT[u] = tl < ntile;
+      if (!onT[u]) tl = 0;
+      const int pr = tl / (tps * tps), rem = tl - pr * tps * tps;
+      bT[u] = pr * 2 * s2;
+      rT[u] = bT[u] + s2 + 8 * (rem / tps);
+      cT[u] = bT[u] + 8 * (rem % tps);
+    }
+#pragma unroll 2
+    for (int kk = 0; kk < s2; kk += 4) {
+#pragma unroll
+      for (int u = 0; u < MAXT; ++u) {
+        if (onT[u]) {                                   // warp-uniform
+          const int k = bT[u] + kk + tq, c = cT[u] + g;
+          const double bv = (k >= c) ? XW(k, c) : 0.0;
+          dmma_leaf(c0[u], c1[u], LW(rT[u] + g, k), bv);
         }
       }
     }
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < NACC; ++u) {
-      const int idx = tid + u * LEAF_THREADS;
-      if (idx < total) {
-        const int cc = idx & (s2 - 1), rr = (idx >> sh) & (s2 - 1), pr = idx >> (2 * sh);
-        const int base = pr * 2 * s2;
-        if (base + s2 + rr < nb) XW(base + s2 + rr, base + cc) = acc[u];
-      }
+    for (int u = 0; u < MAXT; ++u) {
+      const int r = rT[u] + g, c = cT[u] + 2 * tq;
+      if (onT[u] && r < nb) { XW(r, c) = c0[u]; XW(r, c + 1) = c1[u]; }
     }
     __syncthreads();
-    // X21 = -X22 * T
 #pragma unroll
-    for (int u = 0; u < NACC; ++u) {
-      const int idx = tid + u * LEAF_THREADS;
-      if (idx < total) {
-        const int cc = idx & (s2 - 1), rr = (idx >> sh) & (s2 - 1), pr = idx >> (2 * sh);
-        const int base = pr * 2 * s2;
-        const int c = base + cc, r = base + s2 + rr;
-        if (r < nb) {
-          double v = 0.0;
-          for (int k = base + s2; k <= r; ++k) v = fma(XW(r, k), XW(k, c), v);
-          acc[u] = -v;
+    for (int u = 0; u < MAXT; ++u) c0[u] = c1[u] = 0.0;
+#pragma unroll 2
+    for (int kk = 0; kk < s2; kk += 4) {
+#pragma unroll
+      for (int u = 0; u < MAXT; ++u) {
+        if (onT[u]) {
+          const int k = bT[u] + s2 + kk + tq, r = rT[u] + g, c = cT[u] + g;
+          const double av = (k <= r && r < nb) ? XW(r, k) : 0.0;
+          const double bv = (k < nb) ? XW(k, c) : 0.0;
+          dmma_leaf(c0[u], c1[u], av, bv);
         }
       }
     }
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < NACC; ++u) {
-      const int idx = tid + u * LEAF_THREADS;
-      if (idx < total) {
-        const int cc = idx & (s2 - 1), rr = (idx >> sh) & (s2 - 1), pr = idx >> (2 * sh);
-        const int base = pr * 2 * s2;
-        if (base + s2 + rr < nb) XW(base + s2 + rr, base + cc) = acc[u];
-      }
+    for (int u = 0; u < MAXT; ++u) {
+      const int r = rT[u] + g, c = cT[u] + 2 * tq;
+      if (onT[u] && r < nb) { XW(r, c) = -c0[u]; XW(r, c + 1) = -c1[u]; }
     }
     __syncthreads();
   }
+  LEAF_CLK(5);
   for (int j = ty; j < NB; j += LEAF_WARPS)
     for (int i = tx; i < NB; i += 32) {
       double x = (i < nb && j < nb && i >= j) ? XW(i, j) : 0.0;
       Xg[(size_t)j * NB + i] = x;
       if (FACTOR && i < nb && j < nb && i >= j) Ab[(size_t)j * lda + i] = LW(i, j);
     }
+  LEAF_CLK(6);
 }
 
 __global__ void potrf_reset_kernel(int* flag, double* scal, int flag_slot, int mindiag_slot) {
@@ -577,6 +635,15 @@ int trsm_lower(Handle& h, int n, int r, const double* L, int ldl, const double* 
   if (n <= 0 || r <= 0) return CVXB_OK;
   if (r == 1 && n > NB) return trsv_lower(h, n, L, ldl, invD, B, trans);
   return trsm_rec(h, n, r, L, ldl, invD, B, ldb, trans);
+}
+
+int leaf_clocks(long long* out, bool reset) {
+  if (out) CVXB_CUDA_OK(cudaMemcpyFromSymbol(out, g_leaf_clk, 8 * sizeof(long long)));
+  if (reset) {
+    long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CVXB_CUDA_OK(cudaMemcpyToSymbol(g_leaf_clk, z, sizeof(z)));
+  }
+  return CVXB_OK;
 }
 
 int invert_diag_blocks(Handle& h, int n, const double* L, int ldl, double* invD) {
