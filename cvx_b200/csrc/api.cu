@@ -396,16 +396,21 @@ int cvxb_symmetric_solve(cvxb_handle h, int n, const double* Hm, int ldh, const 
   CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
   double asym = 0;
   for (double v : colerr) asym += v;
-  if (!(std::sqrt(asym) < 1e-13)) {
-    cvxb::set_last_error("SymmetricLinearSystem: matrix not symmetric (||Q-Q'|| = %.3g); the svdSolve branch "
-                         "(SymmetricLinearSystem.scala:29) is not implemented on the device", std::sqrt(asym));
-    return CVXB_ENOTSYMMETRIC;
-  }
+  const bool symmetric = std::sqrt(asym) < 1e-13;
   // s = d o r ; u = choleskySolve(Q, s) ; x = d o u
   Staged ds;
   CVXB_TRY(stage_out_alloc(*h, n, 1, ds));
   CVXB_TRY(scale_rows(*h, n, 1, dr.d, pad_ld(n), W->dr2, ds.d, ds.ld, false));
-  st = chol_solve_device(*h, *W, P, dQ.d, dQ.ld, ds.d, 1.0, tol, du.d, info);
+  if (!symmetric) {
+    st = svd_solve_device(*h, n, dQ.d, dQ.ld, ds.d, 1.0, tol, du.d, nullptr);     // svdSolve branch (:29)
+    if (info) { memset(info, 0, sizeof(*info)); info->path = 3; }
+  } else {
+    st = chol_solve_device(*h, *W, P, dQ.d, dQ.ld, ds.d, 1.0, tol, du.d, info);
+    if (st == CVXB_ELINSOLVE) {                                                    // symSolve fallback (:33)
+      st = svd_solve_device(*h, n, dQ.d, dQ.ld, ds.d, 1.0, tol, du.d, nullptr);
+      if (info) info->path = 2;
+    }
+  }
   if (st != CVXB_OK) return st;
   CVXB_TRY(scale_rows(*h, n, 1, du.d, du.ld, W->dr2, dx.d, dx.ld, false));
   CVXB_TRY(copy_out(*h, n, 1, dx, x, n));

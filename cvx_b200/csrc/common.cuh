@@ -66,6 +66,18 @@ struct cvxb_handle_s {
 namespace cvxb {
 
 typedef cvxb_handle_s Handle;
+
+// bump allocator over ONE cudaMalloc: a problem's ~60 buffers cost one driver call instead of sixty
+struct Arena {
+  char* base = nullptr;
+  size_t size = 0, used = 0;
+  void* take(size_t bytes) {
+    size_t a = (used + 255) & ~(size_t)255;
+    if (!base || a + bytes > size) return nullptr;
+    used = a + bytes;
+    return base + a;
+  }
+};
 constexpr int NSCAL = 128, NFLAG = 64;
 constexpr size_t PART_DOUBLES = (size_t)1 << 22;   // 32 MiB of split-K partials for gemv_n
 

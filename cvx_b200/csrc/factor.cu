@@ -413,6 +413,15 @@ inline int split_point(int n) {
 int trsm_right_lt(Handle& h, int M, int n1, const double* L, int ldl, const double* invD, double* A21, int lda) {
   if (M <= 0 || n1 <= 0) return CVXB_OK;
   if (n1 <= NB) {
+    // X = A21 * invL11' through a scratch panel (the product cannot alias its operand once the grid has
+    // more than one tile column), so that small tiles can spread M x 128 outputs over all SMs
+    const int lds = pad_ld(M);
+    if ((size_t)lds * n1 <= PART_DOUBLES - 65536) {
+      double* Xs = h.d_part;
+      GemmArgs g{M, n1, n1, A21, lda, false, invD, NB, false, Xs, lds, 1.0, 0.0, 0};
+      CVXB_TRY(gemm_dmma(h, g));
+      return copy_matrix(h, M, n1, Xs, lds, A21, lda);
+    }
     // in place: the tile grid has a single column (N = n1 <= 128), so a CTA reads only the rows it writes
     GemmArgs g{M, n1, n1, A21, lda, false, invD, NB, false, A21, lda, 1.0, 0.0, 0, 128};
     return gemm_dmma(h, g);
@@ -445,6 +454,13 @@ int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot,
 
 int trsm_rec(Handle& h, int n, int r, const double* L, int ldl, const double* invD, double* B, int ldb, bool trans) {
   if (n <= NB) {
+    const int lds = pad_ld(n);
+    if ((size_t)lds * r <= PART_DOUBLES - 65536) {      // out of place through the scratch panel (see above)
+      double* Ys = h.d_part;
+      GemmArgs g{n, r, n, invD, NB, trans, B, ldb, true, Ys, lds, 1.0, 0.0, 0};
+      CVXB_TRY(gemm_dmma(h, g));
+      return copy_matrix(h, n, r, Ys, lds, B, ldb);
+    }
     // in place: single tile row (M = n <= 128): a CTA reads only the columns it writes
     GemmArgs g{n, r, n, invD, NB, trans, B, ldb, true, B, ldb, 1.0, 0.0, 0, 128};
     return gemm_dmma(h, g);

@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(VT) sub_kernel(int n, const double* __restrict
 
 template <typename T>
 int dev_alloc(KktWork& W, T** ptr, size_t count) {
-  void* q = nullptr;
+  void* q = W.arena ? W.arena->take((count ? count : 1) * sizeof(T)) : nullptr;
+  if (q) { *ptr = (T*)q; return CVXB_OK; }
   CVXB_CUDA_OK(cudaMalloc(&q, (count ? count : 1) * sizeof(T)));
   W.owned.push_back(q);
   *ptr = (T*)q;
@@ -156,8 +157,16 @@ int dev_alloc(KktWork& W, T** ptr, size_t count) {
 
 }  // namespace
 
-int kkt_work_alloc(Handle& h, KktWork& W, int n, int p) {
+size_t kkt_work_bytes(int n, int p) {
+  const size_t ldn = pad_ld(n), ldp = pad_ld(p);
+  const size_t nblk = (n + NB - 1) / NB, pblk = (p + NB - 1) / NB;
+  size_t d = ldn * n + nblk * NB * NB + ldn * (p + 1) + ldp * (p > 0 ? p : 1) + (pblk ? pblk : 1) * NB * NB + 9 * ldn + 3 * ldp;
+  return d * sizeof(double) + 32 * 256;
+}
+
+int kkt_work_alloc(Handle& h, KktWork& W, int n, int p, Arena* arena) {
   (void)h;
+  W.arena = arena;
   W.n = n;
   W.p = p;
   W.ldn = pad_ld(n);
@@ -281,11 +290,8 @@ int kkt_solve_fallbacks(Handle& h, KktWork& W, const cvxb_params& P, const doubl
   CVXB_TRY(kkt_try_path(h, W, P, W.Hk, W.ldn, A, lda, W.qk, b, tol, x, w, false, &reg, &ok));
   if (ok) { fill_info(h, info, 1, reg); return CVXB_OK; }
   fill_info(h, info, 2, reg);
-  // path 2 (KKTSystem.kktSymSolve: eigendecomposition of the (n+p)^2 KKT matrix) is not built yet.
-  set_last_error("KKT solve: Cholesky paths 0 and 1 failed (flags %d, err1 %.3g, err2 %.3g); the eigen "
-                 "fallback (KKTSystem.scala:283-310) is not implemented on the device",
-                 h.h_flag[F_BAD], h.h_scal[S_ERR1], h.h_scal[S_ERR2]);
-  return CVXB_ELINSOLVE;
+  // path 2: KKTSystem.kktSymSolve -- decomposition of the full (n+p)^2 KKT matrix  (KKTSystem.scala:63, 283-310)
+  return kkt_sym_solve_device(h, n, p, Hm, ldh, A, lda, q, b, tol, x, w);
 }
 
 int kkt_solve_device(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, int ldh, const double* A, int lda,

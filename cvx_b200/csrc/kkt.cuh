@@ -17,9 +17,11 @@ struct KktWork {
          *qk = nullptr, *dr2 = nullptr;
   double *z = nullptr, *ax = nullptr, *tp = nullptr;
   std::vector<void*> owned;
+  Arena* arena = nullptr;
 };
 
-int kkt_work_alloc(Handle& h, KktWork& W, int n, int p);
+int kkt_work_alloc(Handle& h, KktWork& W, int n, int p, Arena* arena = nullptr);
+size_t kkt_work_bytes(int n, int p);
 void kkt_work_free(KktWork& W);
 
 // Enqueue one solvePD (KKTSystem.scala:200-246) without host synchronisation:
@@ -47,6 +49,14 @@ int chol_solve_device(Handle& h, KktWork& W, const cvxb_params& P, const double*
 // continue after a flagged optimistic chol_enqueue(regularize=false)
 int chol_solve_retry(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, int ldh, const double* b,
                      double rhs_sign, double tol, double* x, cvxb_kkt_info* info);
+
+// MatrixUtils.symSolve / svdSolve (eig.cu): pseudo-inverse solve of A x = sign*b by one-sided Jacobi SVD with the
+// reference's acceptance tests; CVXB_EUNSOLVABLE = UnsolvableSystemException
+int svd_solve_device(Handle& h, int n, const double* A, int lda, const double* b, double sign, double tol, double* x,
+                     int* sweeps_out);
+// KKTSystem.kktSymSolve on the (n+p)^2 KKT matrix
+int kkt_sym_solve_device(Handle& h, int n, int p, const double* Hm, int ldh, const double* A, int lda, const double* q,
+                         const double* b, double tol, double* x, double* w);
 
 // copies flags + scalars to the pinned mirrors and waits for the stream
 int fetch_status(Handle& h);

@@ -224,7 +224,12 @@ __global__ void __launch_bounds__(VT) mul_kernel(int n, const double* __restrict
 
 template <typename T>
 int palloc2(cvxb_problem_s* P, T** ptr, size_t count) {
-  void* q = nullptr;
+  void* q = P->arena.take((count ? count : 1) * sizeof(T));
+  if (q) {
+    CVXB_CUDA_OK(cudaMemsetAsync(q, 0, (count ? count : 1) * sizeof(T), P->h->stream));
+    *ptr = (T*)q;
+    return CVXB_OK;
+  }
   CVXB_CUDA_OK(cudaMalloc(&q, (count ? count : 1) * sizeof(T)));
   CVXB_CUDA_OK(cudaMemsetAsync(q, 0, (count ? count : 1) * sizeof(T), P->h->stream));
   P->owned.push_back(q);
@@ -282,6 +287,14 @@ int pd_symmetric_enqueue(cvxb_problem_s* P, const cvxb_params& pars, bool regula
   return CVXB_OK;
 }
 
+// symSolve(Q, d o v) then x = d o u   (SymmetricLinearSystem.scala:33, 51-55); Q and d o v are still in place
+int pd_symmetric_eigen(cvxb_problem_s* P, const cvxb_params& pars) {
+  Handle& h = *P->h;
+  CVXB_TRY(svd_solve_device(h, P->n, P->Hreg, P->ldn, P->kw.qk, 1.0, pars.tolEqSolve, P->kw.t2, nullptr));
+  CVXB_LAUNCH(h, mul_kernel, 1, VT, 0, P->n, P->kw.dr2, P->kw.t2, P->dir);
+  return CVXB_OK;
+}
+
 int pd_after_solve(cvxb_problem_s* P, const cvxb_params& pars, double t, bool use_base0) {
   Handle& h = *P->h;
   const int n = P->n, m = P->m, p = P->p;
@@ -336,9 +349,7 @@ int pd_solve_direction(cvxb_problem_s* P, const cvxb_params& pars, cvxb_kkt_info
     if (h.h_flag[F_BAD] == 0) { fill_info(h, info, 0, 1); return CVXB_OK; }
   }
   fill_info(h, info, 2, 0);
-  set_last_error("SymmetricLinearSystem: choleskySolve failed (flags %d); the symSolve (eigendecomposition) fallback "
-                 "(SymmetricLinearSystem.scala:33) is not implemented on the device", h.h_flag[F_BAD]);
-  return CVXB_ELINSOLVE;
+  return pd_symmetric_eigen(P, pars);
 }
 
 }  // namespace
@@ -403,8 +414,8 @@ int pd_loop(cvxb_problem_s* P, const cvxb_params& pars, cvxb_solution* out) {
           info.path = 0; info.regularized = 1;
         }
         if (!ok) {
-          set_last_error("SymmetricLinearSystem: choleskySolve failed; symSolve fallback not implemented on the device");
-          return CVXB_ELINSOLVE;
+          CVXB_TRY(pd_symmetric_eigen(P, pars));
+          info.path = 2; info.regularized = 0;
         }
       }
       if (info.path) fallbacks++;

@@ -266,7 +266,8 @@ __global__ void set_unit_kernel(int n, int k, double* a) {
 
 template <typename T>
 int palloc(cvxb_problem_s* P, T** ptr, size_t count) {
-  void* q = nullptr;
+  void* q = P->arena.take((count ? count : 1) * sizeof(T));     // arena memory is zeroed once at creation
+  if (q) { *ptr = (T*)q; return CVXB_OK; }
   CVXB_CUDA_OK(cudaMalloc(&q, (count ? count : 1) * sizeof(T)));
   CVXB_CUDA_OK(cudaMemsetAsync(q, 0, (count ? count : 1) * sizeof(T), P->h->stream));
   P->owned.push_back(q);
@@ -283,6 +284,19 @@ int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s*
   P->n = n; P->m = m; P->p = p; P->objective = objective;
   P->ldm = pad_ld(m); P->ldn = pad_ld(n); P->ldp = pad_ld(p);
   int st = CVXB_OK;
+  {   // one allocation for everything below (+ the KKT workspace)
+    const size_t ldm = P->ldm, ldn = P->ldn, ldp = P->ldp;
+    size_t d = 2 * ldm * n + ldn * n * (objective == CVXB_OBJ_QUADRATIC ? 2 : 1) + ldp * n + 5 * ldm + 10 * ldn + 4 * ldp;
+    size_t bytes = d * sizeof(double) + 64 * 256 + kkt_work_bytes(n, p);
+    void* base = nullptr;
+    if (cudaMalloc(&base, bytes) == cudaSuccess) {
+      P->owned.push_back(base);
+      P->arena.base = (char*)base; P->arena.size = bytes; P->arena.used = 0;
+      if (cudaMemsetAsync(base, 0, bytes, h.stream) != cudaSuccess) st = CVXB_ECUDA;
+    } else {
+      cudaGetLastError();   // fall back to per-buffer allocations
+    }
+  }
   auto A = [&](double** ptr, size_t c) { if (st == CVXB_OK) st = palloc(P, ptr, c); };
   A(&P->G, (size_t)P->ldm * n); A(&P->gr, P->ldm); A(&P->ub, P->ldm);
   A(&P->A, (size_t)P->ldp * n); A(&P->b, P->ldp);
@@ -292,7 +306,7 @@ int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s*
   A(&P->x, P->ldn); A(&P->gx, P->ldm); A(&P->inv, P->ldm); A(&P->Gd, P->ldm); A(&P->y, P->ldn); A(&P->gt, P->ldn);
   A(&P->dir, P->ldn); A(&P->nu, P->ldp); A(&P->eqdiff, P->ldp); A(&P->Px, P->ldn); A(&P->Pd, P->ldn); A(&P->axv, P->ldp);
   A(&P->Gs, (size_t)P->ldm * n); A(&P->H, (size_t)P->ldn * n);
-  if (st == CVXB_OK) st = kkt_work_alloc(h, P->kw, n, p);
+  if (st == CVXB_OK) st = kkt_work_alloc(h, P->kw, n, p, &P->arena);
   if (st != CVXB_OK) {
     for (void* q : P->owned) cudaFree(q);
     kkt_work_free(P->kw);
@@ -457,11 +471,8 @@ int inner_solve_uncon(cvxb_problem_s* P, const cvxb_params& pars, double t, RunS
         CVXB_TRY(add_diag(h, n, pars.newtonRegDelta, P->Hreg, P->ldn));
         st = chol_solve_device(h, P->kw, pars, P->Hreg, P->ldn, P->y, -1.0, pars.tolEqSolve, P->dir, &info);
         R.fallbacks++;
-        if (st == CVXB_ELINSOLVE) {
-          set_last_error("UnconstrainedSolver: choleskySolve failed on H and on H + 1e-9 I; the symSolve "
-                         "(eigendecomposition) fallback (UnconstrainedSolver.scala:65) is not implemented on the device");
-          return CVXB_ELINSOLVE;
-        }
+        if (st == CVXB_ELINSOLVE)    // MatrixUtils.symSolve(H, -y)   UnconstrainedSolver.scala:65
+          st = svd_solve_device(h, n, P->H, P->ldn, P->y, -1.0, pars.tolEqSolve, P->dir, nullptr);
       }
       if (st != CVXB_OK) return st;
       if (info.regularized) R.regularized++;

@@ -24,4 +24,5 @@ struct cvxb_problem_s {
   cvxb::KktWork kw;
   cvxb_problem_s* phase1 = nullptr;   // the n+1 dimensional feasibility problem (built on demand)
   std::vector<void*> owned;
+  cvxb::Arena arena;
 };

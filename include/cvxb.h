@@ -83,7 +83,8 @@ int cvxb_default_params(cvxb_params* p);
 
 /* ---- seam B: per-step linear algebra on caller-owned matrices -------------------------------- */
 typedef struct cvxb_kkt_info {
-  int path;            /* 0 solvePD(H); 1 solvePD(H+A'A) (KKTSystem.scala:57-59); 2 eigen fallback  */
+  int path;            /* 0 solvePD(H); 1 solvePD(H+A'A) (KKTSystem.scala:57-59); 2 kktSymSolve / symSolve
+                          (decomposition fallback); 3 svdSolve (asymmetric SymmetricLinearSystem)        */
   int regularized;     /* regularizedCholesky took the Q+1e-10 I branch (MatrixUtils.scala:452-461) */
   int ruiz_sweeps;     /* sweeps taken by ruizEquilibrate (MatrixUtils.scala:240-268)                */
   int chol_info;       /* 0, or 1-based column of the first non-positive pivot of the last attempt   */

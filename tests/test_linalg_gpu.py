@@ -208,3 +208,72 @@ def test_dimension_asserts(handle):
     from cvx_b200 import KKTSystem, _lib
     with pytest.raises(AssertionError):
         KKTSystem(np.eye(3), np.ones((1, 4)), np.ones(3), np.ones(1), handle)
+
+
+# ---- decomposition fallbacks (kktSymSolve / symSolve / svdSolve, MatrixUtils.scala:603-751) ------------------
+
+def test_kkt_fallback_path2_eigen(handle):
+    """H negative definite: Cholesky fails on H and on H + A'A, the KKT matrix itself is nonsingular ->
+    KKTSystem.kktSymSolve (KKTSystem.scala:63, 283-310)."""
+    from cvx_b200 import KKTSystem
+    rng = np.random.default_rng(21)
+    n, p = 12, 3
+    H = -np.eye(n) * 50.0
+    A = rng.uniform(-1, 1, (p, n))
+    x, w = rng.uniform(-1, 1, n), rng.uniform(-1, 1, p)
+    q, b = -(H @ x + A.T @ w), A @ x
+    info0 = O.KKTInfo()
+    x0, w0 = O.kkt_solve(H, A, q, b, 1e-8, info0)
+    K = KKTSystem(H, A, q, b, handle)
+    x1, w1 = K.solve(1e-6, None, 1e-8, 0)
+    assert info0.path == 2 and K.info.path == 2
+    assert rel(x1, x) < 1e-9 and rel(w1, w) < 1e-9
+    assert rel(x1, x0) < 1e-9 and rel(w1, w0) < 1e-9
+
+
+@pytest.mark.parametrize("n", [9, 130])
+def test_symmetric_system_indefinite_uses_symsolve(handle, n):
+    """Symmetric indefinite, nonsingular: choleskySolve throws, symSolve answers (SymmetricLinearSystem.scala:31-34)."""
+    from cvx_b200 import SymmetricLinearSystem
+    rng = np.random.default_rng(n)
+    Qm, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    lam = np.concatenate([rng.uniform(1, 3, n // 2), -rng.uniform(1, 3, n - n // 2)])
+    H = (Qm * lam) @ Qm.T
+    H = (H + H.T) / 2
+    x = rng.uniform(-1, 1, n)
+    r = H @ x
+    S = SymmetricLinearSystem(H, r, None, handle)
+    x1 = S.solve(1e-8, 0)
+    x0 = O.symmetricLinearSystemSolve(H, r, 1e-8)
+    assert S.info.path == 2
+    assert rel(x1, x) < 1e-9 and rel(x1, x0) < 1e-9
+
+
+def test_symmetric_system_asymmetric_uses_svdsolve(handle):
+    """||Q - Q'|| >= 1e-13 -> svdSolve (SymmetricLinearSystem.scala:28-29)."""
+    from cvx_b200 import SymmetricLinearSystem
+    rng = np.random.default_rng(5)
+    n = 40
+    H = spd(n, 77) + 1e-3 * rng.uniform(-1, 1, (n, n))
+    x = rng.uniform(-1, 1, n)
+    r = H @ x
+    S = SymmetricLinearSystem(H, r, None, handle)
+    x1 = S.solve(1e-8, 0)
+    x0 = O.symmetricLinearSystemSolve(H, r, 1e-8)
+    assert S.info.path == 3
+    assert rel(x1, x) < 1e-8 and rel(x1, x0) < 1e-8
+
+
+def test_unsolvable_system(handle):
+    """Singular matrix, right-hand side outside its range: UnsolvableSystemException (MatrixUtils.scala:627-633)."""
+    from cvx_b200 import SymmetricLinearSystem, _lib
+    H = np.diag([1.0, 2.0, 0.0, -1.0])
+    r = np.array([1.0, 1.0, 1.0, 1.0])
+    with pytest.raises(O.UnsolvableSystemException):
+        O.symmetricLinearSystemSolve(H, r, 1e-6)
+    with pytest.raises(_lib.UnsolvableSystemException):
+        SymmetricLinearSystem(H, r, None, handle).solve(1e-6, 0)
+    # in range: the pseudo-inverse solution
+    r2 = np.array([1.0, 1.0, 0.0, 1.0])
+    x1 = SymmetricLinearSystem(H, r2, None, handle).solve(1e-6, 0)
+    assert np.allclose(x1, [1.0, 0.5, 0.0, -1.0], atol=1e-12)
