@@ -90,7 +90,7 @@ class ProblemDesc(C.Structure):
     _fields_ = [("n", C.c_int), ("m", C.c_int), ("p", C.c_int), ("objective", C.c_int), ("obj_a", _dp),
                 ("obj_r", C.c_double), ("obj_P", _dp), ("obj_ldP", C.c_int), ("G", _dp), ("ldg", C.c_int),
                 ("g_r", _dp), ("ub", _dp), ("A", _dp), ("lda", C.c_int), ("b", _dp), ("x_feasible", _dp),
-                ("x_defined", _dp)]
+                ("x_defined", _dp), ("mq", C.c_int), ("q_P", _dp), ("q_a", _dp), ("q_r", _dp), ("q_ub", _dp)]
 
 
 class SolutionC(C.Structure):

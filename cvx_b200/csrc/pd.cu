@@ -16,7 +16,10 @@ using namespace cvxb;
 
 namespace cvxb {
 
-int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s** out);
+int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s** out, int mq);
+int quad_refresh(cvxb_problem_s* P);
+int quad_direction(cvxb_problem_s* P, const double* dir);
+int quad_hessian_terms(cvxb_problem_s* P, const double* c);
 int upload_vec(Handle& h, double* dst, const double* src, int n);
 int download_vec(Handle& h, double* dst, const double* src, int n);
 
@@ -32,21 +35,23 @@ __device__ __forceinline__ double grad_f0(int kind, int n, double xj, double aj,
 
 // lam0 = -1/(g(x)-ub)   ConstraintSet.scala:116-120 ; gx holds G x
 __global__ void __launch_bounds__(VT) pd_lambda0_kernel(int m, const double* __restrict__ gx, const double* __restrict__ gr,
-                                                        const double* __restrict__ ub, double* __restrict__ lam) {
-  for (int i = threadIdx.x; i < m; i += VT) lam[i] = -1.0 / ((gr[i] + gx[i]) - ub[i]);
+                                                        const double* __restrict__ ub, const double* __restrict__ qcorr,
+                                                        double* __restrict__ lam) {
+  for (int i = threadIdx.x; i < m; i += VT) lam[i] = -1.0 / ((gr[i] + gx[i] - (qcorr ? qcorr[i] : 0.0)) - ub[i]);
 }
 
 // f = g(x) - ub ; weights -lam/f ; 1/(t f) ; surrogate gap -f.lam ; checks f < 0, lam > 0
 __global__ void __launch_bounds__(VT) pd_cnt_kernel(int m, double t, const double* __restrict__ gr, const double* __restrict__ ub,
                                                     double* __restrict__ gx, const double* __restrict__ lam,
                                                     double* __restrict__ fvec, double* __restrict__ wts,
-                                                    double* __restrict__ inv, double* scal, int* flag) {
+                                                    double* __restrict__ inv, const double* __restrict__ qcorr,
+                                                    double* scal, int* flag) {
   __shared__ double buf[33];
   __shared__ int ibuf[33];
   int bad = 0;
   double gap = 0.0;
   for (int i = threadIdx.x; i < m; i += VT) {
-    double g = gr[i] + gx[i];
+    double g = gr[i] + gx[i] - (qcorr ? qcorr[i] : 0.0);
     gx[i] = g;
     double f = g - ub[i];
     fvec[i] = f;
@@ -104,6 +109,7 @@ struct PdLs {
   // base point of the search (current iterate, or the initial one under bugCompat) and direction
   const double *gx, *ub, *lam, *x, *nu, *rd0, *pres, *Px, *a;
   const double *Gd, *dlam, *dx, *dnu, *rd1, *Adx, *Pd;
+  const double *qq, *rd2;   // quadratic constraints: d'P_k d / 2 per row and the s^2 term of the dual residual (or NULL)
   // iterate to write
   double *xo, *lamo, *nuo;
 };
@@ -114,7 +120,7 @@ __device__ double pd_trial(const PdLs& A, double s, double* buf, int* ibuf, int*
   double sc = 0.0, g_ = 0.0;
   int infeas = 0, ln = 0;
   for (int i = threadIdx.x; i < A.m; i += VT) {
-    double g = A.gx[i] + s * A.Gd[i];
+    double g = A.gx[i] + s * (A.Gd[i] + (A.qq ? s * A.qq[i] : 0.0));
     if (!(g * IN_SET_FACTOR < A.ub[i])) infeas = 1;
     double f = g - A.ub[i];
     double l = A.lam[i] + s * A.dlam[i];
@@ -136,7 +142,7 @@ __device__ double pd_trial(const PdLs& A, double s, double* buf, int* ibuf, int*
       double xj = A.x[j] + s * A.dx[j];
       gf = 1.0 + log(xj) + log((double)A.n);        // NaN for x_s <= 0: the comparison below then fails
     }
-    double r = gf + A.rd0[j] + s * A.rd1[j];
+    double r = gf + A.rd0[j] + s * (A.rd1[j] + (A.rd2 ? s * A.rd2[j] : 0.0));
     sd = fma(r, r, sd);
   }
   sd = block_sum(sd, buf);
@@ -253,9 +259,10 @@ int pd_alloc(cvxb_problem_s* P) {
 int pd_assemble(cvxb_problem_s* P, const cvxb_params& pars, double t) {
   Handle& h = *P->h;
   const int n = P->n, m = P->m, p = P->p;
+  CVXB_TRY(quad_refresh(P));
   CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->x, 0.0, P->gx));
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->Px));
-  CVXB_LAUNCH(h, pd_cnt_kernel, 1, VT, 0, m, t, P->gr, P->ub, P->gx, P->lam, P->tmpm, P->wts, P->inv, h.d_scal, h.d_flag);
+  CVXB_LAUNCH(h, pd_cnt_kernel, 1, VT, 0, m, t, P->gr, P->ub, P->gx, P->lam, P->tmpm, P->wts, P->inv, P->qcorr, h.d_scal, h.d_flag);
   CVXB_TRY(gemv_t(h, m, n, 1.0, P->G, P->ldm, P->inv, 0.0, P->gt));
   CVXB_TRY(gemv_t(h, m, n, 1.0, P->G, P->ldm, P->lam, 0.0, P->rd0));
   if (p > 0) {
@@ -269,6 +276,7 @@ int pd_assemble(cvxb_problem_s* P, const cvxb_params& pars, double t) {
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(fill_matrix(h, n, 1.0, P->obj_P, P->ldn, nullptr, 0.0, P->H, P->ldn));
   else if (P->objective == CVXB_OBJ_KL) CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, 1.0, P->H, P->ldn));
   else CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, nullptr, 0.0, P->H, P->ldn));
+  CVXB_TRY(quad_hessian_terms(P, P->lam));     // + lam_k hess g_k   (PrimalDualSolver.scala:230-236)
   GemmArgs g{n, n, m, P->Gs, P->ldm, true, P->Gs, P->ldm, true, P->H, P->ldn, 1.0, 1.0, 2};
   return gemm_dmma_timed(h, g, (double)m * n * ((double)n + 1.0));
 }
@@ -306,6 +314,13 @@ int pd_after_solve(cvxb_problem_s* P, const cvxb_params& pars, double t, bool us
     CVXB_TRY(gemv_t(h, p, n, 1.0, P->A, P->ldp, P->dnu, 1.0, P->rd1));
     CVXB_TRY(gemv_n(h, p, n, 1.0, P->A, P->ldp, P->dir, 0.0, P->Adx));
   }
+  if (P->mq > 0) {
+    // grad g_k(x + s dx) = (a_k + P_k x) + s P_k dx: the dual residual gains  s * sum lam_k P_k dx  +  s^2 * sum dlam_k P_k dx
+    CVXB_TRY(quad_direction(P, P->dir));
+    if (!P->rd2) CVXB_TRY(palloc2(P, &P->rd2, (size_t)P->ldn));
+    CVXB_TRY(gemv_n(h, n, P->mq, 1.0, P->PDv, P->ldq, (use_base0 ? P->lam0s : P->lam) + P->mlin, 1.0, P->rd1));
+    CVXB_TRY(gemv_n(h, n, P->mq, 1.0, P->PDv, P->ldq, P->dlam + P->mlin, 0.0, P->rd2));
+  }
   PdLs A;
   A.m = m; A.n = n; A.p = p; A.kind = P->objective; A.withEqs = p > 0;
   A.t = t; A.alpha = pars.alpha; A.beta = pars.beta; A.frac = pars.pdStepFraction;
@@ -317,6 +332,7 @@ int pd_after_solve(cvxb_problem_s* P, const cvxb_params& pars, double t, bool us
   A.ub = P->ub; A.a = P->obj_a;
   A.Gd = P->Gd; A.dlam = P->dlam; A.dx = P->dir; A.dnu = P->dnu; A.rd1 = P->rd1; A.Adx = P->Adx; A.Pd = P->Pd;
   A.xo = P->x; A.lamo = P->lam; A.nuo = P->nu;
+  A.qq = P->mq > 0 ? P->qq : nullptr; A.rd2 = P->mq > 0 ? P->rd2 : nullptr;
   CVXB_LAUNCH(h, pd_linesearch_kernel, 1, VT, 0, A, h.d_scal, h.d_flag);
   return CVXB_OK;
 }
@@ -362,12 +378,13 @@ int pd_loop(cvxb_problem_s* P, const cvxb_params& pars, cvxb_solution* out) {
   const double mu = pars.mu, tol = pars.tolSolver;
   CVXB_TRY(pd_alloc(P));
   // lam0 = -1/(g(x0)-ub), nu0 = 0
+  CVXB_TRY(quad_refresh(P));
   CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->x, 0.0, P->gx));
-  CVXB_LAUNCH(h, pd_lambda0_kernel, 1, VT, 0, m, P->gx, P->gr, P->ub, P->lam);
+  CVXB_LAUNCH(h, pd_lambda0_kernel, 1, VT, 0, m, P->gx, P->gr, P->ub, P->qcorr, P->lam);
   CVXB_CUDA_OK(cudaMemsetAsync(P->nu, 0, (size_t)P->ldp * sizeof(double), h.stream));
   CVXB_CUDA_OK(cudaMemsetAsync(P->dnu, 0, (size_t)P->ldp * sizeof(double), h.stream));
   // surrogate gap at the start (t is irrelevant for it)
-  CVXB_LAUNCH(h, pd_cnt_kernel, 1, VT, 0, m, 1.0, P->gr, P->ub, P->gx, P->lam, P->tmpm, P->wts, P->inv, h.d_scal, h.d_flag);
+  CVXB_LAUNCH(h, pd_cnt_kernel, 1, VT, 0, m, 1.0, P->gr, P->ub, P->gx, P->lam, P->tmpm, P->wts, P->inv, P->qcorr, h.d_scal, h.d_flag);
   CVXB_TRY(fetch_status(h));
   if (h.h_flag[F_PD_NOTNEG]) { set_last_error("PrimalDualSolver: starting point not strictly feasible"); return CVXB_ENOTFEASIBLE; }
   double gap = h.h_scal[S_PD_GAP];

@@ -39,13 +39,15 @@ __global__ void __launch_bounds__(VT) eval_cnt_kernel(int m, int n, int kind, do
                                                       const double* __restrict__ gr, const double* __restrict__ ub,
                                                       double* __restrict__ gx, double* __restrict__ inv,
                                                       const double* __restrict__ x, const double* __restrict__ a,
-                                                      const double* __restrict__ Px, double* scal, int* flag) {
+                                                      const double* __restrict__ Px, const double* __restrict__ qcorr,
+                                                      double* scal, int* flag) {
   __shared__ double buf[33];
   __shared__ int ibuf[33];
   double ls = 0.0, mn = 1e308;
   int bad = 0;
   for (int i = threadIdx.x; i < m; i += VT) {
-    double g = (gr ? gr[i] : 0.0) + gx[i];
+    // quadratic rows: G_i = a + P x, so G_i.x counts x'Px twice; g = r + a.x + x'Px/2
+    double g = (gr ? gr[i] : 0.0) + gx[i] - (qcorr ? qcorr[i] : 0.0);
     gx[i] = g;
     double d = ub[i] - g;
     if (!(d > 0.0)) bad = 1;
@@ -101,13 +103,14 @@ struct LsArgs {
   int m, n, kind, mode /*0 equality-constrained, 1 unconstrained*/, iter0;
   double t, alpha, beta, tol;
   const double *gx, *ub, *Gd, *a, *Px, *Pd, *y;
+  const double* qq;      // d'P_k d / 2 on quadratic rows (NULL without quadratic constraints)
   double *x, *dir;
 };
 
 __device__ bool ls_in_set(const LsArgs& A, double s, int* ibuf) {
   int out = 0;
   for (int i = threadIdx.x; i < A.m; i += VT) {
-    double g = A.gx[i] + s * A.Gd[i];
+    double g = A.gx[i] + s * (A.Gd[i] + (A.qq ? s * A.qq[i] : 0.0));
     if (!(g * IN_SET_FACTOR < A.ub[i])) out = 1;
   }
   return block_or(out, ibuf) == 0;
@@ -119,7 +122,7 @@ __device__ double ls_value(const LsArgs& A, double s, double f0, double c1, doub
   double ls = 0.0;
   int bad = 0;
   for (int i = threadIdx.x; i < A.m; i += VT) {
-    double d = A.ub[i] - (A.gx[i] + s * A.Gd[i]);
+    double d = A.ub[i] - (A.gx[i] + s * (A.Gd[i] + (A.qq ? s * A.qq[i] : 0.0)));
     if (!(d > 0.0)) bad = 1;
     ls += log(d);
   }
@@ -217,6 +220,55 @@ __global__ void __launch_bounds__(VT) linesearch_kernel(LsArgs A, double* scal, 
   }
 }
 
+// ---- quadratic constraints ------------------------------------------------------------------------
+// row mlin+k of G := a_k + P_k x (the gradient, QuadraticConstraint.scala:34-36); qcorr := x'P_k x / 2
+__global__ void __launch_bounds__(256) quad_rows_kernel(int n, int mlin, int ldq, const double* __restrict__ qa,
+                                                        const double* __restrict__ PX, const double* __restrict__ x,
+                                                        double* __restrict__ G, int ldg, double* __restrict__ qcorr) {
+  __shared__ double buf[33];
+  const int k = blockIdx.x;
+  double s = 0.0;
+  for (int j = threadIdx.x; j < n; j += 256) {
+    const double px = PX[(size_t)k * ldq + j];
+    G[(size_t)j * ldg + mlin + k] = qa[(size_t)k * ldq + j] + px;
+    s = fma(x[j], px, s);
+  }
+  s = block_sum(s, buf);
+  if (threadIdx.x == 0) qcorr[mlin + k] = 0.5 * s;
+}
+// out[mlin+k] := v' (P_k d) / 2
+__global__ void __launch_bounds__(256) quad_dot_kernel(int n, int mlin, int ldq, const double* __restrict__ PDv,
+                                                       const double* __restrict__ v, double* __restrict__ out) {
+  __shared__ double buf[33];
+  const int k = blockIdx.x;
+  double s = 0.0;
+  for (int j = threadIdx.x; j < n; j += 256) s = fma(v[j], PDv[(size_t)k * ldq + j], s);
+  s = block_sum(s, buf);
+  if (threadIdx.x == 0) out[mlin + k] = 0.5 * s;
+}
+// H += sum_k c[mlin+k] P_k     (hess g_k / d_k in the barrier, lam_k hess g_k in the primal-dual matrix)
+__global__ void quad_hess_kernel(int n, int mq, int mlin, int ldq, const double* __restrict__ Pq, int ldP,
+                                 const double* __restrict__ c, double* __restrict__ Hm, int ldh) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int j = blockIdx.y; j < n; j += gridDim.y) {
+    double s = 0.0;
+    for (int k = 0; k < mq; ++k) s = fma(c[mlin + k], Pq[(size_t)j * ldP + (size_t)k * ldq + i], s);
+    Hm[(size_t)j * ldh + i] += s;
+  }
+}
+// phase I: child blocks P1_k = [P_k 0; 0 0], a1_k = [a_k; -1]
+__global__ void phase1_quad_kernel(int n, int mq, int ldq, const double* __restrict__ Pq, int ldP,
+                                   const double* __restrict__ qa, int ldq1, double* __restrict__ Pq1, int ldP1,
+                                   double* __restrict__ qa1) {
+  const int k = blockIdx.z;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  for (int j = blockIdx.y; j <= n; j += gridDim.y)
+    Pq1[(size_t)j * ldP1 + (size_t)k * ldq1 + i] = (i < n && j < n) ? Pq[(size_t)j * ldP + (size_t)k * ldq + i] : 0.0;
+  if (blockIdx.y == 0) qa1[(size_t)k * ldq1 + i] = (i < n) ? qa[(size_t)k * ldq + i] : -1.0;
+}
+
 // ---- phase I construction -----------------------------------------------------------------------
 // G1 = [G, -1 ; Ae, -1] with Ae rows interleaved (a_i, -a_i), ub1 = [ub ; b_i + tol, -b_i + tol], r1 = [r ; 0]
 __global__ void phase1_build_kernel(int n, int m, int p, const double* __restrict__ G, int ldg,
@@ -251,10 +303,10 @@ __global__ void phase1_build_kernel(int n, int m, int p, const double* __restric
 // start of phase I: (x0, 1 + max_i (g_i(x0) - ub_i))   ConstraintSet.scala:161-163 ; gx holds G1[:, :n] x0 (s column = 0)
 __global__ void __launch_bounds__(VT) phase1_start_kernel(int m1, int n, const double* __restrict__ gx,
                                                           const double* __restrict__ gr1, const double* __restrict__ ub1,
-                                                          double* __restrict__ x1) {
+                                                          const double* __restrict__ qcorr, double* __restrict__ x1) {
   __shared__ double buf[33];
   double mx = -1e308;
-  for (int i = threadIdx.x; i < m1; i += VT) mx = fmax(mx, (gr1[i] + gx[i]) - ub1[i]);
+  for (int i = threadIdx.x; i < m1; i += VT) mx = fmax(mx, (gr1[i] + gx[i] - (qcorr ? qcorr[i] : 0.0)) - ub1[i]);
   mx = -block_min(-mx, buf);
   if (threadIdx.x == 0) x1[n] = 1.0 + mx;
 }
@@ -278,15 +330,19 @@ int palloc(cvxb_problem_s* P, T** ptr, size_t count) {
 }  // namespace
 
 // --------------------------------------------------------------------------------- problem objects
-int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s** out) {
+// m = number of LINEAR constraints; the problem carries m + mq rows in every per-constraint vector
+int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s** out, int mq) {
   cvxb_problem_s* P = new cvxb_problem_s();
   P->h = &h;
+  P->mlin = m; P->mq = mq; P->ldq = pad_ld(n);
+  m += mq;
   P->n = n; P->m = m; P->p = p; P->objective = objective;
   P->ldm = pad_ld(m); P->ldn = pad_ld(n); P->ldp = pad_ld(p);
   int st = CVXB_OK;
   {   // one allocation for everything below (+ the KKT workspace)
     const size_t ldm = P->ldm, ldn = P->ldn, ldp = P->ldp;
-    size_t d = 2 * ldm * n + ldn * n * (objective == CVXB_OBJ_QUADRATIC ? 2 : 1) + ldp * n + 5 * ldm + 10 * ldn + 4 * ldp;
+    size_t d = 2 * ldm * n + ldn * n * (objective == CVXB_OBJ_QUADRATIC ? 2 : 1) + ldp * n + 7 * ldm + 10 * ldn + 4 * ldp;
+    if (mq > 0) d += (size_t)mq * P->ldq * (n + 3) + 4 * 32;
     size_t bytes = d * sizeof(double) + 64 * 256 + kkt_work_bytes(n, p);
     void* base = nullptr;
     if (cudaMalloc(&base, bytes) == cudaSuccess) {
@@ -306,6 +362,10 @@ int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s*
   A(&P->x, P->ldn); A(&P->gx, P->ldm); A(&P->inv, P->ldm); A(&P->Gd, P->ldm); A(&P->y, P->ldn); A(&P->gt, P->ldn);
   A(&P->dir, P->ldn); A(&P->nu, P->ldp); A(&P->eqdiff, P->ldp); A(&P->Px, P->ldn); A(&P->Pd, P->ldn); A(&P->axv, P->ldp);
   A(&P->Gs, (size_t)P->ldm * n); A(&P->H, (size_t)P->ldn * n);
+  if (mq > 0) {
+    A(&P->Pq, (size_t)mq * P->ldq * n); A(&P->qa, (size_t)mq * P->ldq); A(&P->PX, (size_t)mq * P->ldq);
+    A(&P->PDv, (size_t)mq * P->ldq); A(&P->qcorr, P->ldm); A(&P->qq, P->ldm);
+  }
   if (st == CVXB_OK) st = kkt_work_alloc(h, P->kw, n, p, &P->arena);
   if (st != CVXB_OK) {
     for (void* q : P->owned) cudaFree(q);
@@ -327,13 +387,40 @@ void problem_free(cvxb_problem_s* P) {
 
 // ------------------------------------------------------------------------------- barrier function
 // value / gradient / constraint state at P->x for barrier parameter t (E1-E6); no host sync
+// quadratic constraints at P->x: PX = P_k x, gradient rows of G, value corrections
+int quad_refresh(cvxb_problem_s* P) {
+  if (P->mq <= 0) return CVXB_OK;
+  Handle& h = *P->h;
+  CVXB_TRY(gemv_n(h, P->mq * P->ldq, P->n, 1.0, P->Pq, P->mq * P->ldq, P->x, 0.0, P->PX));
+  CVXB_LAUNCH(h, quad_rows_kernel, P->mq, 256, 0, P->n, P->mlin, P->ldq, P->qa, P->PX, P->x, P->G, P->ldm, P->qcorr);
+  return CVXB_OK;
+}
+// d'P_k d / 2 for the direction `dir` -> P->qq (line searches); PDv keeps P_k d
+int quad_direction(cvxb_problem_s* P, const double* dir) {
+  if (P->mq <= 0) return CVXB_OK;
+  Handle& h = *P->h;
+  CVXB_TRY(gemv_n(h, P->mq * P->ldq, P->n, 1.0, P->Pq, P->mq * P->ldq, dir, 0.0, P->PDv));
+  CVXB_LAUNCH(h, quad_dot_kernel, P->mq, 256, 0, P->n, P->mlin, P->ldq, P->PDv, dir, P->qq);
+  return CVXB_OK;
+}
+// H += sum_k c_k P_k
+int quad_hessian_terms(cvxb_problem_s* P, const double* c) {
+  if (P->mq <= 0) return CVXB_OK;
+  Handle& h = *P->h;
+  const int n = P->n;
+  CVXB_LAUNCH(h, quad_hess_kernel, dim3((n + 127) / 128, n > 1024 ? 1024 : n), 128, 0, n, P->mq, P->mlin, P->ldq, P->Pq,
+              P->mq * P->ldq, c, P->H, P->ldn);
+  return CVXB_OK;
+}
+
 int barrier_eval(cvxb_problem_s* P, double t) {
   Handle& h = *P->h;
   const int n = P->n, m = P->m, p = P->p;
+  CVXB_TRY(quad_refresh(P));
   CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->x, 0.0, P->gx));
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->Px));
   CVXB_LAUNCH(h, eval_cnt_kernel, 1, VT, 0, m, n, P->objective, P->obj_r, t, P->gr, P->ub, P->gx, P->inv, P->x,
-              P->obj_a, P->Px, h.d_scal, h.d_flag);
+              P->obj_a, P->Px, P->qcorr, h.d_scal, h.d_flag);
   CVXB_TRY(gemv_t(h, m, n, 1.0, P->G, P->ldm, P->inv, 0.0, P->gt));
   if (p > 0) CVXB_TRY(gemv_n(h, p, n, 1.0, P->A, P->ldp, P->x, 0.0, P->axv));
   CVXB_LAUNCH(h, eval_grad_kernel, 1, VT, 0, n, p, P->objective, t, P->x, P->obj_a, P->Px, P->gt, P->y, P->b, P->axv,
@@ -349,6 +436,7 @@ int barrier_hessian(cvxb_problem_s* P, double t) {
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(fill_matrix(h, n, t, P->obj_P, P->ldn, nullptr, 0.0, P->H, P->ldn));
   else if (P->objective == CVXB_OBJ_KL) CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, t, P->H, P->ldn));
   else CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, nullptr, 0.0, P->H, P->ldn));
+  CVXB_TRY(quad_hessian_terms(P, P->inv));     // + hess g_k / d_k   (BarrierSolver.scala:313)
   GemmArgs g{n, n, m, P->Gs, P->ldm, true, P->Gs, P->ldm, true, P->H, P->ldn, 1.0, 1.0, 2};
   return gemm_dmma_timed(h, g, (double)m * n * ((double)n + 1.0));   // lower triangle, mul + add
 }
@@ -358,11 +446,12 @@ int enqueue_linesearch(cvxb_problem_s* P, const cvxb_params& pars, double t, int
   const int n = P->n, m = P->m;
   CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->dir, 0.0, P->Gd));
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->dir, 0.0, P->Pd));
+  CVXB_TRY(quad_direction(P, P->dir));
   LsArgs A;
   A.m = m; A.n = n; A.kind = P->objective; A.mode = mode; A.iter0 = iter0;
   A.t = t; A.alpha = pars.alpha; A.beta = pars.beta; A.tol = pars.tolSolver;
   A.gx = P->gx; A.ub = P->ub; A.Gd = P->Gd; A.a = P->obj_a; A.Px = P->Px; A.Pd = P->Pd; A.y = P->y;
-  A.x = P->x; A.dir = P->dir;
+  A.x = P->x; A.dir = P->dir; A.qq = P->mq > 0 ? P->qq : nullptr;
   CVXB_LAUNCH(h, linesearch_kernel, 1, VT, 0, A, h.d_scal, h.d_flag);
   return CVXB_OK;
 }
@@ -548,14 +637,20 @@ int barrier_loop(cvxb_problem_s* P, const cvxb_params& pars, int term, RunStats&
 // ConstraintSet.withFeasiblePoint -> phase_I_Analysis (ConstraintSet.scala:326-395, 556-575)
 int run_phase1(cvxb_problem_s* P, const cvxb_params& pars, RunStats& rs, cvxb_solution* ph_out) {
   Handle& h = *P->h;
-  const int n = P->n, m = P->m, p = P->p;
-  const int m1 = m + 2 * p;
+  const int n = P->n, m = P->mlin, p = P->p, mq = P->mq;
+  const int m1 = m + 2 * p;             // linear rows of the feasibility problem; its quadratic rows follow
   if (!P->phase1) {
-    CVXB_TRY(problem_alloc(h, n + 1, m1, 0, CVXB_OBJ_LINEAR, &P->phase1));
+    CVXB_TRY(problem_alloc(h, n + 1, m1, 0, CVXB_OBJ_LINEAR, &P->phase1, mq));
     cvxb_problem_s* Q = P->phase1;
     dim3 grid((m1 + 127) / 128, n + 1 > 1024 ? 1024 : n + 1);
     CVXB_LAUNCH(h, phase1_build_kernel, grid, 128, 0, n, m, p, P->G, P->ldm, P->gr, P->ub, P->A, P->ldp, P->b,
                 pars.phase1EqTol, Q->G, Q->ldm, Q->gr, Q->ub);
+    if (mq > 0) {     // Constraint.phase_I of a quadratic constraint: P1 = [P 0; 0 0], a1 = [a; -1]  (Constraint.scala:64-89)
+      CVXB_LAUNCH(h, phase1_quad_kernel, dim3((n + 1 + 127) / 128, n + 1 > 1024 ? 1024 : n + 1, mq), 128, 0, n, mq, P->ldq,
+                  P->Pq, mq * P->ldq, P->qa, Q->ldq, Q->Pq, mq * Q->ldq, Q->qa);
+      CVXB_CUDA_OK(cudaMemcpyAsync(Q->gr + m1, P->gr + m, mq * sizeof(double), cudaMemcpyDeviceToDevice, h.stream));
+      CVXB_CUDA_OK(cudaMemcpyAsync(Q->ub + m1, P->ub + m, mq * sizeof(double), cudaMemcpyDeviceToDevice, h.stream));
+    }
     CVXB_LAUNCH(h, set_unit_kernel, (n + 1 + 255) / 256, 256, 0, n + 1, n, Q->obj_a);   // f(x,s) = s  (:131-144)
     Q->obj_r = 0.0;
   }
@@ -563,8 +658,9 @@ int run_phase1(cvxb_problem_s* P, const cvxb_params& pars, RunStats& rs, cvxb_so
   // start (pointWhereDefined, 1 + max(g - ub))
   CVXB_CUDA_OK(cudaMemsetAsync(Q->x, 0, (size_t)Q->ldn * sizeof(double), h.stream));
   CVXB_CUDA_OK(cudaMemcpyAsync(Q->x, P->x_def, n * sizeof(double), cudaMemcpyDeviceToDevice, h.stream));
-  CVXB_TRY(gemv_n(h, m1, n + 1, 1.0, Q->G, Q->ldm, Q->x, 0.0, Q->gx));
-  CVXB_LAUNCH(h, phase1_start_kernel, 1, VT, 0, m1, n, Q->gx, Q->gr, Q->ub, Q->x);
+  CVXB_TRY(quad_refresh(Q));
+  CVXB_TRY(gemv_n(h, Q->m, n + 1, 1.0, Q->G, Q->ldm, Q->x, 0.0, Q->gx));
+  CVXB_LAUNCH(h, phase1_start_kernel, 1, VT, 0, Q->m, n, Q->gx, Q->gr, Q->ub, Q->qcorr, Q->x);
   cvxb_solution sol;
   memset(&sol, 0, sizeof(sol));
   int st = barrier_loop(Q, pars, TERM_PHASE1, rs, &sol);
@@ -632,12 +728,12 @@ extern "C" {
 
 int cvxb_problem_create(cvxb_handle h, const cvxb_problem_desc* d, cvxb_problem* out) {
   if (!h || !d || !out) { cvxb::set_last_error("cvxb_problem_create: null argument"); return CVXB_EINVAL; }
-  if (d->n < 1 || d->m < 1 || d->p < 0) {
+  if (d->n < 1 || d->m < 0 || d->m + d->mq < 1 || d->p < 0) {
     cvxb::set_last_error("cvxb_problem_create: need n >= 1, m >= 1, p >= 0 (got %d, %d, %d)", d->n, d->m, d->p);
     return CVXB_EDIM;
   }
   if (d->objective < CVXB_OBJ_LINEAR || d->objective > CVXB_OBJ_KL) { cvxb::set_last_error("unknown objective kind"); return CVXB_EINVAL; }
-  if (!d->G || !d->ub || (d->p > 0 && (!d->A || !d->b)) || (!d->x_feasible && !d->x_defined) ||
+  if ((d->m > 0 && (!d->G || !d->ub)) || (d->p > 0 && (!d->A || !d->b)) || (!d->x_feasible && !d->x_defined) ||
       (d->objective != CVXB_OBJ_KL && !d->obj_a) || (d->objective == CVXB_OBJ_QUADRATIC && !d->obj_P)) {
     cvxb::set_last_error("cvxb_problem_create: missing array for this problem family");
     return CVXB_EINVAL;
@@ -647,8 +743,12 @@ int cvxb_problem_create(cvxb_handle h, const cvxb_problem_desc* d, cvxb_problem*
     return CVXB_EDIM;
   }
   cudaSetDevice(h->device);
+  if (d->mq < 0 || (d->mq > 0 && (!d->q_P || !d->q_a || !d->q_r || !d->q_ub))) {
+    cvxb::set_last_error("cvxb_problem_create: quadratic constraints need q_P, q_a, q_r, q_ub");
+    return CVXB_EINVAL;
+  }
   cvxb_problem_s* P = nullptr;
-  CVXB_TRY(problem_alloc(*h, d->n, d->m, d->p, d->objective, &P));
+  CVXB_TRY(problem_alloc(*h, d->n, d->m, d->p, d->objective, &P, d->mq));
   int st = CVXB_OK;
   auto T = [&](int s) { if (st == CVXB_OK) st = s; };
   T(upload_mat(*h, P->G, P->ldm, d->G, d->ldg, d->m, d->n));
@@ -658,6 +758,13 @@ int cvxb_problem_create(cvxb_handle h, const cvxb_problem_desc* d, cvxb_problem*
   T(upload_vec(*h, P->b, d->b, d->p));
   T(upload_vec(*h, P->obj_a, d->obj_a, d->n));
   if (d->objective == CVXB_OBJ_QUADRATIC) T(upload_mat(*h, P->obj_P, P->ldn, d->obj_P, d->obj_ldP, d->n, d->n));
+  for (int k = 0; k < d->mq; ++k)       // stacked blocks: rows k*ldq.. of an (mq*ldq) x n matrix
+    T(upload_mat(*h, P->Pq + (size_t)k * P->ldq, d->mq * P->ldq, d->q_P + (size_t)k * d->n * d->n, d->n, d->n, d->n));
+  if (d->mq > 0) {
+    T(upload_mat(*h, P->qa, P->ldq, d->q_a, d->n, d->n, d->mq));
+    T(upload_vec(*h, P->gr + d->m, d->q_r, d->mq));
+    T(upload_vec(*h, P->ub + d->m, d->q_ub, d->mq));
+  }
   P->obj_r = d->obj_r;
   if (d->x_feasible) { T(upload_vec(*h, P->x_feas, d->x_feasible, d->n)); P->has_feasible = true; }
   T(upload_vec(*h, P->x_def, d->x_defined ? d->x_defined : d->x_feasible, d->n));

@@ -19,6 +19,14 @@ struct cvxb_problem_s {
          *Adx = nullptr, *pres = nullptr, *x0s = nullptr, *lam0s = nullptr, *nu0s = nullptr, *tmpm = nullptr,
          *gx0s = nullptr, *rd00s = nullptr, *Px0s = nullptr, *vvec = nullptr, *qvec = nullptr, *atnu = nullptr,
          *pres0s = nullptr, *negpres = nullptr;
+  // quadratic constraints: m = mlin + mq rows in every per-constraint vector; rows mlin.. of G hold the
+  // current gradients a_k + P_k x (rewritten at every evaluation)
+  int mlin = 0, mq = 0, ldq = 0;
+  double *Pq = nullptr;      // (mq*ldq) x n stacked: block k = P_k
+  double *qa = nullptr;      // ldq x mq
+  double *PX = nullptr, *PDv = nullptr;   // mq*ldq: P_k x and P_k d
+  double *qcorr = nullptr, *qq = nullptr; // m: x'P_k x / 2 and d'P_k d / 2 on the quadratic rows, 0 elsewhere
+  double *rd2 = nullptr;     // n: PD line search, s^2 coefficient of the dual residual
   // matrices
   double *Gs = nullptr, *H = nullptr, *Hreg = nullptr;
   cvxb::KktWork kw;

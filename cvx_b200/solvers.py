@@ -113,25 +113,41 @@ class KLObjectiveFunction(ObjectiveFunction):
         self.dim, self.r, self.a = int(dim), 0.0, None
 
 
-class ConstraintSet:
-    """Linear inequality block  r + Hx <= u  (one LinearConstraint per row)."""
+class QuadraticConstraint:
+    """QuadraticConstraint(id, dim, ub, r, a, P):  r + a'x + x'Px/2 <= ub, P symmetric (QuadraticConstraint.scala:7-40)."""
 
-    def __init__(self, H, u, pointWhereDefined=None, r=None):
+    def __init__(self, id, dim, ub, r, a, P):
+        self.id, self.dim, self.ub, self.r, self.a, self.P = id, int(dim), float(ub), float(r), fvec(a), fmat(P)
+        if self.a.shape[0] != self.dim:
+            raise ValueError("Vector a must be of dimension %d but length(a) %d" % (self.dim, self.a.shape[0]))
+        if self.P.shape != (self.dim, self.dim):
+            raise ValueError("Matrix P must be square of dimension %d" % self.dim)
+        assert np.linalg.norm(self.P - self.P.T) < 1e-13, "P not symmetric"       # checkSymmetric(P, 1e-13)
+
+
+class ConstraintSet:
+    """Linear inequality block  r + Hx <= u  (one LinearConstraint per row), followed by optional
+    QuadraticConstraints (the closed-form families of ConstraintSet.scala)."""
+
+    def __init__(self, H, u, pointWhereDefined=None, r=None, quadratic=None):
         self.H = fmat(H)
         self.u = fvec(u)
         self.r = None if r is None else fvec(r)
         self.dim = self.H.shape[1]
         assert self.u.shape[0] == self.H.shape[0]
+        self.quadratic = list(quadratic) if quadratic else []
+        assert all(q.dim == self.dim for q in self.quadratic)
         self.pointWhereDefined = None if pointWhereDefined is None else fvec(pointWhereDefined)
         self.feasiblePoint = None
 
     @property
     def numConstraints(self):
-        return self.H.shape[0]
+        return self.H.shape[0] + len(self.quadratic)
 
     def addFeasiblePoint(self, x0):
         """ConstraintSet.addFeasiblePoint (ConstraintSet.scala:43-54)."""
-        c = ConstraintSet(self.H, self.u, self.pointWhereDefined if self.pointWhereDefined is not None else x0, self.r)
+        c = ConstraintSet(self.H, self.u, self.pointWhereDefined if self.pointWhereDefined is not None else x0, self.r,
+                          self.quadratic)
         c.feasiblePoint = fvec(x0)
         return c
 
@@ -147,7 +163,7 @@ class _DeviceProblem:
 
     def __init__(self, objF, cnts: ConstraintSet, eqs: Optional[EqualityConstraint], handle):
         self.handle = handle if handle is not None else _lib.default_handle()
-        n, m = cnts.dim, cnts.numConstraints
+        n, m = cnts.dim, cnts.H.shape[0]
         assert objF.dim == n, "objective / constraint dimension mismatch"
         d = ProblemDesc()
         d.n, d.m, d.p = n, m, 0 if eqs is None else eqs.A.shape[0]
@@ -164,7 +180,15 @@ class _DeviceProblem:
             d.A, d.lda, d.b = dptr(eqs.A), eqs.A.shape[0], dptr(eqs.b)
         d.x_feasible = dptr(cnts.feasiblePoint) if cnts.feasiblePoint is not None else None
         d.x_defined = dptr(cnts.pointWhereDefined) if cnts.pointWhereDefined is not None else None
-        self.n, self.m, self.p = d.n, d.m, d.p
+        mq = len(cnts.quadratic)
+        d.mq = mq
+        if mq:
+            self._qP = np.ascontiguousarray(np.stack([np.asarray(q.P).T for q in cnts.quadratic]))      # packed column-major blocks
+            self._qa = np.ascontiguousarray(np.stack([q.a for q in cnts.quadratic]))                      # mq x n row-major == n x mq column-major
+            self._qr = np.array([q.r for q in cnts.quadratic], dtype=np.float64)
+            self._qub = np.array([q.ub for q in cnts.quadratic], dtype=np.float64)
+            d.q_P, d.q_a, d.q_r, d.q_ub = dptr(self._qP), dptr(self._qa), dptr(self._qr), dptr(self._qub)
+        self.n, self.m, self.p = d.n, d.m + mq, d.p
         self._keep = (objF, cnts, eqs)
         self._p = C.c_void_p()
         check(self.handle.lib.cvxb_problem_create(self.handle._h, C.byref(d), C.byref(self._p)))
@@ -322,7 +346,8 @@ def from_dict(prob: dict, solverType="BR", pars=None, handle=None) -> Optimizati
         objF = QuadraticObjectiveFunction(n, prob["r"], prob["a"], prob["P"])
     else:
         objF = KLObjectiveFunction(n)
-    cnts = ConstraintSet(prob["G"], prob["ub"], prob["xdef"], prob.get("rvec"))
+    quad = [QuadraticConstraint("q%d" % k, n, q["ub"], q["r"], q["a"], q["P"]) for k, q in enumerate(prob.get("quad") or [])]
+    cnts = ConstraintSet(prob["G"], prob["ub"], prob["xdef"], prob.get("rvec"), quad)
     if prob.get("x0") is not None:
         cnts = cnts.addFeasiblePoint(prob["x0"])
     eqs = EqualityConstraint(prob["A"], prob["b"]) if prob.get("A") is not None else None

@@ -149,6 +149,13 @@ typedef struct cvxb_problem_desc {
   const double* b;           /* p      EqualityConstraint.b                                       */
   const double* x_feasible;  /* n: ConstraintSet with FeasiblePoint .feasiblePoint, or NULL        */
   const double* x_defined;   /* n: ConstraintSet.pointWhereDefined (start of phase I)             */
+  /* quadratic constraints  q_r[k] + q_a[:,k]'x + x'P_k x / 2 <= q_ub[k]   (QuadraticConstraint.scala:7-40);
+   * they follow the m linear constraints in every per-constraint vector (lambda, stage order).           */
+  int mq;                    /* number of quadratic constraints (0 = none)                        */
+  const double* q_P;         /* mq symmetric n x n matrices, each column-major with ld n, packed   */
+  const double* q_a;         /* n x mq, column k = a_k                                            */
+  const double* q_r;         /* mq                                                                */
+  const double* q_ub;        /* mq                                                                */
 } cvxb_problem_desc;
 
 /* mirrors Solution.scala:32-43; has_* say which Option fields are Some(...) */

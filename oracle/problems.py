@@ -159,6 +159,40 @@ def batched_problem(i, n=64, m=128, base_seed=1000):
     return slab_qp(n, m // 2, 0, base_seed + i, scale=True)
 
 
+def lin_quad_set(n, m_lin, m_quad, p=0, seed=0, objective="quadratic", feasible_start=True):
+    """FeasibilityTests / ConstraintSets.randomConstraintSet design (src/test/scala/cvx/FeasibilityTests.scala:105-117,
+    ConstraintSets.scala:67-89; Constraints.randomLinearIneqConstraint / randomQuadraticConstraint,
+    Constraints.scala:158-204): m_lin linear and m_quad convex quadratic constraints, all strictly satisfied
+    at a known point x0, optional random equalities through x0; objective: convex quadratic or linear."""
+    rng = np.random.default_rng(seed)
+    x0 = rng.uniform(-1, 1, n)
+    G = rng.uniform(-1, 1, (m_lin, n))
+    ub = G @ x0 + rng.uniform(0.5, 1.5, m_lin)
+    quad = []
+    for k in range(m_quad):
+        B = rng.uniform(-1, 1, (n, n)) / np.sqrt(n)
+        Pk = B.T @ B
+        Pk = (Pk + Pk.T) * 0.5
+        ak = rng.uniform(-1, 1, n)
+        rk = float(rng.uniform(-1, 1))
+        val = rk + ak @ x0 + 0.5 * x0 @ Pk @ x0
+        quad.append(dict(P=Pk, a=ak, r=rk, ub=float(val + rng.uniform(0.5, 1.5))))
+    if objective == "quadratic":
+        R = rng.uniform(-1, 1, (n, n)) / np.sqrt(n)
+        P = R.T @ R + 0.1 * np.eye(n)
+        P = (P + P.T) * 0.5
+        a = rng.uniform(-1, 1, n)
+        prob = dict(kind="quadratic", n=n, a=a, r=0.0, P=P)
+    else:
+        prob = dict(kind="linear", n=n, a=rng.uniform(-1, 1, n), r=0.0, P=None)
+    prob.update(G=G, rvec=np.zeros(m_lin), ub=ub, quad=quad, A=None, b=None, x0=x0 if feasible_start else None,
+                xdef=x0.copy() if feasible_start else x0 + rng.uniform(2.0, 3.0, n))
+    if p > 0:
+        A = rng.uniform(-1, 1, (p, n))
+        prob["A"], prob["b"] = A, A @ x0
+    return prob
+
+
 # ---------------- planted KKT systems (KktTest.scala) ----------------
 
 
@@ -217,7 +251,8 @@ def to_oracle(prob):
         objF = O.KLObjective(prob["n"])
     else:
         raise ValueError(prob["kind"])
-    cnts = O.ConstraintSet(prob["G"], prob["rvec"], prob["ub"], None, prob["xdef"])
+    quad = [O.QuadCnt(q["P"], q["a"], q["r"], q["ub"]) for q in prob.get("quad") or []]
+    cnts = O.ConstraintSet(prob["G"], prob["rvec"], prob["ub"], quad or None, prob["xdef"])
     if prob.get("x0") is not None:
         cnts = cnts.addFeasiblePoint(prob["x0"])
     eqs = O.EqualityConstraint(prob["A"], prob["b"]) if prob.get("A") is not None else None
