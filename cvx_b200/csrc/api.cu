@@ -152,7 +152,11 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
   CVXB_CUDA_OK(cudaMallocHost((void**)&h->h_flag, NFLAG * sizeof(int)));
   CVXB_CUDA_OK(cudaEventCreate(&h->ev0));
   CVXB_CUDA_OK(cudaEventCreate(&h->ev1));
+  CVXB_CUDA_OK(cudaEventCreate(&h->gev0));
+  CVXB_CUDA_OK(cudaEventCreate(&h->gev1));
+  if (const char* e = getenv("CVXB_NO_GRAPHS")) h->use_graphs = (e[0] == '0' || e[0] == 0) ? 1 : 0;
   CVXB_TRY(gemm_dmma_init());
+  CVXB_TRY(factor_init());
   *out = h;
   return CVXB_OK;
 }
@@ -164,7 +168,7 @@ int cvxb_destroy(cvxb_handle h) {
   if (h->kkt_cache) { KktWork* W = (KktWork*)h->kkt_cache; kkt_work_free(*W); delete W; }
   cudaFree(h->d_scal); cudaFree(h->d_flag); cudaFree(h->d_part); cudaFree(h->d_ticket);
   cudaFreeHost(h->h_scal); cudaFreeHost(h->h_flag);
-  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->gev0); cudaEventDestroy(h->gev1);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -185,6 +189,8 @@ int cvxb_profile_enable(cvxb_handle h, int on) {
   h->prof_on = on;
   h->prof_used = 0;
   h->prof_flops = 0.0;
+  h->prof_ms_graph = 0.0;
+  h->prof_launches_graph = 0;
   return CVXB_OK;
 }
 
@@ -197,8 +203,8 @@ int cvxb_profile_read(cvxb_handle h, long long* launches, double* ms_total, doub
     CVXB_CUDA_OK(cudaEventElapsedTime(&t, h->prof_events[i], h->prof_events[i + 1]));
     ms += t;
   }
-  if (launches) *launches = (long long)(h->prof_used / 2);
-  if (ms_total) *ms_total = ms;
+  if (launches) *launches = (long long)(h->prof_used / 2) + h->prof_launches_graph;
+  if (ms_total) *ms_total = ms + h->prof_ms_graph;
   if (flops_total) *flops_total = h->prof_flops;
   return CVXB_OK;
 }

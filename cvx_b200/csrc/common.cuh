@@ -57,6 +57,12 @@ struct cvxb_handle_s {
   void* kkt_cache = nullptr;     // cvxb::KktWork of the last seam-B call (re-used when (n,p) repeat)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // optional per-launch timing of the dominant kernel (Hessian-assembly SYRK), bench.py roofline
+  // CUDA-graph replay of the fixed per-step launch sequence
+  bool capturing = false;
+  cudaEvent_t gev0 = nullptr, gev1 = nullptr;   // external events around the SYRK inside a captured step
+  double prof_ms_graph = 0.0;
+  long long prof_launches_graph = 0;
+  int use_graphs = 1;
   int prof_on = 0;
   std::vector<cudaEvent_t> prof_events;   // start/stop pairs
   size_t prof_used = 0;
@@ -106,7 +112,7 @@ enum Flag {
   F_RUIZ_DONE = 0, F_RUIZ_SWEEPS, F_CHOL_H /* 0 or 1-based failing column */, F_CHOL_S, F_INFEAS /* slack<=0 */,
   F_LS_STATUS /* 0 ok, 1 set-backtrack failed, 2 armijo failed, 3 not feasible in value */, F_LS_TRIALS,
   F_STEP_TAKEN, F_BAD /* any failure upstream: gates the x update */, F_ZERO_DIAG,
-  F_PD_LS_FAIL, F_PD_NOTNEG, F_PD_LAMNEG,
+  F_PD_LS_FAIL, F_PD_NOTNEG, F_PD_LAMNEG, F_ITER0 /* first Newton step of an unconstrained stage */,
   F_COUNT
 };
 
@@ -142,7 +148,7 @@ int gemv_t(Handle& h, int m, int n, double alpha, const double* A, int lda, cons
 int scale_rows(Handle& h, int m, int n, const double* G, int ldg, const double* s, double* Gs, int ldgs, bool sqrt_of_s);
 // C = alpha * A (+ diag)              n x n (objective Hessian prefill); A may be NULL (zero)
 int fill_matrix(Handle& h, int n, double alpha, const double* A, int lda, const double* diag_num, double diag_scale,
-                double* C, int ldc);
+                double* C, int ldc, const double* mul_dev = nullptr);   // alpha, diag_scale *= *mul_dev when given
 // Bt(i,j) = s_i * A(j,i)   (n x p from p x n), s may be NULL
 int transpose_scale(Handle& h, int p, int n, const double* A, int lda, const double* s, double* Bt, int ldbt);
 // C (n x n) += alpha * I
@@ -164,6 +170,7 @@ int potrf_lower(Handle& h, int n, double* A, int lda, double* invD, int flag_slo
 int trsm_lower(Handle& h, int n, int r, const double* L, int ldl, const double* invD, double* B, int ldb, bool trans);
 // inverse diagonal blocks of a given lower-triangular matrix (for cvxb_triangular_solve and
 // solveWithCholFactor); zero diagonal -> F_ZERO_DIAG
+int factor_init();   // kernel attributes (once per process, outside any stream capture)
 int leaf_clocks(long long* out, bool reset);   // per-phase clock64 sums of the leaf kernel (debug builds)
 int invert_diag_blocks(Handle& h, int n, const double* L, int ldl, double* invD);
 

@@ -617,6 +617,8 @@ int leaf_init() {
 
 }  // namespace
 
+int factor_init() { return leaf_init(); }
+
 int ruiz_equilibrate(Handle& h, int n, const double* Hm, int ldh, double* d, double* colsq, int max_sweeps, double tol) {
   if (n <= 0) return CVXB_OK;
   CVXB_LAUNCH(h, ruiz_init_kernel, (n + 255) / 256, 256, 0, n, d, h.d_flag, h.d_scal, h.d_ticket);

@@ -253,6 +253,12 @@ int gemm_dmma_init() {
 }
 
 int gemm_dmma_timed(Handle& h, const GemmArgs& g, double flops) {
+  if (h.capturing) {   // inside a captured Newton step: external event nodes, read back after each replay
+    CVXB_CUDA_OK(cudaEventRecordWithFlags(h.gev0, h.stream, cudaEventRecordExternal));
+    int st = gemm_dmma(h, g);
+    CVXB_CUDA_OK(cudaEventRecordWithFlags(h.gev1, h.stream, cudaEventRecordExternal));
+    return st;
+  }
   if (!h.prof_on) return gemm_dmma(h, g);
   if (h.prof_used + 2 > h.prof_events.size()) {
     for (int i = 0; i < 64; ++i) {

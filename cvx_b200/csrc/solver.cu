@@ -36,13 +36,14 @@ __device__ __forceinline__ double obj_grad(int kind, int n, int j, double xj, co
 
 // E3: gx = r + Gx ; slack, 1/slack, log-sum, feasibility ; objective value f0 and barrier value
 __global__ void __launch_bounds__(VT) eval_cnt_kernel(int m, int n, int kind, double obj_r, double t,
-                                                      const double* __restrict__ gr, const double* __restrict__ ub,
+                                                      const double* __restrict__ t_dev, const double* __restrict__ gr, const double* __restrict__ ub,
                                                       double* __restrict__ gx, double* __restrict__ inv,
                                                       const double* __restrict__ x, const double* __restrict__ a,
                                                       const double* __restrict__ Px, const double* __restrict__ qcorr,
                                                       double* scal, int* flag) {
   __shared__ double buf[33];
   __shared__ int ibuf[33];
+  if (t_dev) t = *t_dev;        // barrier parameter kept on the device when the step is replayed from a CUDA graph
   double ls = 0.0, mn = 1e308;
   int bad = 0;
   for (int i = threadIdx.x; i < m; i += VT) {
@@ -66,18 +67,19 @@ __global__ void __launch_bounds__(VT) eval_cnt_kernel(int m, int n, int kind, do
     scal[S_F0] = f0;
     scal[S_FVAL] = t * f0 - ls;      // BarrierSolver.scala:280-289
     scal[S_MINSLACK] = mn;
-    scal[S_T] = t;
     flag[F_INFEAS] = bad;
   }
 }
 
 // E6: y = t*grad f0 + G'(1/d) ; ||y|| ; eqdiff = b - Ax ; ||eqdiff||     BarrierSolver.scala:291-301
-__global__ void __launch_bounds__(VT) eval_grad_kernel(int n, int p, int kind, double t, const double* __restrict__ x,
+__global__ void __launch_bounds__(VT) eval_grad_kernel(int n, int p, int kind, double t, const double* __restrict__ t_dev,
+                                                       const double* __restrict__ x,
                                                        const double* __restrict__ a, const double* __restrict__ Px,
                                                        const double* __restrict__ gt, double* __restrict__ y,
                                                        const double* __restrict__ b, const double* __restrict__ ax,
                                                        double* __restrict__ eqdiff, double* scal) {
   __shared__ double buf[33];
+  if (t_dev) t = *t_dev;
   double s = 0.0;
   for (int j = threadIdx.x; j < n; j += VT) {
     double v = t * obj_grad(kind, n, j, x[j], a, Px) + gt[j];
@@ -104,6 +106,7 @@ struct LsArgs {
   double t, alpha, beta, tol;
   const double *gx, *ub, *Gd, *a, *Px, *Pd, *y;
   const double* qq;      // d'P_k d / 2 on quadratic rows (NULL without quadratic constraints)
+  const double* t_dev;   // non-NULL: t and the first-step flag live on the device (CUDA-graph replay)
   double *x, *dir;
 };
 
@@ -146,6 +149,7 @@ __device__ double ls_value(const LsArgs& A, double s, double f0, double c1, doub
 __global__ void __launch_bounds__(VT) linesearch_kernel(LsArgs A, double* scal, int* flag) {
   __shared__ double buf[33];
   __shared__ int ibuf[33];
+  if (A.t_dev) { A.t = *A.t_dev; A.iter0 = flag[F_ITER0]; }
   // q = d . grad ;  objective line coefficients
   double q = 0.0, c1 = 0.0, c2 = 0.0;
   for (int j = threadIdx.x; j < A.n; j += VT) {
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(VT) linesearch_kernel(LsArgs A, double* scal, 
     flag[F_LS_STATUS] = status;
     flag[F_LS_TRIALS] = it;
     flag[F_STEP_TAKEN] = taken;
+    if (!upstream_bad) flag[F_ITER0] = 0;       // the next step of this stage is not the first any more
   }
 }
 
@@ -311,6 +316,11 @@ __global__ void __launch_bounds__(VT) phase1_start_kernel(int m1, int n, const d
   if (threadIdx.x == 0) x1[n] = 1.0 + mx;
 }
 
+__global__ void set_stage_kernel(double t, double* scal, int* flag) {
+  scal[S_T] = t;
+  flag[F_ITER0] = 1;
+}
+
 __global__ void set_unit_kernel(int n, int k, double* a) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = (i == k) ? 1.0 : 0.0;
@@ -380,6 +390,8 @@ int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s*
 void problem_free(cvxb_problem_s* P) {
   if (!P) return;
   if (P->phase1) problem_free(P->phase1);
+  for (int k = 0; k < 2; ++k)
+    if (P->step_graph[k]) cudaGraphExecDestroy(P->step_graph[k]);
   for (void* q : P->owned) cudaFree(q);
   kkt_work_free(P->kw);
   delete P;
@@ -413,35 +425,37 @@ int quad_hessian_terms(cvxb_problem_s* P, const double* c) {
   return CVXB_OK;
 }
 
-int barrier_eval(cvxb_problem_s* P, double t) {
+int barrier_eval(cvxb_problem_s* P, double t, const double* t_dev = nullptr) {
   Handle& h = *P->h;
   const int n = P->n, m = P->m, p = P->p;
   CVXB_TRY(quad_refresh(P));
   CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->x, 0.0, P->gx));
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->Px));
-  CVXB_LAUNCH(h, eval_cnt_kernel, 1, VT, 0, m, n, P->objective, P->obj_r, t, P->gr, P->ub, P->gx, P->inv, P->x,
+  CVXB_LAUNCH(h, eval_cnt_kernel, 1, VT, 0, m, n, P->objective, P->obj_r, t, t_dev, P->gr, P->ub, P->gx, P->inv, P->x,
               P->obj_a, P->Px, P->qcorr, h.d_scal, h.d_flag);
   CVXB_TRY(gemv_t(h, m, n, 1.0, P->G, P->ldm, P->inv, 0.0, P->gt));
   if (p > 0) CVXB_TRY(gemv_n(h, p, n, 1.0, P->A, P->ldp, P->x, 0.0, P->axv));
-  CVXB_LAUNCH(h, eval_grad_kernel, 1, VT, 0, n, p, P->objective, t, P->x, P->obj_a, P->Px, P->gt, P->y, P->b, P->axv,
+  CVXB_LAUNCH(h, eval_grad_kernel, 1, VT, 0, n, p, P->objective, t, t_dev, P->x, P->obj_a, P->Px, P->gt, P->y, P->b, P->axv,
               P->eqdiff, h.d_scal);
   return CVXB_OK;
 }
 
 // H = t*hess f0 + G' diag(1/d^2) G     BarrierSolver.scala:303-315 (weighted outer-product sum as one SYRK)
-int barrier_hessian(cvxb_problem_s* P, double t) {
+int barrier_hessian(cvxb_problem_s* P, double t, const double* t_dev = nullptr) {
   Handle& h = *P->h;
   const int n = P->n, m = P->m;
+  const double tv = t_dev ? 1.0 : t;      // with t_dev the kernel multiplies by *t_dev itself
   CVXB_TRY(scale_rows(h, m, n, P->G, P->ldm, P->inv, P->Gs, P->ldm, false));
-  if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(fill_matrix(h, n, t, P->obj_P, P->ldn, nullptr, 0.0, P->H, P->ldn));
-  else if (P->objective == CVXB_OBJ_KL) CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, t, P->H, P->ldn));
+  if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(fill_matrix(h, n, tv, P->obj_P, P->ldn, nullptr, 0.0, P->H, P->ldn, t_dev));
+  else if (P->objective == CVXB_OBJ_KL) CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, tv, P->H, P->ldn, t_dev));
   else CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, nullptr, 0.0, P->H, P->ldn));
   CVXB_TRY(quad_hessian_terms(P, P->inv));     // + hess g_k / d_k   (BarrierSolver.scala:313)
   GemmArgs g{n, n, m, P->Gs, P->ldm, true, P->Gs, P->ldm, true, P->H, P->ldn, 1.0, 1.0, 2};
   return gemm_dmma_timed(h, g, (double)m * n * ((double)n + 1.0));   // lower triangle, mul + add
 }
 
-int enqueue_linesearch(cvxb_problem_s* P, const cvxb_params& pars, double t, int mode, int iter0) {
+int enqueue_linesearch(cvxb_problem_s* P, const cvxb_params& pars, double t, int mode, int iter0,
+                       const double* t_dev = nullptr) {
   Handle& h = *P->h;
   const int n = P->n, m = P->m;
   CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->dir, 0.0, P->Gd));
@@ -451,9 +465,77 @@ int enqueue_linesearch(cvxb_problem_s* P, const cvxb_params& pars, double t, int
   A.m = m; A.n = n; A.kind = P->objective; A.mode = mode; A.iter0 = iter0;
   A.t = t; A.alpha = pars.alpha; A.beta = pars.beta; A.tol = pars.tolSolver;
   A.gx = P->gx; A.ub = P->ub; A.Gd = P->Gd; A.a = P->obj_a; A.Px = P->Px; A.Pd = P->Pd; A.y = P->y;
-  A.x = P->x; A.dir = P->dir; A.qq = P->mq > 0 ? P->qq : nullptr;
+  A.x = P->x; A.dir = P->dir; A.qq = P->mq > 0 ? P->qq : nullptr; A.t_dev = t_dev;
   CVXB_LAUNCH(h, linesearch_kernel, 1, VT, 0, A, h.d_scal, h.d_flag);
   return CVXB_OK;
+}
+
+// One optimistic Newton step (assembly, linear solve, line search, re-evaluation) as a CUDA graph: the launch
+// sequence depends only on the problem's shape, so it is captured once per problem and mode and replayed
+// with t / first-step flag read from device memory.  ~150 kernel launches become one graph launch.
+int enqueue_step(cvxb_problem_s* P, const cvxb_params& pars, double t, int mode, int iter0, const double* t_dev) {
+  Handle& h = *P->h;
+  CVXB_TRY(barrier_hessian(P, t, t_dev));
+  if (mode == 0)
+    CVXB_TRY(kkt_enqueue(h, P->kw, pars, P->H, P->ldn, P->A, P->ldp, P->y, P->eqdiff, pars.tolEqSolve, false, false,
+                         P->dir, P->nu));
+  else
+    CVXB_TRY(chol_enqueue(h, P->kw, pars, P->H, P->ldn, P->y, -1.0, pars.tolEqSolve, false, false, P->dir));
+  CVXB_TRY(enqueue_linesearch(P, pars, t, mode, iter0, t_dev));
+  return barrier_eval(P, t, t_dev);
+}
+
+// the parameters baked into the captured kernels' arguments
+static bool same_step_pars(const cvxb_params& a, const cvxb_params& b) {
+  return a.alpha == b.alpha && a.beta == b.beta && a.tolSolver == b.tolSolver && a.tolEqSolve == b.tolEqSolve &&
+         a.ruizMaxSweeps == b.ruizMaxSweeps && a.ruizTol == b.ruizTol && a.cholRegDelta == b.cholRegDelta &&
+         a.cholMinDiag == b.cholMinDiag;
+}
+
+int run_step(cvxb_problem_s* P, const cvxb_params& pars, double t, int mode, int iter0) {
+  Handle& h = *P->h;
+  if (!h.use_graphs) return enqueue_step(P, pars, t, mode, iter0, nullptr);
+  cudaGraphExec_t& exec = P->step_graph[mode];
+  if (!exec || !same_step_pars(P->graph_pars, pars)) {
+    if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
+    if (P->step_graph[1 - mode]) { cudaGraphExecDestroy(P->step_graph[1 - mode]); P->step_graph[1 - mode] = nullptr; }
+    P->graph_pars = pars;
+    const long long l0 = h.launches;
+    cudaGraph_t graph = nullptr;
+    CVXB_CUDA_OK(cudaStreamBeginCapture(h.stream, cudaStreamCaptureModeThreadLocal));
+    h.capturing = true;
+    int st = enqueue_step(P, pars, t, mode, iter0, h.d_scal + S_T);
+    h.capturing = false;
+    cudaError_t e = cudaStreamEndCapture(h.stream, &graph);
+    if (st != CVXB_OK || e != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      h.launches = l0;
+      h.use_graphs = 0;                    // capture not possible here: fall back to plain launches for good
+      return enqueue_step(P, pars, t, mode, iter0, nullptr);
+    }
+    P->graph_launches[mode] = h.launches - l0;
+    h.launches = l0;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      exec = nullptr;
+      h.use_graphs = 0;
+      return enqueue_step(P, pars, t, mode, iter0, nullptr);
+    }
+  }
+  CVXB_CUDA_OK(cudaGraphLaunch(exec, h.stream));
+  h.launches += P->graph_launches[mode];
+  return CVXB_OK;
+}
+
+// after the step's status read: fold the SYRK's external event pair into the profile
+static void graph_profile_tick(Handle& h) {
+  if (!h.use_graphs || !h.prof_on) return;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, h.gev0, h.gev1) == cudaSuccess) { h.prof_ms_graph += ms; h.prof_launches_graph++; }
+  else cudaGetLastError();
 }
 
 struct InnerResult {
@@ -488,6 +570,7 @@ int inner_solve_eq(cvxb_problem_s* P, const cvxb_params& pars, double t, RunStat
   const double tol = pars.tolSolver;
   R = InnerResult();
   R.nd = tol + 1;
+  CVXB_LAUNCH(h, set_stage_kernel, 1, 1, 0, t, h.d_scal, h.d_flag);
   CVXB_TRY(barrier_eval(P, t));
   CVXB_TRY(fetch_status(h));
   if (h.h_flag[F_INFEAS]) { set_last_error("gradientBarrierFunction: x not strictly feasible"); return CVXB_ENOTFEASIBLE; }
@@ -495,12 +578,9 @@ int inner_solve_eq(cvxb_problem_s* P, const cvxb_params& pars, double t, RunStat
   R.eqGap = h.h_scal[S_EQNORM];
   while (R.iter < pars.maxIter && ((R.nd > tol && R.normGrad > tol) || R.eqGap > tol)) {
     if (rs.limited && rs.budget <= 0) break;
-    CVXB_TRY(barrier_hessian(P, t));
-    CVXB_TRY(kkt_enqueue(h, P->kw, pars, P->H, P->ldn, P->A, P->ldp, P->y, P->eqdiff, pars.tolEqSolve, false, false,
-                         P->dir, P->nu));
-    CVXB_TRY(enqueue_linesearch(P, pars, t, 0, 0));
-    CVXB_TRY(barrier_eval(P, t));
+    CVXB_TRY(run_step(P, pars, t, 0, 0));
     CVXB_TRY(fetch_status(h));
+    graph_profile_tick(h);
     if (h.h_flag[F_BAD]) {
       // optimistic attempt refused on the device (x untouched): walk the reference's fallback chain
       cvxb_kkt_info info;
@@ -539,17 +619,16 @@ int inner_solve_uncon(cvxb_problem_s* P, const cvxb_params& pars, double t, RunS
   const int n = P->n;
   R = InnerResult();
   R.nd = tol + 1;
+  CVXB_LAUNCH(h, set_stage_kernel, 1, 1, 0, t, h.d_scal, h.d_flag);
   CVXB_TRY(barrier_eval(P, t));
   CVXB_TRY(fetch_status(h));
   if (h.h_flag[F_INFEAS]) { set_last_error("gradientBarrierFunction: x not strictly feasible"); return CVXB_ENOTFEASIBLE; }
   R.normGrad = h.h_scal[S_NORMGRAD];
   while (R.iter < pars.maxIter && R.nd > tol && R.normGrad > tol) {
     if (rs.limited && rs.budget <= 0) break;
-    CVXB_TRY(barrier_hessian(P, t));
-    CVXB_TRY(chol_enqueue(h, P->kw, pars, P->H, P->ldn, P->y, -1.0, pars.tolEqSolve, false, false, P->dir));
-    CVXB_TRY(enqueue_linesearch(P, pars, t, 1, R.iter == 0));
-    CVXB_TRY(barrier_eval(P, t));
+    CVXB_TRY(run_step(P, pars, t, 1, R.iter == 0));
     CVXB_TRY(fetch_status(h));
+    graph_profile_tick(h);
     if (h.h_flag[F_BAD]) {
       cvxb_kkt_info info;
       int st = chol_solve_retry(h, P->kw, pars, P->H, P->ldn, P->y, -1.0, pars.tolEqSolve, P->dir, &info);
