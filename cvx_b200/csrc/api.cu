@@ -148,6 +148,11 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
   CVXB_CUDA_OK(cudaMemset(h->d_scal, 0, NSCAL * sizeof(double)));
   CVXB_CUDA_OK(cudaMemset(h->d_flag, 0, NFLAG * sizeof(int)));
   CVXB_CUDA_OK(cudaMemset(h->d_ticket, 0, 16 * sizeof(unsigned)));
+  {
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (coop && !getenv("CVXB_NO_WAVEFRONT")) CVXB_CUDA_OK(cudaMalloc((void**)&h->wave_ready, 1024 * sizeof(int)));
+  }
   CVXB_CUDA_OK(cudaMallocHost((void**)&h->h_scal, NSCAL * sizeof(double)));
   CVXB_CUDA_OK(cudaMallocHost((void**)&h->h_flag, NFLAG * sizeof(int)));
   CVXB_CUDA_OK(cudaEventCreate(&h->ev0));
@@ -166,7 +171,7 @@ int cvxb_destroy(cvxb_handle h) {
   cvxb::DeviceGuard guard(h->device);
   cudaStreamSynchronize(h->stream);
   if (h->kkt_cache) { KktWork* W = (KktWork*)h->kkt_cache; kkt_work_free(*W); delete W; }
-  cudaFree(h->d_scal); cudaFree(h->d_flag); cudaFree(h->d_part); cudaFree(h->d_ticket);
+  cudaFree(h->wave_ready); cudaFree(h->d_scal); cudaFree(h->d_flag); cudaFree(h->d_part); cudaFree(h->d_ticket);
   cudaFreeHost(h->h_scal); cudaFreeHost(h->h_flag);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->gev0); cudaEventDestroy(h->gev1);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
@@ -528,6 +533,33 @@ int cvxb_bench_kernel(cvxb_handle h, int which, int n, int k, int reps, double* 
     }
     *ms_per_launch = total / reps;
     *flops_or_bytes_per_launch = (double)n * n * n / 3.0;
+  } else if (which == 5 || which == 6) {
+    // 5: forward + backward single-RHS solves with a factor of size n; 6: Ruiz equilibration (20 enqueued sweeps)
+    CVXB_CUDA_OK(cudaMalloc((void**)&G, (size_t)ldn * n * sizeof(double)));
+    CVXB_CUDA_OK(cudaMalloc((void**)&C, (size_t)ldn * 4 * sizeof(double)));
+    CVXB_CUDA_OK(cudaMalloc((void**)&invD, (size_t)((n + NB - 1) / NB) * NB * NB * sizeof(double)));
+    fill_random_kernel<<<1024, 256, 0, H.stream>>>((size_t)ldn * n, G, 777ull, -1.0, 1.0);
+    fill_random_kernel<<<64, 256, 0, H.stream>>>((size_t)ldn * 4, C, 5ull, -1.0, 1.0);
+    double total = 0;
+    if (which == 5) {
+      CVXB_TRY(add_diag(H, n, (double)n + 1.0, G, ldn));
+      CVXB_TRY(potrf_lower(H, n, G, ldn, invD, F_CHOL_H, S_MINDIAG_H));
+    }
+    for (int r = -1; r < reps; ++r) {
+      CVXB_CUDA_OK(cudaEventRecord(H.ev0, H.stream));
+      if (which == 5) {
+        CVXB_TRY(trsm_lower(H, n, 1, G, ldn, invD, C, ldn, false));
+        CVXB_TRY(trsm_lower(H, n, 1, G, ldn, invD, C, ldn, true));
+      } else {
+        CVXB_TRY(ruiz_equilibrate(H, n, G, ldn, C, C + ldn, 20, 1e-6));
+      }
+      CVXB_CUDA_OK(cudaEventRecord(H.ev1, H.stream));
+      CVXB_CUDA_OK(cudaEventSynchronize(H.ev1));
+      CVXB_CUDA_OK(cudaEventElapsedTime(&t, H.ev0, H.ev1));
+      if (r >= 0) total += t;
+    }
+    *ms_per_launch = total / reps;
+    *flops_or_bytes_per_launch = which == 5 ? 8.0 * n * n : 8.0 * n * n * 20;
   } else {
     cvxb::set_last_error("cvxb_bench_kernel: unknown kernel %d", which);
     return CVXB_EINVAL;

@@ -54,6 +54,7 @@ struct cvxb_handle_s {
   int* h_flag = nullptr;
   double* d_part = nullptr;   // partial-sum scratch for split reductions (PART_DOUBLES doubles)
   unsigned* d_ticket = nullptr;  // last-block-done counters
+  int* wave_ready = nullptr;     // per-block "y_k published" flags of the wavefront triangular solves
   void* kkt_cache = nullptr;     // cvxb::KktWork of the last seam-B call (re-used when (n,p) repeat)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // optional per-launch timing of the dominant kernel (Hessian-assembly SYRK), bench.py roofline
@@ -113,6 +114,7 @@ enum Flag {
   F_LS_STATUS /* 0 ok, 1 set-backtrack failed, 2 armijo failed, 3 not feasible in value */, F_LS_TRIALS,
   F_STEP_TAKEN, F_BAD /* any failure upstream: gates the x update */, F_ZERO_DIAG,
   F_PD_LS_FAIL, F_PD_NOTNEG, F_PD_LAMNEG, F_ITER0 /* first Newton step of an unconstrained stage */,
+  F_WAVE_ABORT /* a wavefront solve gave up waiting (never expected) */,
   F_COUNT
 };
 

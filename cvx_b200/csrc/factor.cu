@@ -105,7 +105,8 @@ __global__ void scaled_lower_kernel(int n, const double* __restrict__ Hm, int ld
 }
 
 // ------------------------------------------------------------------------------------------- leaf
-constexpr int LDW = NB + 1;                                   // odd stride: conflict-free rows and columns
+constexpr int LDW = NB + 4;   // stride = 4 mod 16 doubles: the DMMA fragment loads of the leaf (8 rows x 4 k) are bank-conflict
+                              // free; the few row-strided sweeps (final store of the inverse) pay an 8-way conflict once
 constexpr int LEAF_SMEM = (NB + 1) * LDW * (int)sizeof(double);   // L (lower) + inverse (transposed, upper, shifted)
 constexpr int LEAF_THREADS = 512;
 constexpr int LEAF_WARPS = LEAF_THREADS / 32;
@@ -314,9 +315,8 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
   }
 
   // ---- triangular inverse.  Zero-fill the strictly-lower X blocks first (the doubling reads them).
-  for (int j = ty; j < nb; j += LEAF_WARPS)
-    for (int i = tx; i < nb; i += 32)
-      if (i >= j) XW(i, j) = 0.0;
+  for (int i = ty; i < nb; i += LEAF_WARPS)          // lanes along j: unit stride in the transposed layout
+    for (int j = tx; j <= i; j += 32) XW(i, j) = 0.0;
   __syncthreads();
   if (ty < nblk) {
     const int o = ty * SUB;
@@ -584,10 +584,186 @@ __global__ void copy_vec_kernel(int n, const double* __restrict__ a, double* __r
   if (i < n) b[i] = a[i];
 }
 
+// ---- single-launch wavefront solves ----------------------------------------------------------------
+// One CTA per 128-row block, all co-resident (cooperative launch; n <= 128 * #SMs).  CTA c folds
+// L[c,k] y_k into its right-hand side as soon as block k publishes y_k (flag in global memory), then
+// solves its own diagonal block with the inverse and publishes y_c.  No launch per block, no grid-wide
+// barrier: the critical path is one flag hand-off + two 128 x 128 GEMVs per block.
+__device__ __forceinline__ bool wait_flag(const int* flag, int* abort_flag) {
+  // thread 0 only; bounded spin so that a scheduling surprise can never hang the GPU
+  const volatile int* f = flag;
+  for (long long spin = 0; spin < (1ll << 26); ++spin) {
+    if (*f) return true;
+    __nanosleep(64);
+  }
+  *abort_flag = 1;
+  return false;
+}
+
+constexpr int WLD = NB + 1;                                        // padded stride of the inverse block in shared memory
+constexpr int WAVE_SMEM = NB * WLD * (int)sizeof(double);
+
+// Both kernels keep the CTA's inverse diagonal block in shared memory (loaded up front, it depends on
+// nothing) and fetch the next off-diagonal block of L into REGISTERS before waiting for its flag, so the
+// per-block critical path holds no global-memory round trip except the hand-off itself.
+__global__ void __launch_bounds__(256, 1) trsv_fwd_wave_kernel(int n, const double* __restrict__ L, int ldl,
+                                                               const double* __restrict__ invD, const double* __restrict__ b,
+                                                               double* __restrict__ out, int* ready, int* abort_flag) {
+  extern __shared__ double Xs[];          // invD_c, element (i,j) at Xs[i + j*WLD]
+  __shared__ double ys[NB];
+  __shared__ double red[2][NB];
+  __shared__ int ok;
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const int r0 = c * NB;
+  const int nbc = (n - r0) < NB ? (n - r0) : NB;
+  const int row = tid & (NB - 1), half = tid >> 7;
+  {
+    const double* Xg = invD + (size_t)c * NB * NB;
+    for (int idx = tid; idx < NB * NB; idx += 256) Xs[(idx & (NB - 1)) + (idx >> 7) * WLD] = Xg[idx];
+  }
+  const double bval = (tid < nbc) ? b[r0 + tid] : 0.0;
+  double acc = 0.0;
+  const bool live = row < nbc;
+  for (int k = 0; k < c; ++k) {
+    double lreg[64];
+    const double* Lr = L + (size_t)(k * NB + half * 64) * ldl + r0 + (live ? row : 0);
+#pragma unroll
+    for (int j = 0; j < 64; ++j) lreg[j] = Lr[(size_t)j * ldl];      // 64 loads in flight, before the wait
+    if (tid == 0) ok = wait_flag(ready + k, abort_flag) ? 1 : 0;
+    __syncthreads();
+    if (!ok) return;
+    if (tid < NB) ys[tid] = __ldcg(out + k * NB + tid);
+    __syncthreads();
+    const double* yy = ys + half * 64;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 64; j += 4) {
+      a0 = fma(lreg[j], yy[j], a0);
+      a1 = fma(lreg[j + 1], yy[j + 1], a1);
+      a2 = fma(lreg[j + 2], yy[j + 2], a2);
+      a3 = fma(lreg[j + 3], yy[j + 3], a3);
+    }
+    if (live) acc += (a0 + a1) + (a2 + a3);
+    __syncthreads();
+  }
+  red[half][row] = acc;
+  __syncthreads();
+  if (tid < NB) ys[tid] = (tid < nbc) ? bval - (red[0][tid] + red[1][tid]) : 0.0;
+  __syncthreads();
+  {   // y_c = invD_c * rhs  (lower triangular, zeros above the diagonal)
+    const double* xr = Xs + row + (half * 64) * WLD;
+    const double* bb = ys + half * 64;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < 64; j += 4) {
+      a0 = fma(xr[j * WLD], bb[j], a0);
+      a1 = fma(xr[(j + 1) * WLD], bb[j + 1], a1);
+      a2 = fma(xr[(j + 2) * WLD], bb[j + 2], a2);
+      a3 = fma(xr[(j + 3) * WLD], bb[j + 3], a3);
+    }
+    red[half][row] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  if (tid < NB) __stcg(out + r0 + tid, (tid < nbc) ? red[0][tid] + red[1][tid] : 0.0);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) atomicExch(ready + c, 1);
+}
+
+__global__ void __launch_bounds__(256, 1) trsv_bwd_wave_kernel(int n, int nblk, const double* __restrict__ L, int ldl,
+                                                               const double* __restrict__ invD, const double* __restrict__ y,
+                                                               double* __restrict__ out, int* ready, int* abort_flag) {
+  extern __shared__ double Xs[];
+  __shared__ double xs[NB];
+  __shared__ double red[2][NB];
+  __shared__ int ok;
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const int c0 = c * NB;
+  const int nbc = (n - c0) < NB ? (n - c0) : NB;
+  const int col = tid & (NB - 1), half = tid >> 7;
+  {
+    const double* Xg = invD + (size_t)c * NB * NB;
+    for (int idx = tid; idx < NB * NB; idx += 256) Xs[(idx & (NB - 1)) + (idx >> 7) * WLD] = Xg[idx];
+  }
+  const double yval = (tid < nbc) ? y[c0 + tid] : 0.0;
+  const bool live = col < nbc;
+  double acc = 0.0;
+  for (int k = nblk - 1; k > c; --k) {
+    const int k0 = k * NB;
+    const int nbk = (n - k0) < NB ? (n - k0) : NB;
+    // column (c0+col) of L, rows k0 + half*64 .. +63: contiguous -> 32 16-byte loads in flight before the wait
+    double2 lreg[32];
+    const double* Lc = L + (size_t)(c0 + (live ? col : 0)) * ldl + k0 + half * 64;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int r = half * 64 + 2 * i;
+      lreg[i] = (r + 1 < nbk) ? *reinterpret_cast<const double2*>(Lc + 2 * i)
+                              : make_double2(r < nbk ? Lc[2 * i] : 0.0, 0.0);
+    }
+    if (tid == 0) ok = wait_flag(ready + k, abort_flag) ? 1 : 0;
+    __syncthreads();
+    if (!ok) return;
+    if (tid < NB) xs[tid] = (tid < nbk) ? __ldcg(out + k0 + tid) : 0.0;
+    __syncthreads();
+    const double* xx = xs + half * 64;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      a0 = fma(lreg[i].x, xx[2 * i], a0);
+      a1 = fma(lreg[i].y, xx[2 * i + 1], a1);
+    }
+    if (live) acc += a0 + a1;
+    __syncthreads();
+  }
+  red[half][col] = acc;
+  __syncthreads();
+  if (tid < NB) xs[tid] = (tid < nbc) ? yval - (red[0][tid] + red[1][tid]) : 0.0;     // rhs of the diagonal solve
+  __syncthreads();
+  {   // x_c(i) = sum_j invD_c(j, i) rhs(j)  (zeros for j < i): thread i walks down column i of the inverse
+    const double* xc = Xs + col * WLD + half * 64;
+    const double* bb = xs + half * 64;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < 64; j += 4) {
+      a0 = fma(xc[j], bb[j], a0);
+      a1 = fma(xc[j + 1], bb[j + 1], a1);
+      a2 = fma(xc[j + 2], bb[j + 2], a2);
+      a3 = fma(xc[j + 3], bb[j + 3], a3);
+    }
+    red[half][col] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  if (tid < NB) __stcg(out + c0 + tid, (tid < nbc) ? red[0][tid] + red[1][tid] : 0.0);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) atomicExch(ready + c, 1);
+}
+
 int trsv_lower(Handle& h, int n, const double* L, int ldl, const double* invD, double* b, bool trans) {
   double* out = h.d_part + (PART_DOUBLES - 32768);     // tail of the scratch block (n <= 32768)
   if (n > 32768) { set_last_error("trsv_lower: n = %d exceeds the single-RHS scratch", n); return CVXB_EINVAL; }
   const int nblk = (n + NB - 1) / NB;
+  if (nblk <= h.sm_count && h.wave_ready) {
+    // wavefront kernel: every CTA must be resident at once -> cooperative launch (fails cleanly otherwise)
+    CVXB_CUDA_OK(cudaMemsetAsync(h.wave_ready, 0, (size_t)(nblk + 1) * sizeof(int), h.stream));
+    int* ready = h.wave_ready;
+    int* abort_flag = h.d_flag + F_WAVE_ABORT;
+    int nn = n, nb = nblk, ld = ldl;
+    cudaError_t e;
+    if (!trans) {
+      void* args[] = {&nn, (void*)&L, &ld, (void*)&invD, (void*)&b, &out, &ready, &abort_flag};
+      e = cudaLaunchCooperativeKernel((void*)trsv_fwd_wave_kernel, dim3(nblk), dim3(256), args, WAVE_SMEM, h.stream);
+    } else {
+      void* args[] = {&nn, &nb, (void*)&L, &ld, (void*)&invD, (void*)&b, &out, &ready, &abort_flag};
+      e = cudaLaunchCooperativeKernel((void*)trsv_bwd_wave_kernel, dim3(nblk), dim3(256), args, WAVE_SMEM, h.stream);
+    }
+    if (e == cudaSuccess) {
+      h.launches++;
+      CVXB_LAUNCH(h, copy_vec_kernel, (n + 255) / 256, 256, 0, n, out, b);
+      return CVXB_OK;
+    }
+    cudaGetLastError();       // not launchable cooperatively here: per-block kernels below
+  }
   if (!trans) {
     for (int k = 0; k < nblk; ++k) {
       int k0 = k * NB, kb = n - k0 < NB ? n - k0 : NB;
@@ -611,6 +787,8 @@ int leaf_init() {
   if (leaf_attr_set) return CVXB_OK;
   CVXB_CUDA_OK(cudaFuncSetAttribute(leaf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
   CVXB_CUDA_OK(cudaFuncSetAttribute(leaf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
+  CVXB_CUDA_OK(cudaFuncSetAttribute(trsv_fwd_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WAVE_SMEM));
+  CVXB_CUDA_OK(cudaFuncSetAttribute(trsv_bwd_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WAVE_SMEM));
   leaf_attr_set = true;
   return CVXB_OK;
 }
