@@ -1,3 +1,4 @@
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 """Large-configuration timing (BASELINE.json configs[3] and configs[4] shapes): a few Newton steps each."""
 import json, sys, time
 import numpy as np

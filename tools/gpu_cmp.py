@@ -1,7 +1,8 @@
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, sys, time
 from oracle import cvx_oracle as O, problems as P
 import cvx_b200 as cb
-sys.path.insert(0, "tests")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from test_barrier_gpu import PROBLEMS
 PROBLEMS = dict(PROBLEMS)
 PROBLEMS["slab_lp_100_eq"] = lambda: P.slab_lp(100, 100, 20, 0)

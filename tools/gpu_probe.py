@@ -1,3 +1,4 @@
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 """First-contact GPU probe: kernel-level timings (DMMA peak, SYRK, Cholesky, HBM copy)."""
 import json, sys
 from cvx_b200 import _lib

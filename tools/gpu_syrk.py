@@ -1,3 +1,4 @@
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 # the dominant kernel at the C2 shape (Hessian-assembly SYRK n=2000, k=m=4000) and at the C4 shape
 import sys
 from cvx_b200 import _lib
