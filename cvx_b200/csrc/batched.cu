@@ -77,6 +77,19 @@ __device__ __forceinline__ void dmma884b(double& c0, double& c1, double a, doubl
                : "d"(a), "d"(b));
 }
 
+#ifndef CVXB_BATCH_TIMING
+#define CVXB_BATCH_TIMING 0
+#endif
+__device__ long long g_batch_clk[12];
+#define BCLK(slot)                                                              \
+  do {                                                                          \
+    if (CVXB_BATCH_TIMING && blockIdx.x == 0 && threadIdx.x == 0) {             \
+      long long _c = clock64();                                                 \
+      g_batch_clk[slot] += _c - g_batch_clk[11];                                \
+      g_batch_clk[11] = _c;                                                     \
+    }                                                                           \
+  } while (0)
+
 #define HL(i, j) S.L[(i) + (j) * LDH]
 #define GG(i, j) S.G[(i) + (j) * LDG]
 
@@ -191,7 +204,7 @@ __device__ void b_hessian(Smem& S, const BatchArgs& A, int kind, const double* P
 
 // ---- Ruiz equilibration of the full symmetric H in S.L -> S.dr  (MatrixUtils.scala:240-268) ---------------
 __device__ void b_ruiz(Smem& S, const BatchArgs& A) {
-  const int tid = threadIdx.x, n = A.n;
+  const int tid = threadIdx.x, n = A.n, lane = tid & 31, warp = tid >> 5;
   if (tid < n) S.dr[tid] = 1.0;
   __syncthreads();
   for (int sweep = 0; sweep < A.P.ruizMaxSweeps; ++sweep) {
@@ -206,15 +219,23 @@ __device__ void b_ruiz(Smem& S, const BatchArgs& A) {
     }
     S_COLSQ[part * BN + j] = s;
     __syncthreads();
-    double dev = 0.0;
-    if (tid < n) {
-      double tot = (S_COLSQ[tid] + S_COLSQ[BN + tid]) + (S_COLSQ[2 * BN + tid] + S_COLSQ[3 * BN + tid]);
-      double u = sqrt(sqrt(tot));
-      if (u > 0) S.dr[tid] = S.dr[tid] * (1.0 / u);
-      dev = fabs(1.0 - u);
-      if (dev != dev) dev = 1e308;
+    // two barriers per sweep: the 64 column owners live in warps 0 and 1, so rho = max|1-u| needs one
+    // shuffle reduction per warp and a two-entry exchange
+    if (warp < 2) {
+      double dev = 0.0;
+      if (tid < n) {
+        double tot = (S_COLSQ[tid] + S_COLSQ[BN + tid]) + (S_COLSQ[2 * BN + tid] + S_COLSQ[3 * BN + tid]);
+        double u = sqrt(sqrt(tot));
+        if (u > 0) S.dr[tid] = S.dr[tid] * (1.0 / u);
+        dev = fabs(1.0 - u);
+        if (dev != dev) dev = 1e308;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+      if (lane == 0) S.red[warp] = dev;
     }
-    double rho = -block_min(-dev, S.red);
+    __syncthreads();
+    const double rho = fmax(S.red[0], S.red[1]);
     if (!(rho > A.P.ruizTol)) break;      // uniform: every thread sees the same rho
   }
   __syncthreads();
@@ -230,7 +251,8 @@ __device__ int b_potrf(Smem& S, int n, double* mind_out) {
     const int o = kb * BSUB;
     const int bs = (n - o) < BSUB ? (n - o) : BSUB;
     if (warp == 0) {
-      double a[BSUB];
+      // branch-free in-warp sweep (factor.cu: warp_diag_factor): selects only, updates unpredicated
+      double a[BSUB], rr[BSUB];
 #pragma unroll
       for (int c = 0; c < BSUB; ++c)
         a[c] = (lane < bs && c < bs && c <= lane) ? HL(o + lane, o + c) : ((c == lane) ? 1.0 : 0.0);
@@ -239,25 +261,24 @@ __device__ int b_potrf(Smem& S, int n, double* mind_out) {
 #pragma unroll
       for (int j = 0; j < BSUB; ++j) {
         double d = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(d > 0.0) || d > 1e300) {
-          if (!fail && j < bs) fail = o + j + 1;
-          d = 1.0;
-        }
+        const bool bad = !(d > 0.0) || d > 1e300;
+        fail = (bad && !fail && j < bs) ? (o + j + 1) : fail;
+        d = bad ? 1.0 : d;
         double r;
-        if (d < 1e-30 || d > 1e30) r = rsqrt(d);
+        if (d < 1e-30 || d > 1e30) r = rsqrt(d);       // warp-uniform
         else {                                   // float seed + one cubic correction (factor.cu: pivot_rsqrt)
           const double y0 = (double)rsqrtf((float)d);
           const double e = fma(-(d * y0), y0, 1.0);
           r = fma(y0, fma(e, 0.375, 0.5) * e, y0);
         }
         const double l = d * r;
-        if (j < bs && l < mind) mind = l;
-        if (lane == j) { a[j] = l; S.rdiag[o + j] = r; }
-        else if (lane > j) a[j] *= r;
+        mind = (j < bs && l < mind) ? l : mind;
+        rr[j] = r;
+        a[j] = (lane == j) ? l : a[j] * r;
 #pragma unroll
         for (int c = j + 1; c < BSUB; ++c) {
           const double tt = __shfl_sync(0xffffffffu, a[j], c);
-          if (lane >= c) a[c] = fma(-a[j], tt, a[c]);
+          a[c] = fma(-a[j], tt, a[c]);
         }
       }
       if (lane == 0) {
@@ -265,8 +286,10 @@ __device__ int b_potrf(Smem& S, int n, double* mind_out) {
         if (mind < S.sc[0]) S.sc[0] = mind;
       }
 #pragma unroll
-      for (int c = 0; c < BSUB; ++c)
+      for (int c = 0; c < BSUB; ++c) {
         if (lane < bs && c <= lane) HL(o + lane, o + c) = a[c];
+        if (lane == c) S.rdiag[o + c] = rr[c];
+      }
     }
     __syncthreads();
     const int r0 = o + BSUB;
@@ -306,21 +329,24 @@ __device__ int b_potrf(Smem& S, int n, double* mind_out) {
 __device__ __forceinline__ void b_trsv_warp(Smem& S, int n, double* v, bool trans) {
   const int lane = threadIdx.x & 31;
   double b0 = lane < n ? v[lane] : 0.0, b1 = lane + 32 < n ? v[lane + 32] : 0.0;
+  // selects instead of branches around the shuffles; entries already solved are simply never read again
   if (!trans) {
     for (int j = 0; j < n; ++j) {
-      double src = (j < 32) ? b0 : b1;
-      double yj = __shfl_sync(0xffffffffu, src, j & 31) * S.rdiag[j];
-      if (lane == (j & 31)) { if (j < 32) b0 = yj; else b1 = yj; }
-      if (lane > j && lane < n) b0 = fma(-HL(lane, j), yj, b0);
-      if (lane + 32 > j && lane + 32 < n) b1 = fma(-HL(lane + 32, j), yj, b1);
+      const double src = (j < 32) ? b0 : b1;
+      const double yj = __shfl_sync(0xffffffffu, src, j & 31) * S.rdiag[j];
+      const double l0 = (lane > j && lane < n) ? HL(lane, j) : 0.0;
+      const double l1 = (lane + 32 > j && lane + 32 < n) ? HL(lane + 32, j) : 0.0;
+      b0 = (lane == j) ? yj : fma(-l0, yj, b0);
+      b1 = (lane + 32 == j) ? yj : fma(-l1, yj, b1);
     }
   } else {
     for (int j = n - 1; j >= 0; --j) {
-      double src = (j < 32) ? b0 : b1;
-      double xj = __shfl_sync(0xffffffffu, src, j & 31) * S.rdiag[j];
-      if (lane == (j & 31)) { if (j < 32) b0 = xj; else b1 = xj; }
-      if (lane < j) b0 = fma(-HL(j, lane), xj, b0);
-      if (lane + 32 < j) b1 = fma(-HL(j, lane + 32), xj, b1);
+      const double src = (j < 32) ? b0 : b1;
+      const double xj = __shfl_sync(0xffffffffu, src, j & 31) * S.rdiag[j];
+      const double l0 = (lane < j) ? HL(j, lane) : 0.0;
+      const double l1 = (lane + 32 < j) ? HL(j, lane + 32) : 0.0;
+      b0 = (lane == j) ? xj : fma(-l0, xj, b0);
+      b1 = (lane + 32 == j) ? xj : fma(-l1, xj, b1);
     }
   }
   if (lane < n) v[lane] = b0;
@@ -381,10 +407,14 @@ __device__ bool b_linear_solve(Smem& S, const BatchArgs& A, const double* Hs, do
   bool have_dr = false;
   for (int attempt = 0; attempt < 2; ++attempt) {
     b_load_H(S, n, Hs, diag_add, rank1);
+    BCLK(3);
     if (!have_dr) { b_ruiz(S, A); have_dr = true; }
+    BCLK(4);
     b_scale_H(S, n, attempt ? A.P.cholRegDelta : 0.0);
     double mind;
+    BCLK(5);
     int fail = b_potrf(S, n, &mind);
+    BCLK(6);
     if (attempt == 0 && (fail || !(mind > A.P.cholMinDiag))) { *regularized = 1; continue; }
     if (fail) return false;
     if (S.pcur == 0) {
@@ -531,8 +561,11 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
       if (!b_eval(S, A, kind, obj_r, Pg, beq, t, &fval, &f0, &normGrad, &eqd)) { status = CVXB_ENOTFEASIBLE; break; }
       double eqnorm = fabs(eqd);
       while (iter < A.P.maxIter && (p ? ((nd > tol && normGrad > tol) || eqnorm > tol) : (nd > tol && normGrad > tol))) {
+        BCLK(0);
         b_hessian(S, A, kind, Pg, t);
+        BCLK(1);
         b_store_H(S, n, Hs);
+        BCLK(2);
         int reg = 0;
         bool ok = b_linear_solve(S, A, Hs, 0.0, false, S.y, eqd, tolEq, &reg);
         if (!ok) {
@@ -546,6 +579,7 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
           }
           if (!ok) { status = CVXB_ELINSOLVE; break; }
         }
+        BCLK(7);
         // q = d . grad
         double q = 0.0, c1 = 0.0, c2 = 0.0;
         if (kind == CVXB_OBJ_QUADRATIC && tid >= 128 && tid < 128 + n) {
@@ -608,11 +642,13 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
             if (it == 100) { status = CVXB_ELINESEARCH; break; }
             step = scl * tt;
           }
+          BCLK(8);
           if (tid < n) S.x[tid] = S.x[tid] + S.dir[tid] * step;
           __syncthreads();
           if (!b_eval(S, A, kind, obj_r, Pg, beq, t, &fval, &f0, &normGrad, &eqd)) { status = CVXB_ENOTFEASIBLE; break; }
           eqnorm = fabs(eqd);
           moved = true;
+          BCLK(9);
         }
         ++iter;
         if (!moved && p && ((nd > tol && normGrad > tol) || eqnorm > tol)) { iter = A.P.maxIter; break; }   // identical repeats
@@ -696,6 +732,15 @@ int cvxb_batch_create(cvxb_handle h, const cvxb_batch_desc* d, cvxb_batch* out) 
   if (st == CVXB_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) st = CVXB_ECUDA;
   if (st != CVXB_OK) { for (void* q : Bt->owned) cudaFree(q); delete Bt; return st; }
   *out = Bt;
+  return CVXB_OK;
+}
+
+int cvxb_debug_batch_clocks(long long* out, int reset) {
+  if (out) CVXB_CUDA_OK(cudaMemcpyFromSymbol(out, g_batch_clk, 12 * sizeof(long long)));
+  if (reset) {
+    long long z[12] = {0};
+    CVXB_CUDA_OK(cudaMemcpyToSymbol(g_batch_clk, z, sizeof(z)));
+  }
   return CVXB_OK;
 }
 
