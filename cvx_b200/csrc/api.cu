@@ -157,6 +157,12 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
   CVXB_CUDA_OK(cudaMallocHost((void**)&h->h_flag, NFLAG * sizeof(int)));
   CVXB_CUDA_OK(cudaEventCreate(&h->ev0));
   CVXB_CUDA_OK(cudaEventCreate(&h->ev1));
+  CVXB_CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  for (int i = 0; i < 600; ++i) {
+    cudaEvent_t e;
+    CVXB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->la_events.push_back(e);
+  }
   CVXB_CUDA_OK(cudaEventCreate(&h->gev0));
   CVXB_CUDA_OK(cudaEventCreate(&h->gev1));
   if (const char* e = getenv("CVXB_NO_GRAPHS")) h->use_graphs = (e[0] == '0' || e[0] == 0) ? 1 : 0;
@@ -175,6 +181,8 @@ int cvxb_destroy(cvxb_handle h) {
   cudaFreeHost(h->h_scal); cudaFreeHost(h->h_flag);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->gev0); cudaEventDestroy(h->gev1);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->la_events) cudaEventDestroy(e);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return CVXB_OK;

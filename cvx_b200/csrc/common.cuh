@@ -54,6 +54,8 @@ struct cvxb_handle_s {
   int* h_flag = nullptr;
   double* d_part = nullptr;   // partial-sum scratch for split reductions (PART_DOUBLES doubles)
   unsigned* d_ticket = nullptr;  // last-block-done counters
+  cudaStream_t stream2 = nullptr;            // look-ahead stream of the blocked Cholesky
+  std::vector<cudaEvent_t> la_events;        // fork / join events of the look-ahead schedule
   int* wave_ready = nullptr;     // per-block "y_k published" flags of the wavefront triangular solves
   void* kkt_cache = nullptr;     // cvxb::KktWork of the last seam-B call (re-used when (n,p) repeat)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -134,8 +136,10 @@ struct GemmArgs {
   double alpha, beta;
   int tri;
   int tile = 0;   // 0 = choose 128 / 64 / 32 by grid size; in-place callers (C aliases A or B) must pin 128
+  bool lower_only = false;   // rectangular C whose rows and columns share an origin: never write elements with m < n
 };
 int gemm_dmma(Handle& h, const GemmArgs& g);
+int gemm_dmma_on(Handle& h, const GemmArgs& g, cudaStream_t st);   // same, on another stream of the handle
 // gemm_dmma bracketed by CUDA events when the handle's profiling is on (flops = algorithmic flops)
 int gemm_dmma_timed(Handle& h, const GemmArgs& g, double flops);
 int gemm_dmma_init();   // sets the dynamic-smem attribute on all instantiations (once per device)

@@ -9,6 +9,10 @@
 #include "common.cuh"
 
 namespace cvxb {
+
+int potrf_lookahead(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0);
+int rl_max_n();
+
 namespace {
 
 // ------------------------------------------------------------------------------------------- Ruiz
@@ -435,21 +439,27 @@ int trsm_right_lt(Handle& h, int M, int n1, const double* L, int ldl, const doub
                        lda);
 }
 
-int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0) {
+// Recursive halving; sub-problems that fit the L2-resident regime switch to the look-ahead schedule.
+int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0, bool plain = false) {
+  if (!plain && n > NB && n <= rl_max_n() && h.stream2)
+    return potrf_lookahead(h, n, A, lda, invD, flag_slot, mindiag_slot, col0);
   if (n <= NB) {
     CVXB_LAUNCH(h, leaf_kernel<true>, 1, LEAF_THREADS, LEAF_SMEM, n, n, A, lda, invD, h.d_flag, h.d_scal, flag_slot,
                 mindiag_slot, col0);
     return CVXB_OK;
   }
   int a = split_point(n), b = n - a;
-  CVXB_TRY(potrf_rec(h, a, A, lda, invD, flag_slot, mindiag_slot, col0));
+  CVXB_TRY(potrf_rec(h, a, A, lda, invD, flag_slot, mindiag_slot, col0, plain));
   double* A21 = A + a;
   double* A22 = A + (size_t)a * lda + a;
   CVXB_TRY(trsm_right_lt(h, b, a, A, lda, invD, A21, lda));
   // A22 -= A21 A21'  lower: A(m,k) = A21[k*lda + m] (M contiguous), B(k,n) = A21(n,k) (N contiguous)
   GemmArgs g{b, b, a, A21, lda, false, A21, lda, false, A22, lda, -1.0, 1.0, 1};
   CVXB_TRY(gemm_dmma(h, g));
-  return potrf_rec(h, b, A22, lda, invD + (size_t)(a / NB) * NB * NB, flag_slot, mindiag_slot, col0 + a);
+  return potrf_rec(h, b, A22, lda, invD + (size_t)(a / NB) * NB * NB, flag_slot, mindiag_slot, col0 + a, plain);
+}
+int potrf_rec_plain(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0) {
+  return potrf_rec(h, n, A, lda, invD, flag_slot, mindiag_slot, col0, true);
 }
 
 int trsm_rec(Handle& h, int n, int r, const double* L, int ldl, const double* invD, double* B, int ldb, bool trans) {
@@ -818,6 +828,70 @@ int scaled_full(Handle& h, int n, const double* Hm, int ldh, const double* d, do
   if (n <= 0) return CVXB_OK;
   CVXB_LAUNCH(h, scaled_lower_kernel, dim3((n + 127) / 128, ygrid(n)), 128, 0, n, Hm, ldh, d, 0.0, Q, ldq, 1);
   return CVXB_OK;
+}
+
+// Right-looking blocked Cholesky with look-ahead for matrices that stay in L2 (n <= RL_MAX_N): per 128-column
+// step the critical chain is  leaf -> panel solve -> update of the NEXT column block  on the main stream, while
+// the bulk of the trailing update runs on a second stream, overlapped with the next leaf (which occupies a
+// single SM).  Fork / join by events, so the whole schedule is capturable into the per-step CUDA graph.
+int potrf_lookahead(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0) {
+  const int nblk = (n + NB - 1) / NB;
+  if (2 * nblk + 2 > (int)h.la_events.size()) return potrf_rec_plain(h, n, A, lda, invD, flag_slot, mindiag_slot, col0);
+  cudaStream_t sa = h.stream, sb = h.stream2;
+  bool forked = false;
+  for (int k = 0; k < nblk; ++k) {
+    const int k0 = k * NB, kb = n - k0 < NB ? n - k0 : NB;
+    const int rem = n - k0 - kb;
+    double* Akk = A + (size_t)k0 * lda + k0;
+    CVXB_LAUNCH(h, leaf_kernel<true>, 1, LEAF_THREADS, LEAF_SMEM, kb, kb, Akk, lda, invD + (size_t)k * NB * NB, h.d_flag,
+                h.d_scal, flag_slot, mindiag_slot, col0 + k0);
+    if (rem <= 0) break;
+    double* A21 = Akk + kb;                                   // rows below the diagonal block, this column block
+    CVXB_TRY(trsm_right_lt(h, rem, kb, Akk, lda, invD + (size_t)k * NB * NB, A21, lda));
+    const int kn = rem < NB ? rem : NB;                       // width of the next column block
+    const int rem2 = rem - kn;
+    cudaEvent_t evP = h.la_events[2 * k], evB = h.la_events[2 * k + 1];
+    if (rem2 > 0) CVXB_CUDA_OK(cudaEventRecord(evP, sa));     // panel k ready
+    if (forked) CVXB_CUDA_OK(cudaStreamWaitEvent(sa, h.la_events[2 * (k - 1) + 1], 0));   // bulk update k-1 done
+    forked = false;
+    // look-ahead: column block k+1 only (rows and columns share the origin k0+kb: keep the upper triangle untouched)
+    double* Anext = A + (size_t)(k0 + kb) * lda + (k0 + kb);
+    GemmArgs gl{rem, kn, kb, A21, lda, false, A21, lda, false, Anext, lda, -1.0, 1.0, 0};
+    gl.lower_only = true;
+    CVXB_TRY(gemm_dmma(h, gl));
+    if (rem2 > 0) {
+      // bulk of the trailing update on the second stream
+      CVXB_CUDA_OK(cudaStreamWaitEvent(sb, evP, 0));
+      double* A31 = A21 + kn;
+      double* A33 = A + (size_t)(k0 + kb + kn) * lda + (k0 + kb + kn);
+      GemmArgs gb{rem2, rem2, kb, A31, lda, false, A31, lda, false, A33, lda, -1.0, 1.0, 1};
+      CVXB_TRY(gemm_dmma_on(h, gb, sb));
+      CVXB_CUDA_OK(cudaEventRecord(evB, sb));
+      forked = true;
+      if (k + 1 == nblk - 1 || rem2 <= 0) {}
+    }
+  }
+  // join (the last bulk update targets blocks that the remaining steps wait for anyway; a dangling fork must not survive)
+  for (int k = 0; k < nblk; ++k) (void)k;
+  if (forked) {
+    int last = -1;
+    for (int k = 0; k < nblk; ++k) {
+      const int rem = n - k * NB - (n - k * NB < NB ? n - k * NB : NB);
+      const int kn = rem < NB ? rem : NB;
+      if (rem - kn > 0) last = k;
+    }
+    if (last >= 0) CVXB_CUDA_OK(cudaStreamWaitEvent(sa, h.la_events[2 * last + 1], 0));
+  }
+  return CVXB_OK;
+}
+
+int rl_max_n() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CVXB_RL_MAX_N");
+    v = e ? atoi(e) : 4608;
+  }
+  return v;
 }
 
 int potrf_lower(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot) {

@@ -71,7 +71,7 @@ __device__ __forceinline__ void load_tile(double* dst, const double* __restrict_
 template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (BM >= 128 ? 1 : 2))
 gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
-                 double* __restrict__ C, int ldc, double alpha, double beta, int tri, int tiles_m) {
+                 double* __restrict__ C, int ldc, double alpha, double beta, int tri, int tiles_m, int lower_only) {
   constexpr int NTHR = WARPS_M * WARPS_N * 32;
   constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
   constexpr int MT = WM / 8, NTL = WN / 8;
@@ -92,6 +92,7 @@ gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, con
     bn = blockIdx.x / tiles_m;
   }
   const int m0 = bm * BM, n0 = bn * BN;
+  if (lower_only && m0 + BM <= n0) return;      // tile entirely above the diagonal
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wm0 = (warp % WARPS_M) * WM, wn0 = (warp / WARPS_M) * WN;
@@ -147,7 +148,7 @@ gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, con
   cp_async_wait<0>();
 
   // epilogue: thread (g,t) of tile (i,j) holds C(m, n), C(m, n+1), m = ..+g, n = ..+2t
-  const bool diag = tri && (bm == bn);
+  const bool diag = (tri && (bm == bn)) || lower_only;
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
     int m = m0 + wm0 + i * 8 + g;
@@ -172,15 +173,17 @@ gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, con
 template <int BM, int WARPS_M, int WARPS_N>
 constexpr int smem_bytes() { return STAGES * 2 * TileElems<BM>::value * (int)sizeof(double); }
 
+thread_local cudaStream_t g_gemm_stream = nullptr;     // set by gemm_dmma_on for the duration of one call
+
 template <int BM, int WARPS_M, int WARPS_N, bool A_KC, bool B_KC>
 int launch(Handle& h, const GemmArgs& g) {
-  cudaStream_t st = h.stream;
+  cudaStream_t st = g_gemm_stream ? g_gemm_stream : h.stream;
   int tm = (g.M + BM - 1) / BM, tn = (g.N + BM - 1) / BM;
   long long grid = g.tri ? (long long)tm * (tm + 1) / 2 : (long long)tm * tn;
   if (grid <= 0) return CVXB_OK;
   gemm_dmma_kernel<BM, BM, WARPS_M, WARPS_N, A_KC, B_KC>
       <<<(unsigned)grid, WARPS_M * WARPS_N * 32, smem_bytes<BM, WARPS_M, WARPS_N>(), st>>>(
-          g.M, g.N, g.K, g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.alpha, g.beta, g.tri, tm);
+          g.M, g.N, g.K, g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.alpha, g.beta, g.tri, tm, g.lower_only ? 1 : 0);
   h.launches++;
   CVXB_CUDA_OK(cudaGetLastError());
   return CVXB_OK;
@@ -273,6 +276,13 @@ int gemm_dmma_timed(Handle& h, const GemmArgs& g, double flops) {
   h.prof_used += 2;
   h.prof_flops += flops;
   return st;
+}
+
+int gemm_dmma_on(Handle& h, const GemmArgs& g, cudaStream_t st) {
+  g_gemm_stream = st;
+  int r = gemm_dmma(h, g);
+  g_gemm_stream = nullptr;
+  return r;
 }
 
 int gemm_dmma(Handle& h, const GemmArgs& g) {
