@@ -62,6 +62,7 @@ struct cvxb_handle_s {
   // optional per-launch timing of the dominant kernel (Hessian-assembly SYRK), bench.py roofline
   // CUDA-graph replay of the fixed per-step launch sequence
   bool capturing = false;
+  double capture_flops = 0.0;                   // algorithmic flops of the timed SYRK inside the step being captured
   cudaEvent_t gev0 = nullptr, gev1 = nullptr;   // external events around the SYRK inside a captured step
   double prof_ms_graph = 0.0;
   long long prof_launches_graph = 0;

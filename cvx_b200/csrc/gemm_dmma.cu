@@ -260,6 +260,7 @@ int gemm_dmma_timed(Handle& h, const GemmArgs& g, double flops) {
     CVXB_CUDA_OK(cudaEventRecordWithFlags(h.gev0, h.stream, cudaEventRecordExternal));
     int st = gemm_dmma(h, g);
     CVXB_CUDA_OK(cudaEventRecordWithFlags(h.gev1, h.stream, cudaEventRecordExternal));
+    h.capture_flops += flops;
     return st;
   }
   if (!h.prof_on) return gemm_dmma(h, g);

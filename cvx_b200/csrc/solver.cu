@@ -504,8 +504,10 @@ int run_step(cvxb_problem_s* P, const cvxb_params& pars, double t, int mode, int
     cudaGraph_t graph = nullptr;
     CVXB_CUDA_OK(cudaStreamBeginCapture(h.stream, cudaStreamCaptureModeThreadLocal));
     h.capturing = true;
+    h.capture_flops = 0.0;
     int st = enqueue_step(P, pars, t, mode, iter0, h.d_scal + S_T);
     h.capturing = false;
+    P->graph_flops[mode] = h.capture_flops;
     cudaError_t e = cudaStreamEndCapture(h.stream, &graph);
     if (st != CVXB_OK || e != cudaSuccess || !graph) {
       if (graph) cudaGraphDestroy(graph);
@@ -531,11 +533,16 @@ int run_step(cvxb_problem_s* P, const cvxb_params& pars, double t, int mode, int
 }
 
 // after the step's status read: fold the SYRK's external event pair into the profile
-static void graph_profile_tick(Handle& h) {
+static void graph_profile_tick(Handle& h, double flops) {
   if (!h.use_graphs || !h.prof_on) return;
   float ms = 0;
-  if (cudaEventElapsedTime(&ms, h.gev0, h.gev1) == cudaSuccess) { h.prof_ms_graph += ms; h.prof_launches_graph++; }
-  else cudaGetLastError();
+  if (cudaEventElapsedTime(&ms, h.gev0, h.gev1) == cudaSuccess) {
+    h.prof_ms_graph += ms;
+    h.prof_launches_graph++;
+    h.prof_flops += flops;
+  } else {
+    cudaGetLastError();
+  }
 }
 
 struct InnerResult {
@@ -580,7 +587,7 @@ int inner_solve_eq(cvxb_problem_s* P, const cvxb_params& pars, double t, RunStat
     if (rs.limited && rs.budget <= 0) break;
     CVXB_TRY(run_step(P, pars, t, 0, 0));
     CVXB_TRY(fetch_status(h));
-    graph_profile_tick(h);
+    graph_profile_tick(h, P->graph_flops[0]);
     if (h.h_flag[F_BAD]) {
       // optimistic attempt refused on the device (x untouched): walk the reference's fallback chain
       cvxb_kkt_info info;
@@ -628,7 +635,7 @@ int inner_solve_uncon(cvxb_problem_s* P, const cvxb_params& pars, double t, RunS
     if (rs.limited && rs.budget <= 0) break;
     CVXB_TRY(run_step(P, pars, t, 1, R.iter == 0));
     CVXB_TRY(fetch_status(h));
-    graph_profile_tick(h);
+    graph_profile_tick(h, P->graph_flops[1]);
     if (h.h_flag[F_BAD]) {
       cvxb_kkt_info info;
       int st = chol_solve_retry(h, P->kw, pars, P->H, P->ldn, P->y, -1.0, pars.tolEqSolve, P->dir, &info);

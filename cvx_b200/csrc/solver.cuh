@@ -32,6 +32,7 @@ struct cvxb_problem_s {
   cvxb::KktWork kw;
   cudaGraphExec_t step_graph[2] = {nullptr, nullptr};   // captured Newton step: [0] with equalities, [1] without
   long long graph_launches[2] = {0, 0};
+  double graph_flops[2] = {0.0, 0.0};
   cvxb_params graph_pars;
   cvxb_problem_s* phase1 = nullptr;   // the n+1 dimensional feasibility problem (built on demand)
   std::vector<void*> owned;
