@@ -14,7 +14,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libcvxb.so")
 
-NVCC_FLAGS = (["-DCVXB_LEAF_TIMING=1"] if os.environ.get("CVXB_LEAF_TIMING") else []) + (["-DCVXB_BATCH_TIMING=1"] if os.environ.get("CVXB_BATCH_TIMING") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = (["-DCVXB_LEAF_TIMING=1"] if os.environ.get("CVXB_LEAF_TIMING") else []) + (["-DCVXB_BATCH_TIMING=1"] if os.environ.get("CVXB_BATCH_TIMING") else []) + (os.environ.get("CVXB_EXTRA_NVCC", "").split()) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
               "-diag-suppress", "177"]
 

@@ -6,7 +6,7 @@
 //   * panel / TRSM updates  B2  -= L21 Y1          (NN)          KKTSystem.scala:116-124 (dtrtrs)
 //   * Schur complement      S  = Y' Y              (TN, tri=2)   KKTSystem.scala:126-139
 //
-// Three CTA tile shapes share one templated mainloop (k-slab 16, 4-stage cp.async ring):
+// Three CTA tile shapes share one templated mainloop (k-slab 32, 3-stage cp.async ring; 16 x 4 stages measured 3% slower):
 //   128x128, 8 warps (2x4), warp tile 64x32 = 8x4 DMMA tiles: each k4-step issues 12 LDS.64 for 32 DMMA
 //            (shared-memory pipe ~19% busy, the tensor pipe is the limiter) -- the big contractions;
 //    64x64,  4 warps (2x2), warp tile 32x32;   32x32, 4 warps (2x2), warp tile 16x16 -- the small GEMMs
@@ -14,15 +14,21 @@
 //            SMs idle and a single CTA would walk the whole K range alone.
 // Operands are staged global->shared with 16-byte cp.async (zero-fill predication at the edges);
 // padded shared layouts make every fragment load bank-conflict free:
-//   K-contiguous operand: [R][16+4] doubles  -> bank = 8*g + 2*t   (g = lane/4, t = lane%4)
-//   M-contiguous operand: [16][R+4] doubles  -> bank = 8*t + 2*g
+//   K-contiguous operand: [R][BK+4] doubles  -> bank = 8*g + 2*t   (g = lane/4, t = lane%4)
+//   M-contiguous operand: [BK][R+4] doubles  -> bank = 8*t + 2*g
 #include "common.cuh"
 
 namespace cvxb {
 
 namespace {
 
-constexpr int BK = 16, STAGES = 4;
+#ifndef CVXB_BK
+#define CVXB_BK 32
+#endif
+#ifndef CVXB_STAGES
+#define CVXB_STAGES 3
+#endif
+constexpr int BK = CVXB_BK, STAGES = CVXB_STAGES;
 constexpr int KC_LD = BK + 4;               // K-contiguous tile row stride (doubles)
 
 template <int R> struct TileElems { static constexpr int value = (R * KC_LD > BK * (R + 4)) ? R * KC_LD : BK * (R + 4); };
@@ -51,7 +57,7 @@ __device__ __forceinline__ void load_tile(double* dst, const double* __restrict_
   for (int it = 0; it < (R * BK / 2) / NTHR; ++it) {
     int c = tid + it * NTHR;
     if (KC) {
-      int r = c >> 3, kc = (c & 7) * 2;
+      int r = c / (BK / 2), kc = (c % (BK / 2)) * 2;
       int gr = r0 + r, gk = k0 + kc;
       int bytes = 0;
       if (gr < rows) { int rem = (kext - gk) * 8; bytes = rem < 0 ? 0 : (rem > 16 ? 16 : rem); }
@@ -250,6 +256,7 @@ int dmma_peak_probe(Handle& h, int iters, double* ms, double* flops) {
 
 int gemm_dmma_init() {
   CVXB_TRY((set_attr<128, 2, 4>()));
+  CVXB_TRY((set_attr<128, 4, 4>()));
   CVXB_TRY((set_attr<64, 2, 2>()));
   CVXB_TRY((set_attr<32, 2, 2>()));
   return CVXB_OK;
@@ -304,7 +311,10 @@ int gemm_dmma(Handle& h, const GemmArgs& g) {
   const long long want = (long long)h.sm_count * 3 / 4;
   int tile = g.tile;
   if (tile == 0) tile = ntiles(128) >= want ? 128 : (ntiles(64) >= want ? 64 : 32);
-  if (tile == 128) return launch_layout<128, 2, 4>(h, g);
+  if (tile == 128) {
+    static const int w16 = getenv("CVXB_GEMM_16WARPS") ? 1 : 0;
+    return w16 ? launch_layout<128, 4, 4>(h, g) : launch_layout<128, 2, 4>(h, g);
+  }
   if (tile == 64) return launch_layout<64, 2, 2>(h, g);
   return launch_layout<32, 2, 2>(h, g);
 }
