@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcvxb.so")
 # cvxb_status
 OK, ELINSOLVE, EUNSOLVABLE, ELINESEARCH, ENOTFEASIBLE, EINFEASIBLE, EDIM, ENOTSYMMETRIC, ECUDA, EINVAL, ENOTIMPL = range(11)
 FLAG_DEVICE_PTRS = 1
-OBJ_LINEAR, OBJ_QUADRATIC, OBJ_KL = 0, 1, 2
+OBJ_LINEAR, OBJ_QUADRATIC, OBJ_KL, OBJ_KLDUAL = 0, 1, 2, 3
 
 
 # ---- exceptions: the reference's exception types (SURVEY.md 8b "Error conventions") ----------------
@@ -90,7 +90,8 @@ class ProblemDesc(C.Structure):
     _fields_ = [("n", C.c_int), ("m", C.c_int), ("p", C.c_int), ("objective", C.c_int), ("obj_a", _dp),
                 ("obj_r", C.c_double), ("obj_P", _dp), ("obj_ldP", C.c_int), ("G", _dp), ("ldg", C.c_int),
                 ("g_r", _dp), ("ub", _dp), ("A", _dp), ("lda", C.c_int), ("b", _dp), ("x_feasible", _dp),
-                ("x_defined", _dp), ("mq", C.c_int), ("q_P", _dp), ("q_a", _dp), ("q_r", _dp), ("q_ub", _dp)]
+                ("x_defined", _dp), ("mq", C.c_int), ("q_P", _dp), ("q_a", _dp), ("q_r", _dp), ("q_ub", _dp),
+                ("obj_k", C.c_int), ("obj_R", _dp)]
 
 
 class SolutionC(C.Structure):
@@ -140,6 +141,7 @@ SYMBOLS = {
     "cvxb_triangular_solve": (C.c_int, [_vp, C.c_char, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int]),
     "cvxb_problem_create": (C.c_int, [_vp, C.POINTER(ProblemDesc), C.POINTER(_vp)]),
     "cvxb_problem_destroy": (C.c_int, [_vp]),
+    "cvxb_kldual_primal_optimum": (C.c_int, [_vp, _vp, _vp]),
     "cvxb_phase1": (C.c_int, [_vp, _vp, C.POINTER(Params), _vp, C.POINTER(SolutionC)]),
     "cvxb_barrier_solve": (C.c_int, [_vp, _vp, C.POINTER(Params), C.POINTER(SolutionC)]),
     "cvxb_pd_solve": (C.c_int, [_vp, _vp, C.POINTER(Params), C.POINTER(SolutionC)]),

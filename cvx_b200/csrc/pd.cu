@@ -16,7 +16,7 @@ using namespace cvxb;
 
 namespace cvxb {
 
-int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s** out, int mq);
+int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s** out, int mq, int kd);
 int quad_refresh(cvxb_problem_s* P);
 int quad_direction(cvxb_problem_s* P, const double* dir);
 int quad_hessian_terms(cvxb_problem_s* P, const double* c);
@@ -376,6 +376,11 @@ int pd_loop(cvxb_problem_s* P, const cvxb_params& pars, cvxb_solution* out) {
   const bool withEqs = p > 0;
   const bool bug = pars.bugCompat && withEqs;
   const double mu = pars.mu, tol = pars.tolSolver;
+  if (P->objective == CVXB_OBJ_KLDUAL) {
+    set_last_error("PrimalDualSolver on the dual KL objective is not built on the device: the residual line search needs "
+                   "grad f(z + s dz) = w - B (R o exp(-B'(z + s dz))), a GEMV per trial; use the barrier solver");
+    return CVXB_ENOTIMPL;
+  }
   CVXB_TRY(pd_alloc(P));
   // lam0 = -1/(g(x0)-ub), nu0 = 0
   CVXB_TRY(quad_refresh(P));

@@ -24,12 +24,13 @@ constexpr double IN_SET_FACTOR = 1.0 + 3e-16;   // Constraint.isSatisfiedStrictl
 // ---- objective families (device) -------------------------------------------------------------------
 // value needs a.x / x.Px/2 / sum x log(n x): partial term of entry j
 __device__ __forceinline__ double obj_term(int kind, int n, int j, double xj, const double* a, const double* Px) {
-  if (kind == CVXB_OBJ_LINEAR) return a[j] * xj;
+  if (kind == CVXB_OBJ_LINEAR || kind == CVXB_OBJ_KLDUAL) return a[j] * xj;    // dual: w'z here, sum_j y_j added by the caller
   if (kind == CVXB_OBJ_QUADRATIC) return a[j] * xj + 0.5 * xj * Px[j];
   return xj * log(xj * (double)n);   // Dist_KL.scala:225-227
 }
 __device__ __forceinline__ double obj_grad(int kind, int n, int j, double xj, const double* a, const double* Px) {
   if (kind == CVXB_OBJ_LINEAR) return a[j];
+  if (kind == CVXB_OBJ_KLDUAL) return a[j] - Px[j];      // w - B y   (Px holds B y)
   if (kind == CVXB_OBJ_QUADRATIC) return a[j] + Px[j];
   return 1.0 + log(xj) + log((double)n);   // Dist_KL.scala:229-233
 }
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(VT) eval_cnt_kernel(int m, int n, int kind, do
                                                       double* __restrict__ gx, double* __restrict__ inv,
                                                       const double* __restrict__ x, const double* __restrict__ a,
                                                       const double* __restrict__ Px, const double* __restrict__ qcorr,
-                                                      double* scal, int* flag) {
+                                                      const double* __restrict__ dual_y, int kd, double* scal, int* flag) {
   __shared__ double buf[33];
   __shared__ int ibuf[33];
   if (t_dev) t = *t_dev;        // barrier parameter kept on the device when the step is replayed from a CUDA graph
@@ -61,6 +62,8 @@ __global__ void __launch_bounds__(VT) eval_cnt_kernel(int m, int n, int kind, do
   bad = block_or(bad, ibuf);
   double f0 = 0.0;
   for (int j = threadIdx.x; j < n; j += VT) f0 += obj_term(kind, n, j, x[j], a, Px);
+  if (kind == CVXB_OBJ_KLDUAL)
+    for (int j = threadIdx.x; j < kd; j += VT) f0 += dual_y[j];      // + R'exp(-B'z)
   f0 = block_sum(f0, buf) + obj_r;
   if (threadIdx.x == 0) {
     scal[S_LOGSUM] = ls;
@@ -107,6 +110,8 @@ struct LsArgs {
   const double *gx, *ub, *Gd, *a, *Px, *Pd, *y;
   const double* qq;      // d'P_k d / 2 on quadratic rows (NULL without quadratic constraints)
   const double* t_dev;   // non-NULL: t and the first-step flag live on the device (CUDA-graph replay)
+  const double *dual_y, *dual_v;   // CVXB_OBJ_KLDUAL: y = R o exp(-B'z), v = B'd ; f(z + s d) = w'z + s w'd + sum y_j exp(-s v_j)
+  int kd;
   double *x, *dir;
 };
 
@@ -140,6 +145,10 @@ __device__ double ls_value(const LsArgs& A, double s, double f0, double c1, doub
       v += xj * log(xj * (double)A.n);
     }
     f0s = block_sum(v, buf);
+  } else if (A.kind == CVXB_OBJ_KLDUAL) {
+    double v = 0.0;
+    for (int j = threadIdx.x; j < A.kd; j += VT) v += A.dual_y[j] * exp(-s * A.dual_v[j]);
+    f0s = f0 + s * c1 + block_sum(v, buf) - c2;     // c1 = w'd, c2 = sum_j y_j (so that f0 + ... replaces the exp term)
   } else {
     f0s = f0 + s * c1 + 0.5 * s * s * c2;   // exact along the ray for linear / quadratic objectives
   }
@@ -155,9 +164,11 @@ __global__ void __launch_bounds__(VT) linesearch_kernel(LsArgs A, double* scal, 
   for (int j = threadIdx.x; j < A.n; j += VT) {
     double dj = A.dir[j];
     q = fma(dj, A.y[j], q);
-    if (A.kind == CVXB_OBJ_LINEAR) c1 = fma(A.a[j], dj, c1);
+    if (A.kind == CVXB_OBJ_LINEAR || A.kind == CVXB_OBJ_KLDUAL) c1 = fma(A.a[j], dj, c1);
     else if (A.kind == CVXB_OBJ_QUADRATIC) { c1 = fma(A.a[j] + A.Px[j], dj, c1); c2 = fma(dj, A.Pd[j], c2); }
   }
+  if (A.kind == CVXB_OBJ_KLDUAL)
+    for (int j = threadIdx.x; j < A.kd; j += VT) c2 += A.dual_y[j];
   q = block_sum(q, buf);
   c1 = block_sum(c1, buf);
   c2 = block_sum(c2, buf);
@@ -223,6 +234,21 @@ __global__ void __launch_bounds__(VT) linesearch_kernel(LsArgs A, double* scal, 
     flag[F_STEP_TAKEN] = taken;
     if (!upstream_bad) flag[F_ITER0] = 0;       // the next step of this stage is not the first any more
   }
+}
+
+// ---- dual KL objective ------------------------------------------------------------------------------
+// y_j = R_j exp(-u_j), u = B'z        (Dist_KL.scala:143-147, primalOptimum :163)
+__global__ void dual_y_kernel(int kd, const double* __restrict__ R, const double* __restrict__ u, double* __restrict__ y) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < kd) y[j] = R[j] * exp(-u[j]);
+}
+// Bs(:, j) = B(:, j) * sqrt(t y_j): then t * hess = Bs Bs'   (Dist_KL.scala:152-159)
+__global__ void dual_scale_cols_kernel(int D, int kd, const double* __restrict__ B, int ldb, const double* __restrict__ y,
+                                       double t, const double* __restrict__ t_dev, double* __restrict__ Bs, int ldbs) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  if (t_dev) t = *t_dev;
+  for (int j = blockIdx.y; j < kd; j += gridDim.y) Bs[(size_t)j * ldbs + i] = B[(size_t)j * ldb + i] * sqrt(t * y[j]);
 }
 
 // ---- quadratic constraints ------------------------------------------------------------------------
@@ -341,7 +367,7 @@ int palloc(cvxb_problem_s* P, T** ptr, size_t count) {
 
 // --------------------------------------------------------------------------------- problem objects
 // m = number of LINEAR constraints; the problem carries m + mq rows in every per-constraint vector
-int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s** out, int mq) {
+int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s** out, int mq, int kd) {
   cvxb_problem_s* P = new cvxb_problem_s();
   P->h = &h;
   P->mlin = m; P->mq = mq; P->ldq = pad_ld(n);
@@ -353,6 +379,7 @@ int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s*
     const size_t ldm = P->ldm, ldn = P->ldn, ldp = P->ldp;
     size_t d = 2 * ldm * n + ldn * n * (objective == CVXB_OBJ_QUADRATIC ? 2 : 1) + ldp * n + 7 * ldm + 10 * ldn + 4 * ldp;
     if (mq > 0) d += (size_t)mq * P->ldq * (n + 3) + 4 * 32;
+    if (objective == CVXB_OBJ_KLDUAL) d += 2 * ldn * (size_t)kd + 4 * (size_t)pad_ld(kd) + 6 * 32;
     size_t bytes = d * sizeof(double) + 64 * 256 + kkt_work_bytes(n, p);
     void* base = nullptr;
     if (cudaMalloc(&base, bytes) == cudaSuccess) {
@@ -372,6 +399,11 @@ int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s*
   A(&P->x, P->ldn); A(&P->gx, P->ldm); A(&P->inv, P->ldm); A(&P->Gd, P->ldm); A(&P->y, P->ldn); A(&P->gt, P->ldn);
   A(&P->dir, P->ldn); A(&P->nu, P->ldp); A(&P->eqdiff, P->ldp); A(&P->Px, P->ldn); A(&P->Pd, P->ldn); A(&P->axv, P->ldp);
   A(&P->Gs, (size_t)P->ldm * n); A(&P->H, (size_t)P->ldn * n);
+  if (objective == CVXB_OBJ_KLDUAL) {
+    P->kd = kd; P->ldk = pad_ld(kd);
+    A(&P->obj_P, (size_t)P->ldn * kd); A(&P->Bs, (size_t)P->ldn * kd);
+    A(&P->objR, P->ldk); A(&P->du, P->ldk); A(&P->dy, P->ldk); A(&P->dv, P->ldk);
+  }
   if (mq > 0) {
     A(&P->Pq, (size_t)mq * P->ldq * n); A(&P->qa, (size_t)mq * P->ldq); A(&P->PX, (size_t)mq * P->ldq);
     A(&P->PDv, (size_t)mq * P->ldq); A(&P->qcorr, P->ldm); A(&P->qq, P->ldm);
@@ -431,8 +463,13 @@ int barrier_eval(cvxb_problem_s* P, double t, const double* t_dev = nullptr) {
   CVXB_TRY(quad_refresh(P));
   CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->x, 0.0, P->gx));
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->Px));
+  if (P->objective == CVXB_OBJ_KLDUAL) {     // u = B'z, y = R o exp(-u), Px := B y
+    CVXB_TRY(gemv_t(h, n, P->kd, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->du));
+    CVXB_LAUNCH(h, dual_y_kernel, (P->kd + 255) / 256, 256, 0, P->kd, P->objR, P->du, P->dy);
+    CVXB_TRY(gemv_n(h, n, P->kd, 1.0, P->obj_P, P->ldn, P->dy, 0.0, P->Px));
+  }
   CVXB_LAUNCH(h, eval_cnt_kernel, 1, VT, 0, m, n, P->objective, P->obj_r, t, t_dev, P->gr, P->ub, P->gx, P->inv, P->x,
-              P->obj_a, P->Px, P->qcorr, h.d_scal, h.d_flag);
+              P->obj_a, P->Px, P->qcorr, P->dy, P->kd, h.d_scal, h.d_flag);
   CVXB_TRY(gemv_t(h, m, n, 1.0, P->G, P->ldm, P->inv, 0.0, P->gt));
   if (p > 0) CVXB_TRY(gemv_n(h, p, n, 1.0, P->A, P->ldp, P->x, 0.0, P->axv));
   CVXB_LAUNCH(h, eval_grad_kernel, 1, VT, 0, n, p, P->objective, t, t_dev, P->x, P->obj_a, P->Px, P->gt, P->y, P->b, P->axv,
@@ -448,6 +485,13 @@ int barrier_hessian(cvxb_problem_s* P, double t, const double* t_dev = nullptr) 
   CVXB_TRY(scale_rows(h, m, n, P->G, P->ldm, P->inv, P->Gs, P->ldm, false));
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(fill_matrix(h, n, tv, P->obj_P, P->ldn, nullptr, 0.0, P->H, P->ldn, t_dev));
   else if (P->objective == CVXB_OBJ_KL) CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, tv, P->H, P->ldn, t_dev));
+  else if (P->objective == CVXB_OBJ_KLDUAL) {
+    // t * B diag(y) B'  as one more weighted SYRK (contraction length = primal dimension), mirrored: exactly symmetric
+    CVXB_LAUNCH(h, dual_scale_cols_kernel, dim3((n + 127) / 128, P->kd > 1024 ? 1024 : P->kd), 128, 0, n, P->kd, P->obj_P,
+                P->ldn, P->dy, t, t_dev, P->Bs, P->ldn);
+    GemmArgs gd{n, n, P->kd, P->Bs, P->ldn, false, P->Bs, P->ldn, false, P->H, P->ldn, 1.0, 0.0, 2};
+    CVXB_TRY(gemm_dmma(h, gd));
+  }
   else CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, nullptr, 0.0, P->H, P->ldn));
   CVXB_TRY(quad_hessian_terms(P, P->inv));     // + hess g_k / d_k   (BarrierSolver.scala:313)
   GemmArgs g{n, n, m, P->Gs, P->ldm, true, P->Gs, P->ldm, true, P->H, P->ldn, 1.0, 1.0, 2};
@@ -461,11 +505,13 @@ int enqueue_linesearch(cvxb_problem_s* P, const cvxb_params& pars, double t, int
   CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->dir, 0.0, P->Gd));
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->dir, 0.0, P->Pd));
   CVXB_TRY(quad_direction(P, P->dir));
+  if (P->objective == CVXB_OBJ_KLDUAL) CVXB_TRY(gemv_t(h, n, P->kd, 1.0, P->obj_P, P->ldn, P->dir, 0.0, P->dv));
   LsArgs A;
   A.m = m; A.n = n; A.kind = P->objective; A.mode = mode; A.iter0 = iter0;
   A.t = t; A.alpha = pars.alpha; A.beta = pars.beta; A.tol = pars.tolSolver;
   A.gx = P->gx; A.ub = P->ub; A.Gd = P->Gd; A.a = P->obj_a; A.Px = P->Px; A.Pd = P->Pd; A.y = P->y;
   A.x = P->x; A.dir = P->dir; A.qq = P->mq > 0 ? P->qq : nullptr; A.t_dev = t_dev;
+  A.dual_y = P->dy; A.dual_v = P->dv; A.kd = P->kd;
   CVXB_LAUNCH(h, linesearch_kernel, 1, VT, 0, A, h.d_scal, h.d_flag);
   return CVXB_OK;
 }
@@ -726,7 +772,7 @@ int run_phase1(cvxb_problem_s* P, const cvxb_params& pars, RunStats& rs, cvxb_so
   const int n = P->n, m = P->mlin, p = P->p, mq = P->mq;
   const int m1 = m + 2 * p;             // linear rows of the feasibility problem; its quadratic rows follow
   if (!P->phase1) {
-    CVXB_TRY(problem_alloc(h, n + 1, m1, 0, CVXB_OBJ_LINEAR, &P->phase1, mq));
+    CVXB_TRY(problem_alloc(h, n + 1, m1, 0, CVXB_OBJ_LINEAR, &P->phase1, mq, 0));
     cvxb_problem_s* Q = P->phase1;
     dim3 grid((m1 + 127) / 128, n + 1 > 1024 ? 1024 : n + 1);
     CVXB_LAUNCH(h, phase1_build_kernel, grid, 128, 0, n, m, p, P->G, P->ldm, P->gr, P->ub, P->A, P->ldp, P->b,
@@ -814,11 +860,15 @@ extern "C" {
 
 int cvxb_problem_create(cvxb_handle h, const cvxb_problem_desc* d, cvxb_problem* out) {
   if (!h || !d || !out) { cvxb::set_last_error("cvxb_problem_create: null argument"); return CVXB_EINVAL; }
-  if (d->n < 1 || d->m < 0 || d->m + d->mq < 1 || d->p < 0) {
-    cvxb::set_last_error("cvxb_problem_create: need n >= 1, m >= 1, p >= 0 (got %d, %d, %d)", d->n, d->m, d->p);
+  if (d->n < 1 || d->m < 0 || d->mq < 0 || d->p < 0) {
+    cvxb::set_last_error("cvxb_problem_create: need n >= 1, m >= 0, p >= 0 (got %d, %d, %d)", d->n, d->m, d->p);
     return CVXB_EDIM;
   }
-  if (d->objective < CVXB_OBJ_LINEAR || d->objective > CVXB_OBJ_KL) { cvxb::set_last_error("unknown objective kind"); return CVXB_EINVAL; }
+  if (d->objective < CVXB_OBJ_LINEAR || d->objective > CVXB_OBJ_KLDUAL) { cvxb::set_last_error("unknown objective kind"); return CVXB_EINVAL; }
+  if (d->objective == CVXB_OBJ_KLDUAL && (d->obj_k < 1 || !d->obj_P || !d->obj_R || !d->obj_a || d->obj_ldP < d->n)) {
+    cvxb::set_last_error("cvxb_problem_create: the dual KL objective needs obj_a = w, obj_P = B (n x obj_k), obj_R, obj_k >= 1");
+    return CVXB_EINVAL;
+  }
   if ((d->m > 0 && (!d->G || !d->ub)) || (d->p > 0 && (!d->A || !d->b)) || (!d->x_feasible && !d->x_defined) ||
       (d->objective != CVXB_OBJ_KL && !d->obj_a) || (d->objective == CVXB_OBJ_QUADRATIC && !d->obj_P)) {
     cvxb::set_last_error("cvxb_problem_create: missing array for this problem family");
@@ -834,7 +884,7 @@ int cvxb_problem_create(cvxb_handle h, const cvxb_problem_desc* d, cvxb_problem*
     return CVXB_EINVAL;
   }
   cvxb_problem_s* P = nullptr;
-  CVXB_TRY(problem_alloc(*h, d->n, d->m, d->p, d->objective, &P, d->mq));
+  CVXB_TRY(problem_alloc(*h, d->n, d->m, d->p, d->objective, &P, d->mq, d->objective == CVXB_OBJ_KLDUAL ? d->obj_k : 0));
   int st = CVXB_OK;
   auto T = [&](int s) { if (st == CVXB_OK) st = s; };
   T(upload_mat(*h, P->G, P->ldm, d->G, d->ldg, d->m, d->n));
@@ -844,6 +894,10 @@ int cvxb_problem_create(cvxb_handle h, const cvxb_problem_desc* d, cvxb_problem*
   T(upload_vec(*h, P->b, d->b, d->p));
   T(upload_vec(*h, P->obj_a, d->obj_a, d->n));
   if (d->objective == CVXB_OBJ_QUADRATIC) T(upload_mat(*h, P->obj_P, P->ldn, d->obj_P, d->obj_ldP, d->n, d->n));
+  if (d->objective == CVXB_OBJ_KLDUAL) {
+    T(upload_mat(*h, P->obj_P, P->ldn, d->obj_P, d->obj_ldP, d->n, d->obj_k));
+    T(upload_vec(*h, P->objR, d->obj_R, d->obj_k));
+  }
   for (int k = 0; k < d->mq; ++k)       // stacked blocks: rows k*ldq.. of an (mq*ldq) x n matrix
     T(upload_mat(*h, P->Pq + (size_t)k * P->ldq, d->mq * P->ldq, d->q_P + (size_t)k * d->n * d->n, d->n, d->n, d->n));
   if (d->mq > 0) {
@@ -936,6 +990,17 @@ int cvxb_barrier_solve(cvxb_handle h, cvxb_problem prob, const cvxb_params* pars
   out->solve_ms = ms;
   if (st != CVXB_OK) return st;
   CVXB_TRY(download_vec(*h, out->x, prob->x, prob->n));
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CVXB_OK;
+}
+
+int cvxb_kldual_primal_optimum(cvxb_handle h, cvxb_problem prob, double* x_primal) {
+  CHECK_HP(h, prob);
+  if (prob->objective != CVXB_OBJ_KLDUAL || !x_primal) { cvxb::set_last_error("not a dual KL problem"); return CVXB_EINVAL; }
+  cvxb_problem_s* P = prob;
+  CVXB_TRY(gemv_t(*h, P->n, P->kd, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->du));
+  CVXB_LAUNCH(*h, dual_y_kernel, (P->kd + 255) / 256, 256, 0, P->kd, P->objR, P->du, P->dy);
+  CVXB_TRY(download_vec(*h, x_primal, P->dy, P->kd));
   CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
   return CVXB_OK;
 }

@@ -27,6 +27,9 @@ struct cvxb_problem_s {
   double *PX = nullptr, *PDv = nullptr;   // mq*ldq: P_k x and P_k d
   double *qcorr = nullptr, *qq = nullptr; // m: x'P_k x / 2 and d'P_k d / 2 on the quadratic rows, 0 elsewhere
   double *rd2 = nullptr;     // n: PD line search, s^2 coefficient of the dual residual
+  // CVXB_OBJ_KLDUAL: f(z) = w'z + sum_j R_j exp(-(B'z)_j); obj_P holds B (n x kd), obj_a holds w
+  int kd = 0, ldk = 0;
+  double *objR = nullptr, *du = nullptr, *dy = nullptr, *dv = nullptr, *Bs = nullptr;   // B'z, R o exp(-B'z), B'd, B diag(sqrt(t y))
   // matrices
   double *Gs = nullptr, *H = nullptr, *Hreg = nullptr;
   cvxb::KktWork kw;

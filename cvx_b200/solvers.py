@@ -26,7 +26,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (KktInfo, Params, ProblemDesc, SolutionC, check, dptr, fmat, fvec, ptr,
-                   OBJ_KL, OBJ_LINEAR, OBJ_QUADRATIC)
+                   OBJ_KL, OBJ_KLDUAL, OBJ_LINEAR, OBJ_QUADRATIC)
 
 
 @dataclass
@@ -113,6 +113,16 @@ class KLObjectiveFunction(ObjectiveFunction):
         self.dim, self.r, self.a = int(dim), 0.0, None
 
 
+class DualKLObjectiveFunction(ObjectiveFunction):
+    """-L_*(z) = w'z + R'exp(-B'z): the objective of Duality.dualProblem for Dist_KL (Dist_KL.scala:143-163)."""
+    kind = OBJ_KLDUAL
+
+    def __init__(self, B, w, R):
+        self.B, self.a, self.R, self.r = fmat(B), fvec(w), fvec(R), 0.0
+        self.dim = self.B.shape[0]
+        assert self.a.shape[0] == self.dim and self.R.shape[0] == self.B.shape[1]
+
+
 class QuadraticConstraint:
     """QuadraticConstraint(id, dim, ub, r, a, P):  r + a'x + x'Px/2 <= ub, P symmetric (QuadraticConstraint.scala:7-40)."""
 
@@ -172,6 +182,8 @@ class _DeviceProblem:
         d.obj_r = objF.r
         if objF.kind == OBJ_QUADRATIC:
             d.obj_P, d.obj_ldP = dptr(objF.P), n
+        if objF.kind == OBJ_KLDUAL:
+            d.obj_P, d.obj_ldP, d.obj_k, d.obj_R = dptr(objF.B), n, objF.B.shape[1], dptr(objF.R)
         d.G, d.ldg = dptr(cnts.H), m
         d.g_r = dptr(cnts.r) if cnts.r is not None else None
         d.ub = dptr(cnts.u)
@@ -318,23 +330,81 @@ class OptimizationProblem:
         return self.solver.solve(debugLevel)
 
 
-def Dist_KL(n, H=None, u=None, A=None, r=None, solverType="BR", pars=None, logger=None, debugLevel=0, handle=None):
-    """Dist_KL.apply (Dist_KL.scala:270-315): min d_KL(x, uniform) s.t. Hx <= u, x >= 0 (positivity rows
-    after the H rows), A x = r and sum x = 1 (stacked last); pointWhereDefined = 1/n, phase I first."""
-    Gpos = -np.eye(n)
-    if H is not None:
-        G = np.vstack([np.asarray(H, float), Gpos])
-        ub = np.concatenate([np.asarray(u, float), np.zeros(n)])
-    else:
-        G, ub = Gpos, np.zeros(n)
-    ones = np.ones((1, n))
-    if A is not None:
-        Aeq, beq = np.vstack([np.asarray(A, float), ones]), np.concatenate([np.asarray(r, float), [1.0]])
-    else:
-        Aeq, beq = ones, np.array([1.0])
-    cnts = ConstraintSet(G, ub, np.full(n, 1.0 / n))
-    return OptimizationProblem("Dist_KL", KLObjectiveFunction(n), cnts, EqualityConstraint(Aeq, beq), solverType, pars,
-                               logger, debugLevel, handle)
+class Dist_KL(OptimizationProblem):
+    """Dist_KL.apply (Dist_KL.scala:270-315): min d_KL(x, uniform) s.t. Hx <= u, x >= 0 (positivity rows after the H
+    rows), A x = r and sum x = 1 (stacked last); pointWhereDefined = 1/n, phase I first.  With Duality
+    (Duality.scala:99-133): `solveDual` solves max L_*(z), lambda >= 0 in dimension rows(H) + rows(A) + 1 and maps
+    the dual optimum back with primalOptimum -- the route the reference prefers for KL problems."""
+
+    E_REF = 2.7182811828459045          # Dist_KL.scala:114 (sic; defect D8), used in vec_R
+
+    def __init__(self, n, H=None, u=None, A=None, r=None, solverType="BR", pars=None, logger=None, debugLevel=0,
+                 handle=None):
+        assert H is not None or A is not None, "Must have some inequality or equality constraints"
+        self.n = int(n)
+        self.H = None if H is None else np.asarray(H, float)
+        self.u = None if u is None else np.asarray(u, float)
+        self.A = None if A is None else np.asarray(A, float)
+        self.r = None if r is None else np.asarray(r, float)
+        self._pars, self._handle = pars, handle
+        Gpos = -np.eye(n)
+        if H is not None:
+            G, ub = np.vstack([self.H, Gpos]), np.concatenate([self.u, np.zeros(n)])
+        else:
+            G, ub = Gpos, np.zeros(n)
+        ones = np.ones((1, n))
+        if A is not None:
+            Aeq, beq = np.vstack([self.A, ones]), np.concatenate([self.r, [1.0]])
+        else:
+            Aeq, beq = ones, np.array([1.0])
+        cnts = ConstraintSet(G, ub, np.full(n, 1.0 / n))
+        super().__init__("Dist_KL", KLObjectiveFunction(n), cnts, EqualityConstraint(Aeq, beq), solverType, pars, logger,
+                         debugLevel, handle)
+
+    # ---- Duality members (Dist_KL.scala:107-163)
+    @property
+    def numInequalities(self):
+        return 0 if self.H is None else self.H.shape[0]
+
+    @property
+    def mat_B(self):
+        ones = np.ones((1, self.n))
+        Aext = ones if self.A is None else np.vstack([ones, self.A])          # A_with_probEQ: sum-to-one row first
+        return Aext if self.H is None else np.vstack([self.H, Aext])
+
+    @property
+    def vec_w(self):
+        rext = np.array([1.0]) if self.r is None else np.concatenate([[1.0], self.r])
+        return rext if self.H is None else np.concatenate([self.u, rext])
+
+    @property
+    def vec_R(self):
+        return np.full(self.n, 1.0 / (self.n * self.E_REF))
+
+    def dualProblem(self, solverType="BR", pars=None, logger=None, debugLevel=0):
+        """Duality.dualProblem (Duality.scala:99-112): min -L_*(z), lambda >= 0, start z = 0.001."""
+        B = self.mat_B
+        D, mI = B.shape[0], self.numInequalities
+        G = np.zeros((mI, D))
+        G[np.arange(mI), np.arange(mI)] = -1.0                                # Constraints.firstCoordinatesPositive
+        cnts = ConstraintSet(G, np.zeros(mI), np.zeros(D)).addFeasiblePoint(np.full(D, 0.001))
+        objF = DualKLObjectiveFunction(B, self.vec_w, self.vec_R)
+        return OptimizationProblem("Dist_KL dual problem", objF, cnts, None, solverType,
+                                   pars if pars is not None else self._pars, logger, debugLevel, self._handle)
+
+    def solveDual(self, solverType="BR", pars=None, logger=None, debugLevel=0) -> Solution:
+        """Duality.solveDual (Duality.scala:119-133): the returned Solution carries the PRIMAL optimum in x and the
+        dual variables in lam / nu."""
+        dP = self.dualProblem(solverType, pars, logger, debugLevel)
+        solD = dP.solve(debugLevel)
+        z = solD.x
+        pr = dP.solver.problem
+        xp = np.empty(self.n)
+        check(pr.handle.lib.cvxb_kldual_primal_optimum(pr.handle._h, pr._p, ptr(xp)))
+        mI = self.numInequalities
+        solD.z = z
+        solD.x, solD.lam, solD.nu = xp, z[:mI].copy(), (z[mI:].copy() if z.shape[0] > mI else None)
+        return solD
 
 
 def from_dict(prob: dict, solverType="BR", pars=None, handle=None) -> OptimizationProblem:

@@ -130,7 +130,10 @@ int cvxb_triangular_solve(cvxb_handle h, char uplo, int n, int nrhs, const doubl
 typedef enum cvxb_objective_kind {
   CVXB_OBJ_LINEAR = 0,    /* r + a'x            LinearObjectiveFunction.scala:5-22     */
   CVXB_OBJ_QUADRATIC = 1, /* r + a'x + x'Px/2   QuadraticObjectiveFunction.scala:11-33 */
-  CVXB_OBJ_KL = 2         /* sum x log(n x)     Dist_KL.scala:223-239                  */
+  CVXB_OBJ_KL = 2,        /* sum x log(n x)     Dist_KL.scala:223-239                  */
+  CVXB_OBJ_KLDUAL = 3     /* w'z + R'exp(-B'z): the convex dual objective -L_*(z) of Dist_KL (Dist_KL.scala:143-163,
+                             Duality.scala:68-75); obj_a = w (n), obj_P = B (n x obj_k, ld obj_ldP), obj_R = R (obj_k).
+                             Barrier solver only.                                              */
 } cvxb_objective_kind;
 
 typedef struct cvxb_problem_desc {
@@ -156,7 +159,13 @@ typedef struct cvxb_problem_desc {
   const double* q_a;         /* n x mq, column k = a_k                                            */
   const double* q_r;         /* mq                                                                */
   const double* q_ub;        /* mq                                                                */
+  /* CVXB_OBJ_KLDUAL only */
+  int obj_k;                 /* columns of B = dimension of the primal KL problem                 */
+  const double* obj_R;       /* obj_k                                                             */
 } cvxb_problem_desc;
+
+/* Duality.primalOptimum for CVXB_OBJ_KLDUAL: x = R o exp(-B'z) at the problem's current iterate (after a solve). */
+int cvxb_kldual_primal_optimum(cvxb_handle h, cvxb_problem prob, double* x_primal);
 
 /* mirrors Solution.scala:32-43; has_* say which Option fields are Some(...) */
 typedef struct cvxb_solution {

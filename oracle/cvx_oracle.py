@@ -480,6 +480,37 @@ class PNormObjective(Objective):
         return np.diag(self.p * (self.p - 1) * np.abs(x) ** (self.p - 2))
 
 
+class DualKLObjective(Objective):
+    """The convex dual objective -L_*(z) = w'z + R'exp(-B'z) of Dist_KL (Dist_KL.scala:143-163 through
+    Duality.objF, Duality.scala:68-75).  B = [H; 1'; A] (Dist_KL.scala:131-137, 181-185), w = (u, 1, r) (:120-125),
+    R = 1/(n e) with the reference's constant e = 2.7182811828459045 (:114-116, defect D8)."""
+    kind = "kldual"
+    E_REF = 2.7182811828459045
+
+    def __init__(self, B, w, R):
+        self.B = np.asarray(B, dtype=np.float64)
+        self.w = np.asarray(w, dtype=np.float64)
+        self.R = np.asarray(R, dtype=np.float64)
+        self.dim = self.B.shape[0]
+
+    def _y(self, z):
+        return self.R * np.exp(-(self.B.T @ z))
+
+    def valueAt(self, z):
+        return float(self.w @ z) + float(np.sum(self._y(z)))
+
+    def gradientAt(self, z):
+        return self.w - self.B @ self._y(z)
+
+    def hessianAt(self, z):
+        y = self._y(z)
+        return _sym_from_lower((self.B * y[None, :]) @ self.B.T)
+
+    def primalOptimum(self, z):
+        """Dist_KL.primalOptimum (:163)."""
+        return self._y(z)
+
+
 @dataclass
 class QuadCnt:
     """QuadraticConstraint.scala:7-40:  r + a'x + x'Px/2 <= ub."""
@@ -1062,6 +1093,39 @@ def solveProblem(objF, cnts, eqs, solverType="BR", pars=None, literal=False, bug
     else:
         sol = PrimalDual(objF, c, eqs, pars, literal, bug_compat).solve()
     return sol, phase1
+
+
+def dist_KL_dual_problem(n, H=None, u=None, A=None, r=None):
+    """Duality.dualProblem for Dist_KL (Duality.scala:77-112): min -L_*(z) s.t. lambda = z[:numInequalities] >= 0
+    (Constraints.firstCoordinatesPositive), no equalities, feasible start z = 0.001."""
+    ones = np.ones((1, n))
+    Aext = ones if A is None else np.vstack([ones, A])                      # A_with_probEQ: the sum-to-one row FIRST
+    rext = np.array([1.0]) if r is None else np.concatenate([[1.0], r])
+    B = Aext if H is None else np.vstack([H, Aext])
+    w = rext if H is None else np.concatenate([u, rext])
+    R = np.full(n, 1.0 / (n * DualKLObjective.E_REF))
+    mI = 0 if H is None else H.shape[0]
+    D = B.shape[0]
+    G = np.zeros((mI, D))
+    G[np.arange(mI), np.arange(mI)] = -1.0
+    cnts = ConstraintSet(G, np.zeros(mI), np.zeros(mI), None, np.zeros(D))
+    cnts = cnts.addFeasiblePoint(np.full(D, 0.001)) if mI > 0 else cnts
+    if mI == 0:
+        cnts.feasiblePoint = np.full(D, 0.001)
+    return DualKLObjective(B, w, R), cnts, mI
+
+
+def solveDual(n, H=None, u=None, A=None, r=None, pars=None):
+    """Duality.solveDual (Duality.scala:119-133) with the barrier solver: returns the primal Solution."""
+    pars = pars or SolverParams.standardParams()
+    objF, cnts, mI = dist_KL_dual_problem(n, H, u, A, r)
+    sol = barrierSolve(objF, cnts, None, pars)
+    z = sol.x
+    sol.lam = z[:mI]
+    sol.nu = z[mI:] if z.shape[0] > mI else None
+    sol.z = z
+    sol.x = objF.primalOptimum(z)
+    return sol
 
 
 def dist_KL_problem(n, H=None, u=None, A=None, r=None):

@@ -150,3 +150,16 @@ def test_pd_bug_compat_does_not_converge():
     assert sol.maxedOut and sol.dualityGap > 1e-3
     sol2, _ = O.solveProblem(objF, cnts, eqs, "PD", bug_compat=False)
     assert not sol2.maxedOut and sol2.dualityGap < 1e-8
+
+
+def test_dual_route_recovers_known_minimisers():
+    """MinimizationTests.scala:28-83: the KL problems solved via Duality.solveDual reach the analytic optimum."""
+    pr = P.kl_1A(20)
+    sol = O.solveDual(20, pr["G"][:2], pr["ub"][:2], None, None)
+    assert np.max(np.abs(sol.x - pr["xopt"])) < 1e-8
+    assert np.all(sol.lam >= 0)
+    pr = P.kl_random(40, 30, 5, 1)
+    sold = O.solveDual(40, pr["G"][:30], pr["ub"][:30], pr["A"][:5], pr["b"][:5])
+    objF, c, e = P.to_oracle(pr)
+    solp, _ = O.solveProblem(objF, c, e, "BR")
+    assert rel(sold.x, solp.x) < 1e-7
