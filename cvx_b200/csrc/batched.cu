@@ -759,11 +759,7 @@ int cvxb_batch_barrier_solve(cvxb_handle h, cvxb_batch Bt, const cvxb_params* pa
   cudaSetDevice(h->device);
   cvxb_params dp;
   if (!pars) { cvxb_default_params(&dp); pars = &dp; }
-  static bool attr = false;
-  if (!attr) {
-    CVXB_CUDA_OK(cudaFuncSetAttribute(batched_barrier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    attr = true;
-  }
+  CVXB_CUDA_OK(cudaFuncSetAttribute(batched_barrier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   BatchArgs A;
   A.B = Bt->B; A.n = Bt->n; A.m = Bt->m; A.p = Bt->p;
   A.objective = Bt->objective; A.pcount = Bt->pcount; A.obj_a = Bt->obj_a; A.obj_r = Bt->obj_r; A.obj_P = Bt->obj_P; A.G = Bt->G; A.ub = Bt->ub;

@@ -602,8 +602,10 @@ __global__ void copy_vec_kernel(int n, const double* __restrict__ a, double* __r
 __device__ __forceinline__ bool wait_flag(const int* flag, int* abort_flag) {
   // thread 0 only; bounded spin so that a scheduling surprise can never hang the GPU
   const volatile int* f = flag;
-  for (long long spin = 0; spin < (1ll << 26); ++spin) {
+  const volatile int* ab = abort_flag;
+  for (int spin = 0; spin < (1 << 22); ++spin) {      // ~0.3 s worst case, then everybody bails out
     if (*f) return true;
+    if (*ab) return false;
     __nanosleep(64);
   }
   *abort_flag = 1;
@@ -793,8 +795,8 @@ int trsv_lower(Handle& h, int n, const double* L, int ldl, const double* invD, d
 }
 
 bool leaf_attr_set = false;
-int leaf_init() {
-  if (leaf_attr_set) return CVXB_OK;
+int leaf_init(bool force = false) {
+  if (leaf_attr_set && !force) return CVXB_OK;
   CVXB_CUDA_OK(cudaFuncSetAttribute(leaf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
   CVXB_CUDA_OK(cudaFuncSetAttribute(leaf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
   CVXB_CUDA_OK(cudaFuncSetAttribute(trsv_fwd_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WAVE_SMEM));
@@ -805,7 +807,7 @@ int leaf_init() {
 
 }  // namespace
 
-int factor_init() { return leaf_init(); }
+int factor_init() { return leaf_init(true); }     // per handle: attributes belong to the current device
 
 int ruiz_equilibrate(Handle& h, int n, const double* Hm, int ldh, double* d, double* colsq, int max_sweeps, double tol) {
   if (n <= 0) return CVXB_OK;

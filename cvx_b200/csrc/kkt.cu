@@ -194,6 +194,14 @@ int fetch_status(Handle& h) {
   CVXB_CUDA_OK(cudaMemcpyAsync(h.h_flag, h.d_flag, NFLAG * sizeof(int), cudaMemcpyDeviceToHost, h.stream));
   CVXB_CUDA_OK(cudaMemcpyAsync(h.h_scal, h.d_scal, NSCAL * sizeof(double), cudaMemcpyDeviceToHost, h.stream));
   CVXB_CUDA_OK(cudaStreamSynchronize(h.stream));
+  if (h.h_flag[F_WAVE_ABORT]) {
+    // a wavefront triangular solve gave up waiting for a predecessor block (its CTAs were not co-resident):
+    // never expected under a cooperative launch; switch to the per-block kernels and report
+    cudaMemsetAsync(h.d_flag + F_WAVE_ABORT, 0, sizeof(int), h.stream);
+    if (h.wave_ready) { cudaFree(h.wave_ready); h.wave_ready = nullptr; }
+    set_last_error("wavefront triangular solve aborted (blocks not co-resident); falling back to per-block kernels, retry the call");
+    return CVXB_ECUDA;
+  }
   return CVXB_OK;
 }
 
