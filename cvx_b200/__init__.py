@@ -9,6 +9,6 @@ from .linalg import KKTSystem, SymmetricLinearSystem, MatrixUtils  # noqa: F401
 
 __version__ = "0.1.0"
 from .solvers import (SolverParams, Solution, LinearObjectiveFunction, QuadraticObjectiveFunction,  # noqa: F401,E402
-                      KLObjectiveFunction, DualKLObjectiveFunction, ConstraintSet, QuadraticConstraint, EqualityConstraint, BarrierSolver, PrimalDualSolver,
+                      KLObjectiveFunction, DualKLObjectiveFunction, PNormObjectiveFunction, ConstraintSet, QuadraticConstraint, EqualityConstraint, BarrierSolver, PrimalDualSolver,
                       OptimizationProblem, Dist_KL, from_dict)
 from .batched import BatchedBarrierSolver, BatchSolution, pack_problems, shard_range, gather_solutions  # noqa: F401,E402

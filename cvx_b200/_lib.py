@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcvxb.so")
 # cvxb_status
 OK, ELINSOLVE, EUNSOLVABLE, ELINESEARCH, ENOTFEASIBLE, EINFEASIBLE, EDIM, ENOTSYMMETRIC, ECUDA, EINVAL, ENOTIMPL = range(11)
 FLAG_DEVICE_PTRS = 1
-OBJ_LINEAR, OBJ_QUADRATIC, OBJ_KL, OBJ_KLDUAL = 0, 1, 2, 3
+OBJ_LINEAR, OBJ_QUADRATIC, OBJ_KL, OBJ_KLDUAL, OBJ_PNORM = 0, 1, 2, 3, 4
 
 
 # ---- exceptions: the reference's exception types (SURVEY.md 8b "Error conventions") ----------------
@@ -91,7 +91,7 @@ class ProblemDesc(C.Structure):
                 ("obj_r", C.c_double), ("obj_P", _dp), ("obj_ldP", C.c_int), ("G", _dp), ("ldg", C.c_int),
                 ("g_r", _dp), ("ub", _dp), ("A", _dp), ("lda", C.c_int), ("b", _dp), ("x_feasible", _dp),
                 ("x_defined", _dp), ("mq", C.c_int), ("q_P", _dp), ("q_a", _dp), ("q_r", _dp), ("q_ub", _dp),
-                ("obj_k", C.c_int), ("obj_R", _dp)]
+                ("obj_k", C.c_int), ("obj_R", _dp), ("obj_pow", C.c_double)]
 
 
 class SolutionC(C.Structure):

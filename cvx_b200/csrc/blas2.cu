@@ -114,13 +114,13 @@ __global__ void scale_rows_kernel(int m, int n, const double* __restrict__ G, in
 // C = alpha*A (A NULL -> 0); diagonal += diag_scale / diag_den[i]  (KL: t * diag(1/x), Dist_KL.scala:236-239)
 __global__ void fill_matrix_kernel(int n, double alpha, const double* __restrict__ A, int lda,
                                    const double* __restrict__ diag_den, double diag_scale, double* __restrict__ C,
-                                   int ldc, const double* __restrict__ mul_dev) {
+                                   int ldc, const double* __restrict__ mul_dev, double diag_exp) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (mul_dev) { alpha *= *mul_dev; diag_scale *= *mul_dev; }   // barrier parameter t read on the device (graph replay)
   for (int j = blockIdx.y; j < n; j += gridDim.y) {
     double v = A ? alpha * A[(size_t)j * lda + i] : 0.0;
-    if (i == j && diag_den) v += diag_scale / diag_den[i];
+    if (i == j && diag_den) v += (diag_exp == -1.0) ? diag_scale / diag_den[i] : diag_scale * pow(fabs(diag_den[i]), diag_exp);
     C[(size_t)j * ldc + i] = v;
   }
 }
@@ -200,10 +200,10 @@ int scale_rows(Handle& h, int m, int n, const double* G, int ldg, const double* 
 }
 
 int fill_matrix(Handle& h, int n, double alpha, const double* A, int lda, const double* diag_den, double diag_scale,
-                double* C, int ldc, const double* mul_dev) {
+                double* C, int ldc, const double* mul_dev, double diag_exp) {
   if (n <= 0) return CVXB_OK;
   CVXB_LAUNCH(h, fill_matrix_kernel, dim3((n + 127) / 128, ygrid(n)), 128, 0, n, alpha, A, lda, diag_den, diag_scale, C,
-              ldc, mul_dev);
+              ldc, mul_dev, diag_exp);
   return CVXB_OK;
 }
 

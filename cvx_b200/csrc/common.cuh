@@ -155,7 +155,8 @@ int gemv_t(Handle& h, int m, int n, double alpha, const double* A, int lda, cons
 int scale_rows(Handle& h, int m, int n, const double* G, int ldg, const double* s, double* Gs, int ldgs, bool sqrt_of_s);
 // C = alpha * A (+ diag)              n x n (objective Hessian prefill); A may be NULL (zero)
 int fill_matrix(Handle& h, int n, double alpha, const double* A, int lda, const double* diag_num, double diag_scale,
-                double* C, int ldc, const double* mul_dev = nullptr);   // alpha, diag_scale *= *mul_dev when given
+                double* C, int ldc, const double* mul_dev = nullptr,   // alpha, diag_scale *= *mul_dev when given
+                double diag_exp = -1.0);   // diagonal += diag_scale * |diag_num|^diag_exp  (-1: KL's 1/x; p-2: p-norm)
 // Bt(i,j) = s_i * A(j,i)   (n x p from p x n), s may be NULL
 int transpose_scale(Handle& h, int p, int n, const double* A, int lda, const double* s, double* Bt, int ldbt);
 // C (n x n) += alpha * I

@@ -27,7 +27,11 @@ namespace {
 
 constexpr double IN_SET_FACTOR = 1.0 + 3e-16;
 
-__device__ __forceinline__ double grad_f0(int kind, int n, double xj, double aj, double pxj) {
+__device__ __forceinline__ double grad_f0(int kind, int n, double xj, double aj, double pxj, double pw = 2.0) {
+  if (kind == CVXB_OBJ_PNORM) {
+    const double sg = fabs(xj) < 1e-14 ? 0.0 : (xj > 0 ? 1.0 : -1.0);
+    return sg * pw * pow(sg * xj, pw - 1.0);
+  }
   if (kind == CVXB_OBJ_LINEAR) return aj;
   if (kind == CVXB_OBJ_QUADRATIC) return aj + pxj;
   return 1.0 + log(xj) + log((double)n);
@@ -76,9 +80,9 @@ __global__ void __launch_bounds__(VT) pd_rhs_kernel(int n, int p, int kind, int 
                                                     const double* __restrict__ gt, const double* __restrict__ Atnu,
                                                     double* __restrict__ rd0, double* __restrict__ v, double* __restrict__ q,
                                                     const double* __restrict__ ax, const double* __restrict__ b,
-                                                    double* __restrict__ pres, double* __restrict__ negpres) {
+                                                    double* __restrict__ pres, double* __restrict__ negpres, double pw) {
   for (int j = threadIdx.x; j < n; j += VT) {
-    double gf = grad_f0(kind, n, x[j], a ? a[j] : 0.0, Px ? Px[j] : 0.0);
+    double gf = grad_f0(kind, n, x[j], a ? a[j] : 0.0, Px ? Px[j] : 0.0, pw);
     double vj = -gf + gt[j];
     double an = p > 0 ? Atnu[j] : 0.0;
     v[j] = vj;
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(VT) pd_dlam_kernel(int m, double t, const doub
 
 struct PdLs {
   int m, n, p, kind, withEqs;
-  double t, alpha, beta, frac;
+  double t, alpha, beta, frac, pw;
   // base point of the search (current iterate, or the initial one under bugCompat) and direction
   const double *gx, *ub, *lam, *x, *nu, *rd0, *pres, *Px, *a;
   const double *Gd, *dlam, *dx, *dnu, *rd1, *Adx, *Pd;
@@ -138,6 +142,7 @@ __device__ double pd_trial(const PdLs& A, double s, double* buf, int* ibuf, int*
     double gf;
     if (A.kind == CVXB_OBJ_LINEAR) gf = A.a[j];
     else if (A.kind == CVXB_OBJ_QUADRATIC) gf = A.a[j] + A.Px[j] + s * A.Pd[j];
+    else if (A.kind == CVXB_OBJ_PNORM) gf = grad_f0(A.kind, A.n, A.x[j] + s * A.dx[j], 0.0, 0.0, A.pw);
     else {
       double xj = A.x[j] + s * A.dx[j];
       gf = 1.0 + log(xj) + log((double)A.n);        // NaN for x_s <= 0: the comparison below then fails
@@ -210,12 +215,13 @@ __global__ void __launch_bounds__(VT) pd_linesearch_kernel(PdLs A, double* scal,
 // objective value at x
 __global__ void __launch_bounds__(VT) pd_objective_kernel(int n, int kind, double obj_r, const double* __restrict__ x,
                                                           const double* __restrict__ a, const double* __restrict__ Px,
-                                                          double* scal) {
+                                                          double pw, double* scal) {
   __shared__ double buf[33];
   double f0 = 0.0;
   for (int j = threadIdx.x; j < n; j += VT) {
     double xj = x[j];
-    if (kind == CVXB_OBJ_LINEAR) f0 += a[j] * xj;
+    if (kind == CVXB_OBJ_PNORM) f0 += pow(fabs(xj), pw);
+    else if (kind == CVXB_OBJ_LINEAR) f0 += a[j] * xj;
     else if (kind == CVXB_OBJ_QUADRATIC) f0 += a[j] * xj + 0.5 * xj * Px[j];
     else f0 += xj * log(xj * (double)n);
   }
@@ -270,11 +276,13 @@ int pd_assemble(cvxb_problem_s* P, const cvxb_params& pars, double t) {
     CVXB_TRY(gemv_n(h, p, n, 1.0, P->A, P->ldp, P->x, 0.0, P->axv));
   }
   CVXB_LAUNCH(h, pd_rhs_kernel, 1, VT, 0, n, p, P->objective, pars.bugCompat && p > 0 ? 1 : 0, P->x, P->obj_a, P->Px, P->gt,
-              P->atnu, P->rd0, P->vvec, P->qvec, P->axv, P->b, P->pres, P->negpres);
+              P->atnu, P->rd0, P->vvec, P->qvec, P->axv, P->b, P->pres, P->negpres, P->obj_pow);
   // H_pd = hess f + G' diag(-lam/f) G
   CVXB_TRY(scale_rows(h, m, n, P->G, P->ldm, P->wts, P->Gs, P->ldm, true));
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(fill_matrix(h, n, 1.0, P->obj_P, P->ldn, nullptr, 0.0, P->H, P->ldn));
   else if (P->objective == CVXB_OBJ_KL) CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, 1.0, P->H, P->ldn));
+  else if (P->objective == CVXB_OBJ_PNORM)
+    CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, P->obj_pow * (P->obj_pow - 1.0), P->H, P->ldn, nullptr, P->obj_pow - 2.0));
   else CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, nullptr, 0.0, P->H, P->ldn));
   CVXB_TRY(quad_hessian_terms(P, P->lam));     // + lam_k hess g_k   (PrimalDualSolver.scala:230-236)
   GemmArgs g{n, n, m, P->Gs, P->ldm, true, P->Gs, P->ldm, true, P->H, P->ldn, 1.0, 1.0, 2};
@@ -323,7 +331,7 @@ int pd_after_solve(cvxb_problem_s* P, const cvxb_params& pars, double t, bool us
   }
   PdLs A;
   A.m = m; A.n = n; A.p = p; A.kind = P->objective; A.withEqs = p > 0;
-  A.t = t; A.alpha = pars.alpha; A.beta = pars.beta; A.frac = pars.pdStepFraction;
+  A.t = t; A.alpha = pars.alpha; A.beta = pars.beta; A.frac = pars.pdStepFraction; A.pw = P->obj_pow;
   if (use_base0) {     // defect D1: the search starts from the initial iterate u0 every time
     A.gx = P->gx0s; A.lam = P->lam0s; A.x = P->x0s; A.nu = P->nu0s; A.rd0 = P->rd00s; A.pres = P->pres0s; A.Px = P->Px0s;
   } else {
@@ -459,7 +467,7 @@ int pd_loop(cvxb_problem_s* P, const cvxb_params& pars, cvxb_solution* out) {
     it++;
   }
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->Px));
-  CVXB_LAUNCH(h, pd_objective_kernel, 1, VT, 0, n, P->objective, P->obj_r, P->x, P->obj_a, P->Px, h.d_scal);
+  CVXB_LAUNCH(h, pd_objective_kernel, 1, VT, 0, n, P->objective, P->obj_r, P->x, P->obj_a, P->Px, P->obj_pow, h.d_scal);
   CVXB_TRY(fetch_status(h));
   out->has_lambda = 1; out->has_nu = withEqs ? 1 : 0;
   out->has_newtonDecrement = 0; out->newtonDecrement = 0;

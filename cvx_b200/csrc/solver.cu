@@ -23,12 +23,18 @@ constexpr double IN_SET_FACTOR = 1.0 + 3e-16;   // Constraint.isSatisfiedStrictl
 
 // ---- objective families (device) -------------------------------------------------------------------
 // value needs a.x / x.Px/2 / sum x log(n x): partial term of entry j
-__device__ __forceinline__ double obj_term(int kind, int n, int j, double xj, const double* a, const double* Px) {
+__device__ __forceinline__ double pnorm_sgn(double u) { return fabs(u) < 1e-14 ? 0.0 : (u > 0 ? 1.0 : -1.0); }
+
+__device__ __forceinline__ double obj_term(int kind, int n, int j, double xj, const double* a, const double* Px,
+                                           double pw = 2.0) {
+  if (kind == CVXB_OBJ_PNORM) return pow(fabs(xj), pw);                          // ObjectiveFunctions.scala:76
   if (kind == CVXB_OBJ_LINEAR || kind == CVXB_OBJ_KLDUAL) return a[j] * xj;    // dual: w'z here, sum_j y_j added by the caller
   if (kind == CVXB_OBJ_QUADRATIC) return a[j] * xj + 0.5 * xj * Px[j];
   return xj * log(xj * (double)n);   // Dist_KL.scala:225-227
 }
-__device__ __forceinline__ double obj_grad(int kind, int n, int j, double xj, const double* a, const double* Px) {
+__device__ __forceinline__ double obj_grad(int kind, int n, int j, double xj, const double* a, const double* Px,
+                                           double pw = 2.0) {
+  if (kind == CVXB_OBJ_PNORM) { const double sg = pnorm_sgn(xj); return sg * pw * pow(sg * xj, pw - 1.0); }   // :77-78
   if (kind == CVXB_OBJ_LINEAR) return a[j];
   if (kind == CVXB_OBJ_KLDUAL) return a[j] - Px[j];      // w - B y   (Px holds B y)
   if (kind == CVXB_OBJ_QUADRATIC) return a[j] + Px[j];
@@ -41,7 +47,8 @@ __global__ void __launch_bounds__(VT) eval_cnt_kernel(int m, int n, int kind, do
                                                       double* __restrict__ gx, double* __restrict__ inv,
                                                       const double* __restrict__ x, const double* __restrict__ a,
                                                       const double* __restrict__ Px, const double* __restrict__ qcorr,
-                                                      const double* __restrict__ dual_y, int kd, double* scal, int* flag) {
+                                                      const double* __restrict__ dual_y, int kd, double pw, double* scal,
+                                                      int* flag) {
   __shared__ double buf[33];
   __shared__ int ibuf[33];
   if (t_dev) t = *t_dev;        // barrier parameter kept on the device when the step is replayed from a CUDA graph
@@ -61,7 +68,7 @@ __global__ void __launch_bounds__(VT) eval_cnt_kernel(int m, int n, int kind, do
   mn = block_min(mn, buf);
   bad = block_or(bad, ibuf);
   double f0 = 0.0;
-  for (int j = threadIdx.x; j < n; j += VT) f0 += obj_term(kind, n, j, x[j], a, Px);
+  for (int j = threadIdx.x; j < n; j += VT) f0 += obj_term(kind, n, j, x[j], a, Px, pw);
   if (kind == CVXB_OBJ_KLDUAL)
     for (int j = threadIdx.x; j < kd; j += VT) f0 += dual_y[j];      // + R'exp(-B'z)
   f0 = block_sum(f0, buf) + obj_r;
@@ -80,12 +87,12 @@ __global__ void __launch_bounds__(VT) eval_grad_kernel(int n, int p, int kind, d
                                                        const double* __restrict__ a, const double* __restrict__ Px,
                                                        const double* __restrict__ gt, double* __restrict__ y,
                                                        const double* __restrict__ b, const double* __restrict__ ax,
-                                                       double* __restrict__ eqdiff, double* scal) {
+                                                       double* __restrict__ eqdiff, double pw, double* scal) {
   __shared__ double buf[33];
   if (t_dev) t = *t_dev;
   double s = 0.0;
   for (int j = threadIdx.x; j < n; j += VT) {
-    double v = t * obj_grad(kind, n, j, x[j], a, Px) + gt[j];
+    double v = t * obj_grad(kind, n, j, x[j], a, Px, pw) + gt[j];
     y[j] = v;
     s = fma(v, v, s);
   }
@@ -112,6 +119,7 @@ struct LsArgs {
   const double* t_dev;   // non-NULL: t and the first-step flag live on the device (CUDA-graph replay)
   const double *dual_y, *dual_v;   // CVXB_OBJ_KLDUAL: y = R o exp(-B'z), v = B'd ; f(z + s d) = w'z + s w'd + sum y_j exp(-s v_j)
   int kd;
+  double pw;             // CVXB_OBJ_PNORM exponent
   double *x, *dir;
 };
 
@@ -144,6 +152,10 @@ __device__ double ls_value(const LsArgs& A, double s, double f0, double c1, doub
       double xj = A.x[j] + s * A.dir[j];
       v += xj * log(xj * (double)A.n);
     }
+    f0s = block_sum(v, buf);
+  } else if (A.kind == CVXB_OBJ_PNORM) {
+    double v = 0.0;
+    for (int j = threadIdx.x; j < A.n; j += VT) v += pow(fabs(A.x[j] + s * A.dir[j]), A.pw);
     f0s = block_sum(v, buf);
   } else if (A.kind == CVXB_OBJ_KLDUAL) {
     double v = 0.0;
@@ -469,11 +481,11 @@ int barrier_eval(cvxb_problem_s* P, double t, const double* t_dev = nullptr) {
     CVXB_TRY(gemv_n(h, n, P->kd, 1.0, P->obj_P, P->ldn, P->dy, 0.0, P->Px));
   }
   CVXB_LAUNCH(h, eval_cnt_kernel, 1, VT, 0, m, n, P->objective, P->obj_r, t, t_dev, P->gr, P->ub, P->gx, P->inv, P->x,
-              P->obj_a, P->Px, P->qcorr, P->dy, P->kd, h.d_scal, h.d_flag);
+              P->obj_a, P->Px, P->qcorr, P->dy, P->kd, P->obj_pow, h.d_scal, h.d_flag);
   CVXB_TRY(gemv_t(h, m, n, 1.0, P->G, P->ldm, P->inv, 0.0, P->gt));
   if (p > 0) CVXB_TRY(gemv_n(h, p, n, 1.0, P->A, P->ldp, P->x, 0.0, P->axv));
   CVXB_LAUNCH(h, eval_grad_kernel, 1, VT, 0, n, p, P->objective, t, t_dev, P->x, P->obj_a, P->Px, P->gt, P->y, P->b, P->axv,
-              P->eqdiff, h.d_scal);
+              P->eqdiff, P->obj_pow, h.d_scal);
   return CVXB_OK;
 }
 
@@ -485,6 +497,8 @@ int barrier_hessian(cvxb_problem_s* P, double t, const double* t_dev = nullptr) 
   CVXB_TRY(scale_rows(h, m, n, P->G, P->ldm, P->inv, P->Gs, P->ldm, false));
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(fill_matrix(h, n, tv, P->obj_P, P->ldn, nullptr, 0.0, P->H, P->ldn, t_dev));
   else if (P->objective == CVXB_OBJ_KL) CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, tv, P->H, P->ldn, t_dev));
+  else if (P->objective == CVXB_OBJ_PNORM)      // t p (p-1) |x|^(p-2) on the diagonal
+    CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, tv * P->obj_pow * (P->obj_pow - 1.0), P->H, P->ldn, t_dev, P->obj_pow - 2.0));
   else if (P->objective == CVXB_OBJ_KLDUAL) {
     // t * B diag(y) B'  as one more weighted SYRK (contraction length = primal dimension), mirrored: exactly symmetric
     CVXB_LAUNCH(h, dual_scale_cols_kernel, dim3((n + 127) / 128, P->kd > 1024 ? 1024 : P->kd), 128, 0, n, P->kd, P->obj_P,
@@ -511,7 +525,7 @@ int enqueue_linesearch(cvxb_problem_s* P, const cvxb_params& pars, double t, int
   A.t = t; A.alpha = pars.alpha; A.beta = pars.beta; A.tol = pars.tolSolver;
   A.gx = P->gx; A.ub = P->ub; A.Gd = P->Gd; A.a = P->obj_a; A.Px = P->Px; A.Pd = P->Pd; A.y = P->y;
   A.x = P->x; A.dir = P->dir; A.qq = P->mq > 0 ? P->qq : nullptr; A.t_dev = t_dev;
-  A.dual_y = P->dy; A.dual_v = P->dv; A.kd = P->kd;
+  A.dual_y = P->dy; A.dual_v = P->dv; A.kd = P->kd; A.pw = P->obj_pow;
   CVXB_LAUNCH(h, linesearch_kernel, 1, VT, 0, A, h.d_scal, h.d_flag);
   return CVXB_OK;
 }
@@ -864,13 +878,17 @@ int cvxb_problem_create(cvxb_handle h, const cvxb_problem_desc* d, cvxb_problem*
     cvxb::set_last_error("cvxb_problem_create: need n >= 1, m >= 0, p >= 0 (got %d, %d, %d)", d->n, d->m, d->p);
     return CVXB_EDIM;
   }
-  if (d->objective < CVXB_OBJ_LINEAR || d->objective > CVXB_OBJ_KLDUAL) { cvxb::set_last_error("unknown objective kind"); return CVXB_EINVAL; }
+  if (d->objective == CVXB_OBJ_PNORM && !(d->obj_pow >= 2.0)) {
+    cvxb::set_last_error("p-norm needs p >= 2 but p = %g", d->obj_pow);       // assert of ObjectiveFunctions.scala:72
+    return CVXB_EINVAL;
+  }
+  if (d->objective < CVXB_OBJ_LINEAR || d->objective > CVXB_OBJ_PNORM) { cvxb::set_last_error("unknown objective kind"); return CVXB_EINVAL; }
   if (d->objective == CVXB_OBJ_KLDUAL && (d->obj_k < 1 || !d->obj_P || !d->obj_R || !d->obj_a || d->obj_ldP < d->n)) {
     cvxb::set_last_error("cvxb_problem_create: the dual KL objective needs obj_a = w, obj_P = B (n x obj_k), obj_R, obj_k >= 1");
     return CVXB_EINVAL;
   }
   if ((d->m > 0 && (!d->G || !d->ub)) || (d->p > 0 && (!d->A || !d->b)) || (!d->x_feasible && !d->x_defined) ||
-      (d->objective != CVXB_OBJ_KL && !d->obj_a) || (d->objective == CVXB_OBJ_QUADRATIC && !d->obj_P)) {
+      (d->objective != CVXB_OBJ_KL && d->objective != CVXB_OBJ_PNORM && !d->obj_a) || (d->objective == CVXB_OBJ_QUADRATIC && !d->obj_P)) {
     cvxb::set_last_error("cvxb_problem_create: missing array for this problem family");
     return CVXB_EINVAL;
   }
@@ -906,6 +924,7 @@ int cvxb_problem_create(cvxb_handle h, const cvxb_problem_desc* d, cvxb_problem*
     T(upload_vec(*h, P->ub + d->m, d->q_ub, d->mq));
   }
   P->obj_r = d->obj_r;
+  P->obj_pow = d->objective == CVXB_OBJ_PNORM ? d->obj_pow : 2.0;
   if (d->x_feasible) { T(upload_vec(*h, P->x_feas, d->x_feasible, d->n)); P->has_feasible = true; }
   T(upload_vec(*h, P->x_def, d->x_defined ? d->x_defined : d->x_feasible, d->n));
   if (st == CVXB_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) { cvxb::set_last_error("upload failed"); st = CVXB_ECUDA; }

@@ -7,6 +7,7 @@ struct cvxb_problem_s {
   int n = 0, m = 0, p = 0, objective = 0;
   int ldm = 0, ldn = 0, ldp = 0;
   double obj_r = 0.0;
+  double obj_pow = 2.0;      // CVXB_OBJ_PNORM exponent
   // problem data (device)
   double *G = nullptr, *gr = nullptr, *ub = nullptr, *A = nullptr, *b = nullptr, *obj_a = nullptr, *obj_P = nullptr;
   double *x_feas = nullptr, *x_def = nullptr;

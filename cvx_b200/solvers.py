@@ -26,7 +26,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (KktInfo, Params, ProblemDesc, SolutionC, check, dptr, fmat, fvec, ptr,
-                   OBJ_KL, OBJ_KLDUAL, OBJ_LINEAR, OBJ_QUADRATIC)
+                   OBJ_KL, OBJ_KLDUAL, OBJ_LINEAR, OBJ_PNORM, OBJ_QUADRATIC)
 
 
 @dataclass
@@ -113,6 +113,15 @@ class KLObjectiveFunction(ObjectiveFunction):
         self.dim, self.r, self.a = int(dim), 0.0, None
 
 
+class PNormObjectiveFunction(ObjectiveFunction):
+    """ObjectiveFunctions.p_norm_p(dim, p): sum |x_j|^p, p >= 2 (ObjectiveFunctions.scala:70-83)."""
+    kind = OBJ_PNORM
+
+    def __init__(self, dim, p):
+        assert p >= 2, "p-norm needs p>=2 but p=%s" % p
+        self.dim, self.p, self.r, self.a = int(dim), float(p), 0.0, None
+
+
 class DualKLObjectiveFunction(ObjectiveFunction):
     """-L_*(z) = w'z + R'exp(-B'z): the objective of Duality.dualProblem for Dist_KL (Dist_KL.scala:143-163)."""
     kind = OBJ_KLDUAL
@@ -182,6 +191,8 @@ class _DeviceProblem:
         d.obj_r = objF.r
         if objF.kind == OBJ_QUADRATIC:
             d.obj_P, d.obj_ldP = dptr(objF.P), n
+        if objF.kind == OBJ_PNORM:
+            d.obj_pow = objF.p
         if objF.kind == OBJ_KLDUAL:
             d.obj_P, d.obj_ldP, d.obj_k, d.obj_R = dptr(objF.B), n, objF.B.shape[1], dptr(objF.R)
         d.G, d.ldg = dptr(cnts.H), m
@@ -414,6 +425,8 @@ def from_dict(prob: dict, solverType="BR", pars=None, handle=None) -> Optimizati
         objF = LinearObjectiveFunction(n, prob["r"], prob["a"])
     elif prob["kind"] == "quadratic":
         objF = QuadraticObjectiveFunction(n, prob["r"], prob["a"], prob["P"])
+    elif prob["kind"] == "pnorm":
+        objF = PNormObjectiveFunction(n, prob["pow"])
     else:
         objF = KLObjectiveFunction(n)
     quad = [QuadraticConstraint("q%d" % k, n, q["ub"], q["r"], q["a"], q["P"]) for k, q in enumerate(prob.get("quad") or [])]

@@ -131,6 +131,7 @@ typedef enum cvxb_objective_kind {
   CVXB_OBJ_LINEAR = 0,    /* r + a'x            LinearObjectiveFunction.scala:5-22     */
   CVXB_OBJ_QUADRATIC = 1, /* r + a'x + x'Px/2   QuadraticObjectiveFunction.scala:11-33 */
   CVXB_OBJ_KL = 2,        /* sum x log(n x)     Dist_KL.scala:223-239                  */
+  CVXB_OBJ_PNORM = 4,     /* sum |x_j|^p, p >= 2  ObjectiveFunctions.p_norm_p, ObjectiveFunctions.scala:70-83 (obj_pow = p) */
   CVXB_OBJ_KLDUAL = 3     /* w'z + R'exp(-B'z): the convex dual objective -L_*(z) of Dist_KL (Dist_KL.scala:143-163,
                              Duality.scala:68-75); obj_a = w (n), obj_P = B (n x obj_k, ld obj_ldP), obj_R = R (obj_k).
                              Barrier solver only.                                              */
@@ -162,6 +163,7 @@ typedef struct cvxb_problem_desc {
   /* CVXB_OBJ_KLDUAL only */
   int obj_k;                 /* columns of B = dimension of the primal KL problem                 */
   const double* obj_R;       /* obj_k                                                             */
+  double obj_pow;            /* CVXB_OBJ_PNORM only: the exponent p >= 2                          */
 } cvxb_problem_desc;
 
 /* Duality.primalOptimum for CVXB_OBJ_KLDUAL: x = R o exp(-B'z) at the problem's current iterate (after a solve). */

@@ -54,6 +54,13 @@ def min_dot_product(a):
                 x0=None, xdef=2.0 * a, xopt=a.copy())
 
 
+def min_pNorm(n, p):
+    """SimpleOptimizationProblems.min_pNorm (src/test/.../SimpleOptimizationProblems.scala:179-209):
+    min sum |x_j|^p  s.t.  x_j >= 0, sum x = 1;  unique optimum x_j = 1/n;  pointWhereDefined = 0 => phase I."""
+    return dict(kind="pnorm", n=n, a=None, r=0.0, P=None, pow=float(p), G=-np.eye(n), rvec=np.zeros(n), ub=np.zeros(n),
+                A=np.ones((1, n)), b=np.array([1.0]), x0=None, xdef=np.zeros(n), xopt=np.full(n, 1.0 / n))
+
+
 def kl_random(n, m_h, p_extra, seed=0):
     """C2 family via Dist_KL.apply semantics: KL objective, m_h rows Hx<=u plus n positivity rows,
     p_extra rows A x = r plus the sum-to-one row (stacked last); start 1/n => phase I."""
@@ -249,6 +256,8 @@ def to_oracle(prob):
         objF = O.QuadraticObjective(prob["P"], prob["a"], prob["r"])
     elif prob["kind"] == "kl":
         objF = O.KLObjective(prob["n"])
+    elif prob["kind"] == "pnorm":
+        objF = O.PNormObjective(prob["n"], prob["pow"])
     else:
         raise ValueError(prob["kind"])
     quad = [O.QuadCnt(q["P"], q["a"], q["r"], q["ub"]) for q in prob.get("quad") or []]

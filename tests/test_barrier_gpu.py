@@ -146,3 +146,22 @@ def test_step_limit(handle):
     prob = P.kl_small(64, 64, 2)
     sol = cb.from_dict(prob, "BR", cb.SolverParams(stepLimit=5), handle).solve()
     assert sol.executed_newton_steps == 5
+
+
+@pytest.mark.parametrize("pw", [2.0, 3.0, 4.5])
+@pytest.mark.parametrize("solver", ["BR", "PD"])
+def test_min_pnorm_known_minimiser(handle, pw, solver):
+    """SimpleOptimizationProblems.min_pNorm (:179-209): min sum |x_j|^p on the simplex, optimum x_j = 1/n; the
+    objective family is ObjectiveFunctions.p_norm_p (ObjectiveFunctions.scala:70-83); phase I from x = 0."""
+    import cvx_b200 as cb
+    prob = P.min_pNorm(10, pw)
+    objF, cnts, eqs = P.to_oracle(prob)
+    sol0, ph0 = O.solveProblem(objF, cnts, eqs, solver)
+    sol = cb.from_dict(prob, solver, None, handle).solve()
+    assert np.max(np.abs(sol.x - prob["xopt"])) < 1e-6
+    assert abs(sol.objective - objF.valueAt(sol0.x)) <= 1e-8 * max(1.0, abs(sol.objective))
+    assert sol.phase1_stages == ph0.outer_stages
+    if solver == "BR":
+        assert sol.outer_stages == sol0.outer_stages
+    else:
+        assert abs(sol.newton_steps - sol0.newton_steps) <= 1
