@@ -287,17 +287,16 @@ int cvxb_kkt_solve_with_chol_factor(cvxb_handle h, int n, int p, const double* L
   CVXB_TRY(stage_in(*h, p, 1, b, p, db));
   CVXB_TRY(stage_out_alloc(*h, n, 1, dx));
   CVXB_TRY(stage_out_alloc(*h, p, 1, dw));
-  // H := L L' (lower, mirrored) and solve through the standard chain with d = 1: build H explicitly so
-  // the identical code path is exercised; the factor is recomputed from it (equal up to rounding).
-  Staged dHm;
-  CVXB_TRY(stage_out_alloc(*h, n, n, dHm));
-  CVXB_TRY(scaled_lower(*h, n, dL.d, dL.ld, nullptr, 0.0, W->L, W->ldn));   // lower(L), zeros above
-  GemmArgs g{n, n, n, W->L, W->ldn, false, W->L, W->ldn, false, dHm.d, dHm.ld, 1.0, 0.0, 2};
-  CVXB_TRY(gemm_dmma(*h, g));
-  cvxb_params P1 = P;
-  P1.ruizMaxSweeps = 0;    // solveWithCholFactor does not equilibrate
-  st = kkt_solve_device(*h, *W, P1, dHm.d, dHm.ld, dA.d, dA.ld, dq.d, db.d, tol, dx.d, dw.d, info);
-  if (st != CVXB_OK) return st;
+  // one attempt with the caller's factor; LinSolveException when the residual test or the Schur Cholesky fails
+  CVXB_TRY(kkt_enqueue(*h, *W, P, dL.d, dL.ld, dA.d, dA.ld, dq.d, db.d, tol, true, true, dx.d, dw.d, true));
+  CVXB_TRY(fetch_status(*h));
+  fill_info(*h, info, 0, 0);
+  if (h->h_flag[F_ZERO_DIAG]) { cvxb::set_last_error("solveWithCholFactor: zero on the diagonal of L"); return CVXB_ELINSOLVE; }
+  if (h->h_flag[F_BAD]) {
+    cvxb::set_last_error("solveWithCholFactor: Error in solution exceeds tolerance (err1 %.3g, err2 %.3g, Schur info %d)",
+                         h->h_scal[S_ERR1], h->h_scal[S_ERR2], h->h_flag[F_CHOL_S]);
+    return CVXB_ELINSOLVE;
+  }
   CVXB_TRY(copy_out(*h, n, 1, dx, x, n));
   CVXB_TRY(copy_out(*h, p, 1, dw, w, p));
   CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));

@@ -139,6 +139,11 @@ __global__ void __launch_bounds__(VT) chol_resid_kernel(int n, double sign, cons
   }
 }
 
+__global__ void prefactored_reset_kernel(int* flag, double* scal) {
+  flag[F_CHOL_H] = 0;
+  scal[S_MINDIAG_H] = 1e300;
+}
+
 // qk = q - t   (t = A'b)
 __global__ void __launch_bounds__(VT) sub_kernel(int n, const double* __restrict__ a, const double* __restrict__ b,
                                                  double* __restrict__ out) {
@@ -217,11 +222,21 @@ void fill_info(Handle& h, cvxb_kkt_info* info, int path, int regularized) {
 }
 
 int kkt_enqueue(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, int ldh, const double* A, int lda,
-                const double* q, const double* b, double tol, bool regularize, bool skip_ruiz, double* x, double* w) {
+                const double* q, const double* b, double tol, bool regularize, bool skip_ruiz, double* x, double* w,
+                bool prefactored) {
   const int n = W.n, p = W.p;
-  if (!skip_ruiz) CVXB_TRY(ruiz_equilibrate(h, n, Hm, ldh, W.dr, W.colsq, P.ruizMaxSweeps, P.ruizTol));
-  CVXB_TRY(scaled_lower(h, n, Hm, ldh, W.dr, regularize ? P.cholRegDelta : 0.0, W.L, W.ldn));
-  CVXB_TRY(potrf_lower(h, n, W.L, W.ldn, W.invD, F_CHOL_H, S_MINDIAG_H));
+  if (prefactored) {
+    // KKTSystem.solveWithCholFactor (KKTSystem.scala:99-167): the caller's factor L is used as is (d = 1, no
+    // equilibration, no factorisation); only its diagonal blocks are inverted for the triangular solves
+    CVXB_TRY(ruiz_equilibrate(h, n, Hm, ldh, W.dr, W.colsq, 0, P.ruizTol));     // d := 1
+    CVXB_TRY(scaled_lower(h, n, Hm, ldh, nullptr, 0.0, W.L, W.ldn));
+    CVXB_LAUNCH(h, prefactored_reset_kernel, 1, 1, 0, h.d_flag, h.d_scal);
+    CVXB_TRY(invert_diag_blocks(h, n, W.L, W.ldn, W.invD));
+  } else {
+    if (!skip_ruiz) CVXB_TRY(ruiz_equilibrate(h, n, Hm, ldh, W.dr, W.colsq, P.ruizMaxSweeps, P.ruizTol));
+    CVXB_TRY(scaled_lower(h, n, Hm, ldh, W.dr, regularize ? P.cholRegDelta : 0.0, W.L, W.ldn));
+    CVXB_TRY(potrf_lower(h, n, W.L, W.ldn, W.invD, F_CHOL_H, S_MINDIAG_H));
+  }
   // right-hand sides  [D A', D q]
   CVXB_TRY(transpose_scale(h, p, n, A, lda, W.dr, W.Y, W.ldn));
   double* yq = W.Y + (size_t)p * W.ldn;

@@ -29,7 +29,8 @@ void kkt_work_free(KktWork& W);
 //   residual check -> x = d o y.  Outcome in d_flag[F_CHOL_H, F_CHOL_S, F_RUIZ_SWEEPS, F_BAD] and
 //   d_scal[S_MINDIAG_H, S_ERR1, S_ERR2].  F_BAD != 0 <=> this attempt must not be used.
 int kkt_enqueue(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, int ldh, const double* A, int lda,
-                const double* q, const double* b, double tol, bool regularize, bool skip_ruiz, double* x, double* w);
+                const double* q, const double* b, double tol, bool regularize, bool skip_ruiz, double* x, double* w,
+                bool prefactored = false);   // prefactored: Hm holds a Cholesky factor L (KKTSystem.solveWithCholFactor)
 
 // KKTSystem.solve (KKTSystem.scala:43-66) on device pointers, with the host reading the status
 // words between attempts: path 0 -> (regularised retry) -> path 1 (H + A'A) -> path 2.
