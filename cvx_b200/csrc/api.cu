@@ -157,6 +157,15 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
   CVXB_CUDA_OK(cudaMallocHost((void**)&h->h_flag, NFLAG * sizeof(int)));
   CVXB_CUDA_OK(cudaEventCreate(&h->ev0));
   CVXB_CUDA_OK(cudaEventCreate(&h->ev1));
+  {   // keep freed problem memory in the device's default pool instead of returning it to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      cudaGetLastError();
+    }
+  }
   CVXB_CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
   for (int i = 0; i < 600; ++i) {
     cudaEvent_t e;

@@ -394,7 +394,10 @@ int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s*
     if (objective == CVXB_OBJ_KLDUAL) d += 2 * ldn * (size_t)kd + 4 * (size_t)pad_ld(kd) + 6 * 32;
     size_t bytes = d * sizeof(double) + 64 * 256 + kkt_work_bytes(n, p);
     void* base = nullptr;
-    if (cudaMalloc(&base, bytes) == cudaSuccess) {
+    // stream-ordered pool of the handle's device (release threshold = keep everything): the second problem of a
+    // similar size re-uses the first one's memory instead of paying a fresh cudaMalloc of hundreds of MB
+    if (cudaMallocAsync(&base, bytes, h.stream) == cudaSuccess) {
+      P->arena_async = true;
       P->owned.push_back(base);
       P->arena.base = (char*)base; P->arena.size = bytes; P->arena.used = 0;
       if (cudaMemsetAsync(base, 0, bytes, h.stream) != cudaSuccess) st = CVXB_ECUDA;
@@ -422,7 +425,9 @@ int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s*
   }
   if (st == CVXB_OK) st = kkt_work_alloc(h, P->kw, n, p, &P->arena);
   if (st != CVXB_OK) {
-    for (void* q : P->owned) cudaFree(q);
+    for (size_t i = 0; i < P->owned.size(); ++i) {
+      if (i == 0 && P->arena_async) cudaFreeAsync(P->owned[i], h.stream); else cudaFree(P->owned[i]);
+    }
     kkt_work_free(P->kw);
     delete P;
     return st;
@@ -436,7 +441,9 @@ void problem_free(cvxb_problem_s* P) {
   if (P->phase1) problem_free(P->phase1);
   for (int k = 0; k < 2; ++k)
     if (P->step_graph[k]) cudaGraphExecDestroy(P->step_graph[k]);
-  for (void* q : P->owned) cudaFree(q);
+  for (size_t i = 0; i < P->owned.size(); ++i) {
+    if (i == 0 && P->arena_async) cudaFreeAsync(P->owned[i], P->h->stream); else cudaFree(P->owned[i]);
+  }
   kkt_work_free(P->kw);
   delete P;
 }

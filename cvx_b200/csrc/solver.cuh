@@ -41,4 +41,5 @@ struct cvxb_problem_s {
   cvxb_problem_s* phase1 = nullptr;   // the n+1 dimensional feasibility problem (built on demand)
   std::vector<void*> owned;
   cvxb::Arena arena;
+  bool arena_async = false;     // owned[0] came from cudaMallocAsync on the handle's stream
 };
