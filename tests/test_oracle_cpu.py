@@ -163,3 +163,52 @@ def test_dual_route_recovers_known_minimisers():
     objF, c, e = P.to_oracle(pr)
     solp, _ = O.solveProblem(objF, c, e, "BR")
     assert rel(sold.x, solp.x) < 1e-7
+
+
+def test_oracle_kkt_against_extended_precision():
+    """Independent of LAPACK: the oracle's KKT solution against a 50-digit mpmath solve of the same system."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    s = P.kkt_planted_pd(12, 3, 7)
+    x, w = O.kkt_solve(s["H"], s["A"], s["q"], s["b"], 1e-9)
+    n, p = 12, 3
+    M = mp.zeros(n + p, n + p)
+    for i in range(n):
+        for j in range(n):
+            M[i, j] = mp.mpf(float(s["H"][i, j]))
+    for i in range(p):
+        for j in range(n):
+            M[n + i, j] = M[j, n + i] = mp.mpf(float(s["A"][i, j]))
+    rhs = mp.matrix([mp.mpf(float(-v)) for v in s["q"]] + [mp.mpf(float(v)) for v in s["b"]])
+    sol = mp.lu_solve(M, rhs)
+    ref = np.array([float(sol[i]) for i in range(n + p)])
+    got = np.concatenate([x, w])
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-10
+
+
+def test_oracle_lp_against_highs():
+    """Whole-solve answer against an independent solver: scipy's HiGHS on the slab LP with equalities (C1 family)."""
+    from scipy.optimize import linprog
+    prob = P.slab_lp(30, 40, 5, 3)
+    objF, cnts, eqs = P.to_oracle(prob)
+    sol, _ = O.solveProblem(objF, cnts, eqs, "BR")
+    res = linprog(prob["a"], A_ub=prob["G"], b_ub=prob["ub"], A_eq=prob["A"], b_eq=prob["b"], bounds=[(None, None)] * 30,
+                  method="highs")
+    assert res.status == 0
+    assert abs(objF.valueAt(sol.x) - res.fun) < 1e-6 * max(1.0, abs(res.fun))
+
+
+def test_oracle_qp_kkt_conditions():
+    """QP with slab constraints: at the barrier solution the KKT conditions of the ORIGINAL problem hold to the
+    duality-gap accuracy with multipliers lambda_i = 1/(t d_i) (B&V 11.2.2)."""
+    prob = P.slab_qp(24, 30, 4, 2)
+    objF, cnts, eqs = P.to_oracle(prob)
+    sol, _ = O.solveProblem(objF, cnts, eqs, "BR")
+    x = sol.x
+    t = 10.0 ** (sol.outer_stages - 1)
+    d = prob["ub"] - prob["G"] @ x
+    lam = 1.0 / (t * d)
+    g = prob["a"] + prob["P"] @ x + prob["G"].T @ lam
+    nu = np.linalg.lstsq(prob["A"].T, -g, rcond=None)[0]
+    assert np.linalg.norm(g + prob["A"].T @ nu) < 1e-5 * max(1.0, np.linalg.norm(prob["a"]))   # lambda = 1/(t d), d ~ 1e-10: rounding in d
+    assert np.all(d > 0) and float(lam @ d) < 1e-7
