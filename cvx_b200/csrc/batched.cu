@@ -485,8 +485,10 @@ __device__ bool b_linear_solve(Smem& S, const BatchArgs& A, const double* Hs, do
 __device__ bool b_in_set(Smem& S, int m, double s) {
   int out = 0;
   if (threadIdx.x < m) {
-    double g = S.gx[threadIdx.x] + s * S.Gd[threadIdx.x];
-    if (!(g * IN_SET < S.ub[threadIdx.x])) out = 1;
+    const double lin = s * S.Gd[threadIdx.x];
+    const double g = S.gx[threadIdx.x] + lin;
+    const double margin = 3.6e-15 * (fabs(S.gx[threadIdx.x]) + fabs(lin) + fabs(S.ub[threadIdx.x]));   // see solver.cu: ls_in_set
+    if (!(g * IN_SET + margin < S.ub[threadIdx.x])) out = 1;
   }
   return block_or(out, S.ired) == 0;
 }

@@ -124,8 +124,10 @@ __device__ double pd_trial(const PdLs& A, double s, double* buf, int* ibuf, int*
   double sc = 0.0, g_ = 0.0;
   int infeas = 0, ln = 0;
   for (int i = threadIdx.x; i < A.m; i += VT) {
-    double g = A.gx[i] + s * (A.Gd[i] + (A.qq ? s * A.qq[i] : 0.0));
-    if (!(g * IN_SET_FACTOR < A.ub[i])) infeas = 1;
+    const double lin = s * A.Gd[i], qd = A.qq ? s * s * A.qq[i] : 0.0;
+    double g = A.gx[i] + (lin + qd);
+    const double margin = 3.6e-15 * (fabs(A.gx[i]) + fabs(lin) + fabs(qd) + fabs(A.ub[i]));   // see solver.cu: ls_in_set
+    if (!(g * IN_SET_FACTOR + margin < A.ub[i])) infeas = 1;
     double f = g - A.ub[i];
     double l = A.lam[i] + s * A.dlam[i];
     if (!(l > 0.0)) ln = 1;

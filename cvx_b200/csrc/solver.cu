@@ -126,8 +126,13 @@ struct LsArgs {
 __device__ bool ls_in_set(const LsArgs& A, double s, int* ibuf) {
   int out = 0;
   for (int i = threadIdx.x; i < A.m; i += VT) {
-    double g = A.gx[i] + s * (A.Gd[i] + (A.qq ? s * A.qq[i] : 0.0));
-    if (!(g * IN_SET_FACTOR < A.ub[i])) out = 1;
+    const double lin = s * A.Gd[i], qd = A.qq ? s * s * A.qq[i] : 0.0;
+    const double g = A.gx[i] + (lin + qd);
+    // The ray value g(x) + s G d (+ s^2 d'Pd/2) and a fresh evaluation at x + s d differ by rounding; a few ulps of
+    // margin keep the accepted point strictly feasible under BOTH, so the next evaluation can never find a
+    // non-positive slack that this test let through (the reference evaluates both with the same function).
+    const double margin = 3.6e-15 * (fabs(A.gx[i]) + fabs(lin) + fabs(qd) + fabs(A.ub[i]));
+    if (!(g * IN_SET_FACTOR + margin < A.ub[i])) out = 1;
   }
   return block_or(out, ibuf) == 0;
 }

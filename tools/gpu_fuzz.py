@@ -1,0 +1,61 @@
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+"""Randomised differential test: device path vs CPU oracle on many small random problems of every family."""
+import time
+import numpy as np
+import cvx_b200 as cb
+from oracle import cvx_oracle as O, problems as P
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 150
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+h = cb.default_handle()
+bad = 0
+t0 = time.time()
+for it in range(N):
+    fam = rng.choice(["slab_lp", "slab_qp", "kl", "quad", "pnorm", "lp_phase1", "kl_phase1"])
+    n = int(rng.integers(2, 45))
+    seed = int(rng.integers(0, 10**6))
+    solver = str(rng.choice(["BR", "PD"]))
+    try:
+        if fam == "slab_lp":
+            prob = P.slab_lp(n, int(rng.integers(n, 2 * n + 2)), int(rng.integers(0, max(1, min(6, n - 1)))), seed)
+        elif fam == "slab_qp":
+            prob = P.slab_qp(n, int(rng.integers(n // 2 + 1, 2 * n + 2)), int(rng.integers(0, max(1, min(6, n - 1)))), seed)
+        elif fam == "kl":
+            prob = P.kl_small(n, int(rng.integers(1, n + 2)), seed)
+        elif fam == "quad":
+            prob = P.lin_quad_set(n, int(rng.integers(0, n + 3)), int(rng.integers(1, 5)), int(rng.integers(0, max(1, min(4, n - 1)))), seed,
+                                  str(rng.choice(["quadratic", "linear"])) if rng.integers(0, 2) else "quadratic", bool(rng.integers(0, 2)))
+            if prob["kind"] == "linear":
+                # bounded: add a box so the LP has a finite optimum
+                prob["G"] = np.vstack([prob["G"], np.eye(n), -np.eye(n)])
+                prob["ub"] = np.concatenate([prob["ub"], prob["xdef"] + 5.0 if prob["x0"] is None else prob["x0"] + 5.0,
+                                             -(prob["xdef"] if prob["x0"] is None else prob["x0"]) + 5.0])
+                prob["rvec"] = np.zeros(prob["G"].shape[0])
+        elif fam == "pnorm":
+            prob = P.min_pNorm(max(n, 2), float(rng.choice([2.0, 2.5, 3.0, 4.0])))
+        elif fam == "lp_phase1":
+            prob = P.slab_lp(n, int(rng.integers(n, 2 * n + 2)), 0, seed, feasible_start=False)
+        else:
+            prob = P.kl_random(max(n, 4), int(rng.integers(1, n + 2)), int(rng.integers(0, max(1, min(5, n - 2)))), seed)
+        objF, cnts, eqs = P.to_oracle(prob)
+        try:
+            sol0, _ = O.solveProblem(objF, cnts, eqs, solver)
+            r0 = ("ok", objF.valueAt(sol0.x))
+        except Exception as e:
+            r0 = (type(e).__name__, None)
+        try:
+            sol = cb.from_dict(prob, solver, None, h).solve()
+            r1 = ("ok", sol.objective)
+        except cb.CvxbError as e:
+            r1 = (type(e).__name__, None)
+        if r0[0] == "ok" and r1[0] == "ok":
+            if abs(r0[1] - r1[1]) > 1e-7 * max(1.0, abs(r0[1])):
+                bad += 1
+                print("MISMATCH", it, fam, n, seed, solver, r0, r1, flush=True)
+        elif (r0[0] == "ok") != (r1[0] == "ok"):
+            bad += 1
+            print("OUTCOME", it, fam, n, seed, solver, r0, r1, flush=True)
+    except Exception as e:
+        bad += 1
+        print("HARNESS", it, fam, n, seed, solver, repr(e), flush=True)
+print("fuzz: %d cases, %d disagreements, %.1f s" % (N, bad, time.time() - t0))
