@@ -5,10 +5,10 @@ There is no CPU path: importing the solver classes without the built library or 
 from . import _lib  # noqa: F401
 from ._lib import (CvxbError, LinSolveException, UnsolvableSystemException, LineSearchFailedException,  # noqa: F401
                    NotStrictlyFeasible, InfeasibleProblemException, DimensionMismatch, Handle, default_handle)
-from .linalg import KKTSystem, SymmetricLinearSystem, MatrixUtils  # noqa: F401
+from .linalg import KKTSystem, KKTData, SolutionSpace, SymmetricLinearSystem, MatrixUtils  # noqa: F401
 
 __version__ = "0.1.0"
 from .solvers import (SolverParams, Solution, LinearObjectiveFunction, QuadraticObjectiveFunction,  # noqa: F401,E402
                       KLObjectiveFunction, DualKLObjectiveFunction, PNormObjectiveFunction, ConstraintSet, QuadraticConstraint, EqualityConstraint, BarrierSolver, PrimalDualSolver,
-                      OptimizationProblem, Dist_KL, from_dict)
+                      OptimizationProblem, Dist_KL, FeasibilityReport, from_dict)
 from .batched import BatchedBarrierSolver, BatchSolution, pack_problems, shard_range, gather_solutions  # noqa: F401,E402

@@ -142,6 +142,16 @@ SYMBOLS = {
     "cvxb_problem_create": (C.c_int, [_vp, C.POINTER(ProblemDesc), C.POINTER(_vp)]),
     "cvxb_problem_destroy": (C.c_int, [_vp]),
     "cvxb_kldual_primal_optimum": (C.c_int, [_vp, _vp, _vp]),
+    "cvxb_kkt_solve_reduced": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_double, _vp, _vp,
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(KktInfo)]),
+    "cvxb_solution_space_create": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.POINTER(C.c_void_p)]),
+    "cvxb_solution_space_destroy": (C.c_int, [_vp]),
+    "cvxb_solution_space_get": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
+    "cvxb_solution_space_parameter": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "cvxb_solution_space_map": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "cvxb_solve_underdetermined": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, C.c_int]),
+    "cvxb_problem_reduce": (C.c_int, [_vp, _vp, _vp, C.POINTER(Params), C.POINTER(C.c_void_p)]),
+    "cvxb_constraint_values": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(C.c_int)]),
     "cvxb_phase1": (C.c_int, [_vp, _vp, C.POINTER(Params), _vp, C.POINTER(SolutionC)]),
     "cvxb_barrier_solve": (C.c_int, [_vp, _vp, C.POINTER(Params), C.POINTER(SolutionC)]),
     "cvxb_pd_solve": (C.c_int, [_vp, _vp, C.POINTER(Params), C.POINTER(SolutionC)]),

@@ -5,6 +5,7 @@
 // device pointers (copied device-to-device only when their alignment / leading dimension does not
 // satisfy the kernels' 16-byte requirement).
 #include <cstdarg>
+#include <vector>
 #include "kkt.cuh"
 
 namespace cvxb {
@@ -78,6 +79,38 @@ struct DeviceGuard {
   explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
   ~DeviceGuard() { cudaSetDevice(prev); }
 };
+
+// KKTData.reduced (KKTData.scala:68-91): column j is "null" when ||H(:,j)|| + ||A(:,j)|| == 0
+__global__ void null_column_kernel(int n, int p, const double* __restrict__ H, int ldh, const double* __restrict__ A, int lda,
+                                   int* __restrict__ keep) {
+  __shared__ double red[256];
+  const int j = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { double v = H[(size_t)j * ldh + i]; s = fma(v, v, s); }
+  for (int i = threadIdx.x; i < p; i += blockDim.x) { double v = A[(size_t)j * lda + i]; s = fma(v, v, s); }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) keep[j] = red[0] > 0.0 ? 1 : 0;
+}
+// reduced system: Hr = H(I,I), Ar = A(:,I), gr = g(I)
+__global__ void gather_reduced_kernel(int nr, int p, const int* __restrict__ I, const double* __restrict__ H, int ldh,
+                                      const double* __restrict__ A, int lda, const double* __restrict__ g,
+                                      double* __restrict__ Hr, int ldhr, double* __restrict__ Ar, int ldar,
+                                      double* __restrict__ gr) {
+  const int jr = blockIdx.x, j = I[jr];
+  for (int ir = threadIdx.x; ir < nr; ir += blockDim.x) Hr[(size_t)jr * ldhr + ir] = H[(size_t)j * ldh + I[ir]];
+  for (int i = threadIdx.x; i < p; i += blockDim.x) Ar[(size_t)jr * ldar + i] = A[(size_t)j * lda + i];
+  if (threadIdx.x == 0) gr[jr] = g[j];
+}
+// KKTData.paddVector (KKTData.scala:105-127): zeros at the eliminated coordinates
+__global__ void pad_vector_kernel(int nr, const int* __restrict__ I, const double* __restrict__ xr, double* __restrict__ x) {
+  int ir = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ir < nr) x[I[ir]] = xr[ir];
+}
 
 __global__ void check_symmetric_kernel(int n, const double* __restrict__ Q, int ldq, double* out) {
   // ||Q - Q'||_F^2 partial per block -> atomic-free: one block per column, then summed by block 0 later
@@ -255,6 +288,144 @@ int cvxb_kkt_solve(cvxb_handle h, int n, int p, const double* H, int ldh, const 
   CVXB_TRY(copy_out(*h, p, 1, dw, w, p));
   CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
   return CVXB_OK;
+}
+
+int cvxb_kkt_solve_reduced(cvxb_handle h, int n, int p, const double* H, int ldh, const double* A, int lda, const double* g,
+                           const double* r, double tol, double* x, double* w, int* null_indices, int* n_null,
+                           cvxb_kkt_info* info) {
+  // KKTData(H,A,g,r).reduced -> KKTSystem(rH,rA,rg,r).solve -> KKTData.paddVector   (KKTData.scala:68-127, KktTest.scala:52-104)
+  CHECK_HANDLE(h);
+  if (n < 1 || p < 1) { cvxb::set_last_error("cvxb_kkt_solve_reduced: need n >= 1 and p >= 1 (got %d, %d)", n, p); return CVXB_EDIM; }
+  if (!x || !w || !g) { cvxb::set_last_error("cvxb_kkt_solve_reduced: null argument"); return CVXB_EINVAL; }
+  if (h->flags & CVXB_FLAG_DEVICE_PTRS) { cvxb::set_last_error("cvxb_kkt_solve_reduced takes host pointers"); return CVXB_EINVAL; }
+  cvxb_params P;
+  cvxb_default_params(&P);
+  Staged dH, dA, dg, db;
+  CVXB_TRY(stage_in(*h, n, n, H, ldh, dH));
+  CVXB_TRY(stage_in(*h, p, n, A, lda, dA));
+  CVXB_TRY(stage_in(*h, n, 1, g, n, dg));
+  CVXB_TRY(stage_in(*h, p, 1, r, p, db));
+  int* d_keep = nullptr;
+  CVXB_CUDA_OK(cudaMalloc((void**)&d_keep, sizeof(int) * 2 * (size_t)n));
+  struct Free { int* p; ~Free() { cudaFree(p); } } guard{d_keep};
+  int* d_idx = d_keep + n;
+  CVXB_LAUNCH(*h, null_column_kernel, n, 256, 0, n, p, dH.d, dH.ld, dA.d, dA.ld, d_keep);
+  std::vector<int> keep((size_t)n), idx;
+  CVXB_CUDA_OK(cudaMemcpyAsync(keep.data(), d_keep, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  int nn = 0;
+  for (int j = 0; j < n; ++j) {
+    if (keep[j]) { idx.push_back(j); continue; }
+    if (!(fabs(g[j]) < 1e-15)) {
+      cvxb::set_last_error("Unsolvable KKT system, row %d is zero with nonzero right hand side.", j);
+      return CVXB_EUNSOLVABLE;
+    }
+    if (null_indices) null_indices[nn] = j;
+    ++nn;
+  }
+  if (n_null) *n_null = nn;
+  const int nr = (int)idx.size();
+  if (nr < 1) { cvxb::set_last_error("cvxb_kkt_solve_reduced: every row of the system is zero"); return CVXB_EUNSOLVABLE; }
+  int st;
+  KktWork* W = cached_work(*h, nr, p, &st);
+  if (!W) return st;
+  Staged dx, dw;
+  CVXB_TRY(stage_out_alloc(*h, nr, 1, dx));
+  CVXB_TRY(stage_out_alloc(*h, p, 1, dw));
+  if (nn == 0) {
+    st = kkt_solve_device(*h, *W, P, dH.d, dH.ld, dA.d, dA.ld, dg.d, db.d, tol, dx.d, dw.d, info);
+    if (st != CVXB_OK) return st;
+    CVXB_TRY(copy_out(*h, n, 1, dx, x, n));
+  } else {
+    Staged rH, rA, rg, xp;
+    CVXB_TRY(stage_out_alloc(*h, nr, nr, rH));
+    CVXB_TRY(stage_out_alloc(*h, p, nr, rA));
+    CVXB_TRY(stage_out_alloc(*h, nr, 1, rg));
+    CVXB_TRY(stage_out_alloc(*h, n, 1, xp));
+    CVXB_CUDA_OK(cudaMemsetAsync(rH.d, 0, sizeof(double) * (size_t)rH.ld * nr, h->stream));
+    CVXB_CUDA_OK(cudaMemsetAsync(rA.d, 0, sizeof(double) * (size_t)rA.ld * nr, h->stream));
+    CVXB_CUDA_OK(cudaMemsetAsync(rg.d, 0, sizeof(double) * (size_t)rg.ld, h->stream));
+    CVXB_CUDA_OK(cudaMemsetAsync(xp.d, 0, sizeof(double) * (size_t)xp.ld, h->stream));
+    CVXB_CUDA_OK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * nr, cudaMemcpyHostToDevice, h->stream));
+    CVXB_LAUNCH(*h, gather_reduced_kernel, nr, 256, 0, nr, p, d_idx, dH.d, dH.ld, dA.d, dA.ld, dg.d, rH.d, rH.ld, rA.d, rA.ld, rg.d);
+    st = kkt_solve_device(*h, *W, P, rH.d, rH.ld, rA.d, rA.ld, rg.d, db.d, tol, dx.d, dw.d, info);
+    if (st != CVXB_OK) return st;
+    CVXB_LAUNCH(*h, pad_vector_kernel, (nr + 255) / 256, 256, 0, nr, d_idx, dx.d, xp.d);
+    CVXB_TRY(copy_out(*h, n, 1, xp, x, n));
+  }
+  CVXB_TRY(copy_out(*h, p, 1, dw, w, p));
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CVXB_OK;
+}
+
+struct cvxb_solution_space_s : cvxb::SolutionSpaceDev {};
+
+int cvxb_solution_space_create(cvxb_handle h, int p, int n, const double* A, int lda, const double* b,
+                               cvxb_solution_space* out) {
+  CHECK_HANDLE(h);
+  if (!A || !b || !out) { cvxb::set_last_error("cvxb_solution_space_create: null argument"); return CVXB_EINVAL; }
+  if (!(p >= 1 && p < n)) { cvxb::set_last_error("SolutionSpace: need 1 <= A.rows < A.cols (got %d x %d)", p, n); return CVXB_EDIM; }
+  Staged dA, db;
+  CVXB_TRY(stage_in(*h, p, n, A, lda, dA));
+  CVXB_TRY(stage_in(*h, p, 1, b, p, db));
+  SolutionSpaceDev* S = nullptr;
+  CVXB_TRY(solution_space_build(*h, p, n, dA.d, dA.ld, db.d, &S));
+  *out = (cvxb_solution_space)S;
+  return CVXB_OK;
+}
+
+int cvxb_solution_space_destroy(cvxb_solution_space space) {
+  if (space) { cudaDeviceSynchronize(); solution_space_free((SolutionSpaceDev*)space); }
+  return CVXB_OK;
+}
+
+int cvxb_solution_space_get(cvxb_handle h, cvxb_solution_space space, double* z0, double* F, int ldf) {
+  CHECK_HANDLE(h);
+  if (!space) { cvxb::set_last_error("null solution space"); return CVXB_EINVAL; }
+  SolutionSpaceDev* S = (SolutionSpaceDev*)space;
+  if (F && ldf < S->n) { cvxb::set_last_error("leading dimension %d < rows %d", ldf, S->n); return CVXB_EDIM; }
+  Staged sz, sf;
+  sz.d = S->z0; sz.ld = pad_ld(S->n);
+  sf.d = S->F(); sf.ld = S->ldq;
+  CVXB_TRY(copy_out(*h, S->n, 1, sz, z0, S->n));
+  CVXB_TRY(copy_out(*h, S->n, S->k(), sf, F, ldf));
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CVXB_OK;
+}
+
+int cvxb_solution_space_parameter(cvxb_handle h, cvxb_solution_space space, const double* x, double* u) {
+  CHECK_HANDLE(h);
+  if (!space || !x || !u) { cvxb::set_last_error("cvxb_solution_space_parameter: null argument"); return CVXB_EINVAL; }
+  SolutionSpaceDev* S = (SolutionSpaceDev*)space;
+  Staged dx, du;
+  CVXB_TRY(stage_in(*h, S->n, 1, x, S->n, dx));
+  CVXB_TRY(stage_out_alloc(*h, S->k(), 1, du));
+  CVXB_TRY(solution_space_parameter(*h, S, dx.d, du.d));
+  CVXB_TRY(copy_out(*h, S->k(), 1, du, u, S->k()));
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CVXB_OK;
+}
+
+int cvxb_solution_space_map(cvxb_handle h, cvxb_solution_space space, const double* u, double* x) {
+  CHECK_HANDLE(h);
+  if (!space || !x || !u) { cvxb::set_last_error("cvxb_solution_space_map: null argument"); return CVXB_EINVAL; }
+  SolutionSpaceDev* S = (SolutionSpaceDev*)space;
+  Staged dx, du;
+  CVXB_TRY(stage_in(*h, S->k(), 1, u, S->k(), du));
+  CVXB_TRY(stage_out_alloc(*h, S->n, 1, dx));
+  CVXB_TRY(solution_space_map(*h, S, du.d, dx.d));
+  CVXB_TRY(copy_out(*h, S->n, 1, dx, x, S->n));
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CVXB_OK;
+}
+
+int cvxb_solve_underdetermined(cvxb_handle h, int p, int n, const double* A, int lda, const double* b, double* z0,
+                               double* F, int ldf) {
+  cvxb_solution_space sp = nullptr;
+  CVXB_TRY(cvxb_solution_space_create(h, p, n, A, lda, b, &sp));
+  int st = cvxb_solution_space_get(h, sp, z0, F, ldf);
+  cvxb_solution_space_destroy(sp);
+  return st;
 }
 
 int cvxb_cholesky_solve(cvxb_handle h, int n, const double* H, int ldh, const double* b, double tol, double* x,

@@ -20,6 +20,20 @@ struct KktWork {
   Arena* arena = nullptr;
 };
 
+// SolutionSpace of A x = b (SolutionSpace.scala:20-33), device resident (qr.cu): x = z0 + F u
+struct SolutionSpaceDev {
+  int n = 0, p = 0, ldq = 0;
+  double* Q = nullptr;      // n x n orthogonal factor of A' = QR; F = Q(:, p..n-1)
+  double* z0 = nullptr;     // minimum-norm solution
+  double* tmp = nullptr;    // 2 * pad_ld(n) scratch
+  double* F() const { return Q + (size_t)p * ldq; }
+  int k() const { return n - p; }
+};
+int solution_space_build(Handle& h, int p, int n, const double* A, int lda, const double* b, SolutionSpaceDev** out);
+void solution_space_free(SolutionSpaceDev* S);
+int solution_space_parameter(Handle& h, SolutionSpaceDev* S, const double* x, double* u);   // u = F'(x - z0)
+int solution_space_map(Handle& h, SolutionSpaceDev* S, const double* u, double* x);         // x = z0 + F u
+
 int kkt_work_alloc(Handle& h, KktWork& W, int n, int p, Arena* arena = nullptr);
 size_t kkt_work_bytes(int n, int p);
 void kkt_work_free(KktWork& W);

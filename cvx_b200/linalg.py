@@ -65,6 +65,43 @@ class KKTSystem:
         return x, w
 
 
+class KKTData:
+    """KKTData(H, A, g, r, nullIndices) (KKTData.scala:31-91):  Hx + A'nu = -g, Ax = r, with the elimination of the
+    variables the system does not depend on.  `solveReduced` = reduced -> KKTSystem.solve -> paddVector in one
+    device call (cvxb_kkt_solve_reduced); it returns (x padded with zeros, nu) and sets `nullIndices`."""
+
+    def __init__(self, H, A, g, r, nullIndices=None, handle=None):
+        self.H, self.A, self.g, self.r = fmat(H), fmat(A), fvec(g), fvec(r)
+        n = self.H.shape[1]
+        if self.H.shape[0] != n:
+            raise _lib.DimensionMismatch("Matrix H not square, n=H.cols=%d, H.rows=%d" % (n, self.H.shape[0]))
+        if self.A.shape[1] != n:
+            raise _lib.DimensionMismatch("A.cols=%d not equal to n=M.rows=%d" % (self.A.shape[1], n))
+        self.nullIndices = None if nullIndices is None else list(nullIndices)
+        self.handle = _h(handle)
+        self.info = KktInfo()
+
+    def solveReduced(self, delta=1e-6, logger=None, tol=1e-1, debugLevel=0):
+        n, p = self.H.shape[1], self.A.shape[0]
+        x = np.empty(n)
+        w = np.empty(p)
+        idx = (C.c_int * n)()
+        cnt = C.c_int(0)
+        hd = self.handle
+        check(hd.lib.cvxb_kkt_solve_reduced(hd._h, n, p, ptr(self.H), n, ptr(self.A), p, ptr(self.g), ptr(self.r), float(tol),
+                                            ptr(x), ptr(w), idx, C.byref(cnt), C.byref(self.info)))
+        self.nullIndices = [int(idx[k]) for k in range(cnt.value)] if cnt.value else None
+        return x, w
+
+    @staticmethod
+    def paddVector(x, nullIndices):
+        """KKTData.paddVector (KKTData.scala:105-127)."""
+        x = fvec(x)
+        z = np.zeros(x.shape[0] + len(nullIndices))
+        z[np.setdiff1d(np.arange(z.shape[0]), np.asarray(nullIndices, dtype=int))] = x
+        return z
+
+
 class SymmetricLinearSystem:
     def __init__(self, H, r, logger=None, handle=None):
         self.H, self.r = fmat(H), fvec(r)
@@ -82,8 +119,81 @@ class SymmetricLinearSystem:
         return x
 
 
+class SolutionSpace:
+    """SolutionSpace(A, b) (SolutionSpace.scala:20-33): all solutions of the underdetermined full-rank system Ax = b as
+    x = z0 + F u, z0 the minimum-norm solution, the columns of F an orthonormal basis of ker(A).  The QR of A' runs
+    on the device (blocked Householder, cvxb_solution_space_create) and (z0, F) stay device resident for
+    BarrierSolver.reduced; `.z0` / `.F` download them on first use."""
+
+    def __init__(self, A, b, handle=None):
+        self.A, self.b = fmat(A), fvec(b)
+        p, n = self.A.shape
+        if p != self.b.shape[0]:
+            raise _lib.DimensionMismatch("SolutionSpace: A.rows != b.length")
+        if not p < n:
+            raise _lib.DimensionMismatch("SolutionSpace: need A.rows < A.cols")
+        self.handle = _h(handle)
+        self._s = C.c_void_p()
+        check(self.handle.lib.cvxb_solution_space_create(self.handle._h, p, n, ptr(self.A), p, ptr(self.b), C.byref(self._s)))
+        self.n, self.p = n, p
+        self._z0 = self._F = None
+
+    def _fetch(self):
+        if self._z0 is None:
+            z0 = np.empty(self.n)
+            F = np.empty((self.n, self.n - self.p), order="F")
+            check(self.handle.lib.cvxb_solution_space_get(self.handle._h, self._s, ptr(z0), ptr(F), self.n))
+            self._z0, self._F = z0, F
+
+    @property
+    def z0(self):
+        self._fetch()
+        return self._z0
+
+    @property
+    def F(self):
+        self._fetch()
+        return self._F
+
+    def parameter(self, x0):
+        """u0 with x0 = z0 + F u0 when A x0 = b:  F'(x0 - z0)  (SolutionSpace.scala:32)."""
+        u = np.empty(self.n - self.p)
+        check(self.handle.lib.cvxb_solution_space_parameter(self.handle._h, self._s, ptr(fvec(x0)), ptr(u)))
+        return u
+
+    def point(self, u):
+        """x = z0 + F u."""
+        x = np.empty(self.n)
+        check(self.handle.lib.cvxb_solution_space_map(self.handle._h, self._s, ptr(fvec(u)), ptr(x)))
+        return x
+
+    def close(self):
+        if getattr(self, "_s", None):
+            self.handle.lib.cvxb_solution_space_destroy(self._s)
+            self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class MatrixUtils:
     """Static methods of the reference's MatrixUtils object that lie on the hot path."""
+
+    @staticmethod
+    def solveUnderdetermined(A, b, handle=None):
+        """(z0, F) of MatrixUtils.solveUnderdetermined (MatrixUtils.scala:536-550)."""
+        A, b = fmat(A), fvec(b)
+        p, n = A.shape
+        if not (p == b.shape[0] and p < n):
+            raise _lib.DimensionMismatch("solveUnderdetermined: need A.rows == b.length and A.rows < A.cols")
+        z0 = np.empty(n)
+        F = np.empty((n, n - p), order="F")
+        hd = _h(handle)
+        check(hd.lib.cvxb_solve_underdetermined(hd._h, p, n, ptr(A), p, ptr(b), ptr(z0), ptr(F), n))
+        return z0, F
 
     @staticmethod
     def choleskySolve(H, b, logger=None, tol=1e-1, debugLevel=0, handle=None, info=None):

@@ -170,11 +170,167 @@ class ConstraintSet:
         c.feasiblePoint = fvec(x0)
         return c
 
+    # ---- evaluation on the device (the set is uploaded once, with a zero objective)
+    def _device(self, handle=None):
+        dev = getattr(self, "_dev", None)
+        if dev is None or (handle is not None and dev.handle is not handle):
+            dev = self._dev = _DeviceProblem(LinearObjectiveFunction(self.dim, 0.0, np.zeros(self.dim)), self, None, handle)
+        return dev
+
+    def valuesAt(self, x, handle=None):
+        """g_i(x) for every constraint (linear rows first, then the quadratic ones)."""
+        return self._values(x, handle)[0]
+
+    def isSatisfiedStrictlyBy(self, x, handle=None) -> bool:
+        """ConstraintSet.scala:28-29."""
+        return self._values(x, handle)[1]
+
+    def _values(self, x, handle=None):
+        dev = self._device(handle)
+        g = np.empty(max(self.numConstraints, 1))
+        ok = C.c_int(0)
+        check(dev.handle.lib.cvxb_constraint_values(dev.handle._h, dev._p, ptr(fvec(x)), ptr(g), C.byref(ok)))
+        return g[:self.numConstraints], bool(ok.value)
+
+    def ub_all(self):
+        return np.concatenate([self.u, np.array([q.ub for q in self.quadratic])]) if self.quadratic else self.u
+
+    # ---- phase I, basic method (ConstraintSet.scala:355-414)
+    def phase_I_Analysis(self, eqs, pars=None, debugLevel=0, handle=None) -> "FeasibilityReport":
+        """Basic phase I ([boyd] 11.4.1 p579): one extra variable s, minimise s until s < 0; with equalities the rows
+        of eqs.asInequalities(1e-6) are appended (ConstraintSet.scala:310-347).  Device-resident (cvxb_phase1)."""
+        pars = pars if pars is not None else SolverParams.standardParams()
+        solver = BarrierSolver(LinearObjectiveFunction(self.dim, 0.0, np.zeros(self.dim)), self, eqs, pars, None, handle)
+        x_feas, ph = solver.phase_I()
+        s_feas = float(ph.x[self.dim])
+        eqError = 0.0 if eqs is None else eqs.errorAt(x_feas)
+        strict = s_feas < 0.0 and (eqs is None or eqError < pars.tolSolver)
+        rep = FeasibilityReport(x_feas, np.array([s_feas]), strict, self, eqError)
+        rep.solution = ph
+        return rep
+
+    # ---- phase I, sum of infeasibilities (ConstraintSet.scala:233-282, 488-545; Constraint.scala:101-159)
+    def phase_I_SOI_ObjectiveFunction(self):
+        """f(x, s) = s_1 + ... + s_p in dimension n + p (ConstraintSet.scala:233-249)."""
+        n, p = self.dim, self.numConstraints
+        a = np.zeros(n + p)
+        a[n:] = 1.0
+        return LinearObjectiveFunction(n + p, 0.0, a)
+
+    def phase_I_SOI_Constraints(self, handle=None) -> "ConstraintSet":
+        """g_j(x) - s_j <= ub_j and -s_j <= 0 in dimension n + p, with the feasible point
+        (x, max(0.5, 1 + g_j(x) - ub_j)) at x = pointWhereDefined (ConstraintSet.scala:259-282).  Rows: linear
+        g_j - s_j, then -s_j <= 0, then the quadratic constraints (the reference lists the positivity rows last)."""
+        n, p, ml = self.dim, self.numConstraints, self.H.shape[0]
+        N = n + p
+        G = np.zeros((ml + p, N), order="F")
+        G[:ml, :n] = self.H
+        G[np.arange(ml), n + np.arange(ml)] = -1.0
+        G[ml + np.arange(p), n + np.arange(p)] = -1.0
+        r = np.concatenate([self.r if self.r is not None else np.zeros(ml), np.zeros(p)])
+        u = np.concatenate([self.u, np.zeros(p)])
+        quad = []
+        for k, q in enumerate(self.quadratic):
+            P1 = np.zeros((N, N))
+            P1[:n, :n] = q.P
+            a1 = np.zeros(N)
+            a1[:n] = q.a
+            a1[n + ml + k] = -1.0
+            quad.append(QuadraticConstraint(str(q.id) + "_phase_I", N, q.ub, q.r, a1, P1))
+        x = self.pointWhereDefined
+        assert x is not None, "phase_I_SOI_Constraints needs pointWhereDefined"
+        viol = self.valuesAt(x, handle) - self.ub_all()
+        fp = np.concatenate([x, np.maximum(0.5, 1.0 + viol)])
+        return ConstraintSet(G, u, fp, r, quad).addFeasiblePoint(fp)
+
+    def phase_I_Analysis_SOI(self, eqs, pars=None, debugLevel=0, handle=None) -> "FeasibilityReport":
+        """ConstraintSet.phase_I_Analysis_SOI (ConstraintSet.scala:511-545): full barrier solve of the SOI problem.
+        isStrictlyFeasible follows the reference's test over `0 until n` (defect D9, see oracle)."""
+        pars = pars if pars is not None else SolverParams.standardParams()
+        n, p = self.dim, self.numConstraints
+        eqs_soi = None if eqs is None else eqs.phase_I_SOI_EqualityConstraint(p)
+        solver = BarrierSolver(self.phase_I_SOI_ObjectiveFunction(), self.phase_I_SOI_Constraints(handle), eqs_soi, pars,
+                               None, handle)
+        sol = solver.solve(debugLevel)
+        x_feas, s_feas = sol.x[:n].copy(), sol.x[n:n + p].copy()
+        eqError = None if eqs is None else eqs.errorAt(x_feas)
+        strict = True
+        for j in range(n):
+            if not (s_feas[j] < 0):            # IndexError for j >= p, as the JVM would throw
+                strict = False
+                break
+        strict = strict and ((0.0 if eqError is None else eqError) < pars.tolSolver)
+        rep = FeasibilityReport(x_feas, s_feas, strict, self, eqError)
+        rep.solution = sol
+        return rep
+
+    def withFeasiblePoint(self, eqs, pars=None, debugLevel=0, handle=None) -> "ConstraintSet":
+        """ConstraintSet.withFeasiblePoint (ConstraintSet.scala:556-575)."""
+        if self.feasiblePoint is not None:
+            return self
+        pars = pars if pars is not None else SolverParams.standardParams()
+        rep = self.phase_I_Analysis(eqs, pars, debugLevel, handle)
+        if not rep.isFeasible(pars.tolSolver):
+            raise _lib.InfeasibleProblemException(rep.reasonWhyInfeasible(pars.tolSolver))
+        return self.addFeasiblePoint(rep.x0)
+
+
+@dataclass
+class FeasibilityReport:
+    """FeasibilityReport.scala:12-48."""
+    x0: np.ndarray
+    s: np.ndarray
+    isStrictlyFeasible: bool
+    constraintSet: ConstraintSet
+    equalityConstraintError: Optional[float]
+    solution: Optional["Solution"] = None
+
+    def violatedConstraints(self, tol: float) -> List[int]:
+        """indices of the constraints with g_i(x0) > ub_i + tol (Constraint.isSatisfiedWithTolerance)."""
+        c = self.constraintSet
+        return [int(i) for i in np.nonzero(~(c.valuesAt(self.x0) <= c.ub_all() + tol))[0]]
+
+    def isFeasible(self, tol: float) -> bool:
+        e = 0.0 if self.equalityConstraintError is None else self.equalityConstraintError
+        return bool(np.max(self.s) < tol and e < tol)
+
+    def reasonWhyInfeasible(self, tol: float) -> str:
+        if self.isFeasible(tol):
+            return "\nCannot determine if problem is feasible.\n"
+        return ("\nProblem not feasible within tolerance %g\nFound point x0:\n%s\nviolates constraints:\n%s"
+                "\nEqualityContraints, error: %s\n" % (tol, self.x0, self.violatedConstraints(tol),
+                                                       self.equalityConstraintError or 0))
+
 
 class EqualityConstraint:
     def __init__(self, A, b):
         self.A, self.b = fmat(A), fvec(b)
         assert self.A.shape[0] == self.b.shape[0]
+
+    def errorAt(self, x) -> float:
+        """||Ax - b|| (EqualityConstraint.scala:26)."""
+        return float(np.linalg.norm(self.A @ fvec(x) - self.b))
+
+    @property
+    def solutionSpace(self):
+        """EqualityConstraint.solutionSpace (EqualityConstraint.scala:21-23).  The reference computes this QR eagerly in
+        the constructor although the main solver paths never use it; here it is lazy and runs on the device."""
+        if getattr(self, "_space", None) is None:
+            from .linalg import SolutionSpace
+            self._space = SolutionSpace(self.A, self.b)
+        return self._space
+
+    @property
+    def F(self):
+        return self.solutionSpace.F
+
+    @property
+    def z0(self):
+        return self.solutionSpace.z0
+
+    def phase_I_SOI_EqualityConstraint(self, p: int) -> "EqualityConstraint":
+        """[A, 0] u = b in dimension n + p (EqualityConstraint.scala:50-55)."""
+        return EqualityConstraint(np.hstack([self.A, np.zeros((self.A.shape[0], int(p)))]), self.b)
 
 
 class _DeviceProblem:
@@ -270,7 +426,38 @@ class Solver:
         raise NotImplementedError
 
 
-class BarrierSolver(Solver):
+class _ReducedMixin:
+    """Solver.reduced(sol) (BarrierSolver.scala:249-256, PrimalDualSolver.scala:699-712): the same problem in the variable
+    u of x = z0 + F u.  As in the reference the returned solver works in u (Solution.x is u); `point(u)` maps back."""
+
+    def reduced(self, sol):
+        red = object.__new__(type(self))
+        red.objF, red.cnts, red.eqs, red.pars = self.objF, self.cnts, None, self.pars
+        red.handle = self.handle
+        red.space = sol
+        red.problem = _ReducedProblem(self.problem, sol, self.pars)
+        return red
+
+    def point(self, u):
+        return self.space.point(u)
+
+
+class _ReducedProblem:
+    def __init__(self, base: "_DeviceProblem", sol, pars):
+        self.handle = base.handle
+        if sol.handle is not base.handle:
+            raise ValueError("solution space and problem live on different handles")
+        self._p = C.c_void_p()
+        cp = pars.to_c(self.handle)
+        check(self.handle.lib.cvxb_problem_reduce(self.handle._h, base._p, sol._s, C.byref(cp), C.byref(self._p)))
+        self.n, self.m, self.p = sol.n - sol.p, base.m, 0
+        self._keep = (base, sol)
+
+    close = _DeviceProblem.close
+    __del__ = _DeviceProblem.__del__
+
+
+class BarrierSolver(_ReducedMixin, Solver):
     """BarrierSolver(objF, cnts, eqs, pars, logger).solve(debugLevel); phase I runs first when the
     constraint set has no feasible point (what OptimizationProblem.withoutFeasiblePoint does)."""
     solverType = "BR"
@@ -304,7 +491,7 @@ class BarrierSolver(Solver):
         return H, g, dx, (nu[:pr.p] if pr.p else None), info
 
 
-class PrimalDualSolver(Solver):
+class PrimalDualSolver(_ReducedMixin, Solver):
     solverType = "PD"
 
     def solve(self, debugLevel: int = 0) -> Solution:

@@ -40,6 +40,7 @@ typedef enum cvxb_status {
 
 typedef struct cvxb_handle_s* cvxb_handle;
 typedef struct cvxb_problem_s* cvxb_problem;
+typedef struct cvxb_solution_space_s* cvxb_solution_space;
 
 enum { CVXB_FLAG_DEVICE_PTRS = 1 };
 
@@ -98,6 +99,16 @@ typedef struct cvxb_kkt_info {
 int cvxb_kkt_solve(cvxb_handle h, int n, int p, const double* H, int ldh, const double* A, int lda,
                    const double* q, const double* b, double tol, double* x, double* w,
                    cvxb_kkt_info* info);
+
+/* KKTData(H,A,g,r,...).reduced + KKTSystem.solve + KKTData.paddVector (KKTData.scala:68-127; exercised by
+ * KktTest.testKktSystemReduction, KktTest.scala:52-104): variables x_j on which neither H, A nor g depend (row and
+ * column j of H, column j of A all zero -- as in phase-I systems with unconstrained variables) are eliminated, the
+ * reduced system  Hr xr + Ar'w = -gr, Ar xr = r  is solved with the cvxb_kkt_solve chain, and x is padded back with
+ * zeros.  A zero row with |g_j| >= 1e-15 gives CVXB_EUNSOLVABLE.  null_indices (n ints, may be NULL) receives the
+ * eliminated indices in increasing order, *n_null their number.  Host pointers only. */
+int cvxb_kkt_solve_reduced(cvxb_handle h, int n, int p, const double* H, int ldh, const double* A, int lda, const double* g,
+                           const double* r, double tol, double* x, double* w, int* null_indices, int* n_null,
+                           cvxb_kkt_info* info);
 
 /* KKTSystem.solveWithCholFactor(L,A,q,b,logger,tol,debugLevel)   KKTSystem.scala:99-167 */
 int cvxb_kkt_solve_with_chol_factor(cvxb_handle h, int n, int p, const double* L, int ldl,
@@ -168,6 +179,39 @@ typedef struct cvxb_problem_desc {
 
 /* Duality.primalOptimum for CVXB_OBJ_KLDUAL: x = R o exp(-B'z) at the problem's current iterate (after a solve). */
 int cvxb_kldual_primal_optimum(cvxb_handle h, cvxb_problem prob, double* x_primal);
+
+/* ---- equality elimination x = z0 + F u   -------------------------------------------------------
+ * MatrixUtils.solveUnderdetermined (MatrixUtils.scala:536-550) / SolutionSpace (SolutionSpace.scala:20-33), which the
+ * reference runs eagerly in every EqualityConstraint constructor (EqualityConstraint.scala:21-23): QR of A' (n x p)
+ * by blocked Householder reflections on the device, F = Q(:, p..n-1) an orthonormal basis of ker A, z0 = the
+ * minimum-norm solution of A x = b.  A is p x n column-major with 1 <= p < n and full rank (not checked, as in the
+ * reference; a zero pivot of R gives CVXB_ELINSOLVE).  Host pointers unless the handle has CVXB_FLAG_DEVICE_PTRS. */
+int cvxb_solution_space_create(cvxb_handle h, int p, int n, const double* A, int lda, const double* b,
+                               cvxb_solution_space* out);
+int cvxb_solution_space_destroy(cvxb_solution_space space);
+/* z0 (n) and F (n x (n-p), leading dimension ldf); either may be NULL */
+int cvxb_solution_space_get(cvxb_handle h, cvxb_solution_space space, double* z0, double* F, int ldf);
+/* SolutionSpace.parameter: u = F'(x - z0) (length n-p) */
+int cvxb_solution_space_parameter(cvxb_handle h, cvxb_solution_space space, const double* x, double* u);
+/* x = z0 + F u */
+int cvxb_solution_space_map(cvxb_handle h, cvxb_solution_space space, const double* u, double* x);
+/* one shot: (z0, F) = MatrixUtils.solveUnderdetermined(A, b) */
+int cvxb_solve_underdetermined(cvxb_handle h, int p, int n, const double* A, int lda, const double* b, double* z0,
+                               double* F, int ldf);
+/* BarrierSolver.reduced(sol) / PrimalDualSolver.reduced(sol) (BarrierSolver.scala:249-256, PrimalDualSolver.scala:699):
+ * the problem of dimension n-p in the variable u, built on the device from a problem WITHOUT equality constraints
+ * (linear or quadratic objective; linear and quadratic constraints): constraints (G F) u <= ub - r - G z0, P -> F'PF,
+ * a -> F'(a + P z0); starting points u0 = F'(x0 - z0), with the reference's check ||x0 - (z0 + F u0)|| < tolEqSolve
+ * (CVXB_EINVAL).  Solve it with cvxb_barrier_solve / cvxb_pd_solve; the solution's x is u, as in the reference --
+ * map it back with cvxb_solution_space_map.  Other objective families: CVXB_ENOTIMPL. */
+int cvxb_problem_reduce(cvxb_handle h, cvxb_problem prob, cvxb_solution_space space, const cvxb_params* pars,
+                        cvxb_problem* reduced);
+
+/* ConstraintSet.valuesAt-style evaluation: g[i] = g_i(x) for the m linear rows then the mq quadratic constraints
+ * (Constraint.valueAt, LinearConstraint.scala:22, QuadraticConstraint.scala:30), and *strictly_satisfied =
+ * ConstraintSet.isSatisfiedStrictlyBy(x) (ConstraintSet.scala:28-29: g_i(x)(1+3e-16) < ub_i for all i).  Host pointers.
+ * Used by the phase-I drivers (starting values of the SOI variables, violated-constraint reports). */
+int cvxb_constraint_values(cvxb_handle h, cvxb_problem prob, const double* x, double* g, int* strictly_satisfied);
 
 /* mirrors Solution.scala:32-43; has_* say which Option fields are Some(...) */
 typedef struct cvxb_solution {

@@ -371,6 +371,65 @@ def kkt_solve(H, A, q, b, tol, info: Optional[KKTInfo] = None):
             return kktSymSolve(H, A, q, b, tol)
 
 
+def solveUnderdetermined(A, b):
+    """MatrixUtils.solveUnderdetermined (MatrixUtils.scala:536-550): A' = QR (Breeze qr = LAPACK dgeqrf + dorgqr, full
+    Q), F = Q(:, m..n-1), y = forwardSolve(R', b), z0 = Q(:, 0..m-1) y.  Returns (z0, F)."""
+    import scipy.linalg as sla
+    m, n = A.shape
+    Q, R = sla.qr(A.T, mode="full")
+    F = Q[:, m:n]
+    y = forwardSolve(R[:m, :].T, b)
+    return Q[:, :m] @ y, F
+
+
+def affineTransformedProblem(objF, cnts, z0, F):
+    """x = z0 + F u for the closed-form families: LinearConstraint.affineTransformed (LinearConstraint.scala:46-52),
+    QuadraticConstraint.affineTransformed (QuadraticConstraint.scala:54-64), ObjectiveFunction.affineTransformed
+    (ObjectiveFunction.scala:26-40) specialised to linear / quadratic objectives; starting points mapped with
+    SolutionSpace.parameter (F'(x - z0)).  Returns (objF_u, cnts_u)."""
+    par = lambda x: None if x is None else F.T @ (np.asarray(x, float) - z0)
+    sym = lambda M: (M + M.T) / 2          # Breeze's cholesky / eigSym insist on exact symmetry
+    quad = [QuadCnt(sym(F.T @ q.P @ F), F.T @ (q.a + q.P @ z0), q.r + float(q.a @ z0) + float(z0 @ (q.P @ z0)) / 2, q.ub)
+            for q in cnts.quad]
+    c = ConstraintSet(cnts.G @ F, cnts.r + cnts.G @ z0, cnts.ub, quad, par(cnts.pointWhereDefined))
+    if cnts.feasiblePoint is not None:
+        c.feasiblePoint = par(cnts.feasiblePoint)
+    if objF.kind == "linear":
+        o = LinearObjective(F.T @ objF.a, objF.r + float(objF.a @ z0))
+    elif objF.kind == "quadratic":
+        Pu = F.T @ objF.P @ F
+        o = QuadraticObjective((Pu + Pu.T) / 2, F.T @ (objF.a + objF.P @ z0),
+                               objF.r + float(objF.a @ z0) + float(z0 @ (objF.P @ z0)) / 2)
+    else:
+        raise NotImplementedError("affine transform of objective kind %s" % objF.kind)
+    return o, c
+
+
+def kktDataReduced(H, A, g, r):
+    """KKTData.reduced (KKTData.scala:68-91): returns (Hr, Ar, gr, r, nullIndices or None)."""
+    n = H.shape[1]
+    keep, null = [], []
+    for j in range(n):
+        t = np.linalg.norm(H[:, j]) + np.linalg.norm(A[:, j])
+        if t > 0:
+            keep.append(j)
+        elif abs(g[j]) < 1e-15:
+            null.append(j)
+        else:
+            raise UnsolvableSystemException("Unsolvable KKT system, row %d is zero with nonzero right hand side." % j)
+    if not null:
+        return H, A, g, r, None
+    I = np.array(keep, dtype=int)
+    return H[np.ix_(I, I)], A[:, I], g[I], r, null
+
+
+def paddVector(x, nullIndices):
+    """KKTData.paddVector (KKTData.scala:105-127)."""
+    z = np.zeros(x.shape[0] + len(nullIndices))
+    z[np.setdiff1d(np.arange(z.shape[0]), np.asarray(nullIndices, dtype=int))] = x
+    return z
+
+
 def symmetricLinearSystemSolve(H, r, tol):
     """SymmetricLinearSystem.scala:15-56 (double Ruiz equilibration, D6)."""
     d, Q = ruizEquilibrate(H)
@@ -886,6 +945,81 @@ def phase_I_Analysis(cnts: ConstraintSet, eqs: Optional[EqualityConstraint], par
     sol = barrierSolve(feasObjF, feasCnts, None, pars, phase_I_TerminationCriterion, literal)
     w = sol.x
     return w[:n], float(w[n]), sol
+
+
+@dataclass
+class FeasibilityReport:
+    """FeasibilityReport.scala:12-48."""
+    x0: np.ndarray
+    s: np.ndarray
+    isStrictlyFeasible: bool
+    constraintSet: "ConstraintSet"
+    equalityConstraintError: Optional[float]
+
+    def isFeasible(self, tol):
+        e = 0.0 if self.equalityConstraintError is None else self.equalityConstraintError
+        return bool(np.max(self.s) < tol and e < tol)
+
+    def violatedConstraints(self, tol):
+        """indices i with g_i(x0) > ub_i + tol (Constraint.isSatisfiedWithTolerance)."""
+        c = self.constraintSet
+        return [int(i) for i in np.nonzero(~(c.valuesAt(self.x0) <= c.ub_all() + tol))[0]]
+
+
+def phase_I_SOI_problem(cnts: ConstraintSet, eqs: Optional[EqualityConstraint]):
+    """Sum-of-infeasibilities phase I, [boyd] 11.4.1 p580: variable u = (x, s_1..s_p), one s_j per constraint,
+    g_j(x) - s_j <= ub_j and -s_j <= 0, objective sum_j s_j.
+    ConstraintSet.phase_I_SOI_ObjectiveFunction / phase_I_SOI_Constraints (ConstraintSet.scala:233-282),
+    Constraint.phase_I_SOI / phase_I_SOI_Constraints (Constraint.scala:101-159),
+    EqualityConstraint.phase_I_SOI_EqualityConstraint (EqualityConstraint.scala:50-55).
+    Row order here: [linear g_j - s_j ; -s_j <= 0 ; quadratic g_j - s_j] (the reference lists the quadratic rows
+    before the positivity rows; only the summation order differs)."""
+    n, p, ml = cnts.dim, cnts.numConstraints, cnts.m_lin
+    N = n + p
+    G = np.zeros((ml + p, N))
+    G[:ml, :n] = cnts.G
+    G[np.arange(ml), n + np.arange(ml)] = -1.0
+    G[ml + np.arange(p), n + np.arange(p)] = -1.0
+    r = np.concatenate([cnts.r, np.zeros(p)])
+    ub = np.concatenate([cnts.ub, np.zeros(p)])
+    quad = []
+    for k, q in enumerate(cnts.quad):
+        P1 = np.zeros((N, N))
+        P1[:n, :n] = q.P
+        a1 = np.zeros(N)
+        a1[:n] = q.a
+        a1[n + ml + k] = -1.0
+        quad.append(QuadCnt(P1, a1, q.r, q.ub))
+    x = cnts.pointWhereDefined
+    viol = cnts.valuesAt(x) - cnts.ub_all()
+    fp = np.concatenate([x, np.maximum(0.5, 1.0 + viol)])           # ConstraintSet.scala:270-272
+    soi = ConstraintSet(G, r, ub, quad, fp)
+    soi.feasiblePoint = fp
+    a = np.zeros(N)
+    a[n:] = 1.0
+    objF = LinearObjective(a, 0.0)
+    eqs_soi = None if eqs is None else EqualityConstraint(np.hstack([eqs.A, np.zeros((eqs.A.shape[0], p))]), eqs.b)
+    return objF, soi, eqs_soi
+
+
+def phase_I_Analysis_SOI(cnts: ConstraintSet, eqs: Optional[EqualityConstraint], pars: SolverParams, literal=False):
+    """ConstraintSet.phase_I_Analysis_SOI (ConstraintSet.scala:511-545): a full barrier solve (standard termination)
+    of the SOI problem.  isStrictlySatisfied reproduces the reference's test `(0 until n).forall(s_feas(j) < 0)`
+    (index range n instead of p -- defect D9; as every s_j > 0 inside the barrier's domain the first index already
+    fails, so no out-of-range access can happen and the flag is always false)."""
+    n, p = cnts.dim, cnts.numConstraints
+    objF, soi, eqs_soi = phase_I_SOI_problem(cnts, eqs)
+    sol = barrierSolve(objF, soi, eqs_soi, pars, None, literal)
+    w = sol.x
+    x_feas, s_feas = w[:n], w[n:n + p]
+    eqError = None if eqs is None else float(np.linalg.norm(eqs.A @ x_feas - eqs.b))
+    strict = True
+    for j in range(n):
+        if not (s_feas[j] < 0):          # j >= p would raise IndexError exactly where the JVM throws
+            strict = False
+            break
+    strict = strict and ((0.0 if eqError is None else eqError) < pars.tolSolver)
+    return FeasibilityReport(x_feas, s_feas, strict, cnts, eqError), sol
 
 
 def withFeasiblePoint(cnts: ConstraintSet, eqs: Optional[EqualityConstraint], pars: SolverParams, literal=False):

@@ -277,3 +277,52 @@ def test_unsolvable_system(handle):
     r2 = np.array([1.0, 1.0, 0.0, 1.0])
     x1 = SymmetricLinearSystem(H, r2, None, handle).solve(1e-6, 0)
     assert np.allclose(x1, [1.0, 0.5, 0.0, -1.0], atol=1e-12)
+
+
+@pytest.mark.parametrize("null", [(0,), (3, 7), (1, 2, 11), ()])
+def test_kkt_system_reduction(handle, null):
+    """KktTest.testKktSystemReduction (KktTest.scala:52-104): wipe rows/columns `null` of H, columns of A and entries
+    of g; reduce, solve, pad with zeros; the padded solution solves the ORIGINAL system."""
+    import cvx_b200 as cb
+    rng = np.random.default_rng(len(null))
+    dim = (null[-1] if null else 6) + 12        # the reference uses last + 5 with indices large enough that dim - |null| > 6 equations
+    Q = rng.uniform(-1, 1, (dim, dim))
+    H = Q.T @ Q
+    A = rng.uniform(-1, 1, (6, dim))
+    g = rng.uniform(-2, 2, dim)
+    r = rng.uniform(-1, 1, 6)
+    for j in null:
+        H[:, j] = 0.0
+        H[j, :] = 0.0
+        A[:, j] = 0.0
+        g[j] = 0.0
+    kd = cb.KKTData(H, A, g, r, None, handle)
+    dx, nu = kd.solveReduced(1e-6, None, 1e-10)
+    assert (kd.nullIndices or []) == list(null)
+    assert np.linalg.norm(H @ dx + A.T @ nu + g) < 1e-9 * max(1.0, np.linalg.norm(g))
+    assert np.linalg.norm(A @ dx - r) < 1e-9
+    assert all(dx[j] == 0.0 for j in null)
+    # against the oracle's reduced -> solve -> pad
+    Hr, Ar, gr, rr, nul0 = O.kktDataReduced(H, A, g, r)
+    xr, nu0 = O.kkt_solve(Hr, Ar, gr, rr, 1e-10)
+    x0 = O.paddVector(xr, nul0) if nul0 else xr
+    assert np.linalg.norm(dx - x0) < 1e-8 * max(1.0, np.linalg.norm(x0)) and np.linalg.norm(nu - nu0) < 1e-8 * max(1.0, np.linalg.norm(nu0))
+    assert np.allclose(cb.KKTData.paddVector(xr, list(null)), x0) if null else True
+
+
+def test_kkt_system_reduction_unsolvable(handle):
+    """A zero row with a nonzero right-hand side: UnsolvableSystemException (KKTData.scala:78-81)."""
+    import cvx_b200 as cb
+    rng = np.random.default_rng(5)
+    Q = rng.uniform(-1, 1, (9, 9))
+    H = Q.T @ Q
+    A = rng.uniform(-1, 1, (3, 9))
+    g = rng.uniform(-2, 2, 9)
+    H[:, 4] = 0.0
+    H[4, :] = 0.0
+    A[:, 4] = 0.0
+    g[4] = 0.5
+    with pytest.raises(cb.UnsolvableSystemException):
+        cb.KKTData(H, A, g, rng.uniform(-1, 1, 3), None, handle).solveReduced()
+    with pytest.raises(O.UnsolvableSystemException):
+        O.kktDataReduced(H, A, g, np.zeros(3))

@@ -212,3 +212,18 @@ def test_oracle_qp_kkt_conditions():
     nu = np.linalg.lstsq(prob["A"].T, -g, rcond=None)[0]
     assert np.linalg.norm(g + prob["A"].T @ nu) < 1e-5 * max(1.0, np.linalg.norm(prob["a"]))   # lambda = 1/(t d), d ~ 1e-10: rounding in d
     assert np.all(d > 0) and float(lam @ d) < 1e-7
+
+
+def test_oracle_phase_I_SOI():
+    """Sum-of-infeasibilities phase I (ConstraintSet.scala:511-545): at a feasible set the optimum is sum s = 0
+    (reached up to the duality gap 2p/t), at the infeasible KL set some s_j stays bounded away from 0."""
+    for prob, feasible in [(P.slab_lp(12, 12, 2, seed=3, feasible_start=False), True), (P.kl_random(10, 5, 2, seed=1), True),
+                           (P.lin_quad_set(8, 6, 2, 1, 5, "quadratic", False), True), (P.infeasible_kl_1(8), False)]:
+        objF, cnts, eqs = P.to_oracle(prob)
+        rep, sol = O.phase_I_Analysis_SOI(cnts, eqs, O.SolverParams())
+        assert rep.s.shape == (cnts.numConstraints,) and np.all(rep.s > 0) and not rep.isStrictlyFeasible
+        assert rep.isFeasible(1e-9) == feasible
+        assert (len(rep.violatedConstraints(1e-9)) == 0) == feasible
+        if feasible:
+            assert rep.s.sum() < 2 * cnts.numConstraints * 1e-9
+            assert rep.equalityConstraintError < 1e-9
