@@ -39,19 +39,25 @@ __global__ void __launch_bounds__(256) ruiz_sweep_kernel(int n, const double* __
   if (j < n) {
     const double* col = Hm + (size_t)j * ldh;
     const double dj = d[j];
-    double s0 = 0, s1 = 0;
+    // four independent loads per lane in flight: the sweep is an L2-latency-bound stream of one column per warp
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     int i = lane;
-    for (; i + 32 < n; i += 64) {
-      double q0 = (d[i] * dj) * col[i];
-      double q1 = (d[i + 32] * dj) * col[i + 32];
+    for (; i + 96 < n; i += 128) {
+      const double h0 = col[i], h1 = col[i + 32], h2 = col[i + 64], h3 = col[i + 96];
+      const double q0 = (d[i] * dj) * h0;
+      const double q1 = (d[i + 32] * dj) * h1;
+      const double q2 = (d[i + 64] * dj) * h2;
+      const double q3 = (d[i + 96] * dj) * h3;
       s0 = fma(q0, q0, s0);
       s1 = fma(q1, q1, s1);
+      s2 = fma(q2, q2, s2);
+      s3 = fma(q3, q3, s3);
     }
     for (; i < n; i += 32) {
       double q0 = (d[i] * dj) * col[i];
       s0 = fma(q0, q0, s0);
     }
-    double s = s0 + s1;
+    double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) colsq[j] = s;
@@ -190,21 +196,74 @@ __device__ __forceinline__ void warp_diag_factor(double* W, double* rdiag, int o
 // L(i,k) broadcast from shared memory, reciprocal pivots from rdiag)
 __device__ __forceinline__ void warp_diag_inverse(double* W, const double* rdiag, int o, int bs) {
   const int lane = threadIdx.x & 31;
+  // right-looking: x[i] is final after one multiply, then folded into every later row (short dependent chain)
   double x[SUB];
 #pragma unroll
-  for (int i = 0; i < SUB; ++i) {
-    double acc = (i == lane) ? 1.0 : 0.0;
-    double ri = 1.0;
-    if (i < bs) {
+  for (int i = 0; i < SUB; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-      for (int k = 0; k < i; ++k) acc = fma(-LW(o + i, o + k), x[k], acc);
-      ri = rdiag[o + i];
+  for (int i = 0; i < SUB; ++i) {
+    if (i < bs) {
+      x[i] = (i >= lane) ? x[i] * rdiag[o + i] : 0.0;
+#pragma unroll
+      for (int i2 = i + 1; i2 < SUB; ++i2)
+        if (i2 < bs) x[i2] = fma(-LW(o + i2, o + i), x[i], x[i2]);
+    } else {
+      x[i] = (i >= lane) ? x[i] : 0.0;
     }
-    x[i] = (i >= lane) ? acc * ri : 0.0;
   }
 #pragma unroll
   for (int i = 0; i < SUB; ++i)
     if (i < bs && lane < bs && i >= lane) XW(o + i, o + lane) = x[i];
+}
+
+// One doubling level of the triangular inverse for ONE pair of S2-blocks at offset b, done by a single warp (full
+// leaf, no bounds): T = L21 X11 into the X21 slot, then X21 = -X22 T.  Used inside the factorisation windows, where
+// the other warps are busy; only __syncwarp is needed between the products.
+template <int S2>
+__device__ __forceinline__ void warp_level_job(double* W, int b) {
+  constexpr int TPS = S2 / 8, NT = TPS * TPS;
+  const int lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  double c0[NT], c1[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int r = b + S2 + 8 * (t / TPS), c = b + 8 * (t % TPS);
+    c0[t] = c1[t] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < S2; kk += 4) {
+      if (kk < 8 * (t % TPS)) continue;              // X11 lower triangular (compile-time after unrolling)
+      const int k = b + kk + tq;
+      const double bv = (k >= c + g) ? XW(k, c + g) : 0.0;
+      dmma_leaf(c0[t], c1[t], LW(r + g, k), bv);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int r = b + S2 + 8 * (t / TPS) + g, c = b + 8 * (t % TPS) + 2 * tq;
+    XW(r, c) = c0[t];
+    XW(r, c + 1) = c1[t];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int r = b + S2 + 8 * (t / TPS) + g, c = b + 8 * (t % TPS) + g;
+    c0[t] = c1[t] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < S2; kk += 4) {
+      if (kk >= 8 * (t / TPS) + 8) continue;         // X22 lower triangular
+      const int k = b + S2 + kk + tq;
+      const double av = (k <= r) ? XW(r, k) : 0.0;
+      dmma_leaf(c0[t], c1[t], av, XW(k, c));
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int r = b + S2 + 8 * (t / TPS) + g, c = b + 8 * (t % TPS) + 2 * tq;
+    XW(r, c) = -c0[t];
+    XW(r, c + 1) = -c1[t];
+  }
+  __syncwarp();
 }
 
 __device__ long long g_leaf_clk[8];
@@ -253,40 +312,58 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
   LEAF_CLK(0);
 
   const int nblk = (nb + SUB - 1) / SUB;
+  const int g = tx >> 2, tq = tx & 3;
+  // ---- zero-fill the X region first (the doubling levels read not-yet-written entries as zeros); when factoring,
+  //      warps 1..15 do it while warp 0 factors the first diagonal block
+  if (!FACTOR || ty > 0)
+    for (int i = FACTOR ? ty - 1 : ty; i < nb; i += FACTOR ? LEAF_WARPS - 1 : LEAF_WARPS)   // lanes along j: unit stride
+      for (int j = tx; j <= i; j += 32) XW(i, j) = 0.0;
+  // In a full leaf the inverse is assembled INSIDE the factorisation windows (see below); first pair of each level
+  // that is still to do when the factorisation ends:
+  const bool pipelined = FACTOR && nb == NB;
+  int first16 = 0, first32 = 0;
+  bool diag_inv_done = false;
   if (FACTOR) {
+    // Software pipeline over the 8 sub-block columns.  The serial pivot chain (warp 0) is the critical path, so
+    // everything else is moved beside it:   window kb = { warp 0: update + factor diagonal block kb+1 }  ||
+    // { warps 1..15: the rest of trailing update kb; warp 15: inverse of diagonal block kb; warps 14 / 13: the
+    // doubling levels of the inverse whose inputs are final }, then the panel solve kb+1.  Two block barriers per
+    // sub-block column instead of three, and only the last levels of the inverse remain after the loop.
+    if (ty == 0) warp_diag_factor(W, rdiag, 0, nb < SUB ? nb : SUB, col0, &s_fail, &s_mind);
+    __syncthreads();
+    LEAF_CLK(1);
     for (int kb = 0; kb < nblk; ++kb) {
       const int o = kb * SUB;
-      const int bs = (nb - o) < SUB ? (nb - o) : SUB;
-      if (ty == 0) warp_diag_factor(W, rdiag, o, bs, col0, &s_fail, &s_mind);
-      __syncthreads();
-      LEAF_CLK(1);
       const int r0 = o + SUB;
       const int nrows = nb - r0;
-      if (nrows <= 0) continue;
+      if (nrows <= 0) break;
       // panel: row r of A(r0.., o..o+15) := row * L_d^-T by forward substitution, one thread per row
       if (tid < nrows) {
         const int r = r0 + tid;
+        // right-looking substitution: once x[c] is known it is folded into all later columns at once, so the
+        // dependent chain is 16 x (multiply + one FMA) instead of the 136 in-order FMAs of the dot-product form
         double x[SUB];
 #pragma unroll
-        for (int c = 0; c < SUB; ++c) {
-          double v = LW(r, o + c);
+        for (int c = 0; c < SUB; ++c) x[c] = LW(r, o + c);
 #pragma unroll
-          for (int k = 0; k < c; ++k) v = fma(-x[k], LW(o + c, o + k), v);
-          x[c] = v * rdiag[o + c];
+        for (int c = 0; c < SUB; ++c) {
+          x[c] *= rdiag[o + c];
+#pragma unroll
+          for (int c2 = c + 1; c2 < SUB; ++c2) x[c2] = fma(-x[c], LW(o + c2, o + c), x[c2]);
         }
 #pragma unroll
         for (int c = 0; c < SUB; ++c) LW(r, o + c) = x[c];
       }
       __syncthreads();
       LEAF_CLK(2);
-      // trailing update: A(r,c) -= sum_k L(r,o+k) L(c,o+k),  r >= c >= r0 ; warp per column, lanes down the rows
+      // window kb.  Trailing update: A(r,c) -= sum_k L(r,o+k) L(c,o+k), r >= c >= r0, as 8 x 8 DMMA tiles
+      // (A(m,k) = L(row, o+k), B(k,n) = L(col, o+k); out-of-range rows only feed discarded outputs).  Tiles 0..2
+      // are the next diagonal block: warp 0 takes them and goes straight on to factor it.
       {
-        // rank-16 update of the lower triangle of A(r0.., r0..) on the DMMA pipe: 8 x 8 output tiles, one
-        // warp per tile, A(m,k) = L(row, o+k), B(k,n) = L(col, o+k); out-of-range rows only feed discarded outputs
-        const int g = tx >> 2, tq = tx & 3;
         const int T = (nrows + 7) >> 3;
         const int ntile = T * (T + 1) / 2;
-        for (int tl = ty; tl < ntile; tl += LEAF_WARPS) {
+        const int nfirst = ntile < 3 ? ntile : 3;
+        auto tile = [&](int tl) {
           int ti = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
           while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
           while (ti * (ti + 1) / 2 > tl) --ti;
@@ -300,14 +377,37 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
             if (cc <= rr) LW(rr, cc) -= c0;
             if (cc + 1 <= rr) LW(rr, cc + 1) -= c1;
           }
+        };
+        // tiles 0..2 = the next diagonal block: warps 1..3 take one each and release warp 0 through a named barrier
+        if (ty <= 3) {
+          if (ty >= 1 && ty - 1 < nfirst) tile(ty - 1);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        // warps 4, 8, 12 share warp 0's scheduler and FP64 pipe: keep them idle so that the pivot chain's dependent
+        // FP64 operations never queue behind DMMAs
+        if ((ty & 3) != 0) {
+          const int wk = ty - 1 - (ty >> 2);         // 0..11
+          for (int tl = nfirst + wk; tl < ntile; tl += LEAF_WARPS - 4) tile(tl);
+        }
+        if (ty == 0) {
+          warp_diag_factor(W, rdiag, r0, nrows < SUB ? nrows : SUB, col0, &s_fail, &s_mind);
+        } else if (pipelined) {
+          if (ty == LEAF_WARPS - 1) warp_diag_inverse(W, rdiag, o, SUB);                      // X_kb,kb
+          if (ty == LEAF_WARPS - 2 && kb >= 2 && (kb & 1) == 0) warp_level_job<16>(W, (kb - 2) * SUB);   // blocks kb-2, kb-1
+          if (ty == LEAF_WARPS - 3 && kb == 5) warp_level_job<32>(W, 0);                       // blocks 0..3
         }
       }
       __syncthreads();
       LEAF_CLK(3);
     }
+    if (pipelined) { first16 = 3; first32 = 1; }
     if (tid == 0) {
       if (s_fail && flag[flag_slot] == 0) flag[flag_slot] = s_fail;
       if (s_mind < scal[mindiag_slot]) scal[mindiag_slot] = s_mind;
+    }
+    if (pipelined) {      // the last diagonal block's inverse
+      if (ty == 0) warp_diag_inverse(W, rdiag, (nblk - 1) * SUB, SUB);
+      diag_inv_done = true;
     }
   } else {
     if (tid < nb) {
@@ -315,26 +415,26 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
       if (pv == 0.0) { flag[F_ZERO_DIAG] = 1; pv = 1.0; }
       rdiag[tid] = 1.0 / pv;
     }
+  }
+  __syncthreads();
+
+  // ---- (rest of the) triangular inverse: the diagonal 16-blocks concurrently, then the doubling levels
+  //      X21 = -X22 (L21 X11) for s = 16, 32, 64
+  if (!diag_inv_done) {
+    if (ty < nblk) {
+      const int o = ty * SUB;
+      warp_diag_inverse(W, rdiag, o, (nb - o) < SUB ? (nb - o) : SUB);
+    }
     __syncthreads();
   }
-
-  // ---- triangular inverse.  Zero-fill the strictly-lower X blocks first (the doubling reads them).
-  for (int i = ty; i < nb; i += LEAF_WARPS)          // lanes along j: unit stride in the transposed layout
-    for (int j = tx; j <= i; j += 32) XW(i, j) = 0.0;
-  __syncthreads();
-  if (ty < nblk) {
-    const int o = ty * SUB;
-    warp_diag_inverse(W, rdiag, o, (nb - o) < SUB ? (nb - o) : SUB);
-  }
-  __syncthreads();
   LEAF_CLK(4);
   for (int sh = 4; (1 << sh) < nb; ++sh) {           // s = 16, 32, 64
     const int s2 = 1 << sh;
-    const int npairs = (nb + 2 * s2 - 1) / (2 * s2);
+    const int pair0 = (sh == 4) ? first16 : (sh == 5 ? first32 : 0);     // pairs before this one are already done
+    const int npairs = (nb + 2 * s2 - 1) / (2 * s2) - pair0;
     // Both products of the level on the DMMA pipe, 8 x 8 output tiles spread over the 16 warps:
     //   T   = L21 * X11      A(m,k) = L(r,k),            B(k,n) = X(k,c) (zero for k < c)
     //   X21 = -X22 * T       A(m,k) = X(r,k) (k <= r),   B(k,n) = T(k,c)
-    const int g = tx >> 2, tq = tx & 3;
     const int tps = s2 >> 3;                         // tiles per side of one block
     const int ntile = npairs * tps * tps;
     constexpr int MAXT = 4;                          // 64 tiles at the widest level / 16 warps
@@ -348,7 +448,7 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
       onT[u] = tl < ntile;
       if (!onT[u]) tl = 0;
       const int pr = tl / (tps * tps), rem = tl - pr * tps * tps;
-      bT[u] = pr * 2 * s2;
+      bT[u] = (pr + pair0) * 2 * s2;
       rT[u] = bT[u] + s2 + 8 * (rem / tps);
       cT[u] = bT[u] + 8 * (rem % tps);
     }
@@ -356,7 +456,7 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
     for (int kk = 0; kk < s2; kk += 4) {
 #pragma unroll
       for (int u = 0; u < MAXT; ++u) {
-        if (onT[u]) {                                   // warp-uniform
+        if (onT[u] && kk >= cT[u] - bT[u]) {            // warp-uniform; X11 is lower triangular: k-blocks above the tile's columns are zero
           const int k = bT[u] + kk + tq, c = cT[u] + g;
           const double bv = (k >= c) ? XW(k, c) : 0.0;
           dmma_leaf(c0[u], c1[u], LW(rT[u] + g, k), bv);
@@ -376,7 +476,7 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
     for (int kk = 0; kk < s2; kk += 4) {
 #pragma unroll
       for (int u = 0; u < MAXT; ++u) {
-        if (onT[u]) {
+        if (onT[u] && kk < rT[u] - bT[u] - s2 + 8) {      // X22 is lower triangular: k-blocks beyond the tile's rows are zero
           const int k = bT[u] + s2 + kk + tq, r = rT[u] + g, c = cT[u] + g;
           const double av = (k <= r && r < nb) ? XW(r, k) : 0.0;
           const double bv = (k < nb) ? XW(k, c) : 0.0;
@@ -838,9 +938,11 @@ int scaled_full(Handle& h, int n, const double* Hm, int ldh, const double* d, do
 // single SM).  Fork / join by events, so the whole schedule is capturable into the per-step CUDA graph.
 int potrf_lookahead(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0) {
   const int nblk = (n + NB - 1) / NB;
-  if (2 * nblk + 2 > (int)h.la_events.size()) return potrf_rec_plain(h, n, A, lda, invD, flag_slot, mindiag_slot, col0);
+  const size_t half = (PART_DOUBLES - 65536) / 2;
+  if (2 * nblk + 2 > (int)h.la_events.size() || (size_t)pad_ld(n) * NB > half)
+    return potrf_rec_plain(h, n, A, lda, invD, flag_slot, mindiag_slot, col0);
   cudaStream_t sa = h.stream, sb = h.stream2;
-  bool forked = false;
+  int pending = -1;      // step whose second-stream work (copy-back + bulk update) the main stream has not yet waited for
   for (int k = 0; k < nblk; ++k) {
     const int k0 = k * NB, kb = n - k0 < NB ? n - k0 : NB;
     const int rem = n - k0 - kb;
@@ -849,41 +951,41 @@ int potrf_lookahead(Handle& h, int n, double* A, int lda, double* invD, int flag
                 h.d_scal, flag_slot, mindiag_slot, col0 + k0);
     if (rem <= 0) break;
     double* A21 = Akk + kb;                                   // rows below the diagonal block, this column block
-    CVXB_TRY(trsm_right_lt(h, rem, kb, Akk, lda, invD + (size_t)k * NB * NB, A21, lda));
+    // panel solve X = A21 L11^-T into one half of the scratch block (alternating halves): the critical chain reads
+    // the panel from there, the copy back into A rides on the second stream
+    double* Xs = h.d_part + (size_t)(k & 1) * half;
+    const int lds = pad_ld(rem);
+    GemmArgs gp{rem, kb, kb, A21, lda, false, invD + (size_t)k * NB * NB, NB, false, Xs, lds, 1.0, 0.0, 0};
+    CVXB_TRY(gemm_dmma(h, gp));
     const int kn = rem < NB ? rem : NB;                       // width of the next column block
     const int rem2 = rem - kn;
     cudaEvent_t evP = h.la_events[2 * k], evB = h.la_events[2 * k + 1];
-    if (rem2 > 0) CVXB_CUDA_OK(cudaEventRecord(evP, sa));     // panel k ready
-    if (forked) CVXB_CUDA_OK(cudaStreamWaitEvent(sa, h.la_events[2 * (k - 1) + 1], 0));   // bulk update k-1 done
-    forked = false;
+    CVXB_CUDA_OK(cudaEventRecord(evP, sa));                   // panel k ready
+    if (pending >= 0) CVXB_CUDA_OK(cudaStreamWaitEvent(sa, h.la_events[2 * pending + 1], 0));   // bulk update k-1 done
     // look-ahead: column block k+1 only (rows and columns share the origin k0+kb: keep the upper triangle untouched)
     double* Anext = A + (size_t)(k0 + kb) * lda + (k0 + kb);
-    GemmArgs gl{rem, kn, kb, A21, lda, false, A21, lda, false, Anext, lda, -1.0, 1.0, 0};
+    GemmArgs gl{rem, kn, kb, Xs, lds, false, Xs, lds, false, Anext, lda, -1.0, 1.0, 0};
     gl.lower_only = true;
     CVXB_TRY(gemm_dmma(h, gl));
+    // second stream: bulk of the trailing update, then the panel's way back into A
+    CVXB_CUDA_OK(cudaStreamWaitEvent(sb, evP, 0));
     if (rem2 > 0) {
-      // bulk of the trailing update on the second stream
-      CVXB_CUDA_OK(cudaStreamWaitEvent(sb, evP, 0));
-      double* A31 = A21 + kn;
+      const double* X31 = Xs + kn;
       double* A33 = A + (size_t)(k0 + kb + kn) * lda + (k0 + kb + kn);
-      GemmArgs gb{rem2, rem2, kb, A31, lda, false, A31, lda, false, A33, lda, -1.0, 1.0, 1};
+      GemmArgs gb{rem2, rem2, kb, X31, lds, false, X31, lds, false, A33, lda, -1.0, 1.0, 1};
       CVXB_TRY(gemm_dmma_on(h, gb, sb));
-      CVXB_CUDA_OK(cudaEventRecord(evB, sb));
-      forked = true;
-      if (k + 1 == nblk - 1 || rem2 <= 0) {}
     }
-  }
-  // join (the last bulk update targets blocks that the remaining steps wait for anyway; a dangling fork must not survive)
-  for (int k = 0; k < nblk; ++k) (void)k;
-  if (forked) {
-    int last = -1;
-    for (int k = 0; k < nblk; ++k) {
-      const int rem = n - k * NB - (n - k * NB < NB ? n - k * NB : NB);
-      const int kn = rem < NB ? rem : NB;
-      if (rem - kn > 0) last = k;
+    {
+      cudaStream_t keep = h.stream;
+      h.stream = sb;
+      int st = copy_matrix(h, rem, kb, Xs, lds, A21, lda);
+      h.stream = keep;
+      if (st != CVXB_OK) return st;
     }
-    if (last >= 0) CVXB_CUDA_OK(cudaStreamWaitEvent(sa, h.la_events[2 * last + 1], 0));
+    CVXB_CUDA_OK(cudaEventRecord(evB, sb));
+    pending = k;
   }
+  if (pending >= 0) CVXB_CUDA_OK(cudaStreamWaitEvent(sa, h.la_events[2 * pending + 1], 0));   // join
   return CVXB_OK;
 }
 
