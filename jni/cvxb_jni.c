@@ -127,3 +127,57 @@ JNIEXPORT void JNICALL Java_cvx_CvxbNative_solve(JNIEnv* env, jclass c, jlong h,
   (*env)->SetDoubleArrayRegion(env, stats, 0, 12, out);
   if (st != CVXB_OK) throw_for(env, st);
 }
+
+/* SolutionSpace(A, b) / MatrixUtils.solveUnderdetermined: fills z0 (n) and F (n x (n-p), column-major, ld n) */
+JNIEXPORT void JNICALL Java_cvx_CvxbNative_solveUnderdetermined(JNIEnv* env, jclass c, jlong h, jint p, jint n,
+                                                                jdoubleArray A, jint aOff, jint lda, jdoubleArray b,
+                                                                jdoubleArray z0, jdoubleArray F) {
+  jdouble* pA = (*env)->GetPrimitiveArrayCritical(env, A, 0);
+  jdouble* pb = (*env)->GetPrimitiveArrayCritical(env, b, 0);
+  jdouble* pz = (*env)->GetPrimitiveArrayCritical(env, z0, 0);
+  jdouble* pF = (*env)->GetPrimitiveArrayCritical(env, F, 0);
+  int st = cvxb_solve_underdetermined((cvxb_handle)(intptr_t)h, p, n, pA + aOff, lda, pb, pz, pF, n);
+  (*env)->ReleasePrimitiveArrayCritical(env, F, pF, 0);
+  (*env)->ReleasePrimitiveArrayCritical(env, z0, pz, 0);
+  (*env)->ReleasePrimitiveArrayCritical(env, b, pb, JNI_ABORT);
+  (*env)->ReleasePrimitiveArrayCritical(env, A, pA, JNI_ABORT);
+  if (st != CVXB_OK) throw_for(env, st);
+}
+
+/* KKTData.reduced -> KKTSystem.solve -> paddVector; nullIdx (n ints) receives the eliminated indices, returns their number */
+JNIEXPORT jint JNICALL Java_cvx_CvxbNative_kktSolveReduced(JNIEnv* env, jclass c, jlong h, jint n, jint p, jdoubleArray H,
+                                                           jint ldh, jdoubleArray A, jint lda, jdoubleArray g,
+                                                           jdoubleArray r, jdouble tol, jdoubleArray x, jdoubleArray w,
+                                                           jintArray nullIdx) {
+  jdouble* pH = (*env)->GetPrimitiveArrayCritical(env, H, 0);
+  jdouble* pA = (*env)->GetPrimitiveArrayCritical(env, A, 0);
+  jdouble* pg = (*env)->GetPrimitiveArrayCritical(env, g, 0);
+  jdouble* pr = (*env)->GetPrimitiveArrayCritical(env, r, 0);
+  jdouble* px = (*env)->GetPrimitiveArrayCritical(env, x, 0);
+  jdouble* pw = (*env)->GetPrimitiveArrayCritical(env, w, 0);
+  jint* pi = (*env)->GetPrimitiveArrayCritical(env, nullIdx, 0);
+  int nn = 0;
+  int st = cvxb_kkt_solve_reduced((cvxb_handle)(intptr_t)h, n, p, pH, ldh, pA, lda, pg, pr, tol, px, pw, (int*)pi, &nn, 0);
+  (*env)->ReleasePrimitiveArrayCritical(env, nullIdx, pi, 0);
+  (*env)->ReleasePrimitiveArrayCritical(env, w, pw, 0);
+  (*env)->ReleasePrimitiveArrayCritical(env, x, px, 0);
+  (*env)->ReleasePrimitiveArrayCritical(env, r, pr, JNI_ABORT);
+  (*env)->ReleasePrimitiveArrayCritical(env, g, pg, JNI_ABORT);
+  (*env)->ReleasePrimitiveArrayCritical(env, A, pA, JNI_ABORT);
+  (*env)->ReleasePrimitiveArrayCritical(env, H, pH, JNI_ABORT);
+  if (st != CVXB_OK) throw_for(env, st);
+  return nn;
+}
+
+/* g_i(x) for every constraint of an uploaded problem; returns 1 when ConstraintSet.isSatisfiedStrictlyBy(x) */
+JNIEXPORT jint JNICALL Java_cvx_CvxbNative_constraintValues(JNIEnv* env, jclass c, jlong h, jlong problem, jdoubleArray x,
+                                                            jdoubleArray g) {
+  jdouble* px = (*env)->GetPrimitiveArrayCritical(env, x, 0);
+  jdouble* pg = (*env)->GetPrimitiveArrayCritical(env, g, 0);
+  int ok = 0;
+  int st = cvxb_constraint_values((cvxb_handle)(intptr_t)h, (cvxb_problem)(intptr_t)problem, px, pg, &ok);
+  (*env)->ReleasePrimitiveArrayCritical(env, g, pg, 0);
+  (*env)->ReleasePrimitiveArrayCritical(env, x, px, JNI_ABORT);
+  if (st != CVXB_OK) throw_for(env, st);
+  return ok;
+}

@@ -30,7 +30,31 @@ object CvxbNative {
   @native def solve(handle: Long, problem: Long, solver: Int, params: Array[Double], x: Array[Double],
                     lambda: Array[Double], nu: Array[Double], stats: Array[Double]): Unit
 
+  /** MatrixUtils.solveUnderdetermined / SolutionSpace: z0 (n), F (n x (n-p), column-major). */
+  @native def solveUnderdetermined(handle: Long, p: Int, n: Int, A: Array[Double], aOff: Int, lda: Int,
+                                   b: Array[Double], z0: Array[Double], F: Array[Double]): Unit
+
+  /** KKTData.reduced -> KKTSystem.solve -> KKTData.paddVector; returns the number of eliminated indices. */
+  @native def kktSolveReduced(handle: Long, n: Int, p: Int, H: Array[Double], ldh: Int, A: Array[Double], lda: Int,
+                              g: Array[Double], r: Array[Double], tol: Double, x: Array[Double], w: Array[Double],
+                              nullIdx: Array[Int]): Int
+
+  /** g_i(x) of an uploaded problem's constraints; returns 1 when all are strictly satisfied. */
+  @native def constraintValues(handle: Long, problem: Long, x: Array[Double], g: Array[Double]): Int
+
   lazy val defaultHandle: Long = create(0)
+
+  /** Drop-in body for SolutionSpace's `sol` member (SolutionSpace.scala:24):
+    * {{{ val sol = CvxbNative.solutionSpace(A, b) }}} */
+  def solutionSpace(A: breeze.linalg.DenseMatrix[Double], b: breeze.linalg.DenseVector[Double])
+      : (breeze.linalg.DenseVector[Double], breeze.linalg.DenseMatrix[Double]) = {
+    val Ad = if (A.isTranspose) A.copy else A
+    val (p, n) = (Ad.rows, Ad.cols)
+    val z0 = new Array[Double](n)
+    val F = new Array[Double](n * (n - p))
+    solveUnderdetermined(defaultHandle, p, n, Ad.data, Ad.offset, Ad.majorStride, b.toArray, z0, F)
+    (breeze.linalg.DenseVector(z0), new breeze.linalg.DenseMatrix(n, n - p, F))
+  }
 }
 
 /** Thrown by the shim for CVXB_EINFEASIBLE; GpuSolver rethrows it as InfeasibleProblemException with a report. */
