@@ -177,10 +177,10 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
   CVXB_CUDA_OK(cudaMalloc((void**)&h->d_scal, NSCAL * sizeof(double)));
   CVXB_CUDA_OK(cudaMalloc((void**)&h->d_flag, NFLAG * sizeof(int)));
   CVXB_CUDA_OK(cudaMalloc((void**)&h->d_part, PART_DOUBLES * sizeof(double)));
-  CVXB_CUDA_OK(cudaMalloc((void**)&h->d_ticket, 16 * sizeof(unsigned)));
+  CVXB_CUDA_OK(cudaMalloc((void**)&h->d_ticket, 16 * sizeof(unsigned) + 64 * sizeof(unsigned long long)));   // + Ruiz rho slots
   CVXB_CUDA_OK(cudaMemset(h->d_scal, 0, NSCAL * sizeof(double)));
   CVXB_CUDA_OK(cudaMemset(h->d_flag, 0, NFLAG * sizeof(int)));
-  CVXB_CUDA_OK(cudaMemset(h->d_ticket, 0, 16 * sizeof(unsigned)));
+  CVXB_CUDA_OK(cudaMemset(h->d_ticket, 0, 16 * sizeof(unsigned) + 64 * sizeof(unsigned long long)));
   {
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);

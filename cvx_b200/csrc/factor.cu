@@ -7,6 +7,7 @@
 // shared memory and also writes the block's triangular inverse, so that every leaf triangular solve is
 // a DMMA GEMM with the inverse too (same device as MAGMA's trsm with inverted diagonal blocks).
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace cvxb {
 
@@ -16,6 +17,7 @@ int rl_max_n();
 namespace {
 
 // ------------------------------------------------------------------------------------------- Ruiz
+constexpr int RUIZ_MAX_FUSED = 64;    // rho slots behind the ticket words (api.cu allocates 16 unsigned + 64 u64)
 __global__ void ruiz_init_kernel(int n, double* d, int* flag, double* scal, unsigned* ticket) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = 1.0;
@@ -24,6 +26,81 @@ __global__ void ruiz_init_kernel(int n, double* d, int* flag, double* scal, unsi
     flag[F_RUIZ_SWEEPS] = 0;
     scal[S_RUIZ_RHO] = 1.0;
     ticket[0] = 0;
+  }
+  if (i < RUIZ_MAX_FUSED) ((unsigned long long*)(ticket + 16))[i] = 0ull;     // per-sweep rho slots of the fused kernel
+}
+
+// The whole equilibration in ONE cooperative launch: CTA per column (128 threads, 16-byte loads, four column
+// chunks and their d entries in flight per thread), u_j / the new d_j computed by the column's own CTA, rho by
+// atomicMax on the bit pattern (non-negative doubles order like unsigned integers; a NaN sorts above +inf and
+// ends the loop exactly like the per-sweep kernel's `!(rho > tol)`), d double-buffered between `d` and `dalt`
+// so that a sweep costs one grid barrier.  Converged early -> the kernel returns: no no-op launches.
+__global__ void __launch_bounds__(128) ruiz_fused_kernel(int n, const double* __restrict__ Hm, int ldh, double* d, double* dalt,
+                                                         unsigned long long* rho_bits, int* flag, double* scal,
+                                                         int max_sweeps, double tol) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* din = d;
+  double* dout = dalt;
+  int sweeps = 0;
+  double rho = 1.0;
+  const int npair = n >> 1;
+  for (int s = 0; s < max_sweeps; ++s) {
+    double rmax = 0.0;
+    for (int j = blockIdx.x; j < n; j += gridDim.x) {
+      const double2* col = reinterpret_cast<const double2*>(Hm + (size_t)j * ldh);
+      const double2* dv = reinterpret_cast<const double2*>(din);
+      const double dj = __ldcg(din + j);       // written by other CTAs in the previous sweep: read through L2
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      int i = tid;
+      for (; i + 384 < npair; i += 512) {
+        const double2 h0 = col[i], h1 = col[i + 128], h2 = col[i + 256], h3 = col[i + 384];
+        const double2 e0 = __ldcg(dv + i), e1 = __ldcg(dv + i + 128), e2 = __ldcg(dv + i + 256), e3 = __ldcg(dv + i + 384);
+        double q;
+        q = (e0.x * dj) * h0.x; s0 = fma(q, q, s0); q = (e0.y * dj) * h0.y; s0 = fma(q, q, s0);
+        q = (e1.x * dj) * h1.x; s1 = fma(q, q, s1); q = (e1.y * dj) * h1.y; s1 = fma(q, q, s1);
+        q = (e2.x * dj) * h2.x; s2 = fma(q, q, s2); q = (e2.y * dj) * h2.y; s2 = fma(q, q, s2);
+        q = (e3.x * dj) * h3.x; s3 = fma(q, q, s3); q = (e3.y * dj) * h3.y; s3 = fma(q, q, s3);
+      }
+      for (; i < npair; i += 128) {
+        const double2 h0 = col[i];
+        const double2 e0 = __ldcg(dv + i);
+        double q;
+        q = (e0.x * dj) * h0.x; s0 = fma(q, q, s0); q = (e0.y * dj) * h0.y; s0 = fma(q, q, s0);
+      }
+      if ((n & 1) && tid == 0) {
+        const double q = (__ldcg(din + n - 1) * dj) * Hm[(size_t)j * ldh + n - 1];
+        s1 = fma(q, q, s1);
+      }
+      double sum = (s0 + s1) + (s2 + s3);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) red[warp] = sum;
+      __syncthreads();
+      if (tid == 0) {
+        const double tot = (red[0] + red[1]) + (red[2] + red[3]);
+        const double u = sqrt(sqrt(tot));
+        dout[j] = u > 0 ? dj * (1.0 / u) : dj;
+        const double a = fabs(1.0 - u);
+        if (a > rmax || a != a) rmax = a;
+      }
+      __syncthreads();
+    }
+    if (tid == 0 && blockIdx.x < n) atomicMax(rho_bits + s, (unsigned long long)__double_as_longlong(rmax));
+    grid.sync();
+    rho = __longlong_as_double((long long)__ldcg(rho_bits + s));
+    double* tmp = din; din = dout; dout = tmp;
+    sweeps = s + 1;
+    if (!(rho > tol)) break;
+  }
+  if (din != d)       // odd number of sweeps: the result sits in the alternate buffer (every read of d is behind a barrier)
+    for (int j = blockIdx.x * blockDim.x + tid; j < n; j += gridDim.x * blockDim.x) d[j] = __ldcg(din + j);
+  if (blockIdx.x == 0 && tid == 0) {
+    scal[S_RUIZ_RHO] = rho;
+    flag[F_RUIZ_SWEEPS] = sweeps;
+    flag[F_RUIZ_DONE] = 1;
   }
 }
 
@@ -912,6 +989,34 @@ int factor_init() { return leaf_init(true); }     // per handle: attributes belo
 int ruiz_equilibrate(Handle& h, int n, const double* Hm, int ldh, double* d, double* colsq, int max_sweeps, double tol) {
   if (n <= 0) return CVXB_OK;
   CVXB_LAUNCH(h, ruiz_init_kernel, (n + 255) / 256, 256, 0, n, d, h.d_flag, h.d_scal, h.d_ticket);
+  if (max_sweeps <= 0) return CVXB_OK;
+  static int fused_occ = -1;          // CTAs of the fused kernel per SM (0: not usable)
+  if (fused_occ < 0) {
+    int occ = 0;
+    if (getenv("CVXB_NO_FUSED_RUIZ") ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ruiz_fused_kernel, 128, 0) != cudaSuccess) {
+      cudaGetLastError();
+      occ = 0;
+    }
+    fused_occ = occ;
+  }
+  if (fused_occ > 0 && h.wave_ready && max_sweeps <= RUIZ_MAX_FUSED && !(ldh & 1) && !((uintptr_t)Hm & 15) &&
+      !((uintptr_t)d & 15) && !((uintptr_t)colsq & 15)) {
+    int grid = fused_occ * h.sm_count;
+    if (grid > n) grid = n;
+    unsigned long long* rho_bits = (unsigned long long*)(h.d_ticket + 16);
+    int nn = n, ld = ldh, ms = max_sweeps;
+    int* flag = h.d_flag;
+    double* scal = h.d_scal;
+    double tl = tol;
+    void* args[] = {&nn, (void*)&Hm, &ld, &d, &colsq, &rho_bits, &flag, &scal, &ms, &tl};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)ruiz_fused_kernel, dim3(grid), dim3(128), args, 0, h.stream);
+    if (e == cudaSuccess) {
+      h.launches++;
+      return CVXB_OK;
+    }
+    cudaGetLastError();       // not launchable cooperatively here: per-sweep kernels below
+  }
   for (int s = 0; s < max_sweeps; ++s)
     CVXB_LAUNCH(h, ruiz_sweep_kernel, (n + 7) / 8, 256, 0, n, Hm, ldh, d, colsq, h.d_flag, h.d_scal, h.d_ticket,
                 max_sweeps, tol);

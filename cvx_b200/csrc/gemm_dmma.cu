@@ -33,10 +33,6 @@ constexpr int KC_LD = BK + 4;               // K-contiguous tile row stride (dou
 
 template <int R> struct TileElems { static constexpr int value = (R * KC_LD > BK * (R + 4)) ? R * KC_LD : BK * (R + 4); };
 
-__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int src_bytes) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -47,32 +43,65 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// Stage one R x 16 operand tile.  `rows` = extent along the R-long (M or N) direction,
-// `kext` = K; (r0, k0) = tile origin.  KC: element (r,k) at src[r*ld + k]; else at src[k*ld + r].
+// Per-thread state for staging one operand's R x BK slabs.  The chunk pattern of a thread is the same in every
+// slab, so the global pointer, the row predicate and the shared-memory offset are computed ONCE; per slab a chunk
+// costs one 64-bit add, one select and the cp.async itself, and the chunks are issued one or two at a time from
+// inside the DMMA stream (see the main loop) instead of as a ~250-instruction block behind the barrier.
+//   KC: element (r,k) at src[r*ld + k]; chunk `it` = row tid/(BK/2) + it*ROWS_PER_IT, columns kc..kc+1
+//   MC: element (r,k) at src[k*ld + r]; chunk `it` = k-row tid/(R/2) + it*ROWS_PER_IT, rows rc..rc+1
+// Out-of-range chunks are issued with src-size 0 (pure zero fill: the source address is never dereferenced).
 template <bool KC, int R, int NTHR>
-__device__ __forceinline__ void load_tile(double* dst, const double* __restrict__ src, int ld, int rows, int kext,
-                                          int r0, int k0, int tid) {
-  constexpr int MC_LD = R + 4;
-#pragma unroll
-  for (int it = 0; it < (R * BK / 2) / NTHR; ++it) {
-    int c = tid + it * NTHR;
+struct SlabLoader {
+  static constexpr int CHUNKS_PER_LINE = KC ? BK / 2 : R / 2;
+  static constexpr int ROWS_PER_IT = NTHR / CHUNKS_PER_LINE;
+  static constexpr int ITERS = (R * BK / 2) / NTHR;
+  static constexpr int LINE_LD = KC ? KC_LD : R + 4;
+  const double* p;        // this thread's chunk 0 of the NEXT slab to load
+  long long it_stride;    // elements between consecutive chunks of this thread
+  unsigned soff;          // byte offset of chunk 0 inside a stage's tile
+  unsigned mask;          // KC: bit it = row of chunk it is inside the matrix
+  int a;                  // KC: kc (k offset inside the slab);  MC: k-row of chunk 0 inside the slab
+  int rbytes;             // MC: bytes of this thread's row pair inside the matrix (0 / 8 / 16)
+  int ld;
+
+  __device__ __forceinline__ void init(const double* src, int ld_, int rows, int r0, int tid) {
+    ld = ld_;
+    const int line = tid / CHUNKS_PER_LINE, c2 = (tid % CHUNKS_PER_LINE) * 2;
+    soff = (unsigned)((line * LINE_LD + c2) * (int)sizeof(double));
     if (KC) {
-      int r = c / (BK / 2), kc = (c % (BK / 2)) * 2;
-      int gr = r0 + r, gk = k0 + kc;
-      int bytes = 0;
-      if (gr < rows) { int rem = (kext - gk) * 8; bytes = rem < 0 ? 0 : (rem > 16 ? 16 : rem); }
-      const double* g = bytes > 0 ? src + (size_t)gr * ld + gk : src;
-      cp_async16(dst + r * KC_LD + kc, g, bytes);
+      a = c2;
+      mask = 0;
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it)
+        if (r0 + line + it * ROWS_PER_IT < rows) mask |= 1u << it;
+      p = src + (size_t)(r0 + line) * ld + c2;
+      it_stride = (long long)ROWS_PER_IT * ld;
+      rbytes = 16;
     } else {
-      int k = c / (R / 2), rc = (c % (R / 2)) * 2;
-      int gk = k0 + k, gr = r0 + rc;
-      int bytes = 0;
-      if (gk < kext) { int rem = (rows - gr) * 8; bytes = rem < 0 ? 0 : (rem > 16 ? 16 : rem); }
-      const double* g = bytes > 0 ? src + (size_t)gk * ld + gr : src;
-      cp_async16(dst + k * MC_LD + rc, g, bytes);
+      a = line;
+      mask = 0;
+      int rem = (rows - (r0 + c2)) * 8;
+      rbytes = rem < 0 ? 0 : (rem > 16 ? 16 : rem);
+      p = src + (size_t)line * ld + r0 + c2;
+      it_stride = (long long)ROWS_PER_IT * ld;
     }
   }
-}
+  // chunk `it` of the slab whose first k index leaves `krem` = K - k0 valid k's
+  __device__ __forceinline__ void issue(unsigned stage_base, int it, int krem) const {
+    int bytes;
+    if (KC) {
+      int kb = (krem - a) * 8;
+      kb = kb < 0 ? 0 : (kb > 16 ? 16 : kb);
+      bytes = ((mask >> it) & 1u) ? kb : 0;
+    } else {
+      bytes = (a + it * ROWS_PER_IT < krem) ? rbytes : 0;
+    }
+    unsigned dst = stage_base + soff + (unsigned)(it * ROWS_PER_IT * LINE_LD * (int)sizeof(double));
+    const double* g = p + (long long)it * it_stride;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(g), "r"(bytes));
+  }
+  __device__ __forceinline__ void advance() { p += KC ? (long long)BK : (long long)BK * ld; }
+};
 
 template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (BM >= 128 ? 1 : 2))
@@ -110,34 +139,52 @@ gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, con
     for (int j = 0; j < NTL; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int KT = (K + BK - 1) / BK;
+  constexpr unsigned STAGE_BYTES = (unsigned)((A_ELEMS + B_ELEMS) * sizeof(double));
+  constexpr unsigned B_OFF = (unsigned)(A_ELEMS * sizeof(double));
+  const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(smem);
   auto stageA = [&](int s) { return smem + (size_t)s * (A_ELEMS + B_ELEMS); };
   auto stageB = [&](int s) { return smem + (size_t)s * (A_ELEMS + B_ELEMS) + A_ELEMS; };
+  typedef SlabLoader<A_KC, BM, NTHR> LoadA;
+  typedef SlabLoader<B_KC, BN, NTHR> LoadB;
+  LoadA la;
+  LoadB lb;
+  la.init(A, lda, M, m0, tid);
+  lb.init(B, ldb, N, n0, tid);
+  constexpr int NCHUNK = LoadA::ITERS + LoadB::ITERS;       // cp.async per thread per slab
+  constexpr int KSTEPS = BK / 4;
+  constexpr int PER_STEP = (NCHUNK + KSTEPS - 1) / KSTEPS;  // issued behind each k4-step's DMMAs
+  auto issue_chunk = [&](unsigned sbase, int c, int krem) {
+    if (c < LoadA::ITERS) la.issue(sbase, c, krem);
+    else lb.issue(sbase + B_OFF, c - LoadA::ITERS, krem);
+  };
 
+  // prologue: slabs 0 .. STAGES-2
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < KT) {
-      load_tile<A_KC, BM, NTHR>(stageA(s), A, lda, M, K, m0, s * BK, tid);
-      load_tile<B_KC, BN, NTHR>(stageB(s), B, ldb, N, K, n0, s * BK, tid);
+      const int krem = K - s * BK;
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) issue_chunk(smem_u32 + s * STAGE_BYTES, c, krem);
+      la.advance();
+      lb.advance();
     }
     cp_async_commit();
   }
 
+  int cs = 0, ls = STAGES - 1;       // stage being consumed / stage being refilled
   for (int kt = 0; kt < KT; ++kt) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {
-      int nk = kt + STAGES - 1;
-      if (nk < KT) {
-        int s = nk % STAGES;
-        load_tile<A_KC, BM, NTHR>(stageA(s), A, lda, M, K, m0, nk * BK, tid);
-        load_tile<B_KC, BN, NTHR>(stageB(s), B, ldb, N, K, n0, nk * BK, tid);
-      }
-      cp_async_commit();
-    }
-    const double* As = stageA(kt % STAGES);
-    const double* Bs = stageB(kt % STAGES);
+    // slab kt+STAGES-1 goes into the stage every warp finished reading before the barrier above; its cp.asyncs
+    // are spread over the k4-steps so that they issue in the shadow of the DMMA pipe
+    const int krem = K - (kt + STAGES - 1) * BK;
+    const bool more = krem > 0;
+    const unsigned lbase = smem_u32 + (unsigned)ls * STAGE_BYTES;
+    const double* As = stageA(cs);
+    const double* Bs = stageB(cs);
 #pragma unroll
-    for (int kk = 0; kk < BK; kk += 4) {
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      const int kk = ks * 4;
       double a[MT], b[NTL];
 #pragma unroll
       for (int i = 0; i < MT; ++i)
@@ -146,10 +193,24 @@ gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, con
       for (int j = 0; j < NTL; ++j)
         b[j] = B_KC ? Bs[(wn0 + j * 8 + g) * KC_LD + kk + t] : Bs[(kk + t) * B_MC_LD + wn0 + j * 8 + g];
 #pragma unroll
-      for (int i = 0; i < MT; ++i)
+      for (int i = 0; i < MT; ++i) {
 #pragma unroll
         for (int j = 0; j < NTL; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        if (i == MT / 2 - 1 || (MT == 1 && i == 0)) {
+          if (more) {
+#pragma unroll
+            for (int c = ks * PER_STEP; c < (ks + 1) * PER_STEP && c < NCHUNK; ++c) issue_chunk(lbase, c, krem);
+          }
+        }
+      }
     }
+    if (more) {
+      la.advance();
+      lb.advance();
+    }
+    cp_async_commit();
+    cs = cs + 1 == STAGES ? 0 : cs + 1;
+    ls = ls + 1 == STAGES ? 0 : ls + 1;
   }
   cp_async_wait<0>();
 
