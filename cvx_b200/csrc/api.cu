@@ -173,7 +173,15 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
   h->flags = flags;
   h->sm_count = prop.multiProcessorCount;
   if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
-  else { CVXB_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  else {
+    // the handle's own stream carries the critical chain of the blocked factorisations (leaf -> panel -> look-ahead
+    // update); give it the highest priority so its CTAs are dispatched ahead of the bulk updates queued on stream2
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (getenv("CVXB_NO_PRIO")) hi = 0;
+    CVXB_CUDA_OK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, hi));
+    h->own_stream = true;
+  }
   CVXB_CUDA_OK(cudaMalloc((void**)&h->d_scal, NSCAL * sizeof(double)));
   CVXB_CUDA_OK(cudaMalloc((void**)&h->d_flag, NFLAG * sizeof(int)));
   CVXB_CUDA_OK(cudaMalloc((void**)&h->d_part, PART_DOUBLES * sizeof(double)));
@@ -185,6 +193,11 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
     if (coop && !getenv("CVXB_NO_WAVEFRONT")) CVXB_CUDA_OK(cudaMalloc((void**)&h->wave_ready, 1024 * sizeof(int)));
+    if (coop && !getenv("CVXB_NO_STREAMK")) {
+      CVXB_CUDA_OK(cudaMalloc((void**)&h->sk_ws, (size_t)h->sm_count * 128 * 128 * sizeof(double)));
+      CVXB_CUDA_OK(cudaMalloc((void**)&h->sk_flags, (size_t)h->sm_count * sizeof(int)));
+      CVXB_CUDA_OK(cudaMemset(h->sk_flags, 0, (size_t)h->sm_count * sizeof(int)));
+    }
   }
   CVXB_CUDA_OK(cudaMallocHost((void**)&h->h_scal, NSCAL * sizeof(double)));
   CVXB_CUDA_OK(cudaMallocHost((void**)&h->h_flag, NFLAG * sizeof(int)));
@@ -199,7 +212,11 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
       cudaGetLastError();
     }
   }
-  CVXB_CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CVXB_CUDA_OK(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, lo));
+  }
   for (int i = 0; i < 600; ++i) {
     cudaEvent_t e;
     CVXB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -219,6 +236,7 @@ int cvxb_destroy(cvxb_handle h) {
   cvxb::DeviceGuard guard(h->device);
   cudaStreamSynchronize(h->stream);
   if (h->kkt_cache) { KktWork* W = (KktWork*)h->kkt_cache; kkt_work_free(*W); delete W; }
+  cudaFree(h->sk_ws); cudaFree(h->sk_flags);
   cudaFree(h->wave_ready); cudaFree(h->d_scal); cudaFree(h->d_flag); cudaFree(h->d_part); cudaFree(h->d_ticket);
   cudaFreeHost(h->h_scal); cudaFreeHost(h->h_flag);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->gev0); cudaEventDestroy(h->gev1);
@@ -635,6 +653,7 @@ int cvxb_test_dgemm(cvxb_handle h, int a_kc, int b_kc, int M, int N, int K, doub
     cptr = dC2.d; cld = dC2.ld;
   }
   GemmArgs g{M, N, K, dA.d, dA.ld, a_kc != 0, dB.d, dB.ld, b_kc != 0, cptr, cld, alpha, beta, tri};
+  g.streamk = tri != 0;      // as the solver's big SYRKs do (taken only when the tile grid leaves a partial wave)
   CVXB_TRY(gemm_dmma(*h, g));
   Staged so; so.d = cptr; so.ld = cld;
   CVXB_TRY(copy_out(*h, M, N, so, C, ldc));
@@ -687,9 +706,11 @@ int cvxb_bench_kernel(cvxb_handle h, int which, int n, int k, int reps, double* 
       if (r == 0) CVXB_CUDA_OK(cudaEventRecord(H.ev0, H.stream));
       if (which == 1) {        // Hessian-assembly SYRK  H = G'G, G k x n (K contiguous)
         GemmArgs g{n, n, k, G, ldk, true, G, ldk, true, C, ldn, 1.0, 0.0, 2};
+        g.streamk = true;
         CVXB_TRY(gemm_dmma(H, g));
       } else if (which == 2) { // Cholesky trailing update  C -= A A', A n x k (M contiguous), lower
         GemmArgs g{n, n, k, G, ldn, false, G, ldn, false, C, ldn, -1.0, 1.0, 1};
+        g.streamk = true;
         CVXB_TRY(gemm_dmma(H, g));
       } else {
         copy_kernel<<<H.sm_count * 8, 512, 0, H.stream>>>(gcount / 2, (const double2*)G, (double2*)C);

@@ -56,6 +56,8 @@ struct cvxb_handle_s {
   unsigned* d_ticket = nullptr;  // last-block-done counters
   cudaStream_t stream2 = nullptr;            // look-ahead stream of the blocked Cholesky
   std::vector<cudaEvent_t> la_events;        // fork / join events of the look-ahead schedule
+  double* sk_ws = nullptr;       // stream-K partial tiles: one 128x128 slot per SM
+  int* sk_flags = nullptr;       // "slot c holds a partial" flags (self-cleaning)
   int* wave_ready = nullptr;     // per-block "y_k published" flags of the wavefront triangular solves
   void* kkt_cache = nullptr;     // cvxb::KktWork of the last seam-B call (re-used when (n,p) repeat)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -138,6 +140,7 @@ struct GemmArgs {
   int tri;
   int tile = 0;   // 0 = choose 128 / 64 / 32 by grid size; in-place callers (C aliases A or B) must pin 128
   bool lower_only = false;   // rectangular C whose rows and columns share an origin: never write elements with m < n
+  bool streamk = false;      // tri != 0, 128x128 tiles, handle's own stream: persistent stream-K grid (no partial last wave)
 };
 int gemm_dmma(Handle& h, const GemmArgs& g);
 int gemm_dmma_on(Handle& h, const GemmArgs& g, cudaStream_t st);   // same, on another stream of the handle

@@ -632,6 +632,7 @@ int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot,
   CVXB_TRY(trsm_right_lt(h, b, a, A, lda, invD, A21, lda));
   // A22 -= A21 A21'  lower: A(m,k) = A21[k*lda + m] (M contiguous), B(k,n) = A21(n,k) (N contiguous)
   GemmArgs g{b, b, a, A21, lda, false, A21, lda, false, A22, lda, -1.0, 1.0, 1};
+  g.streamk = true;      // main stream only (the look-ahead schedule has joined)
   CVXB_TRY(gemm_dmma(h, g));
   return potrf_rec(h, b, A22, lda, invD + (size_t)(a / NB) * NB * NB, flag_slot, mindiag_slot, col0 + a, plain);
 }

@@ -103,137 +103,244 @@ struct SlabLoader {
   __device__ __forceinline__ void advance() { p += KC ? (long long)BK : (long long)BK * ld; }
 };
 
+// linear id -> (bm, bn) with bn <= bm, row-major over the lower triangle of tiles
+__device__ __forceinline__ void tri_tile(int id, int& bm, int& bn) {
+  int r = (int)((sqrt(8.0 * (double)id + 1.0) - 1.0) * 0.5);
+  while ((long long)(r + 1) * (r + 2) / 2 <= id) ++r;
+  while ((long long)r * (r + 1) / 2 > id) --r;
+  bm = r;
+  bn = id - r * (r + 1) / 2;
+}
+
+// One CTA tile: the k-slabs [kt0, kt1) of C(m0.., n0..) accumulated into acc (which the caller zeroes).
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KC, bool B_KC>
+struct CtaTile {
+  static constexpr int NTHR = WARPS_M * WARPS_N * 32;
+  static constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+  static constexpr int MT = WM / 8, NTL = WN / 8;
+  static constexpr int A_ELEMS = TileElems<BM>::value, B_ELEMS = TileElems<BN>::value;
+  static constexpr int A_MC_LD = BM + 4, B_MC_LD = BN + 4;
+
+  __device__ static __forceinline__ void zero(double (&acc)[MT][NTL][2]) {
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NTL; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  }
+
+  __device__ static __forceinline__ void mainloop(double (&acc)[MT][NTL][2], double* smem, int M, int N, int K,
+                                                  const double* __restrict__ A, int lda, const double* __restrict__ B,
+                                                  int ldb, int m0, int n0, int kt0, int kt1) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp % WARPS_M) * WM, wn0 = (warp / WARPS_M) * WN;
+    const int KT = kt1 - kt0;
+    const int Krem0 = K - kt0 * BK;               // valid k's from the first slab of this range on
+    constexpr unsigned STAGE_BYTES = (unsigned)((A_ELEMS + B_ELEMS) * sizeof(double));
+    constexpr unsigned B_OFF = (unsigned)(A_ELEMS * sizeof(double));
+    const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(smem);
+    auto stageA = [&](int s) { return smem + (size_t)s * (A_ELEMS + B_ELEMS); };
+    auto stageB = [&](int s) { return smem + (size_t)s * (A_ELEMS + B_ELEMS) + A_ELEMS; };
+    typedef SlabLoader<A_KC, BM, NTHR> LoadA;
+    typedef SlabLoader<B_KC, BN, NTHR> LoadB;
+    LoadA la;
+    LoadB lb;
+    la.init(A + (A_KC ? (size_t)kt0 * BK : (size_t)kt0 * BK * lda), lda, M, m0, tid);
+    lb.init(B + (B_KC ? (size_t)kt0 * BK : (size_t)kt0 * BK * ldb), ldb, N, n0, tid);
+    constexpr int NCHUNK = LoadA::ITERS + LoadB::ITERS;       // cp.async per thread per slab
+    constexpr int KSTEPS = BK / 4;
+    constexpr int PER_STEP = (NCHUNK + KSTEPS - 1) / KSTEPS;  // issued behind each k4-step's DMMAs
+    auto issue_chunk = [&](unsigned sbase, int c, int krem) {
+      if (c < LoadA::ITERS) la.issue(sbase, c, krem);
+      else lb.issue(sbase + B_OFF, c - LoadA::ITERS, krem);
+    };
+
+    // prologue: slabs 0 .. STAGES-2 of the range
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      if (s < KT) {
+        const int krem = Krem0 - s * BK;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) issue_chunk(smem_u32 + s * STAGE_BYTES, c, krem);
+        la.advance();
+        lb.advance();
+      }
+      cp_async_commit();
+    }
+
+    int cs = 0, ls = STAGES - 1;       // stage being consumed / stage being refilled
+    for (int kt = 0; kt < KT; ++kt) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      // slab kt+STAGES-1 goes into the stage every warp finished reading before the barrier above; its cp.asyncs
+      // are spread over the k4-steps so that they issue in the shadow of the DMMA pipe
+      const int krem = Krem0 - (kt + STAGES - 1) * BK;
+      const bool more = kt + STAGES - 1 < KT;
+      const unsigned lbase = smem_u32 + (unsigned)ls * STAGE_BYTES;
+      const double* As = stageA(cs);
+      const double* Bs = stageB(cs);
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        const int kk = ks * 4;
+        double a[MT], b[NTL];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+          a[i] = A_KC ? As[(wm0 + i * 8 + g) * KC_LD + kk + t] : As[(kk + t) * A_MC_LD + wm0 + i * 8 + g];
+#pragma unroll
+        for (int j = 0; j < NTL; ++j)
+          b[j] = B_KC ? Bs[(wn0 + j * 8 + g) * KC_LD + kk + t] : Bs[(kk + t) * B_MC_LD + wn0 + j * 8 + g];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+#pragma unroll
+          for (int j = 0; j < NTL; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          if (i == MT / 2 - 1 || (MT == 1 && i == 0)) {
+            if (more) {
+#pragma unroll
+              for (int c = ks * PER_STEP; c < (ks + 1) * PER_STEP && c < NCHUNK; ++c) issue_chunk(lbase, c, krem);
+            }
+          }
+        }
+      }
+      if (more) {
+        la.advance();
+        lb.advance();
+      }
+      cp_async_commit();
+      cs = cs + 1 == STAGES ? 0 : cs + 1;
+      ls = ls + 1 == STAGES ? 0 : ls + 1;
+    }
+    cp_async_wait<0>();
+  }
+
+  // thread (g,t) of DMMA tile (i,j) holds C(m, n), C(m, n+1), m = ..+g, n = ..+2t
+  __device__ static __forceinline__ void epilogue(const double (&acc)[MT][NTL][2], int M, int N, double* __restrict__ C,
+                                                  int ldc, double alpha, double beta, int tri, bool diag, int m0, int n0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp % WARPS_M) * WM, wn0 = (warp / WARPS_M) * WN;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      int m = m0 + wm0 + i * 8 + g;
+      if (m >= M) continue;
+#pragma unroll
+      for (int j = 0; j < NTL; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          int n = n0 + wn0 + j * 8 + 2 * t + e;
+          if (n >= N) continue;
+          if (diag && n > m) continue;
+          double v = alpha * acc[i][j][e];
+          size_t idx = (size_t)n * ldc + m;
+          if (beta != 0.0) v += beta * C[idx];
+          C[idx] = v;
+          if (tri == 2 && n != m) C[(size_t)m * ldc + n] = v;
+        }
+      }
+    }
+  }
+};
+
 template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (BM >= 128 ? 1 : 2))
 gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
                  double* __restrict__ C, int ldc, double alpha, double beta, int tri, int tiles_m, int lower_only) {
-  constexpr int NTHR = WARPS_M * WARPS_N * 32;
-  constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
-  constexpr int MT = WM / 8, NTL = WN / 8;
-  constexpr int A_ELEMS = TileElems<BM>::value, B_ELEMS = TileElems<BN>::value;
-  constexpr int A_MC_LD = BM + 4, B_MC_LD = BN + 4;
+  typedef CtaTile<BM, BN, WARPS_M, WARPS_N, A_KC, B_KC> T;
   extern __shared__ __align__(16) double smem[];
   int bm, bn;
   if (tri) {
-    // linear id -> (bm, bn) with bn <= bm, row-major over the lower triangle of tiles
-    int id = blockIdx.x;
-    int r = (int)((sqrt(8.0 * (double)id + 1.0) - 1.0) * 0.5);
-    while ((long long)(r + 1) * (r + 2) / 2 <= id) ++r;
-    while ((long long)r * (r + 1) / 2 > id) --r;
-    bm = r;
-    bn = id - r * (r + 1) / 2;
+    tri_tile(blockIdx.x, bm, bn);
   } else {
     bm = blockIdx.x % tiles_m;
     bn = blockIdx.x / tiles_m;
   }
   const int m0 = bm * BM, n0 = bn * BN;
   if (lower_only && m0 + BM <= n0) return;      // tile entirely above the diagonal
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp % WARPS_M) * WM, wn0 = (warp / WARPS_M) * WN;
+  double acc[T::MT][T::NTL][2];
+  T::zero(acc);
+  T::mainloop(acc, smem, M, N, K, A, lda, B, ldb, m0, n0, 0, (K + BK - 1) / BK);
+  T::epilogue(acc, M, N, C, ldc, alpha, beta, tri, (tri && (bm == bn)) || lower_only, m0, n0);
+}
 
-  double acc[MT][NTL][2];
-#pragma unroll
-  for (int i = 0; i < MT; ++i)
-#pragma unroll
-    for (int j = 0; j < NTL; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
+// Stream-K variant of the 128x128 triangular (SYRK) grid: ONE persistent CTA per SM.  With T tiles and G CTAs the
+// plain grid runs ceil(T/G) waves and leaves the last one partly empty (C2: 136 tiles on 148 SMs; C4: 2080 =
+// 14 waves + 8 tiles).  Here the first T - (G + T%G) tiles are dealt out whole (CTA i takes tiles i, i+G, ...) and
+// the k-slabs of the remaining G + T%G tiles are cut into G equal contiguous shares.  A share starts with the tail
+// (or a middle piece) of a tile -- written as a partial to the CTA's workspace slot and flagged -- and ends with the
+// head of another tile, whose CTA is that tile's owner: it adds the partials of CTAs i+1, i+2, ... in index order
+// (fixed order: results are deterministic and tri=2 stays bitwise symmetric) and runs the epilogue.  The partials
+// an owner needs were produced at the START of the other CTAs' shares, so nobody waits long; co-residency is
+// guaranteed by the cooperative launch.
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256, 1)
+gemm_dmma_streamk_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const double* __restrict__ B,
+                         int ldb, double* __restrict__ C, int ldc, double alpha, double beta, int tri, int tiles_total,
+                         int tiles_whole, double* __restrict__ ws, int* flags) {
+  typedef CtaTile<128, 128, 2, 4, A_KC, B_KC> T;
+  constexpr int PER_THREAD = T::MT * T::NTL * 2;       // 64 accumulators
+  extern __shared__ __align__(16) double smem[];
+  const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x;
   const int KT = (K + BK - 1) / BK;
-  constexpr unsigned STAGE_BYTES = (unsigned)((A_ELEMS + B_ELEMS) * sizeof(double));
-  constexpr unsigned B_OFF = (unsigned)(A_ELEMS * sizeof(double));
-  const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(smem);
-  auto stageA = [&](int s) { return smem + (size_t)s * (A_ELEMS + B_ELEMS); };
-  auto stageB = [&](int s) { return smem + (size_t)s * (A_ELEMS + B_ELEMS) + A_ELEMS; };
-  typedef SlabLoader<A_KC, BM, NTHR> LoadA;
-  typedef SlabLoader<B_KC, BN, NTHR> LoadB;
-  LoadA la;
-  LoadB lb;
-  la.init(A, lda, M, m0, tid);
-  lb.init(B, ldb, N, n0, tid);
-  constexpr int NCHUNK = LoadA::ITERS + LoadB::ITERS;       // cp.async per thread per slab
-  constexpr int KSTEPS = BK / 4;
-  constexpr int PER_STEP = (NCHUNK + KSTEPS - 1) / KSTEPS;  // issued behind each k4-step's DMMAs
-  auto issue_chunk = [&](unsigned sbase, int c, int krem) {
-    if (c < LoadA::ITERS) la.issue(sbase, c, krem);
-    else lb.issue(sbase + B_OFF, c - LoadA::ITERS, krem);
-  };
-
-  // prologue: slabs 0 .. STAGES-2
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < KT) {
-      const int krem = K - s * BK;
-#pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) issue_chunk(smem_u32 + s * STAGE_BYTES, c, krem);
-      la.advance();
-      lb.advance();
-    }
-    cp_async_commit();
+  double acc[T::MT][T::NTL][2];
+  // whole tiles
+  for (int id = cta; id < tiles_whole; id += G) {
+    int bm, bn;
+    tri_tile(id, bm, bn);
+    T::zero(acc);
+    __syncthreads();          // every warp is done with the previous tile's stages
+    T::mainloop(acc, smem, M, N, K, A, lda, B, ldb, bm * 128, bn * 128, 0, KT);
+    T::epilogue(acc, M, N, C, ldc, alpha, beta, tri, bm == bn, bm * 128, bn * 128);
   }
-
-  int cs = 0, ls = STAGES - 1;       // stage being consumed / stage being refilled
-  for (int kt = 0; kt < KT; ++kt) {
-    cp_async_wait<STAGES - 2>();
+  // this CTA's share of the split tiles' slabs
+  const long long W = (long long)(tiles_total - tiles_whole) * KT;
+  long long pos = W * cta / G;
+  const long long end = W * (cta + 1) / G;
+  while (pos < end) {
+    const int tl = (int)(pos / KT);
+    const int kb = (int)(pos - (long long)tl * KT);
+    const int ke = (end - pos < KT - kb) ? kb + (int)(end - pos) : KT;
+    int bm, bn;
+    tri_tile(tiles_whole + tl, bm, bn);
+    T::zero(acc);
     __syncthreads();
-    // slab kt+STAGES-1 goes into the stage every warp finished reading before the barrier above; its cp.asyncs
-    // are spread over the k4-steps so that they issue in the shadow of the DMMA pipe
-    const int krem = K - (kt + STAGES - 1) * BK;
-    const bool more = krem > 0;
-    const unsigned lbase = smem_u32 + (unsigned)ls * STAGE_BYTES;
-    const double* As = stageA(cs);
-    const double* Bs = stageB(cs);
+    T::mainloop(acc, smem, M, N, K, A, lda, B, ldb, bm * 128, bn * 128, kb, ke);
+    if (kb > 0) {
+      // not the owner (only ever the first piece of a share): partial -> slot of this CTA, then the flag
+      double* slot = ws + (size_t)cta * (256 * PER_THREAD);
 #pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks) {
-      const int kk = ks * 4;
-      double a[MT], b[NTL];
+      for (int i = 0; i < T::MT; ++i)
 #pragma unroll
-      for (int i = 0; i < MT; ++i)
-        a[i] = A_KC ? As[(wm0 + i * 8 + g) * KC_LD + kk + t] : As[(kk + t) * A_MC_LD + wm0 + i * 8 + g];
-#pragma unroll
-      for (int j = 0; j < NTL; ++j)
-        b[j] = B_KC ? Bs[(wn0 + j * 8 + g) * KC_LD + kk + t] : Bs[(kk + t) * B_MC_LD + wn0 + j * 8 + g];
-#pragma unroll
-      for (int i = 0; i < MT; ++i) {
-#pragma unroll
-        for (int j = 0; j < NTL; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        if (i == MT / 2 - 1 || (MT == 1 && i == 0)) {
-          if (more) {
-#pragma unroll
-            for (int c = ks * PER_STEP; c < (ks + 1) * PER_STEP && c < NCHUNK; ++c) issue_chunk(lbase, c, krem);
+        for (int j = 0; j < T::NTL; ++j) {
+          slot[((i * T::NTL + j) * 2 + 0) * 256 + tid] = acc[i][j][0];
+          slot[((i * T::NTL + j) * 2 + 1) * 256 + tid] = acc[i][j][1];
+        }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicExch(flags + cta, 1);
+    } else {
+      if (ke < KT) {
+        // owner of a split tile: the rest comes from the CTAs whose shares start inside this tile
+        const long long tile_end = (long long)(tl + 1) * KT;
+        for (int c = cta + 1; c < G && W * c / G < tile_end; ++c) {
+          if (tid == 0) {
+            while (atomicAdd(flags + c, 0) == 0) __nanosleep(64);
+            __threadfence();
           }
+          __syncthreads();
+          const double* slot = ws + (size_t)c * (256 * PER_THREAD);
+#pragma unroll
+          for (int i = 0; i < T::MT; ++i)
+#pragma unroll
+            for (int j = 0; j < T::NTL; ++j) {
+              acc[i][j][0] += __ldcg(slot + ((i * T::NTL + j) * 2 + 0) * 256 + tid);
+              acc[i][j][1] += __ldcg(slot + ((i * T::NTL + j) * 2 + 1) * 256 + tid);
+            }
+          __syncthreads();
+          if (tid == 0) atomicExch(flags + c, 0);      // consumed: clean for the next launch
         }
       }
+      T::epilogue(acc, M, N, C, ldc, alpha, beta, tri, bm == bn, bm * 128, bn * 128);
     }
-    if (more) {
-      la.advance();
-      lb.advance();
-    }
-    cp_async_commit();
-    cs = cs + 1 == STAGES ? 0 : cs + 1;
-    ls = ls + 1 == STAGES ? 0 : ls + 1;
-  }
-  cp_async_wait<0>();
-
-  // epilogue: thread (g,t) of tile (i,j) holds C(m, n), C(m, n+1), m = ..+g, n = ..+2t
-  const bool diag = (tri && (bm == bn)) || lower_only;
-#pragma unroll
-  for (int i = 0; i < MT; ++i) {
-    int m = m0 + wm0 + i * 8 + g;
-    if (m >= M) continue;
-#pragma unroll
-    for (int j = 0; j < NTL; ++j) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        int n = n0 + wn0 + j * 8 + 2 * t + e;
-        if (n >= N) continue;
-        if (diag && n > m) continue;
-        double v = alpha * acc[i][j][e];
-        size_t idx = (size_t)n * ldc + m;
-        if (beta != 0.0) v += beta * C[idx];
-        C[idx] = v;
-        if (tri == 2 && n != m) C[(size_t)m * ldc + n] = v;
-      }
-    }
+    pos += ke - kb;
   }
 }
 
@@ -316,6 +423,10 @@ int dmma_peak_probe(Handle& h, int iters, double* ms, double* flops) {
 }
 
 int gemm_dmma_init() {
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_streamk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    smem_bytes<128, 2, 4>()));
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_streamk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    smem_bytes<128, 2, 4>()));
   CVXB_TRY((set_attr<128, 2, 4>()));
   CVXB_TRY((set_attr<64, 2, 2>()));
   CVXB_TRY((set_attr<32, 2, 2>()));
@@ -371,6 +482,30 @@ int gemm_dmma(Handle& h, const GemmArgs& g) {
   const long long want = (long long)h.sm_count * 3 / 4;
   int tile = g.tile;
   if (tile == 0) tile = ntiles(128) >= want ? 128 : (ntiles(64) >= want ? 64 : 32);
+  if (tile == 128 && g.streamk && g.tri && h.sk_ws && g_gemm_stream == nullptr && g.a_kc == g.b_kc) {
+    // stream-K for the big SYRKs on the handle's own stream (see gemm_dmma_streamk_kernel)
+    const long long T = ntiles(128);
+    const int G = h.sm_count, KT = (g.K + BK - 1) / BK;
+    const int r = (int)(T % G);
+    if (r != 0 && KT >= 16 && T >= G / 2 && T < (1ll << 30)) {
+      const int whole = T >= G + r ? (int)(T - (G + r)) : 0;
+      int M = g.M, N = g.N, K = g.K, lda = g.lda, ldb = g.ldb, ldc = g.ldc, tri = g.tri, tt = (int)T, tw = whole;
+      const double *A = g.A, *B = g.B;
+      double* C = g.C;
+      double alpha = g.alpha, beta = g.beta;
+      double* ws = h.sk_ws;
+      int* fl = h.sk_flags;
+      void* args[] = {&M, &N, &K, &A, &lda, &B, &ldb, &C, &ldc, &alpha, &beta, &tri, &tt, &tw, &ws, &fl};
+      const void* fn = g.a_kc ? (const void*)gemm_dmma_streamk_kernel<true, true>
+                              : (const void*)gemm_dmma_streamk_kernel<false, false>;
+      cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(G), dim3(256), args, smem_bytes<128, 2, 4>(), h.stream);
+      if (e == cudaSuccess) {
+        h.launches++;
+        return CVXB_OK;
+      }
+      cudaGetLastError();       // not launchable cooperatively here: the plain grid below
+    }
+  }
   if (tile == 128) return launch_layout<128, 2, 4>(h, g);    // (a 16-warp 4x4 layout measured 7% slower)
   if (tile == 64) return launch_layout<64, 2, 2>(h, g);
   return launch_layout<32, 2, 2>(h, g);

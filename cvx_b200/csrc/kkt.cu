@@ -244,6 +244,7 @@ int kkt_enqueue(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, i
   CVXB_TRY(trsm_lower(h, n, p + 1, W.L, W.ldn, W.invD, W.Y, W.ldn, false));
   // Schur complement S = Yp'Yp and its (plain, unregularised) Cholesky  KKTSystem.scala:126-140
   GemmArgs g{p, p, n, W.Y, W.ldn, true, W.Y, W.ldn, true, W.S, W.ldp, 1.0, 0.0, 2};
+  g.streamk = true;
   CVXB_TRY(gemm_dmma(h, g));
   CVXB_TRY(potrf_lower(h, p, W.S, W.ldp, W.invDs, F_CHOL_S, S_MINDIAG_S));
   // z = -(b + A H^-1 q) = -(b + Yp' yq) ; w = K^-T K^-1 z
@@ -307,6 +308,7 @@ int kkt_solve_fallbacks(Handle& h, KktWork& W, const cvxb_params& P, const doubl
   }
   CVXB_TRY(copy_matrix(h, n, n, Hm, ldh, W.Hk, W.ldn));
   GemmArgs g{n, n, p, A, lda, true, A, lda, true, W.Hk, W.ldn, 1.0, 1.0, 2};
+  g.streamk = true;
   CVXB_TRY(gemm_dmma(h, g));
   CVXB_TRY(gemv_t(h, p, n, 1.0, A, lda, b, 0.0, W.t1));
   CVXB_LAUNCH(h, sub_kernel, 1, VT, 0, n, q, W.t1, W.qk);

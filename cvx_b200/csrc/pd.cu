@@ -288,6 +288,7 @@ int pd_assemble(cvxb_problem_s* P, const cvxb_params& pars, double t) {
   else CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, nullptr, 0.0, P->H, P->ldn));
   CVXB_TRY(quad_hessian_terms(P, P->lam));     // + lam_k hess g_k   (PrimalDualSolver.scala:230-236)
   GemmArgs g{n, n, m, P->Gs, P->ldm, true, P->Gs, P->ldm, true, P->H, P->ldn, 1.0, 1.0, 2};
+  g.streamk = true;
   return gemm_dmma_timed(h, g, (double)m * n * ((double)n + 1.0));
 }
 

@@ -517,11 +517,13 @@ int barrier_hessian(cvxb_problem_s* P, double t, const double* t_dev = nullptr) 
     CVXB_LAUNCH(h, dual_scale_cols_kernel, dim3((n + 127) / 128, P->kd > 1024 ? 1024 : P->kd), 128, 0, n, P->kd, P->obj_P,
                 P->ldn, P->dy, t, t_dev, P->Bs, P->ldn);
     GemmArgs gd{n, n, P->kd, P->Bs, P->ldn, false, P->Bs, P->ldn, false, P->H, P->ldn, 1.0, 0.0, 2};
+    gd.streamk = true;
     CVXB_TRY(gemm_dmma(h, gd));
   }
   else CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, nullptr, 0.0, P->H, P->ldn));
   CVXB_TRY(quad_hessian_terms(P, P->inv));     // + hess g_k / d_k   (BarrierSolver.scala:313)
   GemmArgs g{n, n, m, P->Gs, P->ldm, true, P->Gs, P->ldm, true, P->H, P->ldn, 1.0, 1.0, 2};
+  g.streamk = true;
   return gemm_dmma_timed(h, g, (double)m * n * ((double)n + 1.0));   // lower triangle, mul + add
 }
 

@@ -49,3 +49,28 @@ def test_syrk_nt_lower_only(handle):
     assert np.array_equal(out[iu], C0[iu])
     il = np.tril_indices(n)
     assert np.max(np.abs(out[il] - ref[il])) <= 1e-12
+
+
+@pytest.mark.parametrize("n,k", [(2000, 700), (1700, 513), (2001, 2500), (2300, 520)])
+def test_syrk_streamk_shapes(handle, n, k):
+    """Tile grids with a partial last wave run the persistent stream-K kernel (split tiles summed in a fixed
+    order): H = G'G exactly symmetric and equal to numpy; the NT lower update leaves the upper triangle alone;
+    two launches give bitwise identical results (deterministic fix-up)."""
+    from cvx_b200.linalg import dgemm
+    rng = np.random.default_rng(n * 7 + k)
+    G = rng.uniform(-1, 1, (k, n))
+    C0 = rng.uniform(-1, 1, (n, n))
+    C0 = C0 + C0.T
+    H = dgemm(1, 1, n, n, k, 1.0, G, G, 0.5, C0, 2, handle)
+    ref = G.T @ G + 0.5 * C0
+    assert np.array_equal(H, H.T)
+    assert np.max(np.abs(H - ref)) <= 1e-13 * np.max(np.abs(ref))
+    H2 = dgemm(1, 1, n, n, k, 1.0, G, G, 0.5, C0, 2, handle)
+    assert np.array_equal(H, H2)
+    A = np.asfortranarray(G.T)            # n x k, M contiguous
+    out = dgemm(0, 0, n, n, k, -1.0, A, A, 1.0, C0, 1, handle)
+    iu = np.triu_indices(n, 1)
+    assert np.array_equal(out[iu], C0[iu])
+    il = np.tril_indices(n)
+    ref2 = C0 - A @ A.T
+    assert np.max(np.abs(out[il] - ref2[il])) <= 1e-13 * np.max(np.abs(ref2))
