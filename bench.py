@@ -360,11 +360,12 @@ def main():
         pk_ms, pk_fl = h.bench_kernel(0, 30000, 0, 1)
         fp64_peak = pk_fl / pk_ms / 1e9
         achieved = syrk_flops / (syrk_ms / 1e3) / 1e12 if syrk_ms > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<TN> (Hessian assembly G' diag(w) G, FP64 DMMA m8n8k4)",
+        roofline = {"bound": "tensor", "kernel": "gemm_dmma_streamk_kernel<TN> (Hessian assembly G' diag(w) G, FP64 DMMA m8n8k4, persistent stream-K grid)",
                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                    "traffic": 68.7e6 if args.workload == "c2" else None, "traffic_source": "dram__bytes_read+write per launch, ncu --set full, "
-                    "profiles/r1_ncu_full_syrk_hessian_c2_n2000_m4000.txt (algorithmic: 64 MB read of G + 32 MB write of H, "
-                    "the write mostly absorbed by L2)" if args.workload == "c2" else None, "launches": n_syrk, "avg_launch_ms": syrk_ms / max(n_syrk, 1),
+                    "traffic": 111.9e6 if args.workload == "c2" else None, "traffic_source": "dram__bytes_read+write per launch, ncu --set full, "
+                    "profiles/r1_ncu_full_syrk_hessian_c2_n2000_m4000.txt (algorithmic: 64 MB read of G + 32 MB write of H; "
+                    "the rest is the stream-K partial tiles, 148 x 128 KB written and read back, and re-reads of G that "
+                    "miss L2 in ncu's cold-cache replay)" if args.workload == "c2" else None, "launches": n_syrk, "avg_launch_ms": syrk_ms / max(n_syrk, 1),
                     "flops_per_launch": syrk_flops / max(n_syrk, 1),
                     "peak_source": "FP64 DMMA issue-rate probe measured in this run (MEASURED_PEAKS.json has HBM and bf16 "
                                    "only: hbm_gbs=%s); cuBLAS DGEMM 8192^3 on this pool measured 35.5 TFLOP/s" % peaks.get("hbm_gbs"),

@@ -26,7 +26,7 @@ for r in rd:
     cnt[name] += 1
 probe = sum(v for k, v in tot.items() if "dmma_peak" in k)
 total = sum(tot.values()) - probe
-syrk = [k for k in cnt if "gemm_dmma_kernel<128, 128, 2, 4, 1, 1>" in k]
+syrk = [k for k in cnt if "gemm_dmma_kernel<128, 128, 2, 4, 1, 1>" in k or "gemm_dmma_streamk_kernel<1, 1>" in k]
 steps = sum(cnt[k] for k in syrk)
 print("total %.3f ms excluding the DMMA peak probe; %d Hessian SYRK launches = Newton steps in the capture -> %.3f ms per step"
       % (total / 1e3, steps, total / 1e3 / max(steps, 1)))
