@@ -331,7 +331,9 @@ def main():
         lo, hi = cb.shard_range(Bt, rank, world)
         bprobs = [P.batched_problem(i, 64, 128, 1000) for i in range(lo, hi)]
         solver = cb.BatchedBarrierSolver(cb.pack_problems(bprobs), cb.SolverParams(), h)
-        solver.solve()                                    # warm-up (same shapes)
+        wsol = solver.solve()                             # warm-up (same shapes)
+        if world > 1:
+            cb.gather_solutions(wsol, Bt, 64)             # and of the exchange: NCCL connects its all-gather rings on first use
         barrier()
         t0 = time.perf_counter()
         bsol = solver.solve()
