@@ -177,6 +177,9 @@ int scaled_full(Handle& h, int n, const double* Hm, int ldh, const double* d, do
 // in-place blocked Cholesky of the lower triangle; inverse diagonal blocks to invD (ceil(n/NB) * NB*NB);
 // failure column -> d_flag[flag_slot] (first failure wins), min diag -> d_scal[mindiag_slot]
 int potrf_lower(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot);
+// same, and B (n x r) := L^-1 B computed along the way (the forward substitution overlaps the factorisation)
+int potrf_lower_rhs(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, double* B, int ldb,
+                    int r);
 // B (n x r) := L^-1 B   /  L^-T B, using the inverse diagonal blocks
 int trsm_lower(Handle& h, int n, int r, const double* L, int ldl, const double* invD, double* B, int ldb, bool trans);
 // inverse diagonal blocks of a given lower-triangular matrix (for cvxb_triangular_solve and

@@ -11,10 +11,13 @@
 
 namespace cvxb {
 
-int potrf_lookahead(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0);
+int potrf_lookahead(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0,
+                    double* B = nullptr, int ldb = 0, int r = 0);
 int rl_max_n();
 
 namespace {
+
+int trsm_rec(Handle& h, int n, int r, const double* L, int ldl, const double* invD, double* B, int ldb, bool trans);
 
 // ------------------------------------------------------------------------------------------- Ruiz
 constexpr int RUIZ_MAX_FUSED = 64;    // rho slots behind the ticket words (api.cu allocates 16 unsigned + 64 u64)
@@ -617,16 +620,21 @@ int trsm_right_lt(Handle& h, int M, int n1, const double* L, int ldl, const doub
 }
 
 // Recursive halving; sub-problems that fit the L2-resident regime switch to the look-ahead schedule.
-int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0, bool plain = false) {
+// With a right-hand-side block B (n x r) the forward substitution B := L^-1 B rides along: every piece of it is
+// issued as soon as the columns of L it needs exist (in the look-ahead regime on the second stream, in the shadow
+// of the leaf chain), instead of as a separate sweep over L after the factorisation.
+int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0, bool plain = false,
+              double* B = nullptr, int ldb = 0, int r = 0) {
   if (!plain && n > NB && n <= rl_max_n() && h.stream2)
-    return potrf_lookahead(h, n, A, lda, invD, flag_slot, mindiag_slot, col0);
+    return potrf_lookahead(h, n, A, lda, invD, flag_slot, mindiag_slot, col0, B, ldb, r);
   if (n <= NB) {
     CVXB_LAUNCH(h, leaf_kernel<true>, 1, LEAF_THREADS, LEAF_SMEM, n, n, A, lda, invD, h.d_flag, h.d_scal, flag_slot,
                 mindiag_slot, col0);
+    if (B) return trsm_rec(h, n, r, A, lda, invD, B, ldb, false);
     return CVXB_OK;
   }
   int a = split_point(n), b = n - a;
-  CVXB_TRY(potrf_rec(h, a, A, lda, invD, flag_slot, mindiag_slot, col0, plain));
+  CVXB_TRY(potrf_rec(h, a, A, lda, invD, flag_slot, mindiag_slot, col0, plain, B, ldb, r));
   double* A21 = A + a;
   double* A22 = A + (size_t)a * lda + a;
   CVXB_TRY(trsm_right_lt(h, b, a, A, lda, invD, A21, lda));
@@ -634,10 +642,16 @@ int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot,
   GemmArgs g{b, b, a, A21, lda, false, A21, lda, false, A22, lda, -1.0, 1.0, 1};
   g.streamk = true;      // main stream only (the look-ahead schedule has joined)
   CVXB_TRY(gemm_dmma(h, g));
-  return potrf_rec(h, b, A22, lda, invD + (size_t)(a / NB) * NB * NB, flag_slot, mindiag_slot, col0 + a, plain);
+  if (B) {   // B2 -= L21 Y1
+    GemmArgs gu{b, r, a, A21, lda, false, B, ldb, true, B + a, ldb, -1.0, 1.0, 0};
+    CVXB_TRY(gemm_dmma(h, gu));
+  }
+  return potrf_rec(h, b, A22, lda, invD + (size_t)(a / NB) * NB * NB, flag_slot, mindiag_slot, col0 + a, plain,
+                   B ? B + a : nullptr, ldb, r);
 }
-int potrf_rec_plain(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0) {
-  return potrf_rec(h, n, A, lda, invD, flag_slot, mindiag_slot, col0, true);
+int potrf_rec_plain(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0,
+                    double* B = nullptr, int ldb = 0, int r = 0) {
+  return potrf_rec(h, n, A, lda, invD, flag_slot, mindiag_slot, col0, true, B, ldb, r);
 }
 
 int trsm_rec(Handle& h, int n, int r, const double* L, int ldl, const double* invD, double* B, int ldb, bool trans) {
@@ -1042,19 +1056,23 @@ int scaled_full(Handle& h, int n, const double* Hm, int ldh, const double* d, do
 // step the critical chain is  leaf -> panel solve -> update of the NEXT column block  on the main stream, while
 // the bulk of the trailing update runs on a second stream, overlapped with the next leaf (which occupies a
 // single SM).  Fork / join by events, so the whole schedule is capturable into the per-step CUDA graph.
-int potrf_lookahead(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0) {
+int potrf_lookahead(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0,
+                    double* B, int ldb, int r) {
   const int nblk = (n + NB - 1) / NB;
   const size_t half = (PART_DOUBLES - 65536) / 2;
-  if (2 * nblk + 2 > (int)h.la_events.size() || (size_t)pad_ld(n) * NB > half)
-    return potrf_rec_plain(h, n, A, lda, invD, flag_slot, mindiag_slot, col0);
+  const size_t ys_doubles = B ? (size_t)NB * r : 0;     // Y_k = invD_k B_k, kept beside the panel in the same half
+  if (2 * nblk + 2 > (int)h.la_events.size() || (size_t)pad_ld(n) * NB + ys_doubles > half)
+    return potrf_rec_plain(h, n, A, lda, invD, flag_slot, mindiag_slot, col0, B, ldb, r);
   cudaStream_t sa = h.stream, sb = h.stream2;
   int pending = -1;      // step whose second-stream work (copy-back + bulk update) the main stream has not yet waited for
+  int last_k0 = 0, last_kb = 0;
   for (int k = 0; k < nblk; ++k) {
     const int k0 = k * NB, kb = n - k0 < NB ? n - k0 : NB;
     const int rem = n - k0 - kb;
     double* Akk = A + (size_t)k0 * lda + k0;
     CVXB_LAUNCH(h, leaf_kernel<true>, 1, LEAF_THREADS, LEAF_SMEM, kb, kb, Akk, lda, invD + (size_t)k * NB * NB, h.d_flag,
                 h.d_scal, flag_slot, mindiag_slot, col0 + k0);
+    last_k0 = k0; last_kb = kb;
     if (rem <= 0) break;
     double* A21 = Akk + kb;                                   // rows below the diagonal block, this column block
     // panel solve X = A21 L11^-T into one half of the scratch block (alternating halves): the critical chain reads
@@ -1081,17 +1099,30 @@ int potrf_lookahead(Handle& h, int n, double* A, int lda, double* invD, int flag
       GemmArgs gb{rem2, rem2, kb, X31, lds, false, X31, lds, false, A33, lda, -1.0, 1.0, 1};
       CVXB_TRY(gemm_dmma_on(h, gb, sb));
     }
-    {
-      cudaStream_t keep = h.stream;
-      h.stream = sb;
-      int st = copy_matrix(h, rem, kb, Xs, lds, A21, lda);
-      h.stream = keep;
-      if (st != CVXB_OK) return st;
+    cudaStream_t keep = h.stream;
+    h.stream = sb;
+    int st = copy_matrix(h, rem, kb, Xs, lds, A21, lda);
+    if (st == CVXB_OK && B) {
+      // forward substitution riding along: Y_k = invD_k B_k (B_k is final: every earlier update ran on this
+      // stream), B_rest -= L_rest,k Y_k with the panel still in scratch, Y_k back into B
+      double* Ys = Xs + (half - ys_doubles);
+      GemmArgs gy{kb, r, kb, invD + (size_t)k * NB * NB, NB, false, B + k0, ldb, true, Ys, NB, 1.0, 0.0, 0};
+      st = gemm_dmma_on(h, gy, sb);
+      if (st == CVXB_OK) {
+        GemmArgs gu{rem, r, kb, Xs, lds, false, Ys, NB, true, B + k0 + kb, ldb, -1.0, 1.0, 0};
+        st = gemm_dmma_on(h, gu, sb);
+      }
+      if (st == CVXB_OK) st = copy_matrix(h, kb, r, Ys, NB, B + k0, ldb);
     }
+    h.stream = keep;
+    if (st != CVXB_OK) return st;
     CVXB_CUDA_OK(cudaEventRecord(evB, sb));
     pending = k;
   }
   if (pending >= 0) CVXB_CUDA_OK(cudaStreamWaitEvent(sa, h.la_events[2 * pending + 1], 0));   // join
+  if (B)      // last diagonal block: Y = invD B on the main stream (everything else has joined)
+    CVXB_TRY(trsm_rec(h, last_kb, r, A + (size_t)last_k0 * lda + last_k0, lda, invD + (size_t)(last_k0 / NB) * NB * NB,
+                      B + last_k0, ldb, false));
   return CVXB_OK;
 }
 
@@ -1109,6 +1140,19 @@ int potrf_lower(Handle& h, int n, double* A, int lda, double* invD, int flag_slo
   CVXB_LAUNCH(h, potrf_reset_kernel, 1, 1, 0, h.d_flag, h.d_scal, flag_slot, mindiag_slot);
   if (n <= 0) return CVXB_OK;
   return potrf_rec(h, n, A, lda, invD, flag_slot, mindiag_slot, 0);
+}
+
+int potrf_lower_rhs(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, double* B, int ldb,
+                    int r) {
+  if (!B || r <= 0 || (ldb & 1) || ((uintptr_t)B & 15) || getenv("CVXB_NO_FUSED_TRSM")) {
+    CVXB_TRY(potrf_lower(h, n, A, lda, invD, flag_slot, mindiag_slot));
+    if (B && r > 0) return trsm_lower(h, n, r, A, lda, invD, B, ldb, false);
+    return CVXB_OK;
+  }
+  CVXB_TRY(leaf_init());
+  CVXB_LAUNCH(h, potrf_reset_kernel, 1, 1, 0, h.d_flag, h.d_scal, flag_slot, mindiag_slot);
+  if (n <= 0) return CVXB_OK;
+  return potrf_rec(h, n, A, lda, invD, flag_slot, mindiag_slot, 0, false, B, ldb, r);
 }
 
 int trsm_lower(Handle& h, int n, int r, const double* L, int ldl, const double* invD, double* B, int ldb, bool trans) {

@@ -235,22 +235,22 @@ int kkt_enqueue(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, i
   } else {
     if (!skip_ruiz) CVXB_TRY(ruiz_equilibrate(h, n, Hm, ldh, W.dr, W.colsq, P.ruizMaxSweeps, P.ruizTol));
     CVXB_TRY(scaled_lower(h, n, Hm, ldh, W.dr, regularize ? P.cholRegDelta : 0.0, W.L, W.ldn));
-    CVXB_TRY(potrf_lower(h, n, W.L, W.ldn, W.invD, F_CHOL_H, S_MINDIAG_H));
   }
   // right-hand sides  [D A', D q]
   CVXB_TRY(transpose_scale(h, p, n, A, lda, W.dr, W.Y, W.ldn));
   double* yq = W.Y + (size_t)p * W.ldn;
   CVXB_LAUNCH(h, kkt_rhs_kernel, 1, VT, 0, n, p, W.dr, q, b, W.qs, yq, h.d_scal, h.d_flag);
-  CVXB_TRY(trsm_lower(h, n, p + 1, W.L, W.ldn, W.invD, W.Y, W.ldn, false));
+  if (prefactored) CVXB_TRY(trsm_lower(h, n, p + 1, W.L, W.ldn, W.invD, W.Y, W.ldn, false));
+  else   // factorisation with Y = L^-1 [DA', Dq] riding along
+    CVXB_TRY(potrf_lower_rhs(h, n, W.L, W.ldn, W.invD, F_CHOL_H, S_MINDIAG_H, W.Y, W.ldn, p + 1));
   // Schur complement S = Yp'Yp and its (plain, unregularised) Cholesky  KKTSystem.scala:126-140
   GemmArgs g{p, p, n, W.Y, W.ldn, true, W.Y, W.ldn, true, W.S, W.ldp, 1.0, 0.0, 2};
   g.streamk = true;
   CVXB_TRY(gemm_dmma(h, g));
-  CVXB_TRY(potrf_lower(h, p, W.S, W.ldp, W.invDs, F_CHOL_S, S_MINDIAG_S));
-  // z = -(b + A H^-1 q) = -(b + Yp' yq) ; w = K^-T K^-1 z
+  // z = -(b + A H^-1 q) = -(b + Yp' yq) ; w = K^-T K^-1 z  (the forward half rides along with the factorisation of S)
   CVXB_TRY(gemv_t(h, n, p, 1.0, W.Y, W.ldn, yq, 0.0, W.tp));
   CVXB_LAUNCH(h, kkt_z_kernel, 1, VT, 0, p, b, W.tp, w);
-  CVXB_TRY(trsm_lower(h, p, 1, W.S, W.ldp, W.invDs, w, W.ldp, false));
+  CVXB_TRY(potrf_lower_rhs(h, p, W.S, W.ldp, W.invDs, F_CHOL_S, S_MINDIAG_S, w, W.ldp, 1));
   CVXB_TRY(trsm_lower(h, p, 1, W.S, W.ldp, W.invDs, w, W.ldp, true));
   // x = -L^-T (yq + Yp w)
   CVXB_TRY(gemv_n(h, n, p, 1.0, W.Y, W.ldn, w, 1.0, yq));
@@ -332,9 +332,8 @@ int chol_enqueue(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, 
   const int n = W.n;
   if (!skip_ruiz) CVXB_TRY(ruiz_equilibrate(h, n, Hm, ldh, W.dr, W.colsq, P.ruizMaxSweeps, P.ruizTol));
   CVXB_TRY(scaled_lower(h, n, Hm, ldh, W.dr, regularize ? P.cholRegDelta : 0.0, W.L, W.ldn));
-  CVXB_TRY(potrf_lower(h, n, W.L, W.ldn, W.invD, F_CHOL_H, S_MINDIAG_H));
   CVXB_LAUNCH(h, chol_rhs_kernel, 1, VT, 0, n, rhs_sign, W.dr, b, W.qs, h.d_scal, h.d_flag);
-  CVXB_TRY(trsm_lower(h, n, 1, W.L, W.ldn, W.invD, W.qs, W.ldn, false));
+  CVXB_TRY(potrf_lower_rhs(h, n, W.L, W.ldn, W.invD, F_CHOL_H, S_MINDIAG_H, W.qs, W.ldn, 1));     // w = L^-1 (d o b) rides along
   CVXB_TRY(trsm_lower(h, n, 1, W.L, W.ldn, W.invD, W.qs, W.ldn, true));
   CVXB_LAUNCH(h, kkt_unscale_kernel, 1, VT, 0, n, 1.0, W.qs, W.dr, W.xs, x);
   CVXB_TRY(gemv_n(h, n, n, 1.0, Hm, ldh, x, 0.0, W.t1));
