@@ -364,6 +364,80 @@ __device__ long long g_leaf_clk[8];
 // solve by per-row forward substitution, rank-16 trailing update -- three block barriers.  The
 // triangular inverse is assembled afterwards: the 8 diagonal inverses concurrently (one warp each), then
 // three doubling levels X21 = -X22 (L21 X11).
+// Tail of the pipelined leaf: the products of one doubling level for the pair of s2-blocks at `base`, their 8 x 8
+// output tiles dealt to the warps wr = 0..wn-1 of a group (tile tl = wr + u*wn).
+//   level_T:  T = L21 * X11, written straight into the X21 slot (it reads only L21 and X11: no hazard)
+//   level_X:  X21 = -X22 * T into registers; the caller stores after a barrier (T lives where X21 goes)
+template <int MAXT>
+__device__ __forceinline__ void level_T(double* W, int s2, int base, int wr, int wn, int g, int tq) {
+  const int tps = s2 >> 3, ntile = tps * tps;
+  double c0[MAXT], c1[MAXT];
+  int rT[MAXT], cT[MAXT];
+  bool on[MAXT];
+#pragma unroll
+  for (int u = 0; u < MAXT; ++u) {
+    c0[u] = c1[u] = 0.0;
+    int tl = wr + u * wn;
+    on[u] = tl < ntile;
+    if (!on[u]) tl = 0;
+    rT[u] = base + s2 + 8 * (tl / tps);
+    cT[u] = base + 8 * (tl % tps);
+  }
+#pragma unroll 2
+  for (int kk = 0; kk < s2; kk += 4) {
+#pragma unroll
+    for (int u = 0; u < MAXT; ++u) {
+      if (on[u] && kk >= cT[u] - base) {              // X11 lower triangular: k-blocks above the tile's columns are zero
+        const int k = base + kk + tq, c = cT[u] + g;
+        const double bv = (k >= c) ? XW(k, c) : 0.0;
+        dmma_leaf(c0[u], c1[u], LW(rT[u] + g, k), bv);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < MAXT; ++u) {
+    const int r = rT[u] + g, c = cT[u] + 2 * tq;
+    if (on[u]) { XW(r, c) = c0[u]; XW(r, c + 1) = c1[u]; }
+  }
+}
+
+template <int MAXT>
+struct LevelX {
+  double c0[MAXT], c1[MAXT];
+  int rT[MAXT], cT[MAXT];
+  bool on[MAXT];
+  __device__ __forceinline__ void compute(double* W, int s2, int base, int wr, int wn, int g, int tq) {
+    const int tps = s2 >> 3, ntile = tps * tps;
+#pragma unroll
+    for (int u = 0; u < MAXT; ++u) {
+      c0[u] = c1[u] = 0.0;
+      int tl = wr + u * wn;
+      on[u] = wr >= 0 && tl < ntile;
+      if (!on[u]) tl = 0;
+      rT[u] = base + s2 + 8 * (tl / tps);
+      cT[u] = base + 8 * (tl % tps);
+    }
+#pragma unroll 2
+    for (int kk = 0; kk < s2; kk += 4) {
+#pragma unroll
+      for (int u = 0; u < MAXT; ++u) {
+        if (on[u] && kk < rT[u] - base - s2 + 8) {      // X22 lower triangular: k-blocks beyond the tile's rows are zero
+          const int k = base + s2 + kk + tq, r = rT[u] + g, c = cT[u] + g;
+          const double av = (k <= r) ? XW(r, k) : 0.0;
+          dmma_leaf(c0[u], c1[u], av, XW(k, c));
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void store(double* W, int g, int tq) {
+#pragma unroll
+    for (int u = 0; u < MAXT; ++u) {
+      const int r = rT[u] + g, c = cT[u] + 2 * tq;
+      if (on[u]) { XW(r, c) = -c0[u]; XW(r, c + 1) = -c1[u]; }
+    }
+  }
+};
+
 template <bool FACTOR>
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
 leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* flag, double* scal, int flag_slot,
@@ -402,7 +476,7 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
   // that is still to do when the factorisation ends:
   const bool pipelined = FACTOR && nb == NB;
   int first16 = 0, first32 = 0;
-  bool diag_inv_done = false;
+  bool diag_inv_done = false, tail_done = false;
   if (FACTOR) {
     // Software pipeline over the 8 sub-block columns.  The serial pivot chain (warp 0) is the critical path, so
     // everything else is moved beside it:   window kb = { warp 0: update + factor diagonal block kb+1 }  ||
@@ -485,9 +559,38 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
       if (s_fail && flag[flag_slot] == 0) flag[flag_slot] = s_fail;
       if (s_mind < scal[mindiag_slot]) scal[mindiag_slot] = s_mind;
     }
-    if (pipelined) {      // the last diagonal block's inverse
+    if (pipelined) {
+      // Tail of the inverse.  What is left: the last diagonal block's inverse, pair 3 of level 16 (blocks 6,7), pair 1
+      // of level 32 (blocks 4..7) and level 64.  Every T = L21 X11 of these depends only on data that is final by now
+      // (X(6,6); X(4..5,4..5); X(0..3,0..3)), so all three are computed in ONE phase beside the last diagonal inverse;
+      // afterwards only the three X21 = -X22 T products remain in sequence: 4 dependent phases instead of 7.
       if (ty == 0) warp_diag_inverse(W, rdiag, (nblk - 1) * SUB, SUB);
+      else if (ty == 1) level_T<4>(W, 16, 96, 0, 1, g, tq);                 // 4 tiles
+      else if (ty <= 5) level_T<4>(W, 32, 64, ty - 2, 4, g, tq);            // 16 tiles on 4 warps
+      else level_T<7>(W, 64, 0, ty - 6, LEAF_WARPS - 6, g, tq);             // 64 tiles on 10 warps
+      __syncthreads();
+      {
+        LevelX<1> x16;
+        x16.compute(W, 16, 96, ty < 4 ? ty : -1, 4, g, tq);
+        __syncthreads();
+        x16.store(W, g, tq);
+        __syncthreads();
+      }
+      {
+        LevelX<1> x32;
+        x32.compute(W, 32, 64, ty, LEAF_WARPS, g, tq);
+        __syncthreads();
+        x32.store(W, g, tq);
+        __syncthreads();
+      }
+      {
+        LevelX<4> x64;
+        x64.compute(W, 64, 0, ty, LEAF_WARPS, g, tq);
+        __syncthreads();
+        x64.store(W, g, tq);
+      }
       diag_inv_done = true;
+      tail_done = true;
     }
   } else {
     if (tid < nb) {
@@ -508,7 +611,7 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
     __syncthreads();
   }
   LEAF_CLK(4);
-  for (int sh = 4; (1 << sh) < nb; ++sh) {           // s = 16, 32, 64
+  for (int sh = 4; !tail_done && (1 << sh) < nb; ++sh) {           // s = 16, 32, 64
     const int s2 = 1 << sh;
     const int pair0 = (sh == 4) ? first16 : (sh == 5 ? first32 : 0);     // pairs before this one are already done
     const int npairs = (nb + 2 * s2 - 1) / (2 * s2) - pair0;
