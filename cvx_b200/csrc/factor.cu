@@ -442,7 +442,7 @@ template <bool FACTOR>
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
 leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* flag, double* scal, int flag_slot,
             int mindiag_slot, int col0) {
-  extern __shared__ double W[];
+  extern __shared__ __align__(16) double W[];
   __shared__ double rdiag[NB];
   __shared__ double s_mind;
   __shared__ int s_fail;
@@ -458,9 +458,24 @@ leaf_kernel(int n_total, int nb_first, double* A, int lda, double* invD, int* fl
   double* Ab = A + (size_t)off * lda + off;
   double* Xg = invD + (size_t)(FACTOR ? 0 : blockIdx.x) * NB * NB;
   long long _t0 = CVXB_LEAF_TIMING ? clock64() : 0;
-  for (int j = ty; j < nb; j += LEAF_WARPS)
-    for (int i = tx; i < nb; i += 32)
-      if (i >= j) LW(i, j) = Ab[(size_t)j * lda + i];
+  if (FACTOR && nb == NB && !(lda & 1) && !((uintptr_t)Ab & 15)) {
+    // full block: 16-byte cp.async straight into shared memory, all 16 chunks of a thread in flight at once (the
+    // chunk straddling the diagonal drags one element of the X region along; that region is zero-filled below)
+#pragma unroll
+    for (int c = tid; c < NB * (NB / 2); c += LEAF_THREADS) {
+      const int j = c >> 6, q = c & 63;
+      if (2 * q + 1 >= j) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&LW(2 * q, j));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ab + (size_t)j * lda + 2 * q));
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+  } else {
+    for (int j = ty; j < nb; j += LEAF_WARPS)
+      for (int i = tx; i < nb; i += 32)
+        if (i >= j) LW(i, j) = Ab[(size_t)j * lda + i];
+  }
   if (tid == 0) { s_fail = 0; s_mind = 1e300; }
   __syncthreads();
   LEAF_CLK(0);
