@@ -768,6 +768,24 @@ int cvxb_bench_kernel(cvxb_handle h, int which, int n, int k, int reps, double* 
     }
     *ms_per_launch = total / reps;
     *flops_or_bytes_per_launch = which == 5 ? 8.0 * n * n : 8.0 * n * n * 20;
+  } else if (which == 7 || which == 8) {
+    // 7: gemv_n  y = G x (G k x n: slacks, line-search direction);  8: gemv_t  y = G' w (gradient)  -- HBM-bound, 8kn bytes
+    CVXB_CUDA_OK(cudaMalloc((void**)&G, (size_t)ldk * n * sizeof(double)));
+    CVXB_CUDA_OK(cudaMalloc((void**)&C, (size_t)(ldk + ldn) * 2 * sizeof(double)));
+    fill_random_kernel<<<1024, 256, 0, H.stream>>>((size_t)ldk * n, G, 4242ull, -1.0, 1.0);
+    fill_random_kernel<<<64, 256, 0, H.stream>>>((size_t)(ldk + ldn) * 2, C, 7ull, -1.0, 1.0);
+    double* xv = C;                       // length max(k, n)
+    double* yv = C + (ldk + ldn);
+    for (int r = -1; r < reps; ++r) {
+      if (r == 0) CVXB_CUDA_OK(cudaEventRecord(H.ev0, H.stream));
+      if (which == 7) CVXB_TRY(gemv_n(H, k, n, 1.0, G, ldk, xv, 0.0, yv));
+      else CVXB_TRY(gemv_t(H, k, n, 1.0, G, ldk, xv, 0.0, yv));
+    }
+    CVXB_CUDA_OK(cudaEventRecord(H.ev1, H.stream));
+    CVXB_CUDA_OK(cudaEventSynchronize(H.ev1));
+    CVXB_CUDA_OK(cudaEventElapsedTime(&t, H.ev0, H.ev1));
+    *ms_per_launch = t / reps;
+    *flops_or_bytes_per_launch = 8.0 * (double)k * n;
   } else {
     cvxb::set_last_error("cvxb_bench_kernel: unknown kernel %d", which);
     return CVXB_EINVAL;

@@ -25,6 +25,20 @@ __global__ void __launch_bounds__(256) gemv_n_kernel(int m, int n, double alpha,
   double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
   if (r + 1 < m) {
     int j = c0 + warp;
+    // four columns (16-byte loads) in flight per lane: the kernel is a latency-bound stream otherwise
+    double e0 = 0, e1 = 0, f0 = 0, f1 = 0;
+    for (; j + 3 * GN_WARPS < c1; j += 4 * GN_WARPS) {
+      double2 v = *reinterpret_cast<const double2*>(A + (size_t)j * lda + r);
+      double2 w = *reinterpret_cast<const double2*>(A + (size_t)(j + GN_WARPS) * lda + r);
+      double2 u = *reinterpret_cast<const double2*>(A + (size_t)(j + 2 * GN_WARPS) * lda + r);
+      double2 z = *reinterpret_cast<const double2*>(A + (size_t)(j + 3 * GN_WARPS) * lda + r);
+      double xj = x[j], xk = x[j + GN_WARPS], xl = x[j + 2 * GN_WARPS], xm = x[j + 3 * GN_WARPS];
+      a0 = fma(v.x, xj, a0); a1 = fma(v.y, xj, a1);
+      b0 = fma(w.x, xk, b0); b1 = fma(w.y, xk, b1);
+      e0 = fma(u.x, xl, e0); e1 = fma(u.y, xl, e1);
+      f0 = fma(z.x, xm, f0); f1 = fma(z.y, xm, f1);
+    }
+    a0 += e0; a1 += e1; b0 += f0; b1 += f1;
     for (; j + GN_WARPS < c1; j += 2 * GN_WARPS) {
       double2 v = *reinterpret_cast<const double2*>(A + (size_t)j * lda + r);
       double2 w = *reinterpret_cast<const double2*>(A + (size_t)(j + GN_WARPS) * lda + r);
@@ -74,6 +88,24 @@ __global__ void __launch_bounds__(256) gemv_t_kernel(int m, int n, double alpha,
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
   const int m2 = m & ~1;
   int i = 2 * lane;
+  {   // four 16-byte loads of the column (and of x) in flight per lane
+    double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    for (; i + 192 < m2; i += 256) {
+      double2 v = *reinterpret_cast<const double2*>(col + i);
+      double2 w = *reinterpret_cast<const double2*>(col + i + 64);
+      double2 u = *reinterpret_cast<const double2*>(col + i + 128);
+      double2 z = *reinterpret_cast<const double2*>(col + i + 192);
+      double2 xv = *reinterpret_cast<const double2*>(x + i);
+      double2 xw = *reinterpret_cast<const double2*>(x + i + 64);
+      double2 xu = *reinterpret_cast<const double2*>(x + i + 128);
+      double2 xz = *reinterpret_cast<const double2*>(x + i + 192);
+      s0 = fma(v.x, xv.x, s0); s1 = fma(v.y, xv.y, s1);
+      s2 = fma(w.x, xw.x, s2); s3 = fma(w.y, xw.y, s3);
+      t0 = fma(u.x, xu.x, t0); t1 = fma(u.y, xu.y, t1);
+      t2 = fma(z.x, xz.x, t2); t3 = fma(z.y, xz.y, t3);
+    }
+    s0 += t0; s1 += t1; s2 += t2; s3 += t3;
+  }
   for (; i + 64 < m2; i += 128) {
     double2 v = *reinterpret_cast<const double2*>(col + i);
     double2 w = *reinterpret_cast<const double2*>(col + i + 64);

@@ -144,6 +144,9 @@ struct GemmArgs {
 };
 int gemm_dmma(Handle& h, const GemmArgs& g);
 int gemm_dmma_on(Handle& h, const GemmArgs& g, cudaStream_t st);   // same, on another stream of the handle
+// same on the handle's stream, launched as a programmatic dependent of the kernel enqueued just before it (its
+// prologue overlaps that kernel's tail); only for launches with no other operation between the two
+int gemm_dmma_pdl(Handle& h, const GemmArgs& g);
 // gemm_dmma bracketed by CUDA events when the handle's profiling is on (flops = algorithmic flops)
 int gemm_dmma_timed(Handle& h, const GemmArgs& g, double flops);
 int gemm_dmma_init();   // sets the dynamic-smem attribute on all instantiations (once per device)

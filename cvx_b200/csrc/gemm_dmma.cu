@@ -254,10 +254,14 @@ gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, con
     bn = blockIdx.x / tiles_m;
   }
   const int m0 = bm * BM, n0 = bn * BN;
+  // programmatic dependent launch (no-ops for a plain launch): everything above overlapped the previous kernel's
+  // tail; its results are visible after the wait.  Our own dependents may start launching once the mainloop is done.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (lower_only && m0 + BM <= n0) return;      // tile entirely above the diagonal
   double acc[T::MT][T::NTL][2];
   T::zero(acc);
   T::mainloop(acc, smem, M, N, K, A, lda, B, ldb, m0, n0, 0, (K + BK - 1) / BK);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   T::epilogue(acc, M, N, C, ldc, alpha, beta, tri, (tri && (bm == bn)) || lower_only, m0, n0);
 }
 
@@ -348,6 +352,7 @@ template <int BM, int WARPS_M, int WARPS_N>
 constexpr int smem_bytes() { return STAGES * 2 * TileElems<BM>::value * (int)sizeof(double); }
 
 thread_local cudaStream_t g_gemm_stream = nullptr;     // set by gemm_dmma_on for the duration of one call
+thread_local bool g_gemm_pdl = false;                  // set by gemm_dmma_pdl: launch as a programmatic dependent
 
 template <int BM, int WARPS_M, int WARPS_N, bool A_KC, bool B_KC>
 int launch(Handle& h, const GemmArgs& g) {
@@ -355,6 +360,22 @@ int launch(Handle& h, const GemmArgs& g) {
   int tm = (g.M + BM - 1) / BM, tn = (g.N + BM - 1) / BM;
   long long grid = g.tri ? (long long)tm * (tm + 1) / 2 : (long long)tm * tn;
   if (grid <= 0) return CVXB_OK;
+  if (g_gemm_pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(WARPS_M * WARPS_N * 32);
+    cfg.dynamicSmemBytes = smem_bytes<BM, WARPS_M, WARPS_N>();
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CVXB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_dmma_kernel<BM, BM, WARPS_M, WARPS_N, A_KC, B_KC>, g.M, g.N, g.K, g.A, g.lda,
+                                    g.B, g.ldb, g.C, g.ldc, g.alpha, g.beta, g.tri, tm, g.lower_only ? 1 : 0));
+    h.launches++;
+    return CVXB_OK;
+  }
   gemm_dmma_kernel<BM, BM, WARPS_M, WARPS_N, A_KC, B_KC>
       <<<(unsigned)grid, WARPS_M * WARPS_N * 32, smem_bytes<BM, WARPS_M, WARPS_N>(), st>>>(
           g.M, g.N, g.K, g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.alpha, g.beta, g.tri, tm, g.lower_only ? 1 : 0);
@@ -455,6 +476,13 @@ int gemm_dmma_timed(Handle& h, const GemmArgs& g, double flops) {
   h.prof_used += 2;
   h.prof_flops += flops;
   return st;
+}
+
+int gemm_dmma_pdl(Handle& h, const GemmArgs& g) {
+  g_gemm_pdl = true;
+  int r = gemm_dmma(h, g);
+  g_gemm_pdl = false;
+  return r;
 }
 
 int gemm_dmma_on(Handle& h, const GemmArgs& g, cudaStream_t st) {

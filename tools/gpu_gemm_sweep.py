@@ -10,3 +10,7 @@ for which, n, k in [(1, 2000, 4000), (1, 2001, 5000), (1, 8192, 16384), (2, 2048
 for n in (2000, 8192):
     ms, by = h.bench_kernel(6, n, 0, 5)
     print("ruiz n=%d: %.4f ms per equilibration" % (n, ms))
+for which, name in ((7, "gemv_n"), (8, "gemv_t")):
+    for n, k in ((2000, 4000), (8192, 16384)):
+        ms, by = h.bench_kernel(which, n, k, 10)
+        print("%s G %dx%d: %.4f ms, %.0f GB/s" % (name, k, n, ms, by / ms / 1e6))
