@@ -372,6 +372,16 @@ def main():
                     "peak_source": "FP64 DMMA issue-rate probe measured in this run (MEASURED_PEAKS.json has HBM and bf16 "
                                    "only: hbm_gbs=%s); cuBLAS DGEMM 8192^3 on this pool measured 35.5 TFLOP/s" % peaks.get("hbm_gbs"),
                     "share_of_step": syrk_ms / dev_ms if dev_ms > 0 else None}
+        # the HBM-bound kernels of the step (slack / gradient / line-search GEMVs over G), timed alone on this handle
+        hbm_peak = peaks.get("hbm_gbs")
+        hbm = {}
+        if args.workload == "c2":
+            for which, name in ((7, "gemv_n (G x, G d)"), (8, "gemv_t (G' (1/d))")):
+                ms_k, by_k = h.bench_kernel(which, 2000, 4000, 20)
+                gbs = by_k / ms_k / 1e6
+                hbm[name] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": gbs / hbm_peak if hbm_peak else None, "bytes_per_launch": by_k,
+                             "note": "G is 64 MB: partly L2-resident between repeated launches"}
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count()
@@ -398,7 +408,7 @@ def main():
                 "flops_per_step": f_step(n, m, p), "tflops": f_step(n, m, p) * value / world / 1e12,
                 "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d / max(e2e_steps, 1),
                         "d2h_bytes_per_step": d2h / max(e2e_steps, 1), "steps": e2e_steps, "seconds": e2e_s, "checksum": xsum},
-                "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu, "batched": batched,
+                "gpu_launches": int(total_launches), "roofline": roofline, "hbm_kernels": hbm, "cpu_baseline": cpu, "batched": batched,
                 "last_solution": {"objective": last.objective, "outer_stages": last.outer_stages,
                                   "newton_steps": last.newton_steps, "phase1_newton_steps": last.phase1_newton_steps}}
         print(json.dumps(line))
