@@ -59,7 +59,10 @@ def f_step(n, m, p):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    """SM clock + throttle reasons while the timed region runs (B200_PROFILING.md's clocks line).  Sampled in-process
+    through NVML every 20 ms (a query costs microseconds); `nvidia-smi -lms` as a fallback -- its start-up (NVML
+    init in a second process, under the driver's locks) overlapped the short timed region of this latency-bound
+    workload and showed up as occasional slow runs."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -67,8 +70,53 @@ class ClockSampler:
 
     def __init__(self, device):
         self.device, self.rows, self.proc = device, [], None
+        self.nv, self.nvh, self.stop_flag, self.samples = None, None, False, []
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = None
+            try:
+                import torch
+                u = getattr(torch.cuda.get_device_properties(device), "uuid", None)
+                if u is not None:
+                    hnd = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(u)).encode())
+            except Exception:
+                hnd = None
+            if hnd is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = device
+                if vis:
+                    try:
+                        idx = int(vis.split(",")[device])
+                    except Exception:
+                        idx = device
+                hnd = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM)      # probe
+            self.nv, self.nvh = pynvml, hnd
+        except Exception:
+            self.nv = None
+
+    def _sample_nvml(self):
+        nv, hnd = self.nv, self.nvh
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(hnd, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(hnd, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(hnd)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(hnd)
+                self.samples.append((float(sm), float(mx), {k for k, b_ in bits.items() if rs & b_}))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._sample_nvml, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -83,6 +131,16 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            sm = [s_[0] for s_ in self.samples]
+            mx = [s_[1] for s_ in self.samples]
+            reasons = set()
+            for s_ in self.samples:
+                reasons |= s_[2]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                    "reasons": sorted(reasons), "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -101,7 +159,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def run_steps(instances, budget, stats):

@@ -1277,7 +1277,7 @@ int rl_max_n() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("CVXB_RL_MAX_N");
-    v = e ? atoi(e) : 2560;
+    v = e ? atoi(e) : 4608;
   }
   return v;
 }
