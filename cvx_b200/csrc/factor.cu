@@ -745,7 +745,11 @@ int trsm_right_lt(Handle& h, int M, int n1, const double* L, int ldl, const doub
 // of the leaf chain), instead of as a separate sweep over L after the factorisation.
 int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0, bool plain = false,
               double* B = nullptr, int ldb = 0, int r = 0) {
-  if (!plain && n > NB && n <= rl_max_n() && h.stream2)
+  // a wide right-hand-side block adds (rem x r x 128) of rank-128 GEMM work per step to the second stream: beyond
+  // ~2560 columns that no longer fits in the shadow of the leaf chain (C4, r = 2049: 57.1 ms per step with the
+  // look-ahead schedule up to 4608 against 54.3 ms with the switch at 2560)
+  const int la_max = (r > 1024 && rl_max_n() > 2560) ? 2560 : rl_max_n();
+  if (!plain && n > NB && n <= la_max && h.stream2)
     return potrf_lookahead(h, n, A, lda, invD, flag_slot, mindiag_slot, col0, B, ldb, r);
   if (n <= NB) {
     CVXB_LAUNCH(h, leaf_kernel<true>, 1, LEAF_THREADS, LEAF_SMEM, n, n, A, lda, invD, h.d_flag, h.d_scal, flag_slot,

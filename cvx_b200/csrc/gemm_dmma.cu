@@ -12,7 +12,10 @@
 //    64x64,  4 warps (2x2), warp tile 32x32;   32x32, 4 warps (2x2), warp tile 16x16 -- the small GEMMs
 //            of the recursive Cholesky / TRSM levels, where a 128x128 grid would leave most of the 148
 //            SMs idle and a single CTA would walk the whole K range alone.
-// Operands are staged global->shared with 16-byte cp.async (zero-fill predication at the edges);
+// The big SYRKs on the handle's own stream run as ONE persistent CTA per SM with stream-K splitting of the tiles that
+// would otherwise form a partial last wave (gemm_dmma_streamk_kernel: deterministic fix-up, bitwise symmetric).
+// Operands are staged global->shared with 16-byte cp.async (zero-fill predication at the edges), each thread's
+// chunk pattern computed once (SlabLoader) and the copies issued from inside the DMMA stream;
 // padded shared layouts make every fragment load bank-conflict free:
 //   K-contiguous operand: [R][BK+4] doubles  -> bank = 8*g + 2*t   (g = lane/4, t = lane%4)
 //   M-contiguous operand: [BK][R+4] doubles  -> bank = 8*t + 2*g
