@@ -215,28 +215,47 @@ struct CtaTile {
     cp_async_wait<0>();
   }
 
-  // thread (g,t) of DMMA tile (i,j) holds C(m, n), C(m, n+1), m = ..+g, n = ..+2t
+  // thread (g,t) of DMMA tile (i,j) holds C(m, n), C(m, n+1), m = ..+g, n = ..+2t.
+  // With beta != 0 the old values of C are fetched in batches of IB row-tiles (IB*NTL*2 predicated loads in flight)
+  // BEFORE any of them is used: an element-by-element load -> fma -> store loop is one dependent L2 round trip per
+  // element (64 per thread in the 128x128 tile: ~50 us per tile, more than the whole mainloop of a rank-128 update).
+  template <int IB = (MT >= 4 ? 4 : (MT >= 2 ? 2 : 1))>
   __device__ static __forceinline__ void epilogue(const double (&acc)[MT][NTL][2], int M, int N, double* __restrict__ C,
                                                   int ldc, double alpha, double beta, int tri, bool diag, int m0, int n0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm0 = (warp % WARPS_M) * WM, wn0 = (warp / WARPS_M) * WN;
+    const bool use_c = beta != 0.0;
 #pragma unroll
-    for (int i = 0; i < MT; ++i) {
-      int m = m0 + wm0 + i * 8 + g;
-      if (m >= M) continue;
+    for (int ib = 0; ib < MT; ib += IB) {
+      double cv[IB][NTL][2];
 #pragma unroll
-      for (int j = 0; j < NTL; ++j) {
+      for (int ii = 0; ii < IB; ++ii) {
+        const int m = m0 + wm0 + (ib + ii) * 8 + g;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          int n = n0 + wn0 + j * 8 + 2 * t + e;
-          if (n >= N) continue;
-          if (diag && n > m) continue;
-          double v = alpha * acc[i][j][e];
-          size_t idx = (size_t)n * ldc + m;
-          if (beta != 0.0) v += beta * C[idx];
-          C[idx] = v;
-          if (tri == 2 && n != m) C[(size_t)m * ldc + n] = v;
+        for (int j = 0; j < NTL; ++j) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int n = n0 + wn0 + j * 8 + 2 * t + e;
+            const bool ok = use_c && m < M && n < N && !(diag && n > m);
+            cv[ii][j][e] = ok ? C[(size_t)n * ldc + m] : 0.0;
+          }
+        }
+      }
+#pragma unroll
+      for (int ii = 0; ii < IB; ++ii) {
+        const int m = m0 + wm0 + (ib + ii) * 8 + g;
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int n = n0 + wn0 + j * 8 + 2 * t + e;
+            if (m >= M || n >= N || (diag && n > m)) continue;
+            double v = alpha * acc[ib + ii][j][e];
+            if (use_c) v += beta * cv[ii][j][e];
+            C[(size_t)n * ldc + m] = v;
+            if (tri == 2 && n != m) C[(size_t)m * ldc + n] = v;
+          }
         }
       }
     }
@@ -295,7 +314,7 @@ gemm_dmma_streamk_kernel(int M, int N, int K, const double* __restrict__ A, int 
     T::zero(acc);
     __syncthreads();          // every warp is done with the previous tile's stages
     T::mainloop(acc, smem, M, N, K, A, lda, B, ldb, bm * 128, bn * 128, 0, KT);
-    T::epilogue(acc, M, N, C, ldc, alpha, beta, tri, bm == bn, bm * 128, bn * 128);
+    T::template epilogue<2>(acc, M, N, C, ldc, alpha, beta, tri, bm == bn, bm * 128, bn * 128);
   }
   // this CTA's share of the split tiles' slabs
   const long long W = (long long)(tiles_total - tiles_whole) * KT;
@@ -345,7 +364,7 @@ gemm_dmma_streamk_kernel(int M, int N, int K, const double* __restrict__ A, int 
           if (tid == 0) atomicExch(flags + c, 0);      // consumed: clean for the next launch
         }
       }
-      T::epilogue(acc, M, N, C, ldc, alpha, beta, tri, bm == bn, bm * 128, bn * 128);
+      T::template epilogue<2>(acc, M, N, C, ldc, alpha, beta, tri, bm == bn, bm * 128, bn * 128);   // (4-row batches spill here)
     }
     pos += ke - kb;
   }
