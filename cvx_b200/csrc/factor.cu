@@ -748,7 +748,8 @@ int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot,
   // a wide right-hand-side block adds (rem x r x 128) of rank-128 GEMM work per step to the second stream: beyond
   // ~2560 columns that no longer fits in the shadow of the leaf chain (C4, r = 2049: 57.1 ms per step with the
   // look-ahead schedule up to 4608 against 54.3 ms with the switch at 2560)
-  const int la_max = (r > 1024 && rl_max_n() > 2560) ? 2560 : rl_max_n();
+  static const int la_wide = getenv("CVXB_LA_WIDE") ? atoi(getenv("CVXB_LA_WIDE")) : 2560;
+  const int la_max = (r > 1024 && rl_max_n() > la_wide) ? la_wide : rl_max_n();
   if (!plain && n > NB && n <= la_max && h.stream2)
     return potrf_lookahead(h, n, A, lda, invD, flag_slot, mindiag_slot, col0, B, ldb, r);
   if (n <= NB) {
