@@ -158,6 +158,25 @@ def test_kkt_planted_pd(handle, n, p, seed):
     assert rel(w, s["w"]) < 10 * rel(w0, s["w"]) + 1e-12
 
 
+@pytest.mark.parametrize("n,p,seed", [(300, 40, 5), (1000, 100, 6), (2304, 300, 7), (4800, 130, 8)])
+def test_kkt_fused_forward_substitution(handle, n, p, seed, monkeypatch):
+    """The forward substitutions Y = L^-1 [DA', Dq], K^-1 z that ride along with the Cholesky (potrf_lower_rhs: updates
+    on the look-ahead stream, recursive split above the look-ahead limit) give the same solution as separate triangular
+    sweeps after the factorisation (CVXB_NO_FUSED_TRSM), to rounding; both meet the planted-solution bar."""
+    from cvx_b200 import KKTSystem, MatrixUtils
+    s = P.kkt_planted_pd(n, p, seed)
+    K = KKTSystem(s["H"], s["A"], s["q"], s["b"], handle)
+    x, w = K.solve(1e-6, None, 1e-7, 0)
+    c = MatrixUtils.choleskySolve(s["H"], s["q"], None, 1e-7, 0, handle)
+    monkeypatch.setenv("CVXB_NO_FUSED_TRSM", "1")
+    x1, w1 = KKTSystem(s["H"], s["A"], s["q"], s["b"], handle).solve(1e-6, None, 1e-7, 0)
+    c1 = MatrixUtils.choleskySolve(s["H"], s["q"], None, 1e-7, 0, handle)
+    monkeypatch.delenv("CVXB_NO_FUSED_TRSM")
+    assert rel(x, x1) < 1e-7 and rel(w, w1) < 1e-7 and rel(c, c1) < 1e-7
+    assert rel(x, s["x"]) < 1e-5 and rel(w, s["w"]) < 1e-5
+    assert rel(s["H"] @ c, s["q"]) < 1e-9
+
+
 @pytest.mark.parametrize("n,p,seed", [(50, 5, 0), (400, 60, 1)])
 def test_solve_with_chol_factor(handle, n, p, seed):
     """KktTest.testSolutionWithCholFactor (:117-184)."""
