@@ -31,7 +31,10 @@ namespace {
 #ifndef CVXB_STAGES
 #define CVXB_STAGES 3
 #endif
-constexpr int BK = CVXB_BK, STAGES = CVXB_STAGES;
+constexpr int BK = CVXB_BK;
+// cp.async ring depth per tile shape (a 4-stage ring for the 32x32 tile -- all four slabs of a rank-128 GEMM in
+// flight from the prologue on -- measured no gain on the Cholesky chain)
+template <int BM> struct StagesFor { static constexpr int value = CVXB_STAGES; };
 constexpr int KC_LD = BK + 4;               // K-contiguous tile row stride (doubles)
 
 template <int R> struct TileElems { static constexpr int value = (R * KC_LD > BK * (R + 4)) ? R * KC_LD : BK * (R + 4); };
@@ -123,6 +126,7 @@ struct CtaTile {
   static constexpr int MT = WM / 8, NTL = WN / 8;
   static constexpr int A_ELEMS = TileElems<BM>::value, B_ELEMS = TileElems<BN>::value;
   static constexpr int A_MC_LD = BM + 4, B_MC_LD = BN + 4;
+  static constexpr int STAGES = StagesFor<BM>::value;
 
   __device__ static __forceinline__ void zero(double (&acc)[MT][NTL][2]) {
 #pragma unroll
@@ -300,7 +304,7 @@ template <bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(256, 1)
 gemm_dmma_streamk_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const double* __restrict__ B,
                          int ldb, double* __restrict__ C, int ldc, double alpha, double beta, int tri, int tiles_total,
-                         int tiles_whole, double* __restrict__ ws, int* flags) {
+                         int tiles_whole, double* __restrict__ ws, int* flags, int* abort_flag) {
   typedef CtaTile<128, 128, 2, 4, A_KC, B_KC> T;
   constexpr int PER_THREAD = T::MT * T::NTL * 2;       // 64 accumulators
   extern __shared__ __align__(16) double smem[];
@@ -347,11 +351,22 @@ gemm_dmma_streamk_kernel(int M, int N, int K, const double* __restrict__ A, int 
         // owner of a split tile: the rest comes from the CTAs whose shares start inside this tile
         const long long tile_end = (long long)(tl + 1) * KT;
         for (int c = cta + 1; c < G && W * c / G < tile_end; ++c) {
+          int ok = 1;
           if (tid == 0) {
-            while (atomicAdd(flags + c, 0) == 0) __nanosleep(64);
+            // bounded (~0.3 s): a partial that never arrives means the grid was not co-resident after all -- never
+            // expected under a cooperative launch; flag it (the host then drops the stream-K path) instead of hanging
+            int spins = 0;
+            while (atomicAdd(flags + c, 0) == 0) {
+              __nanosleep(64);
+              if (++spins > (1 << 22) || ((spins & 1023) == 0 && *(volatile int*)abort_flag)) {
+                *(volatile int*)abort_flag = 1;
+                ok = 0;
+                break;
+              }
+            }
             __threadfence();
           }
-          __syncthreads();
+          if (!__syncthreads_and(ok)) break;
           const double* slot = ws + (size_t)c * (256 * PER_THREAD);
 #pragma unroll
           for (int i = 0; i < T::MT; ++i)
@@ -371,7 +386,7 @@ gemm_dmma_streamk_kernel(int M, int N, int K, const double* __restrict__ A, int 
 }
 
 template <int BM, int WARPS_M, int WARPS_N>
-constexpr int smem_bytes() { return STAGES * 2 * TileElems<BM>::value * (int)sizeof(double); }
+constexpr int smem_bytes() { return StagesFor<BM>::value * 2 * TileElems<BM>::value * (int)sizeof(double); }
 
 thread_local cudaStream_t g_gemm_stream = nullptr;     // set by gemm_dmma_on for the duration of one call
 thread_local bool g_gemm_pdl = false;                  // set by gemm_dmma_pdl: launch as a programmatic dependent
@@ -545,7 +560,8 @@ int gemm_dmma(Handle& h, const GemmArgs& g) {
       double alpha = g.alpha, beta = g.beta;
       double* ws = h.sk_ws;
       int* fl = h.sk_flags;
-      void* args[] = {&M, &N, &K, &A, &lda, &B, &ldb, &C, &ldc, &alpha, &beta, &tri, &tt, &tw, &ws, &fl};
+      int* ab = h.d_flag + F_WAVE_ABORT;
+      void* args[] = {&M, &N, &K, &A, &lda, &B, &ldb, &C, &ldc, &alpha, &beta, &tri, &tt, &tw, &ws, &fl, &ab};
       const void* fn = g.a_kc ? (const void*)gemm_dmma_streamk_kernel<true, true>
                               : (const void*)gemm_dmma_streamk_kernel<false, false>;
       cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(G), dim3(256), args, smem_bytes<128, 2, 4>(), h.stream);

@@ -204,7 +204,9 @@ int fetch_status(Handle& h) {
     // never expected under a cooperative launch; switch to the per-block kernels and report
     cudaMemsetAsync(h.d_flag + F_WAVE_ABORT, 0, sizeof(int), h.stream);
     if (h.wave_ready) { cudaFree(h.wave_ready); h.wave_ready = nullptr; }
-    set_last_error("wavefront triangular solve aborted (blocks not co-resident); falling back to per-block kernels, retry the call");
+    if (h.sk_ws) { cudaFree(h.sk_ws); h.sk_ws = nullptr; }       // the stream-K SYRK waits on peers the same way
+    set_last_error("a cooperative kernel (wavefront triangular solve / stream-K SYRK) gave up waiting for a peer block "
+                   "(blocks not co-resident); falling back to the non-cooperative kernels, retry the call");
     return CVXB_ECUDA;
   }
   return CVXB_OK;
