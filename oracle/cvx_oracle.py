@@ -113,6 +113,17 @@ class OptimizationState:
     normDualResidual: Optional[float] = None
 
 
+def _ieee_div(a, b):
+    """a / b with JVM (IEEE-754) semantics: a zero divisor gives +-Infinity or NaN instead of Python's exception
+    (PrimalDualSolver.scala:576,612: `t = mu*numIneqs/dualityGap` with a surrogate gap of exactly 0.0)."""
+    a, b = float(a), float(b)
+    if b != 0.0:
+        return a / b
+    if a == 0.0 or a != a:
+        return float("nan")
+    return math.copysign(float("inf"), a) * math.copysign(1.0, b)
+
+
 DOUBLE_MAX = float(np.finfo(np.float64).max)
 
 # ======================================================================================
@@ -1183,7 +1194,7 @@ class PrimalDual:
         dualityGap = self.surrogateDualityGap(x, lam)
         equalityGap = DOUBLE_MAX if withEqs else 0.0
         normDualResidual = DOUBLE_MAX
-        t = mu * self.numIneqs / dualityGap
+        t = _ieee_div(mu * self.numIneqs, dualityGap)
         state = OptimizationState(None, None, dualityGap, equalityGap, DOUBLE_MAX, normDualResidual)
         maxIter = (1500 if withEqs else 2000) / mu
         if max_steps is not None:
@@ -1205,7 +1216,7 @@ class PrimalDual:
             else:
                 normDualResidual = float(np.linalg.norm(self.dualResidual(x, lam)))
             state = OptimizationState(None, None, dualityGap, equalityGap, objValue, normDualResidual)
-            t = mu * self.numIneqs / dualityGap
+            t = _ieee_div(mu * self.numIneqs, dualityGap)
             it += 1
         return Solution(x, lam, nu, None, dualityGap, equalityGap if withEqs else None, None, normDualResidual,
                         it - 1, it == maxIter, newton_steps=it, linesearch_trials=trials)

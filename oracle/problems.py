@@ -61,6 +61,46 @@ def min_pNorm(n, p):
                 A=np.ones((1, n)), b=np.array([1.0]), x0=None, xdef=np.zeros(n), xopt=np.full(n, 1.0 / n))
 
 
+def rank_one_simplex(n):
+    """SimpleOptimizationProblems.rankOneProblemSimplex (src/test/.../SimpleOptimizationProblems.scala:221-255):
+    min (a'x)^2 = x'(aa')x  (QuadraticObjectiveFunction with P = aa', i.e. x'Px/2) s.t. x >= 0, sum x = 1,
+    a = linspace(1, 2, n); rank-one Hessian; unique optimum e_1; pointWhereDefined 1/n => phase I."""
+    a = np.linspace(1.0, 2.0, n)
+    xopt = np.zeros(n)
+    xopt[0] = 1.0
+    return dict(kind="quadratic", n=n, a=np.zeros(n), r=0.0, P=np.outer(a, a), G=-np.eye(n), rvec=np.zeros(n),
+                ub=np.zeros(n), A=np.ones((1, n)), b=np.array([1.0]), x0=None, xdef=np.full(n, 1.0 / n), xopt=xopt)
+
+
+def norm_squared_free_variables(n):
+    """SimpleOptimizationProblems.normSquaredWithFreeVariables (:308-340): min ||x||^2/2 s.t. x_1 <= -1 -- one
+    constraint, n-1 variables it does not depend on (phase I sees a rank-one barrier Hessian); optimum (-1,0,..,0);
+    pointWhereDefined = 1 (infeasible) => phase I."""
+    G = np.zeros((1, n))
+    G[0, 0] = 1.0
+    xopt = np.zeros(n)
+    xopt[0] = -1.0
+    return dict(kind="quadratic", n=n, a=np.zeros(n), r=0.0, P=np.eye(n), G=G, rvec=np.zeros(1), ub=np.array([-1.0]),
+                A=None, b=None, x0=None, xdef=np.ones(n), xopt=xopt)
+
+
+def jopt_p1(n):
+    """SimpleOptimizationProblems.joptP1 (:347-377): min sum(x) s.t. ||x||^2/2 <= 1/2 (Constraints.oneHalfNorm2BoundedBy,
+    Constraints.scala:299-309: value x'x/2, gradient x, Hessian I -- the quadratic constraint r + a'x + x'Px/2 with
+    P = I, a = 0, r = 0); optimum x_j = -1/sqrt(n); pointWhereDefined = 2 (infeasible) => phase I."""
+    quad = [dict(P=np.eye(n), a=np.zeros(n), r=0.0, ub=0.5)]
+    return dict(kind="linear", n=n, a=np.ones(n), r=0.0, P=None, G=np.zeros((0, n)), rvec=np.zeros(0), ub=np.zeros(0),
+                quad=quad, A=None, b=None, x0=None, xdef=np.full(n, 2.0), xopt=np.full(n, -1.0 / np.sqrt(n)))
+
+
+def jopt_p2():
+    """SimpleOptimizationProblems.joptP2 (:384-414; docs/OptimizerExamples.pdf example 1.5): min x'Px/2, P = [[1,.4],[.4,1]],
+    s.t. x >= 0, x_1 + x_2 = 1; optimum (1/2, 1/2); pointWhereDefined = (2, 2) (infeasible) => phase I."""
+    P_ = np.array([[1.0, 0.4], [0.4, 1.0]])
+    return dict(kind="quadratic", n=2, a=np.zeros(2), r=0.0, P=P_, G=-np.eye(2), rvec=np.zeros(2), ub=np.zeros(2),
+                A=np.ones((1, 2)), b=np.array([1.0]), x0=None, xdef=np.full(2, 2.0), xopt=np.array([0.5, 0.5]))
+
+
 def kl_random(n, m_h, p_extra, seed=0):
     """C2 family via Dist_KL.apply semantics: KL objective, m_h rows Hx<=u plus n positivity rows,
     p_extra rows A x = r plus the sum-to-one row (stacked last); start 1/n => phase I."""
