@@ -804,8 +804,9 @@ int run_phase1(cvxb_problem_s* P, const cvxb_params& pars, RunStats& rs, cvxb_so
     CVXB_TRY(problem_alloc(h, n + 1, m1, 0, CVXB_OBJ_LINEAR, &P->phase1, mq, 0));
     cvxb_problem_s* Q = P->phase1;
     dim3 grid((m1 + 127) / 128, n + 1 > 1024 ? 1024 : n + 1);
-    CVXB_LAUNCH(h, phase1_build_kernel, grid, 128, 0, n, m, p, P->G, P->ldm, P->gr, P->ub, P->A, P->ldp, P->b,
-                pars.phase1EqTol, Q->G, Q->ldm, Q->gr, Q->ub);
+    if (m1 > 0)      // a problem may have quadratic constraints only (joptP1, SimpleOptimizationProblems.scala:347-377)
+      CVXB_LAUNCH(h, phase1_build_kernel, grid, 128, 0, n, m, p, P->G, P->ldm, P->gr, P->ub, P->A, P->ldp, P->b,
+                  pars.phase1EqTol, Q->G, Q->ldm, Q->gr, Q->ub);
     if (mq > 0) {     // Constraint.phase_I of a quadratic constraint: P1 = [P 0; 0 0], a1 = [a; -1]  (Constraint.scala:64-89)
       CVXB_LAUNCH(h, phase1_quad_kernel, dim3((n + 1 + 127) / 128, n + 1 > 1024 ? 1024 : n + 1, mq), 128, 0, n, mq, P->ldq,
                   P->Pq, mq * P->ldq, P->qa, Q->ldq, Q->Pq, mq * Q->ldq, Q->qa);
