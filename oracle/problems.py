@@ -101,6 +101,35 @@ def jopt_p2():
                 A=np.ones((1, 2)), b=np.array([1.0]), x0=None, xdef=np.full(2, 2.0), xopt=np.array([0.5, 0.5]))
 
 
+def probability_simplex_problem(n):
+    """SimpleOptimizationProblems.probabilitySimplexProblem (:425-453): min (sum(x) - 1)^2 / 2 =
+    QuadraticObjectiveFunction(n, 0.5, -1, 11') over x >= 0; every point of the probability simplex is a minimiser
+    (objective 0; the listed one is 1/n); pointWhereDefined = 2 (feasible, but phase I runs: withoutFeasiblePoint)."""
+    return dict(kind="quadratic", n=n, a=-np.ones(n), r=0.5, P=np.ones((n, n)), G=-np.eye(n), rvec=np.zeros(n),
+                ub=np.zeros(n), A=None, b=None, x0=None, xdef=np.full(n, 2.0), xopt=np.full(n, 1.0 / n))
+
+
+def distance_from_origin(n, sliced=False):
+    """SimpleOptimizationProblems.distanceFromOrigin0 / distanceFromOrigin1 (:462-552): in R^{n+1}, min ||x||^2/2 on
+    the ball ||x - 2 e_{n+1}||^2/2 <= 1/2 (QuadraticConstraint(ub = 0, r = 1.5, a = -2 e_{n+1}, P = I)); `sliced` adds the
+    2n linear constraints -(e_j + e_{n+1})'x <= -1 exactly as the reference builds them (its second constraint of each
+    pair re-uses `-a` instead of `-b`, so every row appears twice); optimum e_{n+1}; pointWhereDefined = 0 => phase I."""
+    d = n + 1
+    e = np.zeros(d)
+    e[n] = 1.0
+    quad = [dict(P=np.eye(d), a=-2.0 * e, r=1.5, ub=0.0)]
+    rows = []
+    if sliced:
+        for j in range(n):
+            a = e.copy()
+            a[j] += 1.0
+            rows += [-a, -a]
+    G = np.array(rows) if rows else np.zeros((0, d))
+    m = G.shape[0]
+    return dict(kind="quadratic", n=d, a=np.zeros(d), r=0.0, P=np.eye(d), G=G, rvec=np.zeros(m), ub=np.full(m, -1.0),
+                quad=quad, A=None, b=None, x0=None, xdef=np.zeros(d), xopt=e)
+
+
 def kl_random(n, m_h, p_extra, seed=0):
     """C2 family via Dist_KL.apply semantics: KL objective, m_h rows Hx<=u plus n positivity rows,
     p_extra rows A x = r plus the sum-to-one row (stacked last); start 1/n => phase I."""

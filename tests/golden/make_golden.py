@@ -30,6 +30,9 @@ CASES = {
     "norm_squared_free_variables_8": lambda: P.norm_squared_free_variables(8),
     "jopt_p1_6": lambda: P.jopt_p1(6),
     "jopt_p2": lambda: P.jopt_p2(),
+    "probability_simplex_8": lambda: P.probability_simplex_problem(8),
+    "distance_from_origin0_5": lambda: P.distance_from_origin(5),
+    "distance_from_origin1_5": lambda: P.distance_from_origin(5, True),
 }
 
 
