@@ -231,3 +231,87 @@ def test_oracle_phase_I_SOI():
         if feasible:
             assert rep.s.sum() < 2 * cnts.numConstraints * 1e-9
             assert rep.equalityConstraintError < 1e-9
+
+
+# ---- the remaining test designs of the reference's MatrixUtilsTests / KktTest, with seeds added ------------------
+
+@pytest.mark.parametrize("n,seed", [(10, 0), (40, 1), (120, 2)])
+def test_solve_underdetermined(n, seed):
+    """MatrixUtilsTests.testSolveUnderdetermined (:206-233): m = n/2 equations, A, b ~ U(0,1), +1 on A's diagonal;
+    the solution space (z0, F) satisfies A z0 = b, A F = 0; F has orthonormal columns and z0 is orthogonal to them
+    (z0 = Q1 R'^-1 b, F = Q2 of the QR of A', MatrixUtils.scala:536-550)."""
+    rng = np.random.default_rng(seed)
+    m = n // 2
+    A = rng.uniform(0, 1, (m, n))
+    A[np.arange(m), np.arange(m)] += 1.0
+    b = rng.uniform(0, 1, m)
+    z0, F = O.solveUnderdetermined(A, b)
+    assert F.shape == (n, n - m)
+    assert np.linalg.norm(A @ F) < 1e-12 * n
+    assert np.linalg.norm(A @ z0 - b) < 1e-12 * n
+    assert np.linalg.norm(F.T @ F - np.eye(n - m)) < 1e-12 * n
+    assert np.linalg.norm(F.T @ z0) < 1e-12 * n
+
+
+def _ill_conditioned_system(dim, condNum, dimKernel, seed):
+    """MatrixUtilsTests.testEquationSolve (:264-320): A = U D U' (randomOrthogonalMatrix, diagonalMatrix: d_j =
+    exp(-j log(condNum)/n), the last dimKernel set to zero; MatrixUtils.scala:46-63), made exactly symmetric, and
+    nastyRHS b = U w, w_j ~ U(1,3) where d_j != 0, else 0 (:573-580)."""
+    rng = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rng.normal(0, 1, (dim, dim)))
+    d = np.exp(-np.arange(dim) * (np.log(condNum) / dim))
+    if dimKernel:
+        d[dim - dimKernel:] = 0.0
+    Q = (U * d) @ U.T
+    A = (Q + Q.T) * 0.5
+    w = np.where(np.abs(d) > 0, 1 + 2 * rng.uniform(0, 1, dim), 0.0)
+    return A, U @ w, d
+
+
+@pytest.mark.parametrize("dim,condNum,dimKernel,seed", [(30, 1e3, 0, 0), (60, 1e6, 0, 1), (40, 1e4, 3, 2)])
+def test_equation_solve_ill_conditioned(dim, condNum, dimKernel, seed):
+    """svdSolve and symSolve accept the ill-conditioned (and, with dimKernel > 0, singular but consistent) systems of
+    the reference's testEquationSolve and return a solution within the reference's residual bar; choleskySolve
+    answers the nonsingular ones and, as in the reference, has no answer for an exactly singular matrix."""
+    A, b, d = _ill_conditioned_system(dim, condNum, dimKernel, seed)
+    tol = 1e-6
+    for solve in (O.svdSolve, O.symSolve):
+        x = solve(A, b, tol)
+        assert np.linalg.norm(A @ x - b) <= tol * np.sqrt(2 * dim) * max(1.0, np.linalg.norm(b))
+    if dimKernel == 0:
+        x = O.choleskySolve(A, b, tol)
+        assert O.relativeSize(A @ x - b, b, tol) <= tol
+    else:
+        with pytest.raises(Exception):
+            O.choleskySolve(A, b, 1e-12)
+
+
+@pytest.mark.parametrize("shift,seed", [(-2, 0), (0, 1), (4, 2)])
+def test_kkt_system_reduction_and_padding(shift, seed):
+    """KktTest.testSolutionPadding / testKktSystemReduction (:19-104): variables the system does not depend on (zero
+    rows and columns of H, zero columns of A, zero entries of g) are eliminated (KKTData.reduced), the reduced system
+    is solved, the solution padded with zeros (KKTData.paddVector) solves the original system."""
+    null = [2 + shift, 4 + shift, 8 + shift]
+    z = O.paddVector(np.ones(10), null)
+    assert z.shape == (13,) and all(z[j] == 0 for j in null) and z.sum() == 10
+    rng = np.random.default_rng(seed)
+    dim = null[-1] + 5
+    Q = rng.uniform(-1, 1, (dim, dim))
+    H = Q.T @ Q
+    H[:, null] = 0
+    H[null, :] = 0
+    A = rng.uniform(-1, 1, (6, dim))
+    A[:, null] = 0
+    g = rng.uniform(-2, 2, dim)
+    g[null] = 0
+    r = rng.uniform(-1, 1, 6)
+    Hr, Ar, gr, rr, found = O.kktDataReduced(H, A, g, r)
+    assert found == null and Hr.shape == (dim - 3, dim - 3) and Ar.shape == (6, dim - 3)
+    rdx, nu = O.kkt_solve(Hr, Ar, gr, rr, 1e-9)
+    dx = O.paddVector(rdx, null)
+    assert np.linalg.norm(H @ dx + A.T @ nu + g) < 1e-8 * max(1.0, np.linalg.norm(g))
+    assert np.linalg.norm(A @ dx - r) < 1e-8
+    g2 = g.copy()
+    g2[null[0]] = 1.0          # zero row with a nonzero right-hand side: no solution (KKTData.scala:80-84)
+    with pytest.raises(O.UnsolvableSystemException):
+        O.kktDataReduced(H, A, g2, r)
