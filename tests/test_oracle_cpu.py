@@ -315,3 +315,16 @@ def test_kkt_system_reduction_and_padding(shift, seed):
     g2[null[0]] = 1.0          # zero row with a nonzero right-hand side: no solution (KKTData.scala:80-84)
     with pytest.raises(O.UnsolvableSystemException):
         O.kktDataReduced(H, A, g2, r)
+
+
+@pytest.mark.parametrize("solver", ["BR", "PD"])
+@pytest.mark.parametrize("maker,n", [(P.kl_1A, 12), (P.kl_1A, 14), (P.kl_1A, 40), (P.kl_2A, 12), (P.kl_2A, 30)])
+def test_kl_analytic_solutions_both_branches(maker, n, solver):
+    """OptimizationProblems.kl1_analyticSolution / kl2_analyticSolution (:134-141, :247-252): the symmetric minimisers
+    of the KL problems, in both regimes of kl_1 (n <= 15: the P(A) >= 0.36 constraint is inactive; n > 15: active)."""
+    prob = maker(n)
+    objF, cnts, eqs = P.to_oracle(prob)
+    sol, _ = O.solveProblem(objF, cnts, eqs, solver)
+    assert abs(objF.valueAt(sol.x) - objF.valueAt(prob["xopt"])) < 1e-8
+    assert np.max(np.abs(sol.x - prob["xopt"])) < 1e-6
+    assert abs(sol.x.sum() - 1.0) < 1e-8 and np.all(sol.x > 0)
