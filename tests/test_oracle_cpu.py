@@ -328,3 +328,53 @@ def test_kl_analytic_solutions_both_branches(maker, n, solver):
     assert abs(objF.valueAt(sol.x) - objF.valueAt(prob["xopt"])) < 1e-8
     assert np.max(np.abs(sol.x - prob["xopt"])) < 1e-6
     assert abs(sol.x.sum() - 1.0) < 1e-8 and np.all(sol.x > 0)
+
+
+@pytest.mark.parametrize("with_eqs", [False, True])
+def test_oracle_pd_direction_against_full_newton_system(with_eqs):
+    """Independent of the oracle's block elimination (kktMatrix_noEqs, rhs1, deltaLambda: PrimalDualSolver.scala:162-240)
+    and of LAPACK: the primal-dual search direction against a 50-digit mpmath solve of the FULL linearised system
+    (Boyd & Vandenberghe (11.54)):
+        [ hess f + sum lam_i hess g_i   Dg'        A' ] [dx  ]     [ r_dual ]
+        [ -diag(lam) Dg                 -diag(g)   0  ] [dlam] = - [ r_cent ]
+        [ A                             0          0  ] [dnu ]     [ r_pri  ]
+    with a quadratic objective, linear and quadratic constraints."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    prob = P.lin_quad_set(7, 6, 2, 2 if with_eqs else 0, 11, "quadratic", True)
+    objF, cnts, eqs = P.to_oracle(prob)
+    pd = O.PrimalDual(objF, cnts, eqs, O.SolverParams.standardParams(), False, False)
+    rng = np.random.default_rng(3)
+    x = prob["x0"] + 0.01 * rng.normal(0, 1, 7)      # off the equality manifold: r_pri != 0
+    assert cnts.isSatisfiedStrictlyBy(x)
+    lam = cnts.lambda0(x) * rng.uniform(0.5, 1.5, cnts.numConstraints)
+    nu = rng.normal(0, 1, eqs.A.shape[0]) if with_eqs else None
+    t = 7.0
+    dx, dlam, dnu = pd.newton_direction(t, x, lam, nu)
+    n, m = 7, cnts.numConstraints
+    p = eqs.A.shape[0] if with_eqs else 0
+    g = cnts.constraintFunctionAt(x)                     # g_i(x) - ub_i < 0
+    Dg = cnts.gradientMatrixAt(x)
+    Hf = objF.hessianAt(x)
+    Hg = sum(lam[prob["G"].shape[0] + k] * q["P"] for k, q in enumerate(prob["quad"]))
+    r_dual = objF.gradientAt(x) + Dg.T @ lam + (eqs.A.T @ nu if with_eqs else 0.0)
+    r_cent = -lam * g - 1.0 / t
+    N = n + m + p
+    M = np.zeros((N, N))
+    M[:n, :n] = Hf + Hg
+    M[:n, n:n + m] = Dg.T
+    M[n:n + m, :n] = -lam[:, None] * Dg
+    M[n:n + m, n:n + m] = -np.diag(g)
+    rhs = np.concatenate([-r_dual, -r_cent])
+    if with_eqs:
+        M[:n, n + m:] = eqs.A.T
+        M[n + m:, :n] = eqs.A
+        rhs = np.concatenate([rhs, -(eqs.A @ x - eqs.b)])
+    Mm = mp.matrix(N, N)
+    for i in range(N):
+        for j in range(N):
+            Mm[i, j] = mp.mpf(float(M[i, j]))
+    sol = mp.lu_solve(Mm, mp.matrix([mp.mpf(float(v)) for v in rhs]))
+    ref = np.array([float(sol[i]) for i in range(N)])
+    got = np.concatenate([dx, dlam] + ([dnu] if with_eqs else []))
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-9
