@@ -378,3 +378,32 @@ def test_oracle_pd_direction_against_full_newton_system(with_eqs):
     ref = np.array([float(sol[i]) for i in range(N)])
     got = np.concatenate([dx, dlam] + ([dnu] if with_eqs else []))
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-9
+
+
+@pytest.mark.parametrize("maker", [lambda: P.lin_quad_set(6, 5, 2, 0, 4, "quadratic", True), lambda: P.kl_small(8, 4, 1),
+                                   lambda: P.min_pNorm(5, 3.0)])
+def test_barrier_gradient_and_hessian_by_finite_differences(maker):
+    """BarrierSolver.scala:280-315 restated: the gradient and Hessian of t f(x) - sum log(ub_i - g_i(x)) against central
+    differences of the barrier VALUE (a check that does not share the closed-form derivative formulas)."""
+    prob = maker()
+    objF, cnts, eqs = P.to_oracle(prob)
+    bf = O.BarrierFunctions(objF, cnts)
+    n = prob["n"]
+    x = prob["x0"].copy() if prob.get("x0") is not None else np.full(n, 1.0 / n) * (1 + 0.1 * np.cos(np.arange(n)))
+    if prob["kind"] == "pnorm":
+        x = np.full(n, 0.2) * (1 + 0.2 * np.cos(np.arange(n)))
+    assert cnts.isSatisfiedStrictlyBy(x)
+    t = 3.0
+    g = bf.gradient(t, x)
+    H = bf.hessian(t, x)
+    h = 1e-5
+    g_fd = np.zeros(n)
+    H_fd = np.zeros((n, n))
+    for i in range(n):
+        e = np.zeros(n)
+        e[i] = h
+        g_fd[i] = (bf.value(t, x + e) - bf.value(t, x - e)) / (2 * h)
+        H_fd[:, i] = (bf.gradient(t, x + e) - bf.gradient(t, x - e)) / (2 * h)
+    assert np.linalg.norm(g - g_fd) / np.linalg.norm(g) < 1e-7
+    assert np.linalg.norm(H - H_fd) / np.linalg.norm(H) < 1e-7
+    assert np.array_equal(H, H.T)
