@@ -48,7 +48,7 @@ WORKLOADS = {
 
 
 def make_problem(workload, seed):
-    from oracle import problems as P       # input generation only (numpy)
+    import synthetic as P                  # input generation only (numpy; no oracle code on the GPU arm)
     w = WORKLOADS[workload]
     return getattr(P, w["gen"])(seed=seed, **w["args"])
 
@@ -384,7 +384,7 @@ def main():
     # of the solutions + convergence all-reduce.  Strong scaling: B is fixed as N grows.
     batched = None
     if not args.no_batched:
-        from oracle import problems as P
+        import synthetic as P
         Bt = args.batch
         lo, hi = cb.shard_range(Bt, rank, world)
         bprobs = [P.batched_problem(i, 64, 128, 1000) for i in range(lo, hi)]

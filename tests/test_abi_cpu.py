@@ -97,3 +97,31 @@ def test_pack_problems_layout():
     assert flat[3 * 16 + 5] == probs[1]["G"][5, 3]
     assert np.array_equal(pk["obj_P"][1], probs[1]["P"].T)
     assert cb.shard_range(10, 0, 4) == (0, 3) and cb.shard_range(10, 3, 4) == (9, 10) and cb.shard_range(2, 3, 4) == (2, 2)
+
+
+def test_bench_gpu_arm_never_imports_the_oracle():
+    """bench.py may execute oracle/ only in its CPU legs (cpu_baseline, --impl reference): every import of it sits
+    inside cpu_reference_leg; synthetic.py (input generation for both arms) does not import it at all."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+
+    def oracle_imports(node):
+        out = []
+        for sub in ast.walk(node):
+            if isinstance(sub, ast.ImportFrom) and (sub.module or "").split(".")[0] == "oracle":
+                out.append(sub.lineno)
+            if isinstance(sub, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in sub.names):
+                out.append(sub.lineno)
+        return out
+
+    allowed = []
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == "cpu_reference_leg":
+            allowed = oracle_imports(node)
+    assert allowed, "cpu_reference_leg should be the one place that imports oracle/"
+    assert sorted(oracle_imports(tree)) == sorted(allowed)
+    syn = ast.parse(open(os.path.join(root, "synthetic.py")).read())
+    assert oracle_imports(syn) == []
+    for name in ("gpu_big.py", "gpu_batch.py", "gpu_syrk.py", "gpu_potrf.py", "gpu_gemm_sweep.py"):
+        assert oracle_imports(ast.parse(open(os.path.join(root, "tools", name)).read())) == []

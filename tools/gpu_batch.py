@@ -1,6 +1,6 @@
 import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import time, numpy as np, sys
-from oracle import problems as P
+import synthetic as P
 import cvx_b200 as cb
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 t0=time.time(); probs = [P.batched_problem(i, 64, 128, 1000) for i in range(B)]; packed = cb.pack_problems(probs); print('gen+pack', time.time()-t0)

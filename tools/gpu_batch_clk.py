@@ -1,7 +1,7 @@
 import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C
 import cvx_b200 as cb
-from oracle import problems as P
+import synthetic as P
 h = cb.default_handle()
 lib = h.lib
 lib.cvxb_debug_batch_clocks.argtypes = [C.POINTER(C.c_longlong), C.c_int]

@@ -3,7 +3,7 @@ import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspa
 import json, sys, time
 import numpy as np
 import cvx_b200 as cb
-from oracle import problems as P
+import synthetic as P
 
 which = sys.argv[1] if len(sys.argv) > 1 else "c4"
 h = cb.default_handle()

@@ -2,7 +2,7 @@ import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspa
 """Small end-to-end pass over every kernel family (for compute-sanitizer memcheck)."""
 import numpy as np
 import cvx_b200 as cb
-from oracle import problems as P
+import synthetic as P
 h = cb.default_handle()
 s = P.kkt_planted_pd(300, 40, 2)
 x, w = cb.KKTSystem(s["H"], s["A"], s["q"], s["b"], h).solve(1e-6, None, 1e-7, 0)
