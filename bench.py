@@ -1,23 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- FP64 Newton (KKT) steps/s of the interior-point hot path on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c4|c5] [--impl cvxb|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c5|...] [--impl cvxb|reference]
 
-A "step" is ONE Newton step of the barrier method (Hessian + gradient assembly over the m inequality
-constraints, KKT solve by Cholesky + Schur complement, backtracking line search, update) on the
-workload BASELINE.json's metric is quoted on at one GPU: configs[1], the KL-distance minimisation
-n=2000, m=4000 inequalities, p=500 equalities, barrier solver, phase I included (Dist_KL.apply
-semantics), synthetic seeded data, FP64.  K timed steps are taken from the start of full solves
-(several seeded instances, uploaded before the timed region).  N > 1: the path shards only across
-independent problems, so each rank runs its own instances (weak scaling, "replicas only", no data-path
-collective); time = max over ranks.
+Headline workload (default, `config.workload`): BASELINE.json configs[3] -- the configuration north_star's target
+"FP64 KKT Newton steps/sec at n=8192" is quoted on: one dense QP, n = 8192 variables, m = 16384 inequality rows,
+p = 2048 equality rows, PRIMAL-DUAL solver (PrimalDualSolver.solve_withEQs, PrimalDualSolver.scala:550-621), FP64,
+synthetic seeded data (3.4 GB of device state: fits one GPU).  A "step" is ONE primal-dual Newton iteration: Hessian
+H_pd = hess f + G' diag(-lam/f) G assembled as one weighted SYRK on FP64 DMMA, residual GEMVs, Ruiz equilibration,
+Cholesky of H with the forward substitution of [DA', Dq] riding along, Schur complement + its Cholesky, back
+substitution, residual check, delta-lambda, residual line search, update.  The K timed steps are taken from the start
+of full solves of pre-uploaded seeded instances (device time by CUDA events on the library's stream, barrier +
+synchronize on both sides, max over ranks).  N > 1: the path shards only across independent problems, so each rank
+runs its own instances (weak scaling, "replicas only", no data-path collective).
 
 The JSON line also carries
-  roofline      the dominant kernel (Hessian-assembly SYRK on FP64 DMMA), timed per launch with CUDA
-                events on the library's stream inside the timed region
-  cpu_baseline  the CPU oracle (numpy/LAPACK restatement of the reference) on this box's host cores
-  e2e           the same metric through the public API with host buffers (upload + solve + download timed)
---impl reference times the reference's CPU algorithm (oracle/) on the host cores for the same config.
+  roofline               the dominant kernel (Hessian-assembly SYRK), timed per launch with CUDA events inside the
+                         timed region, against the FP64 DMMA issue-rate peak measured in the same run
+  roofline_chol_trailing the Cholesky trailing updates A22 -= A21 A21' (north_star's >= 60 % target), same method
+  step_breakdown         share of the step spent in each timed range (SYRK / Ruiz / factorisation+TRSM / Schur / GEMV)
+  hbm_kernels            the HBM-bound GEMVs over G (1.07 GB, far above the 126 MB L2) against MEASURED_PEAKS.json
+  cpu_baseline           the CPU oracle (numpy/LAPACK restatement of the reference) on this box's host cores
+  e2e                    ONE FULL primal-dual solve through the public API with HOST (pinned) buffers -- problem
+                         creation, upload, every Newton step to termination, download -- divided by its steps
+  legs                   the other single-GPU configs (C2 KL barrier with phase I, C5 LP phase I) as extra records
+  batched                configs[2]: B = 8192 problems n=64, m=128 sharded over the ranks + one NCCL all-gather
+--impl reference times the reference's CPU algorithm (oracle/) on the host cores, same workload, same kind of steps.
 """
 from __future__ import annotations
 
@@ -35,15 +43,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (generator name, kwargs, solver)
-    "c1": dict(desc="small dense LP n=100 m=200 p=20, barrier", gen="slab_lp", args=dict(n=100, m_half=100, p=20)),
+    # name: description, generator (synthetic.py), its arguments, solver type
+    "c4": dict(desc="dense QP n=8192 m=16384 p=2048, primal-dual solver (BASELINE.json configs[3], the north-star config)",
+               gen="slab_qp", args=dict(n=8192, m_half=8192, p=2048), solver="PD"),
+    "c4s": dict(desc="dense QP n=1024 m=2048 p=256, primal-dual solver (smoke size of c4)", gen="slab_qp",
+                args=dict(n=1024, m_half=1024, p=256), solver="PD"),
+    "c4b": dict(desc="dense QP n=8192 m=16384 p=2048, barrier solver", gen="slab_qp", args=dict(n=8192, m_half=8192, p=2048),
+                solver="BR"),
+    "c1": dict(desc="small dense LP n=100 m=200 p=20, barrier", gen="slab_lp", args=dict(n=100, m_half=100, p=20), solver="BR"),
     "c2": dict(desc="KL-distance minimisation n=2000 m=4000 p=500, barrier, phase I included", gen="kl_random",
-               args=dict(n=2000, m_h=2000, p_extra=499)),
+               args=dict(n=2000, m_h=2000, p_extra=499), solver="BR"),
     "c2s": dict(desc="KL-distance minimisation n=400 m=800 p=100 (smoke size)", gen="kl_random",
-                args=dict(n=400, m_h=400, p_extra=99)),
-    "c4b": dict(desc="dense QP n=8192 m=16384 p=2048, barrier solver", gen="slab_qp", args=dict(n=8192, m_half=8192, p=2048)),
+                args=dict(n=400, m_h=400, p_extra=99), solver="BR"),
     "c5": dict(desc="random dense LP n=16384 m=32768 p=0, phase I then barrier", gen="slab_lp",
-               args=dict(n=16384, m_half=16384, p=0, feasible_start=False)),
+               args=dict(n=16384, m_half=16384, p=0, feasible_start=False), solver="BR"),
+    "c5s": dict(desc="random dense LP n=2048 m=4096 p=0, phase I then barrier (smoke size of c5)", gen="slab_lp",
+                args=dict(n=2048, m_half=2048, p=0, feasible_start=False), solver="BR"),
 }
 
 
@@ -162,78 +177,202 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def run_steps(instances, budget, stats):
-    """Consume `budget` Newton steps from the start of full solves; returns device ms."""
+def steps_of(sol):
+    return int(sol.executed_newton_steps + sol.phase1_executed_steps)
+
+
+def run_steps(instances, budget, stats, cycle):
+    """Consume `budget` Newton steps from the start of full solves; returns device ms (CUDA events on the library's
+    stream, cvxb_solution.solve_ms).  cycle: instances with a given feasible start can be solved again from scratch
+    (every solve recomputes everything from the uploaded problem data)."""
     ms = 0.0
-    for op in instances:
-        if budget <= 0:
+    while budget > 0:
+        progressed = False
+        for op in instances:
+            if budget <= 0:
+                break
+            op.solver.pars.stepLimit = budget
+            sol = op.solve()
+            done = steps_of(sol)
+            ms += sol.solve_ms
+            budget -= done
+            stats["steps"] += done
+            stats["solves"] += 1
+            stats["last"] = sol
+            progressed = progressed or done > 0
+        if not cycle or not progressed:
             break
-        op.solver.pars.stepLimit = budget
-        sol = op.solve()
-        done = sol.executed_newton_steps + sol.phase1_executed_steps
-        ms += sol.solve_ms
-        budget -= done
-        stats["steps"] += done
-        stats["solves"] += 1
-        stats["last"] = sol
     if budget > 0:
         raise RuntimeError("not enough problem instances for the requested number of steps")
     return ms
 
 
+def _blas_threads(n=None):
+    """BLAS threads of the CPU arm: torchrun exports OMP_NUM_THREADS=1 to every rank, which would throttle the
+    reference's LAPACK calls; the CPU arm uses every host core the box has."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n or os.cpu_count())
+    except Exception:
+        pass
+    return n or os.cpu_count()
+
+
 def cpu_reference_leg(workload, steps, warmup, seed=0):
-    """The reference's CPU algorithm (oracle restatement: numpy + LAPACK dpotrf/dtrtrs/dgemm, all host
-    threads the BLAS uses) on a bounded sample: `steps` Newton steps of the barrier stage loop started at
-    the strictly feasible point the generator knows (no phase I needed on the CPU side)."""
+    """The reference's CPU algorithm (oracle restatement: numpy + LAPACK dpotrf/dtrtrs/dgemm, all host threads the
+    BLAS uses) on a bounded sample of the SAME workload and the SAME kind of steps as the GPU arm: `warmup` untimed +
+    `steps` timed Newton steps from the start of a solve.  Returns (steps/s, steps done, seconds, sample text)."""
     from oracle import cvx_oracle as O
     from oracle import problems as P
+    cores = _blas_threads()
+    w = WORKLOADS[workload]
     prob = make_problem(workload, seed)
-    if prob.get("x0") is None and "qstar" in prob:
-        prob["x0"] = prob["qstar"].copy()
-    if prob.get("x0") is None:
-        prob["x0"] = None
     objF, cnts, eqs = P.to_oracle(prob)
-    if cnts.feasiblePoint is None:      # workloads that really need phase I (c5): include it in the sample
+    if w["solver"] == "PD":
+        # primal-dual iterations (corrected solver: bug_compat=False, like the GPU arm) from the strictly feasible start
+        pd = O.PrimalDual(objF, cnts, eqs, O.SolverParams(), False, False)
+        marks = []
+        inner = pd.newton_direction
+
+        def stamped(*a, **k):
+            marks.append(time.perf_counter())
+            return inner(*a, **k)
+        pd.newton_direction = stamped
+        sol = pd.solve(max_steps=warmup + steps)
+        marks.append(time.perf_counter())
+        done_all = len(marks) - 1
+        w_ = min(warmup, max(done_all - 1, 0))
+        done = done_all - w_
+        dt = marks[-1] - marks[w_]
+        return done / dt, done, dt, ("primal-dual Newton iterations %d..%d of a solve from the strictly feasible start "
+                                     "(%d untimed warm-up iterations before them)" % (w_ + 1, done_all, w_)), cores
+    if cnts.feasiblePoint is None and "qstar" not in prob:      # workloads that really need phase I (c5)
         pars = O.SolverParams(maxIter=max(1, steps + warmup))
         t0 = time.perf_counter()
         x0, s, sol = O.phase_I_Analysis(cnts, eqs, pars)
         dt = time.perf_counter() - t0
-        return sol.newton_steps / dt, sol.newton_steps, dt, "phase-I Newton steps from pointWhereDefined"
+        return sol.newton_steps / dt, sol.newton_steps, dt, "phase-I Newton steps from pointWhereDefined", cores
+    # barrier workloads: K/2 phase-I steps + K/2 main-phase steps, as the GPU arm does (c2), or all main-phase
+    done, dt = 0, 0.0
+    sample = []
+    if cnts.feasiblePoint is None:
+        k1 = steps // 2
+        if k1 > 0:
+            pars = O.SolverParams(maxIter=k1)
+            t0 = time.perf_counter()
+            x0, s, sol = O.phase_I_Analysis(cnts, eqs, pars)
+            dt += time.perf_counter() - t0
+            done += sol.newton_steps
+            sample.append("%d phase-I Newton steps from pointWhereDefined" % sol.newton_steps)
+        steps -= k1
+        cnts = cnts.addFeasiblePoint(prob["qstar"])
     bf = O.BarrierFunctions(objF, cnts)
     x = np.array(cnts.feasiblePoint)
     t = 1.0
-    done, dt = 0, 0.0
-    todo_w, todo = warmup, steps
+    todo_w, todo, d2 = warmup, steps, 0
     while todo > 0:
         k = todo_w if todo_w > 0 else todo
         pars = O.SolverParams(maxIter=k)
         t0 = time.perf_counter()
-        if eqs is not None:
-            sol = O.equalityConstrainedSolve(bf, t, x, eqs.A, eqs.b, pars)
-        else:
-            sol = O.unconstrainedSolve(bf, t, x, pars)
+        sol = O.equalityConstrainedSolve(bf, t, x, eqs.A, eqs.b, pars) if eqs is not None else O.unconstrainedSolve(bf, t, x, pars)
         el = time.perf_counter() - t0
         x = sol.x
         if todo_w > 0:
             todo_w -= max(1, sol.newton_steps)
         else:
             todo -= max(1, sol.newton_steps)
-            done += sol.newton_steps
+            d2 += sol.newton_steps
             dt += el
         if not sol.maxedOut:
             t *= 10.0
-    return done / dt, done, dt, "barrier-stage Newton steps from the generator's strictly feasible point"
+    done += d2
+    sample.append("%d barrier-stage Newton steps from the strictly feasible point" % d2)
+    return done / dt, done, dt, " + ".join(sample), cores
+
+
+def pinned_problem(prob):
+    """The problem's matrices as column-major (Breeze layout) views on pinned host memory: what a long-running caller
+    hands to the C ABI.  Returns (problem dict, bytes uploaded per cvxb_problem_create, keep-alive list)."""
+    import torch
+    out, keep, nbytes = dict(prob), [], 0
+    for k_ in ("G", "A", "P"):
+        if prob.get(k_) is not None:
+            a = np.asarray(prob[k_], dtype=np.float64)
+            tpin = torch.empty(a.shape[::-1], dtype=torch.float64).pin_memory()    # (cols, rows) C-order == (rows, cols) F-order
+            tpin.numpy()[...] = a.T
+            keep.append(tpin)
+            out[k_] = tpin.numpy().T
+            nbytes += a.nbytes
+    for k_ in ("a", "ub", "b", "rvec", "xdef", "x0"):
+        if isinstance(prob.get(k_), np.ndarray):
+            nbytes += prob[k_].nbytes
+    return out, nbytes, keep
+
+
+def roofline_from_range(rng, kernel, peak, peak_source, dev_ms, extra=None):
+    """rng = (count, total ms, total algorithmic flops) of a timed range (Handle.profile_read_range)."""
+    cnt, ms, work = rng
+    ach = work / (ms / 1e3) / 1e12 if ms > 0 else 0.0
+    r = {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+         "frac": ach / peak if peak else None, "traffic": None, "launches": cnt, "avg_launch_ms": ms / max(cnt, 1),
+         "flops_per_launch": work / max(cnt, 1), "peak_source": peak_source, "share_of_step": ms / dev_ms if dev_ms > 0 else None}
+    if extra:
+        r.update(extra)
+    return r
+
+
+def extra_leg(cb, h, workload, steps, warmup_steps):
+    """One of the other single-GPU configs as an extra record: `steps` Newton steps from the start of a full solve."""
+    w = WORKLOADS[workload]
+    pr = make_problem(workload, 7)
+    n, m = pr["n"], pr["G"].shape[0]
+    p = 0 if pr.get("A") is None else pr["A"].shape[0]
+    two_kinds = pr.get("x0") is None and "qstar" in pr
+    ops = [cb.from_dict(pr, w["solver"], cb.SolverParams(), h)]
+    if two_kinds:
+        q = dict(pr)
+        q["x0"] = pr["qstar"].copy()
+        ops.append(cb.from_dict(q, w["solver"], cb.SolverParams(), h))
+    for op in ops:                                   # warm-up: same kernels, same shapes
+        op.solver.pars.stepLimit = warmup_steps
+        op.solve()
+    if two_kinds:                                    # the warm-up left a feasible point behind: start again from scratch
+        ops[0].solver.problem.close()
+        ops[0] = cb.from_dict(pr, w["solver"], cb.SolverParams(), h)
+    h.profile_enable(True)
+    ms, done, kinds = 0.0, 0, []
+    per = max(1, steps // len(ops))
+    for op in ops:
+        op.solver.pars.stepLimit = per
+        sol = op.solve()
+        ms += sol.solve_ms
+        done += steps_of(sol)
+        kinds.append("%d phase-I + %d main-phase" % (sol.phase1_executed_steps, sol.executed_newton_steps))
+    cnt, sms, sfl = h.profile_read()
+    h.profile_enable(False)
+    for op in ops:
+        op.solver.problem.close()
+    nn = n + 1 if (pr.get("x0") is None and not two_kinds) else n      # phase-I dimension for c5
+    return {"workload": workload + ": " + w["desc"], "metric": "newton_steps_per_sec", "value": done / (ms / 1e3), "unit": "steps/s",
+            "steps": done, "ms_per_step": ms / max(done, 1), "n": n, "m": m, "p": p, "steps_counted": " ; ".join(kinds),
+            "tflops": f_step(nn, m + (2 * p if nn != n else 0), 0 if nn != n else p) * done / (ms / 1e3) / 1e12,
+            "hessian_syrk": {"launches": cnt, "avg_launch_ms": sms / max(cnt, 1),
+                             "achieved_tflops": sfl / (sms / 1e3) / 1e12 if sms > 0 else None,
+                             "share_of_step": sms / ms if ms > 0 else None}}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="cvxb", choices=["cvxb", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the extra single-GPU legs (c2, c5)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--legs", default="c2,c5", help="comma-separated extra workloads run at N=1 after the headline")
     ap.add_argument("--batch", type=int, default=8192, help="problems in the batched leg (configs[2])")
     ap.add_argument("--cpu-steps", type=int, default=0, help="Newton steps of the CPU-baseline sample (0 = auto)")
     args = ap.parse_args()
@@ -242,19 +381,18 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     K, W = max(1, args.steps), max(0, args.warmup)
     w = WORKLOADS[args.workload]
-    prob0 = None
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cores = os.cpu_count()
-        val, done, dt, sample = cpu_reference_leg(args.workload, K, W)
+        val, done, dt, sample, cores = cpu_reference_leg(args.workload, K, W)
         line = {"impl": "reference", "metric": "newton_steps_per_sec", "value": val, "unit": "steps/s", "n_gpus": args.gpus,
                 "steps": K, "warmup": W, "ms_per_step": 1000.0 * dt / max(done, 1), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.workload + ": " + w["desc"], **w["args"]},
+                "config": {"workload": args.workload + ": " + w["desc"], **w["args"], "solver": w["solver"]},
                 "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port",
-                                 "sample": "%d %s (numpy/LAPACK oracle of the Scala reference; no JVM on this image)" % (done, sample)},
+                                 "sample": "%d %s; %.1f s (numpy/LAPACK oracle of the Scala reference, BLAS threads = %d; no JVM "
+                                           "on this image)" % (done, sample, dt, cores)},
                 "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -272,43 +410,42 @@ def main():
     h = _lib.Handle(local_rank)
 
     # ---- inputs: seeded instances, generated on the host and uploaded BEFORE the timed region ----------
-    # Two kinds of instance so that the K timed steps cover both halves of the solve of this config:
-    #   "phase1"  starts at pointWhereDefined = 1/n: phase-I Newton steps (dimension n+1, no equalities,
-    #             m + 2p inequality rows, UnconstrainedSolver / choleskySolve path)
-    #   "main"    starts at the generator's strictly feasible point: barrier Newton steps with the p
-    #             equalities (EqualityConstrainedSolver / KKTSystem Schur-complement path)
-    # K/2 steps are taken from each kind (all from "main" when the workload has a feasible start).
     base_seed = 100 * rank
     prob0 = make_problem(args.workload, base_seed)
     n, m = prob0["n"], prob0["G"].shape[0]
     p = 0 if prob0.get("A") is None else prob0["A"].shape[0]
+    solver_type = w["solver"]
+    # two kinds of instance for configs whose solve has two halves (c2: phase I in dimension n+1 without equalities, then
+    # the main phase with p equalities): K/2 steps from each, each taken from the start of full solves
     two_kinds = prob0.get("x0") is None and "qstar" in prob0
+    cycle = prob0.get("x0") is not None           # a given feasible start: the same instance can be solved again from scratch
 
-    def feasible_variant(pr):
-        q = dict(pr)
-        q["x0"] = pr["qstar"].copy()
-        return q
-
-    def make_instances(seed0, count, feasible):
+    def make_instances(seed0, count, feasible, first=None):
         out = []
         for i in range(count):
-            pr = make_problem(args.workload, seed0 + i)
+            pr = first if (first is not None and i == 0) else make_problem(args.workload, seed0 + i)
             if feasible:
-                pr = feasible_variant(pr)
-            out.append(cb.from_dict(pr, "BR", cb.SolverParams(), h))
+                pr = dict(pr)
+                pr["x0"] = pr["qstar"].copy()
+            out.append(cb.from_dict(pr, solver_type, cb.SolverParams(), h))
         return out
 
-    K1 = K // 2 if two_kinds else 0            # phase-I steps
-    K2 = K - K1                                 # main-phase steps
-    inst1 = make_instances(base_seed, (K1 + 89) // 90 + 1, False) if K1 else []       # >= 90 phase-I steps per solve
-    inst2 = make_instances(base_seed + 40, (K2 + 29) // 30 + 1, two_kinds)            # >= 30 main-phase steps per solve
-    warm = make_instances(base_seed + 90, 1, False) + (make_instances(base_seed + 91, 1, True) if two_kinds else [])
+    K1 = K // 2 if two_kinds else 0
+    K2 = K - K1
+    if cycle:
+        inst1, inst2 = [], make_instances(base_seed, 2 if n <= 8192 else 1, False, prob0)
+        warm = inst2                       # every timed instance has run once (first-use allocations, pool growth)
+    else:
+        inst1 = make_instances(base_seed, (K1 + 89) // 90 + 1, False) if K1 else []
+        inst2 = make_instances(base_seed + 40, (K2 + 29) // 30 + 1, two_kinds)
+        warm = make_instances(base_seed + 90, 1, False) + (make_instances(base_seed + 91, 1, True) if two_kinds else [])
+    del prob0
     h.synchronize()
 
     # ---- warm-up: W untimed Newton steps (same kernels, same shapes) ------------------------------------
     st = {"steps": 0, "solves": 0, "last": None}
     for wi in warm:
-        run_steps([wi], min(max(W, 3), 25), st)      # a single solve has > 25 steps; more warm-up adds nothing
+        run_steps([wi], max(W, 3), st, False)
     h.synchronize()
 
     def barrier():
@@ -325,11 +462,12 @@ def main():
     l0 = h.launches
     st = {"steps": 0, "solves": 0, "last": None}
     t0 = time.perf_counter()
-    dev_ms = (run_steps(inst1, K1, st) if K1 else 0.0) + run_steps(inst2, K2, st)
+    dev_ms = (run_steps(inst1, K1, st, False) if K1 else 0.0) + run_steps(inst2, K2, st, cycle)
     h.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches = h.launches - l0
     n_syrk, syrk_ms, syrk_flops = h.profile_read()
+    ranges = {k_: h.profile_read_range(k_) for k_ in ("chol_trailing_update", "factor_h_with_trsm", "schur_syrk", "ruiz", "gemv_g")}
     h.profile_enable(False)
     barrier()
     clk = clocks.stop()
@@ -342,46 +480,49 @@ def main():
     dev_ms_max, wall_ms_max = tmax.tolist()
     total_steps, total_launches = tot.tolist()
     value = total_steps / (dev_ms_max / 1e3)
-
-    # ---- e2e: public API with host buffers; upload + solve + download inside the timed region ------------
-    # steady state of a long-running service: earlier problems have been destroyed, their device memory sits in the
-    # handle's pool; the timed call still creates its problem, uploads, solves and downloads
-    for op_ in inst1 + inst2 + warm:
+    last = st["last"]
+    for op_ in {id(o): o for o in inst1 + inst2 + warm}.values():
         op_.solver.problem.close()
     del inst1, inst2, warm
-    e2e_prob = make_problem(args.workload, base_seed + 50)
-    if two_kinds and K2 >= K1:
-        pass        # e2e runs the user's call as is: full problem from pointWhereDefined (phase I first)
-    pinned = {}
-    for k_ in ("G", "A", "P"):
-        if e2e_prob.get(k_) is not None:
-            a = np.asfortranarray(e2e_prob[k_])
-            tpin = torch.empty(a.shape[::-1], dtype=torch.float64).pin_memory()      # (cols, rows) C-order == F-order (rows, cols)
-            tpin.numpy()[...] = a.T
-            pinned[k_] = tpin
-            e2e_prob[k_] = tpin.numpy().T                                             # column-major view on pinned memory
-    h2d = sum(int(np.asarray(v).nbytes) for k_, v in e2e_prob.items()
-              if isinstance(v, np.ndarray) and k_ in ("G", "A", "P", "a", "ub", "b", "rvec", "xdef", "x0"))
-    barrier()
-    e2e_budget = K
-    t0 = time.perf_counter()
-    op = cb.from_dict(e2e_prob, "BR", cb.SolverParams(stepLimit=e2e_budget), h)
-    sol = op.solve()
-    xsum = float(np.sum(sol.x))                 # result read back on the host
-    h.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_steps = sol.executed_newton_steps + sol.phase1_executed_steps
-    d2h = sol.x.nbytes + 128 * 8
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    e2e_n = torch.tensor([float(e2e_steps)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_n, op=dist.ReduceOp.SUM)
-    e2e_value = e2e_n.item() / e2e_t.item()
 
-    # ---- batched leg (BASELINE.json configs[2]): B = 8192 independent n=64, m=128 problems (half KL with
-    # p=1, half QP with p=0), contiguous shards over the ranks, one CTA per problem, then the NCCL gather
-    # of the solutions + convergence all-reduce.  Strong scaling: B is fixed as N grows.
+    # ---- e2e: ONE FULL solve through the public API with host (pinned) buffers -----------------------------------------
+    # Timed: problem creation (device allocation from the handle's pool), upload of every matrix and vector, every Newton
+    # step to termination, download of the solution, a host read of the result.  Steady state of a long-running caller:
+    # earlier problems were destroyed, their device memory sits in the handle's pool.
+    e2e = None
+    if not args.no_e2e:
+        e2e_prob, h2d, keep = pinned_problem(make_problem(args.workload, base_seed + 50))
+        barrier()
+        t0 = time.perf_counter()
+        op = cb.from_dict(e2e_prob, solver_type, cb.SolverParams(), h)
+        sol = op.solve()
+        xsum = float(np.sum(sol.x))                 # result read back on the host
+        h.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_steps = steps_of(sol)
+        d2h = sol.x.nbytes + (0 if sol.lam is None else sol.lam.nbytes) + (0 if sol.nu is None else sol.nu.nbytes)
+        d2h += e2e_steps * (128 * 8 + 64 * 4)       # the status block the host reads once per Newton step
+        e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        e2e_n = torch.tensor([float(e2e_steps)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(e2e_n, op=dist.ReduceOp.SUM)
+        e2e = {"value": e2e_n.item() / e2e_t.item(), "unit": "steps/s", "h2d_bytes_per_step": h2d / max(e2e_steps, 1),
+               "d2h_bytes_per_step": d2h / max(e2e_steps, 1), "steps": e2e_steps, "seconds": e2e_s, "device_ms": sol.solve_ms,
+               "what": "one full %s solve to termination through the public API: cvxb_problem_create with pinned host buffers "
+                       "(%.2f GB uploaded), all Newton steps, solution downloaded; value = steps / wall seconds"
+                       % (solver_type, h2d / 1e9),
+               "solution": {"objective": sol.objective, "dualityGap": sol.dualityGap, "equalityGap": sol.equalityGap,
+                            "normDualResidual": sol.normDualResidual, "newton_steps": sol.newton_steps,
+                            "phase1_newton_steps": sol.phase1_newton_steps, "maxedOut": sol.maxedOut},
+               "checksum": xsum}
+        op.solver.problem.close()
+        del op, e2e_prob, keep
+
+    # ---- batched leg (BASELINE.json configs[2]): B = 8192 independent n=64, m=128 problems (half KL with p=1, half QP
+    # with p=0), contiguous shards over the ranks, one CTA per problem, results left on the device, then ONE NCCL
+    # all-gather of the packed records (x + objective + gap + status + steps + stages) and one device-to-host copy.
+    # Strong scaling: B is fixed as N grows.
     batched = None
     if not args.no_batched:
         import synthetic as P
@@ -389,84 +530,124 @@ def main():
         lo, hi = cb.shard_range(Bt, rank, world)
         bprobs = [P.batched_problem(i, 64, 128, 1000) for i in range(lo, hi)]
         solver = cb.BatchedBarrierSolver(cb.pack_problems(bprobs), cb.SolverParams(), h)
-        wsol = solver.solve()                             # warm-up (same shapes)
+        solver.solve(download=False)                      # warm-up (same shapes)
         if world > 1:
-            cb.gather_solutions(wsol, Bt, 64)             # and of the exchange: NCCL connects its all-gather rings on first use
+            cb.gather_solutions(solver, Bt, 64)           # and of the exchange: NCCL connects its rings on first use
         barrier()
         t0 = time.perf_counter()
-        bsol = solver.solve()
         if world > 1:
-            g = cb.gather_solutions(bsol, Bt, 64)
-            conv, mxs = g["converged"], g["max_newton_steps"]
+            bsol = solver.solve(download=False)
+            g = cb.gather_solutions(solver, Bt, 64)
+            conv, mxs, nsteps = g["converged"], g["max_newton_steps"], float(g["newton_steps"].sum())
         else:
-            conv, mxs = int((bsol.status == 0).sum()), int(bsol.newton_steps.max())
+            bsol = solver.solve()
+            conv, mxs, nsteps = int((bsol.status == 0).sum()), int(bsol.newton_steps.max()), float(bsol.newton_steps.sum())
         torch.cuda.synchronize()
         bt = torch.tensor([time.perf_counter() - t0, bsol.solve_ms / 1e3], dtype=torch.float64, device="cuda")
-        bn = torch.tensor([float(bsol.newton_steps.sum())], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(bt, op=dist.ReduceOp.MAX)
-            dist.all_reduce(bn, op=dist.ReduceOp.SUM)
         wall_s, dev_s = bt.tolist()
+        fl_b = 6.69e5 * nsteps                  # algorithmic flops of one n=64, m=128 Newton step
         batched = {"metric": "batched_barrier_solves_per_sec", "value": Bt / wall_s, "unit": "solves/s", "B": Bt, "n": 64,
                    "m": 128, "scaling": "strong", "device_only_value": Bt / dev_s, "converged": conv,
-                   "max_newton_steps": mxs, "newton_steps_per_sec": bn.item() / wall_s,
-                   "includes": "kernel + device-to-host of the shard + NCCL all-gather of x and status + all-reduce"
+                   "max_newton_steps": mxs, "newton_steps_per_sec": nsteps / wall_s,
+                   "tflops_algorithmic": fl_b / dev_s / 1e12,
+                   "includes": "kernel + ONE NCCL all-gather of the packed device records + one device-to-host copy"
                                if world > 1 else "kernel + device-to-host of the results"}
+        solver.close()
+
+    # ---- the other single-GPU configs as extra legs (N = 1 only) -------------------------------------------------------
+    legs = {}
+    if world == 1 and not args.no_legs:
+        for name in [s_ for s_ in args.legs.split(",") if s_ and s_ != args.workload]:
+            try:
+                legs[name] = extra_leg(cb, h, name, 20 if WORKLOADS[name]["args"].get("n", 0) <= 4096 else 4, 3 if name != "c5" else 1)
+            except Exception as e:          # never lose the headline to a leg
+                legs[name] = {"workload": name, "failed": repr(e)}
 
     if rank == 0:
-        # ---- roofline of the dominant kernel ---------------------------------------------------------------
+        # ---- rooflines -------------------------------------------------------------------------------------------------
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         peaks = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
         pk_ms, pk_fl = h.bench_kernel(0, 30000, 0, 1)
         fp64_peak = pk_fl / pk_ms / 1e9
+        peak_source = ("FP64 DMMA issue-rate probe measured in this run (MEASURED_PEAKS.json has HBM and bf16 only: hbm_gbs=%s); "
+                       "cuBLAS DGEMM 8192^3 on this pool measured 35.5 TFLOP/s" % peaks.get("hbm_gbs"))
         achieved = syrk_flops / (syrk_ms / 1e3) / 1e12 if syrk_ms > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": "gemm_dmma_streamk_kernel<TN> (Hessian assembly G' diag(w) G, FP64 DMMA m8n8k4, persistent stream-K grid)",
+        big = n >= 8192
+        roofline = {"bound": "tensor",
+                    "kernel": "gemm_dmma_streamk_kernel<TN> (Hessian assembly G' diag(w) G, FP64 DMMA m8n8k4, persistent stream-K grid)",
                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                    "traffic": 111.9e6 if args.workload == "c2" else None, "traffic_source": "dram__bytes_read+write per launch, ncu --set full, "
-                    "profiles/r1_ncu_full_syrk_hessian_c2_n2000_m4000.txt (algorithmic: 64 MB read of G + 32 MB write of H; "
-                    "the rest is the stream-K partial tiles, 148 x 128 KB written and read back, and re-reads of G that "
-                    "miss L2 in ncu's cold-cache replay)" if args.workload == "c2" else None, "launches": n_syrk, "avg_launch_ms": syrk_ms / max(n_syrk, 1),
-                    "flops_per_launch": syrk_flops / max(n_syrk, 1),
-                    "peak_source": "FP64 DMMA issue-rate probe measured in this run (MEASURED_PEAKS.json has HBM and bf16 "
-                                   "only: hbm_gbs=%s); cuBLAS DGEMM 8192^3 on this pool measured 35.5 TFLOP/s" % peaks.get("hbm_gbs"),
-                    "share_of_step": syrk_ms / dev_ms if dev_ms > 0 else None}
-        # the HBM-bound kernels of the step (slack / gradient / line-search GEMVs over G), timed alone on this handle
+                    "traffic": 13.2e9 + 0.55e9 if big else (111.9e6 if args.workload == "c2" else None),
+                    "traffic_source": ("dram__bytes_read+write per launch, ncu --set full, profiles/r1_ncu_full_syrk_hessian_c4_n8192_m16384.txt "
+                                       "(algorithmic: 1.07 GB read of G + 0.54 GB write of H; the rest is tile rows re-reading G through "
+                                       "L2, 5 % of DRAM peak: the kernel is tensor-bound)") if big else None,
+                    "launches": n_syrk, "avg_launch_ms": syrk_ms / max(n_syrk, 1), "flops_per_launch": syrk_flops / max(n_syrk, 1),
+                    "peak_source": peak_source, "share_of_step": syrk_ms / dev_ms if dev_ms > 0 else None}
+        chol = roofline_from_range(
+            ranges["chol_trailing_update"],
+            "gemm_dmma_streamk_kernel<NT> (Cholesky trailing update A22 -= A21 A21', lower triangle, K = 2048..4096 at the "
+            "recursive levels of the n = %d factorisation)" % n, fp64_peak, peak_source, dev_ms)
+        # the same kernel timed alone at the two extreme shapes of the n = 8192 factorisation
+        alone = {}
+        for tag, (nn_, kk_) in (("top_level_4096x4096_K4096", (4096, 4096)), ("rank128_update_8064x8064_K128", (8064, 128))):
+            try:
+                ms_k, fl_k = h.bench_kernel(2, nn_, kk_, 5)
+                alone[tag] = {"ms": ms_k, "tflops": fl_k / ms_k / 1e9, "frac": fl_k / ms_k / 1e9 / fp64_peak}
+            except Exception as e:
+                alone[tag] = {"failed": repr(e)}
+        chol["timed_alone"] = alone
+        fcnt, fms, fwk = ranges["factor_h_with_trsm"]
+        breakdown = {"hessian_syrk": syrk_ms / dev_ms if dev_ms > 0 else None}
+        for k_, (c_, ms_, wk_) in ranges.items():
+            breakdown[k_] = {"share_of_step": ms_ / dev_ms if dev_ms > 0 else None, "ms_per_step": ms_ / max(steps_done, 1),
+                             "count": c_}
+        if fms > 0:
+            breakdown["factor_h_with_trsm"]["tflops"] = fwk / fms / 1e9
+        gc_, gms_, gby_ = ranges["gemv_g"]
+        # the HBM-bound kernels of the step (slack / gradient / line-search GEMVs over G): in-solve and timed alone
         hbm_peak = peaks.get("hbm_gbs")
         hbm = {}
-        if args.workload == "c2":
-            for which, name in ((7, "gemv_n (G x, G d)"), (8, "gemv_t (G' (1/d))")):
-                ms_k, by_k = h.bench_kernel(which, 2000, 4000, 20)
+        if gms_ > 0:
+            gbs = gby_ / gms_ / 1e6
+            hbm["gemv over G inside the solve (G x and G'(1/f), CUDA events in the timed region)"] = {
+                "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if hbm_peak else None,
+                "bytes_per_launch": gby_ / max(gc_, 1), "launches": gc_}
+        for which, name in ((7, "gemv_n (G x, G d) alone"), (8, "gemv_t (G' w) alone")):
+            try:
+                ms_k, by_k = h.bench_kernel(which, n, m, 10)
                 gbs = by_k / ms_k / 1e6
                 hbm[name] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": gbs / hbm_peak if hbm_peak else None, "bytes_per_launch": by_k,
-                             "note": "G is 64 MB: partly L2-resident between repeated launches"}
+                             "note": "G is %.0f MB (L2 is 126 MB)" % (by_k / 1e6)}
+            except Exception as e:
+                hbm[name] = {"failed": repr(e)}
         cpu = None
         if not args.no_cpu_baseline:
-            cores = os.cpu_count()
-            cs = args.cpu_steps or (40 if args.workload == "c2" else 20)
+            cs = args.cpu_steps or (2 if big else 20)
             try:
-                val, done, dt, sample = cpu_reference_leg(args.workload, cs, 2)
+                val, done, dt, sample, cores = cpu_reference_leg(args.workload, cs, 1)
                 cpu = {"value": val, "unit": "steps/s", "cores": cores, "kind": "port",
-                       "sample": "%d %s, %.1f s of CPU time (numpy/LAPACK oracle; the Scala reference needs a JVM this image lacks)"
-                                 % (done, sample, dt)}
+                       "sample": "%d %s, %.1f s of CPU time (numpy/LAPACK oracle, BLAS threads = %d; the Scala reference needs a JVM "
+                                 "this image lacks)" % (done, sample, dt, cores)}
             except Exception as e:      # never lose the GPU line to a CPU-side problem
-                cpu = {"value": None, "unit": "steps/s", "cores": cores, "kind": "port", "sample": "failed: %r" % (e,)}
-        last = st["last"]
+                cpu = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
         line = {"metric": "newton_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dev_ms_max / max(steps_done, 1), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.workload + ": " + w["desc"], "n": n, "m": m, "p": p,
+                "config": {"workload": args.workload + ": " + w["desc"], "n": n, "m": m, "p": p, "solver": solver_type,
                            "parallelism": "replicas only (one independent problem stream per GPU, no data-path collective)",
                            "l2": "working set per step (G, scaled G, H, L, RHS: %.0f MB) exceeds the 126 MB L2; no flush needed"
                                  % ((2 * m * n + 3 * n * n + n * (p + 1)) * 8 / 1e6),
                            "solves_started": st["solves"],
-                           "steps_counted": "%d phase-I Newton steps (dimension n+1, p = 0) + %d main-phase Newton steps "
-                                            "(p equalities, Schur complement), each from the start of full solves" % (K1, K2)},
+                           "steps_counted": ("%d primal-dual Newton iterations, each from the start of full solves" % K2) if solver_type == "PD"
+                           else ("%d phase-I Newton steps (dimension n+1, p = 0) + %d main-phase Newton steps (p equalities, Schur "
+                                 "complement), each from the start of full solves" % (K1, K2))},
                 "clocks": clk, "wall_ms_per_step": wall_ms_max / max(steps_done, 1),
                 "flops_per_step": f_step(n, m, p), "tflops": f_step(n, m, p) * value / world / 1e12,
-                "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d / max(e2e_steps, 1),
-                        "d2h_bytes_per_step": d2h / max(e2e_steps, 1), "steps": e2e_steps, "seconds": e2e_s, "checksum": xsum},
-                "gpu_launches": int(total_launches), "roofline": roofline, "hbm_kernels": hbm, "cpu_baseline": cpu, "batched": batched,
+                "tflops_frac_of_fp64_tensor_peak": f_step(n, m, p) * value / world / 1e12 / fp64_peak if fp64_peak else None,
+                "e2e": e2e, "gpu_launches": int(total_launches), "roofline": roofline, "roofline_chol_trailing": chol,
+                "step_breakdown": breakdown, "hbm_kernels": hbm, "cpu_baseline": cpu, "batched": batched, "legs": legs,
                 "last_solution": {"objective": last.objective, "outer_stages": last.outer_stages,
                                   "newton_steps": last.newton_steps, "phase1_newton_steps": last.phase1_newton_steps}}
         print(json.dumps(line))

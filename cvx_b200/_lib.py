@@ -130,6 +130,8 @@ SYMBOLS = {
     "cvxb_default_params": (C.c_int, [C.POINTER(Params)]),
     "cvxb_profile_enable": (C.c_int, [_vp, C.c_int]),
     "cvxb_profile_read": (C.c_int, [_vp, C.POINTER(C.c_longlong), _dp, _dp]),
+    "cvxb_profile_read_range": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_longlong), _dp, _dp]),
+    "cvxb_batch_device_records": (C.c_int, [_vp, C.POINTER(_vp), _ip]),
     "cvxb_kkt_solve": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_double, _vp, _vp,
                                  C.POINTER(KktInfo)]),
     "cvxb_kkt_solve_with_chol_factor": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp,
@@ -145,6 +147,7 @@ SYMBOLS = {
     "cvxb_kkt_solve_reduced": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_double, _vp, _vp,
                                          C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(KktInfo)]),
     "cvxb_solution_space_create": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.POINTER(C.c_void_p)]),
+    "cvxb_solution_space_from_basis": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.POINTER(C.c_void_p)]),
     "cvxb_solution_space_destroy": (C.c_int, [_vp]),
     "cvxb_solution_space_get": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
     "cvxb_solution_space_parameter": (C.c_int, [_vp, _vp, _vp, _vp]),
@@ -253,6 +256,16 @@ class Handle:
         n, ms, fl = C.c_longlong(), C.c_double(), C.c_double()
         check(self.lib.cvxb_profile_read(self._h, C.byref(n), C.byref(ms), C.byref(fl)))
         return n.value, ms.value, fl.value
+
+    PROF_RANGES = {"hessian_syrk": 0, "chol_trailing_update": 1, "factor_h_with_trsm": 2, "schur_syrk": 3, "ruiz": 4,
+                   "gemv_g": 5}
+
+    def profile_read_range(self, which):
+        """(count, total ms, total algorithmic work) of one timed range of the step (cvxb_profile_read_range)."""
+        rid = self.PROF_RANGES[which] if isinstance(which, str) else int(which)
+        n, ms, wk = C.c_longlong(), C.c_double(), C.c_double()
+        check(self.lib.cvxb_profile_read_range(self._h, rid, C.byref(n), C.byref(ms), C.byref(wk)))
+        return n.value, ms.value, wk.value
 
     # measurement helper (bench.py)
     def bench_kernel(self, which: int, n: int, k: int, reps: int):

@@ -86,20 +86,43 @@ class BatchedBarrierSolver:
         self._b = C.c_void_p()
         check(self.handle.lib.cvxb_batch_create(self.handle._h, C.byref(d), C.byref(self._b)))
 
-    def solve(self) -> BatchSolution:
+    def solve(self, download: bool = True) -> BatchSolution:
+        """One launch of the batched barrier kernel.  download=False leaves every result on the device (the packed
+        records of cvxb_batch_device_records, which `gather_solutions` ships with one all-gather)."""
         B, n = self.B, self.n
+        r = BatchResult()
+        cp = self.pars.to_c(self.handle)
+        if not download:
+            check(self.handle.lib.cvxb_batch_barrier_solve(self.handle._h, self._b, C.byref(cp), C.byref(r)))
+            return BatchSolution(None, None, None, None, None, None, None, float(r.solve_ms))
         x = np.empty((B, n))
         status = np.empty(B, dtype=np.int32)
         steps = np.empty(B, dtype=np.int32)
         stages = np.empty(B, dtype=np.int32)
         objv, gap, eqg = np.empty(B), np.empty(B), np.empty(B)
-        r = BatchResult()
         ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
         r.x, r.status, r.newton_steps, r.outer_stages = dptr(x), ip(status), ip(steps), ip(stages)
         r.objective, r.duality_gap, r.equality_gap = dptr(objv), dptr(gap), dptr(eqg)
-        cp = self.pars.to_c(self.handle)
         check(self.handle.lib.cvxb_batch_barrier_solve(self.handle._h, self._b, C.byref(cp), C.byref(r)))
         return BatchSolution(x, status, steps, stages, objv, gap, eqg, float(r.solve_ms))
+
+    def device_records(self):
+        """(device pointer, doubles per row) of the packed results of the last solve:
+        rows [x(n), objective, duality gap, status, newton steps, outer stages]."""
+        p = C.c_void_p()
+        row = C.c_int()
+        check(self.handle.lib.cvxb_batch_device_records(self._b, C.byref(p), C.byref(row)))
+        return int(p.value), int(row.value)
+
+    def device_records_tensor(self):
+        """The packed results as a torch CUDA tensor that aliases the library's buffer (no copy)."""
+        import torch
+        ptr_, row = self.device_records()
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (self.B, row), "typestr": "<f8", "data": (ptr_, False), "version": 3,
+                                        "strides": None}
+        return torch.as_tensor(_View(), device=torch.device("cuda", self.handle.device))
 
     def close(self):
         if getattr(self, "_b", None):
@@ -120,31 +143,55 @@ def shard_range(B: int, rank: int, world: int):
     return lo, min(B, lo + per)
 
 
-def gather_solutions(local: BatchSolution, B: int, n: int, group=None):
-    """Final exchange of the sharded batch: all-gather of x (B x n doubles) and of the per-problem
-    status / step counts, plus one all-reduce of (converged count, max Newton steps).  Works on any
-    torch.distributed backend (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+RECORD_EXTRA = 5     # CVXB_BATCH_RECORD_EXTRA: objective, duality gap, status, newton steps, outer stages
+
+
+def pack_records(local: BatchSolution) -> np.ndarray:
+    """Host-side twin of the device record layout (used on the gloo path of the CPU tests)."""
+    k, n = local.x.shape
+    rec = np.empty((k, n + RECORD_EXTRA))
+    rec[:, :n] = local.x
+    rec[:, n] = local.objective
+    rec[:, n + 1] = local.dualityGap
+    rec[:, n + 2] = local.status
+    rec[:, n + 3] = local.newton_steps
+    rec[:, n + 4] = local.outer_stages
+    return rec
+
+
+def gather_solutions(local, B: int, n: int, group=None):
+    """Final exchange of the sharded batch: ONE all-gather of the packed per-problem records
+    [x(n), objective, gap, status, newton steps, outer stages]; the global convergence figures (converged count, max
+    Newton steps) are computed from the gathered status / step columns, so no separate reduction is needed.
+    `local` is a BatchedBarrierSolver whose results are still on the device (NCCL over NVLink: the library's record
+    buffer is handed to the all-gather as is, then one device-to-host copy of the gathered block) or a BatchSolution
+    on the host (gloo in the CPU tests)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     per = (B + world - 1) // world
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    xbuf = torch.zeros(per, n, dtype=torch.float64, device=dev)
-    ibuf = torch.zeros(per, 3, dtype=torch.int32, device=dev)
-    k = local.x.shape[0]
-    if k:
-        xbuf[:k] = torch.from_numpy(local.x).to(dev)
-        ibuf[:k, 0] = torch.from_numpy(local.status).to(dev)
-        ibuf[:k, 1] = torch.from_numpy(local.newton_steps).to(dev)
-        ibuf[:k, 2] = torch.from_numpy(local.outer_stages).to(dev)
-    xs = torch.empty(world * per, n, dtype=torch.float64, device=dev)
-    is_ = torch.empty(world * per, 3, dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(xs, xbuf, group=group)
-    dist.all_gather_into_tensor(is_, ibuf, group=group)
-    conv = torch.tensor([int((local.status == 0).sum())], dtype=torch.int64, device=dev)
-    mx = torch.tensor([int(local.newton_steps.max()) if k else 0], dtype=torch.int64, device=dev)
-    dist.all_reduce(conv, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    xs, is_ = xs[:B].cpu().numpy(), is_[:B].cpu().numpy()
-    return dict(x=xs, status=is_[:, 0], newton_steps=is_[:, 1], outer_stages=is_[:, 2], converged=int(conv.item()),
-                max_newton_steps=int(mx.item()))
+    row = n + RECORD_EXTRA
+    nccl = dist.get_backend(group) == "nccl"
+    if isinstance(local, BatchedBarrierSolver):
+        rec = local.device_records_tensor()
+        dev = rec.device
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+        rec = torch.from_numpy(pack_records(local)).to(dev) if local.x.shape[0] else torch.zeros(0, row, dtype=torch.float64, device=dev)
+    k = rec.shape[0]
+    if k != per:          # the last shard may be short: pad with status -1 rows
+        pad = torch.zeros(per, row, dtype=torch.float64, device=dev)
+        pad[:, n + 2] = -1.0
+        pad[:k] = rec
+        rec = pad
+    out = torch.empty(world * per, row, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
+    # drop the padding rows of short shards, keep problem order
+    keep = torch.cat([torch.arange(r_ * per, r_ * per + (shard_range(B, r_, world)[1] - shard_range(B, r_, world)[0]))
+                      for r_ in range(world)]).to(dev)
+    g = out.index_select(0, keep).cpu().numpy()
+    status = g[:, n + 2].astype(np.int32)
+    steps = g[:, n + 3].astype(np.int32)
+    return dict(x=np.ascontiguousarray(g[:, :n]), objective=g[:, n].copy(), dualityGap=g[:, n + 1].copy(), status=status,
+                newton_steps=steps, outer_stages=g[:, n + 4].astype(np.int32), converged=int((status == 0).sum()),
+                max_newton_steps=int(steps.max()) if steps.size else 0)

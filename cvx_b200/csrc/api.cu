@@ -74,11 +74,27 @@ static KktWork* cached_work(Handle& h, int n, int p, int* status) {
   return W;
 }
 
-struct DeviceGuard {
-  int prev = 0;
-  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
-  ~DeviceGuard() { cudaSetDevice(prev); }
-};
+int prof_begin(Handle& h, int id) {
+  if (!h.prof_on || h.capturing || id <= 0 || id >= PROF_COUNT) return CVXB_OK;
+  Handle::ProfRange& R = h.prof_range[id];
+  if (R.used + 2 > R.ev.size())
+    for (int i = 0; i < 64; ++i) {
+      cudaEvent_t e;
+      CVXB_CUDA_OK(cudaEventCreate(&e));
+      R.ev.push_back(e);
+    }
+  CVXB_CUDA_OK(cudaEventRecord(R.ev[R.used], h.stream));
+  return CVXB_OK;
+}
+int prof_end(Handle& h, int id, double work) {
+  if (!h.prof_on || h.capturing || id <= 0 || id >= PROF_COUNT) return CVXB_OK;
+  Handle::ProfRange& R = h.prof_range[id];
+  if (R.used + 2 > R.ev.size()) return CVXB_OK;
+  CVXB_CUDA_OK(cudaEventRecord(R.ev[R.used + 1], h.stream));
+  R.used += 2;
+  R.work += work;
+  return CVXB_OK;
+}
 
 // KKTData.reduced (KKTData.scala:68-91): column j is "null" when ||H(:,j)|| + ||A(:,j)|| == 0
 __global__ void null_column_kernel(int n, int p, const double* __restrict__ H, int ldh, const double* __restrict__ A, int lda,
@@ -160,7 +176,7 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
     return CVXB_ECUDA;
   }
   if (device < 0 || device >= count) { cvxb::set_last_error("cvxb_create: bad device %d", device); return CVXB_EINVAL; }
-  CVXB_CUDA_OK(cudaSetDevice(device));
+  cvxb::DeviceGuard _guard(device);
   cudaDeviceProp prop;
   CVXB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) {
@@ -241,6 +257,7 @@ int cvxb_destroy(cvxb_handle h) {
   cudaFreeHost(h->h_scal); cudaFreeHost(h->h_flag);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->gev0); cudaEventDestroy(h->gev1);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  for (auto& R : h->prof_range) for (cudaEvent_t e : R.ev) cudaEventDestroy(e);
   for (cudaEvent_t e : h->la_events) cudaEventDestroy(e);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -264,6 +281,25 @@ int cvxb_profile_enable(cvxb_handle h, int on) {
   h->prof_flops = 0.0;
   h->prof_ms_graph = 0.0;
   h->prof_launches_graph = 0;
+  for (auto& R : h->prof_range) { R.used = 0; R.work = 0.0; }
+  return CVXB_OK;
+}
+
+int cvxb_profile_read_range(cvxb_handle h, int range, long long* count, double* ms_total, double* work_total) {
+  CHECK_HANDLE(h);
+  if (range == PROF_HESSIAN) return cvxb_profile_read(h, count, ms_total, work_total);
+  if (range < 0 || range >= PROF_COUNT) { cvxb::set_last_error("cvxb_profile_read_range: unknown range %d", range); return CVXB_EINVAL; }
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  Handle::ProfRange& R = h->prof_range[range];
+  double ms = 0;
+  for (size_t i = 0; i + 1 < R.used; i += 2) {
+    float t = 0;
+    CVXB_CUDA_OK(cudaEventElapsedTime(&t, R.ev[i], R.ev[i + 1]));
+    ms += t;
+  }
+  if (count) *count = (long long)(R.used / 2);
+  if (ms_total) *ms_total = ms;
+  if (work_total) *work_total = R.work;
   return CVXB_OK;
 }
 
@@ -392,8 +428,43 @@ int cvxb_solution_space_create(cvxb_handle h, int p, int n, const double* A, int
   return CVXB_OK;
 }
 
+int cvxb_solution_space_from_basis(cvxb_handle h, int n, int k, const double* z0, const double* F, int ldf,
+                                   cvxb_solution_space* out) {
+  CHECK_HANDLE(h);
+  if (!z0 || !F || !out) { cvxb::set_last_error("cvxb_solution_space_from_basis: null argument"); return CVXB_EINVAL; }
+  if (!(k >= 1 && k <= n)) { cvxb::set_last_error("affineTransformed: need 1 <= F.cols <= F.rows (got %d x %d)", n, k); return CVXB_EDIM; }
+  if (ldf < n) { cvxb::set_last_error("leading dimension %d < rows %d", ldf, n); return CVXB_EDIM; }
+  SolutionSpaceDev* S = new SolutionSpaceDev();
+  S->n = n; S->p = n - k; S->ldq = pad_ld(n);
+  S->device = h->device; S->stream = h->stream;
+  const bool dev = (h->flags & CVXB_FLAG_DEVICE_PTRS) != 0;
+  const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  cudaError_t e = cudaMalloc((void**)&S->Fext, sizeof(double) * (size_t)S->ldq * k);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&S->z0, sizeof(double) * (size_t)S->ldq);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&S->tmp, sizeof(double) * 2 * (size_t)S->ldq);
+  if (e == cudaSuccess) e = cudaMemsetAsync(S->Fext, 0, sizeof(double) * (size_t)S->ldq * k, h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(S->z0, 0, sizeof(double) * (size_t)S->ldq, h->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(S->Fext, sizeof(double) * (size_t)S->ldq, F, sizeof(double) * (size_t)ldf, sizeof(double) * (size_t)n, k,
+                          kind, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(S->z0, z0, sizeof(double) * (size_t)n, kind, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) {
+    cvxb::set_last_error("CUDA error %s in cvxb_solution_space_from_basis", cudaGetErrorString(e));
+    solution_space_free(S);
+    return CVXB_ECUDA;
+  }
+  *out = (cvxb_solution_space)S;
+  return CVXB_OK;
+}
+
 int cvxb_solution_space_destroy(cvxb_solution_space space) {
-  if (space) { cudaDeviceSynchronize(); solution_space_free((SolutionSpaceDev*)space); }
+  if (space) {
+    SolutionSpaceDev* S = (SolutionSpaceDev*)space;
+    cvxb::DeviceGuard _guard(S->device);
+    if (S->stream) cudaStreamSynchronize(S->stream); else cudaDeviceSynchronize();
+    solution_space_free(S);
+  }
   return CVXB_OK;
 }
 

@@ -26,6 +26,7 @@ struct cvxb_batch_s {
   // outputs (device)
   double *x = nullptr, *objval = nullptr, *gap = nullptr, *eqgap = nullptr;
   int *status = nullptr, *steps = nullptr, *stages = nullptr;
+  double* records = nullptr;     // B x (n + CVXB_BATCH_RECORD_EXTRA): [x, objective, gap, status, steps, stages] per problem
   double* scratch = nullptr;     // per-CTA copy of H (n x n)
   unsigned* counter = nullptr;
   int grid = 0;
@@ -49,6 +50,7 @@ struct BatchArgs {
   const double *obj_a, *obj_r, *obj_P, *G, *ub, *A, *b, *x0;
   double *x, *objval, *gap, *eqgap;
   int *status, *steps, *stages;
+  double* records;
   double* scratch;
   unsigned* counter;
   cvxb_params P;
@@ -664,6 +666,14 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
       ++stage;
     }
     if (tid < n) A.x[(size_t)pid * n + tid] = S.x[tid];
+    {   // the packed record the multi-GPU gather ships (one all-gather, no host staging)
+      double* rec = A.records + (size_t)pid * (n + CVXB_BATCH_RECORD_EXTRA);
+      if (tid < n) rec[tid] = S.x[tid];
+      if (tid == 0) {
+        rec[n] = objv; rec[n + 1] = gap; rec[n + 2] = (double)status; rec[n + 3] = (double)total_steps;
+        rec[n + 4] = (double)stage;
+      }
+    }
     if (tid == 0) {
       A.status[pid] = status;
       A.steps[pid] = total_steps;
@@ -710,7 +720,30 @@ int cvxb_batch_create(cvxb_handle h, const cvxb_batch_desc* d, cvxb_batch* out) 
     cvxb::set_last_error("cvxb_batch_create: missing array");
     return CVXB_EINVAL;
   }
-  cudaSetDevice(h->device);
+  if (!(h->flags & CVXB_FLAG_DEVICE_PTRS)) {
+    // host descriptors: refuse what the kernel has no branch for instead of solving something else silently
+    for (int i = 0; i < d->B; ++i) {
+      const int k = d->objective[i];
+      if (k != CVXB_OBJ_LINEAR && k != CVXB_OBJ_QUADRATIC && k != CVXB_OBJ_KL) {
+        cvxb::set_last_error("cvxb_batch_create: problem %d has objective kind %d; the batched solver handles LINEAR, "
+                             "QUADRATIC and KL", i, k);
+        return CVXB_ENOTIMPL;
+      }
+      if ((k == CVXB_OBJ_LINEAR || k == CVXB_OBJ_QUADRATIC) && (!d->obj_a || !d->obj_r)) {
+        cvxb::set_last_error("cvxb_batch_create: problem %d is linear / quadratic but obj_a or obj_r is NULL", i);
+        return CVXB_EINVAL;
+      }
+      if (k == CVXB_OBJ_QUADRATIC && !d->obj_P) {
+        cvxb::set_last_error("cvxb_batch_create: problem %d is quadratic but obj_P is NULL", i);
+        return CVXB_EINVAL;
+      }
+      if (d->pcount && (d->pcount[i] < 0 || d->pcount[i] > d->p)) {
+        cvxb::set_last_error("cvxb_batch_create: pcount[%d] = %d outside 0..p = %d", i, d->pcount[i], d->p);
+        return CVXB_EDIM;
+      }
+    }
+  }
+  cvxb::DeviceGuard _guard(h->device);
   cvxb_batch_s* Bt = new cvxb_batch_s();
   Bt->h = h; Bt->B = d->B; Bt->n = d->n; Bt->m = d->m; Bt->p = d->p;
   const size_t B = d->B, n = d->n, m = d->m;
@@ -727,6 +760,7 @@ int cvxb_batch_create(cvxb_handle h, const cvxb_batch_desc* d, cvxb_batch* out) 
   T(bupload(Bt, &Bt->x0, d->x0, B * n));
   T(balloc(Bt, &Bt->x, B * n)); T(balloc(Bt, &Bt->objval, B)); T(balloc(Bt, &Bt->gap, B)); T(balloc(Bt, &Bt->eqgap, B));
   T(balloc(Bt, &Bt->status, B)); T(balloc(Bt, &Bt->steps, B)); T(balloc(Bt, &Bt->stages, B));
+  T(balloc(Bt, &Bt->records, B * (n + CVXB_BATCH_RECORD_EXTRA)));
   Bt->grid = h->sm_count * 2;
   if (Bt->grid > d->B) Bt->grid = d->B;
   T(balloc(Bt, &Bt->scratch, (size_t)Bt->grid * BN * BN));
@@ -746,9 +780,16 @@ int cvxb_debug_batch_clocks(long long* out, int reset) {
   return CVXB_OK;
 }
 
+int cvxb_batch_device_records(cvxb_batch Bt, double** dev_records, int* row_doubles) {
+  if (!Bt || !dev_records) { cvxb::set_last_error("cvxb_batch_device_records: null argument"); return CVXB_EINVAL; }
+  *dev_records = Bt->records;
+  if (row_doubles) *row_doubles = Bt->n + CVXB_BATCH_RECORD_EXTRA;
+  return CVXB_OK;
+}
+
 int cvxb_batch_destroy(cvxb_batch Bt) {
   if (!Bt) return CVXB_OK;
-  cudaSetDevice(Bt->h->device);
+  cvxb::DeviceGuard _guard(Bt->h->device);
   cudaStreamSynchronize(Bt->h->stream);
   for (void* q : Bt->owned) cudaFree(q);
   delete Bt;
@@ -758,7 +799,7 @@ int cvxb_batch_destroy(cvxb_batch Bt) {
 int cvxb_batch_barrier_solve(cvxb_handle h, cvxb_batch Bt, const cvxb_params* pars, cvxb_batch_result* out) {
   if (!h || !Bt || !out) { cvxb::set_last_error("cvxb_batch_barrier_solve: null argument"); return CVXB_EINVAL; }
   if (Bt->h != h) { cvxb::set_last_error("batch belongs to another handle"); return CVXB_EINVAL; }
-  cudaSetDevice(h->device);
+  cvxb::DeviceGuard _guard(h->device);
   cvxb_params dp;
   if (!pars) { cvxb_default_params(&dp); pars = &dp; }
   CVXB_CUDA_OK(cudaFuncSetAttribute(batched_barrier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
@@ -767,7 +808,7 @@ int cvxb_batch_barrier_solve(cvxb_handle h, cvxb_batch Bt, const cvxb_params* pa
   A.objective = Bt->objective; A.pcount = Bt->pcount; A.obj_a = Bt->obj_a; A.obj_r = Bt->obj_r; A.obj_P = Bt->obj_P; A.G = Bt->G; A.ub = Bt->ub;
   A.A = Bt->A; A.b = Bt->b; A.x0 = Bt->x0;
   A.x = Bt->x; A.objval = Bt->objval; A.gap = Bt->gap; A.eqgap = Bt->eqgap;
-  A.status = Bt->status; A.steps = Bt->steps; A.stages = Bt->stages;
+  A.status = Bt->status; A.steps = Bt->steps; A.stages = Bt->stages; A.records = Bt->records;
   A.scratch = Bt->scratch; A.counter = Bt->counter; A.P = *pars;
   CVXB_CUDA_OK(cudaMemsetAsync(Bt->counter, 0, sizeof(unsigned), h->stream));
   CVXB_CUDA_OK(cudaEventRecord(h->ev0, h->stream));

@@ -70,9 +70,18 @@ struct cvxb_handle_s {
   long long prof_launches_graph = 0;
   int use_graphs = 1;
   int prof_on = 0;
-  std::vector<cudaEvent_t> prof_events;   // start/stop pairs
+  std::vector<cudaEvent_t> prof_events;   // start/stop pairs (range PROF_HESSIAN)
   size_t prof_used = 0;
   double prof_flops = 0.0;
+  // further timed ranges of one Newton step (cvxb_profile_read_range; plain launches only, not inside a captured step)
+  struct ProfRange {
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    double work = 0.0;
+  };
+  ProfRange prof_range[8];
+  // a stream-K grid may be asked to leave some SMs to the kernels of a concurrent critical chain
+  int sk_reserve = 0;
 };
 
 namespace cvxb {
@@ -91,6 +100,26 @@ struct Arena {
   }
 };
 constexpr int NSCAL = 128, NFLAG = 64;
+
+// every extern "C" entry point switches to the handle's device and restores the caller's on return
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// timed ranges (cvxb_profile_read_range): CUDA events on the handle's stream around a piece of the step
+enum ProfId {
+  PROF_HESSIAN = 0,      // Hessian-assembly SYRK G' diag(w) G (kept in prof_events for the captured-step path)
+  PROF_CHOL_TRAIL = 1,   // Cholesky trailing updates A22 -= A21 A21' of the recursive levels (NT SYRK, lower)
+  PROF_FACTOR = 2,       // Ruiz-scaled Cholesky of H with the forward substitution of [DA', Dq] riding along
+  PROF_SCHUR = 3,        // Schur complement S = Y'Y (TN SYRK, mirrored)
+  PROF_RUIZ = 4,         // ruizEquilibrate(H)
+  PROF_GEMV = 5,         // the HBM-bound GEMVs over G of one step (bytes instead of flops)
+  PROF_COUNT = 8
+};
+int prof_begin(cvxb_handle_s& h, int id);
+int prof_end(cvxb_handle_s& h, int id, double work);
 constexpr size_t PART_DOUBLES = (size_t)1 << 22;   // 32 MiB of split-K partials for gemv_n
 
 // count + launch + error check

@@ -766,7 +766,9 @@ int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot,
   // A22 -= A21 A21'  lower: A(m,k) = A21[k*lda + m] (M contiguous), B(k,n) = A21(n,k) (N contiguous)
   GemmArgs g{b, b, a, A21, lda, false, A21, lda, false, A22, lda, -1.0, 1.0, 1};
   g.streamk = true;      // main stream only (the look-ahead schedule has joined)
+  CVXB_TRY(prof_begin(h, PROF_CHOL_TRAIL));
   CVXB_TRY(gemm_dmma(h, g));
+  CVXB_TRY(prof_end(h, PROF_CHOL_TRAIL, (double)a * b * ((double)b + 1.0)));      // lower triangle, mul + add
   if (B) {   // B2 -= L21 Y1
     GemmArgs gu{b, r, a, A21, lda, false, B, ldb, true, B + a, ldb, -1.0, 1.0, 0};
     CVXB_TRY(gemm_dmma(h, gu));

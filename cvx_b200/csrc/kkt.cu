@@ -235,7 +235,11 @@ int kkt_enqueue(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, i
     CVXB_LAUNCH(h, prefactored_reset_kernel, 1, 1, 0, h.d_flag, h.d_scal);
     CVXB_TRY(invert_diag_blocks(h, n, W.L, W.ldn, W.invD));
   } else {
-    if (!skip_ruiz) CVXB_TRY(ruiz_equilibrate(h, n, Hm, ldh, W.dr, W.colsq, P.ruizMaxSweeps, P.ruizTol));
+    if (!skip_ruiz) {
+      CVXB_TRY(prof_begin(h, PROF_RUIZ));
+      CVXB_TRY(ruiz_equilibrate(h, n, Hm, ldh, W.dr, W.colsq, P.ruizMaxSweeps, P.ruizTol));
+      CVXB_TRY(prof_end(h, PROF_RUIZ, 8.0 * n * n));       // bytes per sweep; sweeps taken are in F_RUIZ_SWEEPS
+    }
     CVXB_TRY(scaled_lower(h, n, Hm, ldh, W.dr, regularize ? P.cholRegDelta : 0.0, W.L, W.ldn));
   }
   // right-hand sides  [D A', D q]
@@ -243,12 +247,17 @@ int kkt_enqueue(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, i
   double* yq = W.Y + (size_t)p * W.ldn;
   CVXB_LAUNCH(h, kkt_rhs_kernel, 1, VT, 0, n, p, W.dr, q, b, W.qs, yq, h.d_scal, h.d_flag);
   if (prefactored) CVXB_TRY(trsm_lower(h, n, p + 1, W.L, W.ldn, W.invD, W.Y, W.ldn, false));
-  else   // factorisation with Y = L^-1 [DA', Dq] riding along
+  else {  // factorisation with Y = L^-1 [DA', Dq] riding along
+    CVXB_TRY(prof_begin(h, PROF_FACTOR));
     CVXB_TRY(potrf_lower_rhs(h, n, W.L, W.ldn, W.invD, F_CHOL_H, S_MINDIAG_H, W.Y, W.ldn, p + 1));
+    CVXB_TRY(prof_end(h, PROF_FACTOR, (double)n * n * n / 3.0 + (double)n * n * (p + 1)));
+  }
   // Schur complement S = Yp'Yp and its (plain, unregularised) Cholesky  KKTSystem.scala:126-140
   GemmArgs g{p, p, n, W.Y, W.ldn, true, W.Y, W.ldn, true, W.S, W.ldp, 1.0, 0.0, 2};
   g.streamk = true;
+  CVXB_TRY(prof_begin(h, PROF_SCHUR));
   CVXB_TRY(gemm_dmma(h, g));
+  CVXB_TRY(prof_end(h, PROF_SCHUR, (double)n * p * ((double)p + 1.0)));
   // z = -(b + A H^-1 q) = -(b + Yp' yq) ; w = K^-T K^-1 z  (the forward half rides along with the factorisation of S)
   CVXB_TRY(gemv_t(h, n, p, 1.0, W.Y, W.ldn, yq, 0.0, W.tp));
   CVXB_LAUNCH(h, kkt_z_kernel, 1, VT, 0, p, b, W.tp, w);

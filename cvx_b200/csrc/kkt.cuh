@@ -23,10 +23,13 @@ struct KktWork {
 // SolutionSpace of A x = b (SolutionSpace.scala:20-33), device resident (qr.cu): x = z0 + F u
 struct SolutionSpaceDev {
   int n = 0, p = 0, ldq = 0;
+  int device = 0;           // the creating handle's device and stream (destroy synchronises that stream only)
+  cudaStream_t stream = nullptr;
   double* Q = nullptr;      // n x n orthogonal factor of A' = QR; F = Q(:, p..n-1)
   double* z0 = nullptr;     // minimum-norm solution
   double* tmp = nullptr;    // 2 * pad_ld(n) scratch
-  double* F() const { return Q + (size_t)p * ldq; }
+  double* Fext = nullptr;   // basis handed in by the caller (cvxb_solution_space_from_basis): n x k, leading dimension ldq; Q unused
+  double* F() const { return Fext ? Fext : Q + (size_t)p * ldq; }
   int k() const { return n - p; }
 };
 int solution_space_build(Handle& h, int p, int n, const double* A, int lda, const double* b, SolutionSpaceDev** out);

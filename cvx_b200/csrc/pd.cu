@@ -259,7 +259,8 @@ int pd_alloc(cvxb_problem_s* P) {
   for (double** v : nv) CVXB_TRY(palloc2(P, v, (size_t)P->ldn));
   double** pv[] = {&P->dnu, &P->Adx, &P->pres, &P->nu0s, &P->pres0s, &P->negpres};
   for (double** v : pv) CVXB_TRY(palloc2(P, v, (size_t)P->ldp));
-  CVXB_TRY(palloc2(P, &P->Hreg, (size_t)P->ldn * P->n));
+  // the n x n scratch of SymmetricLinearSystem.solve is only needed without equality constraints
+  if (P->p == 0 && !P->Hreg) CVXB_TRY(palloc2(P, &P->Hreg, (size_t)P->ldn * P->n));
   return CVXB_OK;
 }
 
@@ -268,10 +269,14 @@ int pd_assemble(cvxb_problem_s* P, const cvxb_params& pars, double t) {
   Handle& h = *P->h;
   const int n = P->n, m = P->m, p = P->p;
   CVXB_TRY(quad_refresh(P));
+  CVXB_TRY(prof_begin(h, PROF_GEMV));
   CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->x, 0.0, P->gx));
+  CVXB_TRY(prof_end(h, PROF_GEMV, 8.0 * m * n));
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->Px));
   CVXB_LAUNCH(h, pd_cnt_kernel, 1, VT, 0, m, t, P->gr, P->ub, P->gx, P->lam, P->tmpm, P->wts, P->inv, P->qcorr, h.d_scal, h.d_flag);
+  CVXB_TRY(prof_begin(h, PROF_GEMV));
   CVXB_TRY(gemv_t(h, m, n, 1.0, P->G, P->ldm, P->inv, 0.0, P->gt));
+  CVXB_TRY(prof_end(h, PROF_GEMV, 8.0 * m * n));
   CVXB_TRY(gemv_t(h, m, n, 1.0, P->G, P->ldm, P->lam, 0.0, P->rd0));
   if (p > 0) {
     CVXB_TRY(gemv_t(h, p, n, 1.0, P->A, P->ldp, P->nu, 0.0, P->atnu));
@@ -499,8 +504,8 @@ extern "C" {
 int cvxb_pd_solve(cvxb_handle h, cvxb_problem prob, const cvxb_params* pars, cvxb_solution* out) {
   if (!h || !prob || !out) { cvxb::set_last_error("cvxb_pd_solve: null argument"); return CVXB_EINVAL; }
   if (prob->h != h) { cvxb::set_last_error("problem belongs to another handle"); return CVXB_EINVAL; }
-  cudaSetDevice(h->device);
-  cvxb_params dp;
+  cvxb::DeviceGuard guard(h->device);
+  cvxb_params dp, lp;
   if (!pars) { cvxb_default_params(&dp); pars = &dp; }
   double *ox = out->x, *ol = out->lambda, *onu = out->nu;
   memset(out, 0, sizeof(*out));
@@ -515,6 +520,22 @@ int cvxb_pd_solve(cvxb_handle h, cvxb_problem prob, const cvxb_params* pars, cvx
     out->phase1_newton_steps = ph.newton_steps; out->phase1_executed_steps = ph.executed_newton_steps;
     out->phase1_stages = ph.outer_stages; out->phase1_s = ph.phase1_s;
     if (st != CVXB_OK) return st;
+    if (limited) {
+      if (budget <= 0 || !prob->has_feasible) {
+        // step budget used up inside phase I (no feasible point yet): report the phase-I iterate, as cvxb_barrier_solve does
+        cudaEventRecord(h->ev1, h->stream);
+        cudaEventSynchronize(h->ev1);
+        float ms1 = 0;
+        cudaEventElapsedTime(&ms1, h->ev0, h->ev1);
+        out->solve_ms = ms1;
+        CVXB_TRY(download_vec(*h, out->x, prob->phase1->x, prob->n));
+        CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+        return CVXB_OK;
+      }
+      lp = *pars;
+      lp.stepLimit = budget;           // the primal-dual loop gets what phase I left over
+      pars = &lp;
+    }
   }
   CVXB_CUDA_OK(cudaMemcpyAsync(prob->x, prob->x_feas, prob->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   int st = pd_loop(prob, *pars, out);
@@ -536,7 +557,7 @@ int cvxb_pd_newton_direction(cvxb_handle h, cvxb_problem prob, const cvxb_params
                              double* dnu, cvxb_kkt_info* info) {
   if (!h || !prob || !x || !lambda) { cvxb::set_last_error("cvxb_pd_newton_direction: null argument"); return CVXB_EINVAL; }
   if (prob->h != h) { cvxb::set_last_error("problem belongs to another handle"); return CVXB_EINVAL; }
-  cudaSetDevice(h->device);
+  cvxb::DeviceGuard guard(h->device);
   cvxb_params dp;
   if (!pars) { cvxb_default_params(&dp); pars = &dp; }
   cvxb_problem_s* P = prob;

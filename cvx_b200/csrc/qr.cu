@@ -150,6 +150,7 @@ __global__ void add_vec_kernel(int n, const double* __restrict__ a, double* __re
 void solution_space_free(SolutionSpaceDev* S) {
   if (!S) return;
   if (S->Q) cudaFree(S->Q);
+  if (S->Fext) cudaFree(S->Fext);
   if (S->z0) cudaFree(S->z0);
   if (S->tmp) cudaFree(S->tmp);
   delete S;
@@ -160,6 +161,7 @@ int solution_space_build(Handle& h, int p, int n, const double* A, int lda, cons
   if (!(p >= 1 && p < n)) { set_last_error("SolutionSpace: need 1 <= A.rows < A.cols (got %d x %d)", p, n); return CVXB_EDIM; }
   SolutionSpaceDev* S = new SolutionSpaceDev();
   S->n = n; S->p = p; S->ldq = pad_ld(n);
+  S->device = h.device; S->stream = h.stream;
   const int ldm = pad_ld(n);
   double *M = nullptr, *V = nullptr, *T = nullptr, *W = nullptr;
   int* d_flag = nullptr;

@@ -398,7 +398,8 @@ int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s*
     size_t d = 2 * ldm * n + ldn * n * (objective == CVXB_OBJ_QUADRATIC ? 2 : 1) + ldp * n + 7 * ldm + 10 * ldn + 4 * ldp;
     if (mq > 0) d += (size_t)mq * P->ldq * (n + 3) + 4 * 32;
     if (objective == CVXB_OBJ_KLDUAL) d += 2 * ldn * (size_t)kd + 4 * (size_t)pad_ld(kd) + 6 * 32;
-    size_t bytes = d * sizeof(double) + 64 * 256 + kkt_work_bytes(n, p);
+    d += 6 * ldm + 9 * ldn + 6 * ldp;      // primal-dual work vectors (pd_alloc): no allocation inside the first PD solve
+    size_t bytes = d * sizeof(double) + 96 * 256 + kkt_work_bytes(n, p);
     void* base = nullptr;
     // stream-ordered pool of the handle's device (release threshold = keep everything): the second problem of a
     // similar size re-uses the first one's memory instead of paying a fresh cudaMalloc of hundreds of MB
@@ -884,7 +885,7 @@ int download_vec(Handle& h, double* dst, const double* src, int n) {
 #define CHECK_HP(h, prob)                                                                        \
   if (!(h) || !(prob)) { cvxb::set_last_error("null handle or problem"); return CVXB_EINVAL; }  \
   if ((prob)->h != (h)) { cvxb::set_last_error("problem belongs to another handle"); return CVXB_EINVAL; } \
-  int _prev_dev = 0; cudaGetDevice(&_prev_dev); cudaSetDevice((h)->device)
+  cvxb::DeviceGuard _guard((h)->device)
 
 extern "C" {
 
@@ -912,7 +913,7 @@ int cvxb_problem_create(cvxb_handle h, const cvxb_problem_desc* d, cvxb_problem*
     cvxb::set_last_error("cvxb_problem_create: leading dimension too small");
     return CVXB_EDIM;
   }
-  cudaSetDevice(h->device);
+  cvxb::DeviceGuard _guard(h->device);
   if (d->mq < 0 || (d->mq > 0 && (!d->q_P || !d->q_a || !d->q_r || !d->q_ub))) {
     cvxb::set_last_error("cvxb_problem_create: quadratic constraints need q_P, q_a, q_r, q_ub");
     return CVXB_EINVAL;
@@ -1080,7 +1081,7 @@ int cvxb_problem_reduce(cvxb_handle h, cvxb_problem prob, cvxb_solution_space sp
 
 int cvxb_problem_destroy(cvxb_problem prob) {
   if (!prob) return CVXB_OK;
-  cudaSetDevice(prob->h->device);
+  cvxb::DeviceGuard _guard(prob->h->device);
   cudaStreamSynchronize(prob->h->stream);
   problem_free(prob);
   return CVXB_OK;

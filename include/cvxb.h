@@ -58,6 +58,12 @@ long long cvxb_launch_count(cvxb_handle h);
  * stream: enable, run solves, then read {launches, total milliseconds, total algorithmic flops}. */
 int cvxb_profile_enable(cvxb_handle h, int on);
 int cvxb_profile_read(cvxb_handle h, long long* launches, double* ms_total, double* flops_total);
+/* Further timed ranges of the Newton step (same enable switch; plain launches only, i.e. the primal-dual loop and the
+ * seam-B calls, not the captured barrier step): {count, total ms, total algorithmic work}.  range: 0 = Hessian SYRK
+ * (same as cvxb_profile_read), 1 = Cholesky trailing updates A22 -= A21 A21' of the recursive levels (flops),
+ * 2 = factorisation of H with the forward substitution of [DA', Dq] riding along (flops), 3 = Schur complement SYRK
+ * (flops), 4 = ruizEquilibrate (bytes of ONE sweep over H per call), 5 = the GEMVs G x and G'(1/f) (bytes). */
+int cvxb_profile_read_range(cvxb_handle h, int range, long long* count, double* ms_total, double* work_total);
 
 /* ---- parameters: SolverParams.scala:24-46 plus the constants hard-coded in the solvers ------- */
 typedef struct cvxb_params {
@@ -188,6 +194,12 @@ int cvxb_kldual_primal_optimum(cvxb_handle h, cvxb_problem prob, double* x_prima
  * reference; a zero pivot of R gives CVXB_ELINSOLVE).  Host pointers unless the handle has CVXB_FLAG_DEVICE_PTRS. */
 int cvxb_solution_space_create(cvxb_handle h, int p, int n, const double* A, int lda, const double* b,
                                cvxb_solution_space* out);
+/* The same object from a caller-supplied affine map x = z0 + F u (Solver.affineTransformed(z0, F, u0), Solver.scala:33-46;
+ * BarrierSolver.affineTransformed, BarrierSolver.scala:209-247): F is n x k column-major with leading dimension ldf.
+ * Nothing is assumed about F (the reference does not check orthonormality either); cvxb_solution_space_parameter
+ * computes F'(x - z0), which inverts the map only for an orthonormal F. */
+int cvxb_solution_space_from_basis(cvxb_handle h, int n, int k, const double* z0, const double* F, int ldf,
+                                   cvxb_solution_space* out);
 int cvxb_solution_space_destroy(cvxb_solution_space space);
 /* z0 (n) and F (n x (n-p), leading dimension ldf); either may be NULL */
 int cvxb_solution_space_get(cvxb_handle h, cvxb_solution_space space, double* z0, double* F, int ldf);
@@ -307,8 +319,14 @@ typedef struct cvxb_batch_result {
 typedef struct cvxb_batch_s* cvxb_batch;
 int cvxb_batch_create(cvxb_handle h, const cvxb_batch_desc* desc, cvxb_batch* out);
 int cvxb_batch_destroy(cvxb_batch batch);
+/* Any array pointer of `out` may be NULL: that result is then not copied to the caller (it stays on the device). */
 int cvxb_batch_barrier_solve(cvxb_handle h, cvxb_batch batch, const cvxb_params* pars,
                              cvxb_batch_result* out);
+/* The results of the last cvxb_batch_barrier_solve as they lie on the device: B rows of *row_doubles = n +
+ * CVXB_BATCH_RECORD_EXTRA doubles, [x(n), objective, duality gap, status, newton steps, outer stages] -- the buffer the
+ * multi-GPU driver hands to ONE NCCL all-gather without staging through the host.  Owned by the batch. */
+enum { CVXB_BATCH_RECORD_EXTRA = 5 };
+int cvxb_batch_device_records(cvxb_batch batch, double** dev_records, int* row_doubles);
 
 /* ---- calibration / measurement helpers (bench.py, not part of the reference surface) ---------- */
 /* C = alpha*op(A)op(B) + beta*C through the DMMA kernel on HOST column-major arrays (tests) */

@@ -8,7 +8,9 @@ import breeze.linalg.{DenseMatrix, DenseVector}
   *
   * To switch the reference over, replace the body of KKTSystem.solve by
   *   GpuKKTSystem(M, A, q, b).solve(delta, logger, tol, debugLevel)
-  * UNVERIFIED (no JVM in the build image).
+  * Failures arrive as the reference's own exception types: LinSolveException (built by the shim with its real
+  * 4-argument constructor, matrices null: they stay on the device) and UnsolvableSystemException.
+  * Not compiled in this repository (no JVM in the build image); see CvxbNative for what is checked.
   */
 class GpuKKTSystem(val H: DenseMatrix[Double], val A: DenseMatrix[Double],
                    val q: DenseVector[Double], val b: DenseVector[Double]) {
@@ -25,7 +27,7 @@ class GpuKKTSystem(val H: DenseMatrix[Double], val A: DenseMatrix[Double],
   def solve(delta: Double, logger: Logger, tol: Double, debugLevel: Int): (DenseVector[Double], DenseVector[Double]) = {
     val Hd = dense(H); val Ad = dense(A)
     val x = new Array[Double](n); val w = new Array[Double](p)
-    val info = new Array[Int](3)
+    val info = new Array[Int](4)
     CvxbNative.kktSolve(CvxbNative.defaultHandle, n, p, Hd.data, Hd.offset, Hd.majorStride, Ad.data, Ad.offset,
                         Ad.majorStride, q.toArray, b.toArray, tol, x, w, info)
     if (debugLevel > 1) logger.println("GpuKKTSystem: path " + info(0) + ", regularized " + info(1) + ", Ruiz sweeps " + info(2))

@@ -1,5 +1,6 @@
-"""The multi-GPU exchange of the batched path (contiguous sharding, all-gather of the solutions and the
-convergence all-reduce) on the gloo backend with world_size 2 -- host logic only, no GPU."""
+"""The multi-GPU exchange of the batched path (contiguous sharding, ONE all-gather of the packed per-problem records,
+convergence figures derived from the gathered status / step columns) on the gloo backend with world_size 2 -- host
+logic only, no GPU."""
 import os
 import socket
 
@@ -29,6 +30,7 @@ def _worker(rank, world, port, B, n, q):
                              newton_steps=(10 + idx).astype(np.int32), outer_stages=np.full(k, 12, dtype=np.int32),
                              objective=np.zeros(k), dualityGap=np.zeros(k), equalityGap=np.zeros(k), solve_ms=1.0)
     out = cb.gather_solutions(local, B, n)
+    assert out["x"].shape == (B, n) and out["outer_stages"].tolist() == [12] * B
     q.put((rank, out["x"][:, 0].tolist(), out["status"].tolist(), out["newton_steps"].tolist(), out["converged"],
            out["max_newton_steps"]))
     dist.destroy_process_group()
