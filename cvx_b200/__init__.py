@@ -12,3 +12,5 @@ from .solvers import (SolverParams, Solution, LinearObjectiveFunction, Quadratic
                       KLObjectiveFunction, DualKLObjectiveFunction, PNormObjectiveFunction, ConstraintSet, QuadraticConstraint, EqualityConstraint, BarrierSolver, PrimalDualSolver,
                       OptimizationProblem, Dist_KL, FeasibilityReport, from_dict)
 from .batched import BatchedBarrierSolver, BatchSolution, pack_problems, shard_range, gather_solutions  # noqa: F401,E402
+from . import generic  # noqa: F401,E402
+from .generic import StagedSystem  # noqa: F401,E402

@@ -115,7 +115,7 @@ class BatchDesc(C.Structure):
 
 class BatchResult(C.Structure):
     _fields_ = [("x", _dp), ("status", _ip), ("newton_steps", _ip), ("outer_stages", _ip), ("objective", _dp),
-                ("duality_gap", _dp), ("equality_gap", _dp), ("solve_ms", C.c_double)]
+                ("duality_gap", _dp), ("equality_gap", _dp), ("solve_ms", C.c_double), ("stage_newton_steps", _ip)]
 
 
 # every symbol include/cvxb.h declares: name -> (restype, argtypes)
@@ -147,6 +147,14 @@ SYMBOLS = {
     "cvxb_kkt_solve_reduced": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_double, _vp, _vp,
                                          C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(KktInfo)]),
     "cvxb_solution_space_create": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.POINTER(C.c_void_p)]),
+    "cvxb_stage_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "cvxb_stage_destroy": (C.c_int, [_vp]),
+    "cvxb_stage_buffer": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), _ip]),
+    "cvxb_stage_push": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "cvxb_stage_wait": (C.c_int, [_vp, C.c_int]),
+    "cvxb_stage_set_equalities": (C.c_int, [_vp, _vp, C.c_int]),
+    "cvxb_stage_cholesky_solve": (C.c_int, [_vp, _vp, C.c_double, _vp, C.POINTER(KktInfo)]),
+    "cvxb_stage_kkt_solve": (C.c_int, [_vp, _vp, _vp, C.c_double, _vp, _vp, C.POINTER(KktInfo)]),
     "cvxb_solution_space_from_basis": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.POINTER(C.c_void_p)]),
     "cvxb_solution_space_destroy": (C.c_int, [_vp]),
     "cvxb_solution_space_get": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),

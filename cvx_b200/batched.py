@@ -27,6 +27,7 @@ class BatchSolution:
     dualityGap: np.ndarray     # B
     equalityGap: np.ndarray    # B
     solve_ms: float
+    stage_newton_steps: Optional[np.ndarray] = None    # B x 16: Newton steps per outer stage
 
 
 def pack_problems(probs: Sequence[dict]):
@@ -103,8 +104,10 @@ class BatchedBarrierSolver:
         ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
         r.x, r.status, r.newton_steps, r.outer_stages = dptr(x), ip(status), ip(steps), ip(stages)
         r.objective, r.duality_gap, r.equality_gap = dptr(objv), dptr(gap), dptr(eqg)
+        stage_steps = np.zeros((B, 16), dtype=np.int32)
+        r.stage_newton_steps = ip(stage_steps)
         check(self.handle.lib.cvxb_batch_barrier_solve(self.handle._h, self._b, C.byref(cp), C.byref(r)))
-        return BatchSolution(x, status, steps, stages, objv, gap, eqg, float(r.solve_ms))
+        return BatchSolution(x, status, steps, stages, objv, gap, eqg, float(r.solve_ms), stage_steps)
 
     def device_records(self):
         """(device pointer, doubles per row) of the packed results of the last solve:

@@ -537,6 +537,156 @@ int cvxb_cholesky_solve(cvxb_handle h, int n, const double* H, int ldh, const do
   return CVXB_OK;
 }
 
+// ---- seam B with pinned, double-buffered staging (general objectives: the Hessian is assembled on the host) ----------
+// The caller fills one pinned buffer with a block of columns of H while the previous block is still on its way to the
+// device on a copy stream of its own; the solves then run on the device-resident matrix.
+struct cvxb_stage_s {
+  cvxb_handle_s* h = nullptr;
+  int n = 0, p = 0, ldn = 0, ldp = 0, block_cols = 0;
+  double *dH = nullptr, *dA = nullptr, *dvec = nullptr;     // device: H (ldn x n), A (ldp x n), vectors q | b | x | w
+  double* pin[2] = {nullptr, nullptr};                      // pinned host buffers, n x block_cols each (leading dimension n)
+  cudaEvent_t done[2] = {nullptr, nullptr};                 // buffer i may be overwritten once done[i] has completed
+  cudaEvent_t all = nullptr;
+  cudaStream_t copy = nullptr;
+  long long pushed_cols = 0;
+  KktWork W;
+};
+
+static void stage_free(cvxb_stage_s* S) {
+  if (!S) return;
+  cudaFree(S->dH); cudaFree(S->dA); cudaFree(S->dvec);
+  for (int i = 0; i < 2; ++i) { if (S->pin[i]) cudaFreeHost(S->pin[i]); if (S->done[i]) cudaEventDestroy(S->done[i]); }
+  if (S->all) cudaEventDestroy(S->all);
+  if (S->copy) cudaStreamDestroy(S->copy);
+  kkt_work_free(S->W);
+  delete S;
+}
+
+int cvxb_stage_create(cvxb_handle h, int n, int p, int block_cols, cvxb_stage* out) {
+  CHECK_HANDLE(h);
+  if (!out) { cvxb::set_last_error("cvxb_stage_create: null argument"); return CVXB_EINVAL; }
+  if (n < 1 || p < 0) { cvxb::set_last_error("cvxb_stage_create: need n >= 1, p >= 0 (got %d, %d)", n, p); return CVXB_EDIM; }
+  if (block_cols < 1) block_cols = n < 256 ? n : 256;
+  if (block_cols > n) block_cols = n;
+  cvxb_stage_s* S = new cvxb_stage_s();
+  S->h = h; S->n = n; S->p = p; S->ldn = pad_ld(n); S->ldp = pad_ld(p); S->block_cols = block_cols;
+  cudaError_t e = cudaMalloc((void**)&S->dH, sizeof(double) * (size_t)S->ldn * n);
+  if (e == cudaSuccess) e = cudaMemsetAsync(S->dH, 0, sizeof(double) * (size_t)S->ldn * n, h->stream);
+  if (e == cudaSuccess && p > 0) e = cudaMalloc((void**)&S->dA, sizeof(double) * (size_t)S->ldp * n);
+  if (e == cudaSuccess && p > 0) e = cudaMemsetAsync(S->dA, 0, sizeof(double) * (size_t)S->ldp * n, h->stream);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&S->dvec, sizeof(double) * (2 * (size_t)S->ldn + 2 * (size_t)S->ldp));
+  if (e == cudaSuccess) e = cudaMemsetAsync(S->dvec, 0, sizeof(double) * (2 * (size_t)S->ldn + 2 * (size_t)S->ldp), h->stream);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaMallocHost((void**)&S->pin[i], sizeof(double) * (size_t)n * block_cols);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S->done[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S->all, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&S->copy, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  int st = e == cudaSuccess ? kkt_work_alloc(*h, S->W, n, p) : CVXB_ECUDA;
+  if (st != CVXB_OK) {
+    if (e != cudaSuccess) cvxb::set_last_error("CUDA error %s in cvxb_stage_create", cudaGetErrorString(e));
+    stage_free(S);
+    return st;
+  }
+  *out = S;
+  return CVXB_OK;
+}
+
+int cvxb_stage_destroy(cvxb_stage S) {
+  if (!S) return CVXB_OK;
+  cvxb::DeviceGuard guard(S->h->device);
+  cudaStreamSynchronize(S->copy);
+  cudaStreamSynchronize(S->h->stream);
+  stage_free(S);
+  return CVXB_OK;
+}
+
+int cvxb_stage_buffer(cvxb_stage S, int which, double** host_buffer, int* block_cols) {
+  if (!S || which < 0 || which > 1 || !host_buffer) { cvxb::set_last_error("cvxb_stage_buffer: bad argument"); return CVXB_EINVAL; }
+  *host_buffer = S->pin[which];
+  if (block_cols) *block_cols = S->block_cols;
+  return CVXB_OK;
+}
+
+int cvxb_stage_wait(cvxb_stage S, int which) {
+  if (!S || which < 0 || which > 1) { cvxb::set_last_error("cvxb_stage_wait: bad argument"); return CVXB_EINVAL; }
+  cvxb::DeviceGuard guard(S->h->device);
+  CVXB_CUDA_OK(cudaEventSynchronize(S->done[which]));
+  return CVXB_OK;
+}
+
+int cvxb_stage_push(cvxb_stage S, int which, int col0, int ncols) {
+  if (!S || which < 0 || which > 1) { cvxb::set_last_error("cvxb_stage_push: bad argument"); return CVXB_EINVAL; }
+  if (col0 < 0 || ncols < 1 || ncols > S->block_cols || col0 + ncols > S->n) {
+    cvxb::set_last_error("cvxb_stage_push: columns %d..%d outside 0..%d or more than %d at once", col0, col0 + ncols, S->n, S->block_cols);
+    return CVXB_EDIM;
+  }
+  cvxb::DeviceGuard guard(S->h->device);
+  if (S->pushed_cols == 0)      // first block of a new matrix: the previous solve on the handle's stream must have finished with H
+    CVXB_CUDA_OK(cudaStreamSynchronize(S->h->stream));
+  CVXB_CUDA_OK(cudaMemcpy2DAsync(S->dH + (size_t)col0 * S->ldn, sizeof(double) * (size_t)S->ldn, S->pin[which],
+                                 sizeof(double) * (size_t)S->n, sizeof(double) * (size_t)S->n, ncols, cudaMemcpyHostToDevice,
+                                 S->copy));
+  CVXB_CUDA_OK(cudaEventRecord(S->done[which], S->copy));
+  S->pushed_cols += ncols;
+  return CVXB_OK;
+}
+
+// the solves wait for the copy stream on the device (no host stall), then run on the handle's stream
+static int stage_join(cvxb_stage_s* S) {
+  CVXB_CUDA_OK(cudaEventRecord(S->all, S->copy));
+  CVXB_CUDA_OK(cudaStreamWaitEvent(S->h->stream, S->all, 0));
+  S->pushed_cols = 0;
+  return CVXB_OK;
+}
+
+int cvxb_stage_cholesky_solve(cvxb_stage S, const double* b, double tol, double* x, cvxb_kkt_info* info) {
+  if (!S || !b || !x) { cvxb::set_last_error("cvxb_stage_cholesky_solve: null argument"); return CVXB_EINVAL; }
+  cvxb_handle h = S->h;
+  cvxb::DeviceGuard guard(h->device);
+  cvxb_params P;
+  cvxb_default_params(&P);
+  double *db = S->dvec, *dx = S->dvec + S->ldn;
+  CVXB_TRY(stage_join(S));
+  CVXB_CUDA_OK(cudaMemcpyAsync(db, b, sizeof(double) * (size_t)S->n, cudaMemcpyHostToDevice, h->stream));
+  int st = chol_solve_device(*h, S->W, P, S->dH, S->ldn, db, 1.0, tol, dx, info);
+  if (st != CVXB_OK) return st;
+  CVXB_CUDA_OK(cudaMemcpyAsync(x, dx, sizeof(double) * (size_t)S->n, cudaMemcpyDeviceToHost, h->stream));
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CVXB_OK;
+}
+
+int cvxb_stage_set_equalities(cvxb_stage S, const double* A, int lda) {
+  if (!S || !A || S->p < 1) { cvxb::set_last_error("cvxb_stage_set_equalities: no equalities in this stage"); return CVXB_EINVAL; }
+  if (lda < S->p) { cvxb::set_last_error("leading dimension %d < rows %d", lda, S->p); return CVXB_EDIM; }
+  cvxb::DeviceGuard guard(S->h->device);
+  CVXB_CUDA_OK(cudaMemcpy2DAsync(S->dA, sizeof(double) * (size_t)S->ldp, A, sizeof(double) * (size_t)lda,
+                                 sizeof(double) * (size_t)S->p, S->n, cudaMemcpyHostToDevice, S->h->stream));
+  CVXB_CUDA_OK(cudaStreamSynchronize(S->h->stream));
+  return CVXB_OK;
+}
+
+int cvxb_stage_kkt_solve(cvxb_stage S, const double* q, const double* b, double tol, double* x, double* w,
+                         cvxb_kkt_info* info) {
+  if (!S || !q || !b || !x || !w) { cvxb::set_last_error("cvxb_stage_kkt_solve: null argument"); return CVXB_EINVAL; }
+  if (S->p < 1) { cvxb::set_last_error("cvxb_stage_kkt_solve: stage created with p = 0"); return CVXB_EDIM; }
+  cvxb_handle h = S->h;
+  cvxb::DeviceGuard guard(h->device);
+  cvxb_params P;
+  cvxb_default_params(&P);
+  double *dq = S->dvec, *dx = S->dvec + S->ldn, *db = S->dvec + 2 * (size_t)S->ldn, *dw = db + S->ldp;
+  CVXB_TRY(stage_join(S));
+  CVXB_CUDA_OK(cudaMemcpyAsync(dq, q, sizeof(double) * (size_t)S->n, cudaMemcpyHostToDevice, h->stream));
+  CVXB_CUDA_OK(cudaMemcpyAsync(db, b, sizeof(double) * (size_t)S->p, cudaMemcpyHostToDevice, h->stream));
+  int st = kkt_solve_device(*h, S->W, P, S->dH, S->ldn, S->dA, S->ldp, dq, db, tol, dx, dw, info);
+  if (st != CVXB_OK) return st;
+  CVXB_CUDA_OK(cudaMemcpyAsync(x, dx, sizeof(double) * (size_t)S->n, cudaMemcpyDeviceToHost, h->stream));
+  CVXB_CUDA_OK(cudaMemcpyAsync(w, dw, sizeof(double) * (size_t)S->p, cudaMemcpyDeviceToHost, h->stream));
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  return CVXB_OK;
+}
+
 int cvxb_kkt_solve_with_chol_factor(cvxb_handle h, int n, int p, const double* L, int ldl, const double* A, int lda,
                                     const double* q, const double* b, double tol, double* x, double* w,
                                     cvxb_kkt_info* info) {

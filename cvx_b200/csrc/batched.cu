@@ -26,6 +26,7 @@ struct cvxb_batch_s {
   // outputs (device)
   double *x = nullptr, *objval = nullptr, *gap = nullptr, *eqgap = nullptr;
   int *status = nullptr, *steps = nullptr, *stages = nullptr;
+  int* stage_steps = nullptr;    // B x CVXB_BATCH_STAGES: Newton steps of each of the first outer stages
   double* records = nullptr;     // B x (n + CVXB_BATCH_RECORD_EXTRA): [x, objective, gap, status, steps, stages] per problem
   double* scratch = nullptr;     // per-CTA copy of H (n x n)
   unsigned* counter = nullptr;
@@ -50,6 +51,7 @@ struct BatchArgs {
   const double *obj_a, *obj_r, *obj_P, *G, *ub, *A, *b, *x0;
   double *x, *objval, *gap, *eqgap;
   int *status, *steps, *stages;
+  int* stage_steps;
   double* records;
   double* scratch;
   unsigned* counter;
@@ -67,6 +69,7 @@ struct Smem {
   double sc[16];
   int fl[8];
   int pcur;                 // equalities of the current problem (0 or 1)
+  int stage_steps[CVXB_BATCH_STAGES];
 };
 #define S_T1 (S.work)
 #define S_T2 (S.work + BN)
@@ -555,6 +558,7 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
     const double beq = p ? A.b[pid] : 0.0;
     __syncthreads();
 
+    if (tid < CVXB_BATCH_STAGES) S.stage_steps[tid] = 0;
     int status = CVXB_OK, stage = 0, total_steps = 0;
     double t = A.P.t0, gap = 1.7976931348623157e308, eqgap = 1.7976931348623157e308, objv = 0.0;
     const double maxStage = 1000.0 / A.P.mu;
@@ -659,6 +663,7 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
       }
       if (status != CVXB_OK) break;
       total_steps += iter;
+      if (tid == 0 && stage < CVXB_BATCH_STAGES) S.stage_steps[stage] = iter;
       objv = f0;
       gap = (double)m / t;
       eqgap = p ? eqnorm : 0.0;
@@ -674,6 +679,8 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
         rec[n + 4] = (double)stage;
       }
     }
+    __syncthreads();
+    if (tid < CVXB_BATCH_STAGES) A.stage_steps[(size_t)pid * CVXB_BATCH_STAGES + tid] = S.stage_steps[tid];
     if (tid == 0) {
       A.status[pid] = status;
       A.steps[pid] = total_steps;
@@ -761,6 +768,7 @@ int cvxb_batch_create(cvxb_handle h, const cvxb_batch_desc* d, cvxb_batch* out) 
   T(balloc(Bt, &Bt->x, B * n)); T(balloc(Bt, &Bt->objval, B)); T(balloc(Bt, &Bt->gap, B)); T(balloc(Bt, &Bt->eqgap, B));
   T(balloc(Bt, &Bt->status, B)); T(balloc(Bt, &Bt->steps, B)); T(balloc(Bt, &Bt->stages, B));
   T(balloc(Bt, &Bt->records, B * (n + CVXB_BATCH_RECORD_EXTRA)));
+  T(balloc(Bt, &Bt->stage_steps, B * CVXB_BATCH_STAGES));
   Bt->grid = h->sm_count * 2;
   if (Bt->grid > d->B) Bt->grid = d->B;
   T(balloc(Bt, &Bt->scratch, (size_t)Bt->grid * BN * BN));
@@ -808,7 +816,7 @@ int cvxb_batch_barrier_solve(cvxb_handle h, cvxb_batch Bt, const cvxb_params* pa
   A.objective = Bt->objective; A.pcount = Bt->pcount; A.obj_a = Bt->obj_a; A.obj_r = Bt->obj_r; A.obj_P = Bt->obj_P; A.G = Bt->G; A.ub = Bt->ub;
   A.A = Bt->A; A.b = Bt->b; A.x0 = Bt->x0;
   A.x = Bt->x; A.objval = Bt->objval; A.gap = Bt->gap; A.eqgap = Bt->eqgap;
-  A.status = Bt->status; A.steps = Bt->steps; A.stages = Bt->stages; A.records = Bt->records;
+  A.status = Bt->status; A.steps = Bt->steps; A.stages = Bt->stages; A.records = Bt->records; A.stage_steps = Bt->stage_steps;
   A.scratch = Bt->scratch; A.counter = Bt->counter; A.P = *pars;
   CVXB_CUDA_OK(cudaMemsetAsync(Bt->counter, 0, sizeof(unsigned), h->stream));
   CVXB_CUDA_OK(cudaEventRecord(h->ev0, h->stream));
@@ -823,6 +831,8 @@ int cvxb_batch_barrier_solve(cvxb_handle h, cvxb_batch Bt, const cvxb_params* pa
   if (out->status) CVXB_CUDA_OK(cudaMemcpyAsync(out->status, Bt->status, B * sizeof(int), k, h->stream));
   if (out->newton_steps) CVXB_CUDA_OK(cudaMemcpyAsync(out->newton_steps, Bt->steps, B * sizeof(int), k, h->stream));
   if (out->outer_stages) CVXB_CUDA_OK(cudaMemcpyAsync(out->outer_stages, Bt->stages, B * sizeof(int), k, h->stream));
+  if (out->stage_newton_steps)
+    CVXB_CUDA_OK(cudaMemcpyAsync(out->stage_newton_steps, Bt->stage_steps, B * CVXB_BATCH_STAGES * sizeof(int), k, h->stream));
   if (out->objective) CVXB_CUDA_OK(cudaMemcpyAsync(out->objective, Bt->objval, B * sizeof(double), k, h->stream));
   if (out->duality_gap) CVXB_CUDA_OK(cudaMemcpyAsync(out->duality_gap, Bt->gap, B * sizeof(double), k, h->stream));
   if (out->equality_gap) CVXB_CUDA_OK(cudaMemcpyAsync(out->equality_gap, Bt->eqgap, B * sizeof(double), k, h->stream));

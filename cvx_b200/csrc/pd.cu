@@ -20,6 +20,10 @@ int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s*
 int quad_refresh(cvxb_problem_s* P);
 int quad_direction(cvxb_problem_s* P, const double* dir);
 int quad_hessian_terms(cvxb_problem_s* P, const double* c);
+int composed_refresh(cvxb_problem_s* P);
+int composed_hessian(cvxb_problem_s* P, double t, const double* t_dev);
+int dual_refresh(cvxb_problem_s* P);
+int dual_hessian(cvxb_problem_s* P, double t, const double* t_dev);
 int upload_vec(Handle& h, double* dst, const double* src, int n);
 int download_vec(Handle& h, double* dst, const double* src, int n);
 
@@ -34,6 +38,8 @@ __device__ __forceinline__ double grad_f0(int kind, int n, double xj, double aj,
   }
   if (kind == CVXB_OBJ_LINEAR) return aj;
   if (kind == CVXB_OBJ_QUADRATIC) return aj + pxj;
+  if (kind == CVXB_OBJ_COMPOSED) return pxj;          // F' grad f_inner(z0 + F u)
+  if (kind == CVXB_OBJ_KLDUAL) return aj - pxj;       // w - B y
   return 1.0 + log(xj) + log((double)n);
 }
 
@@ -116,7 +122,42 @@ struct PdLs {
   const double *qq, *rd2;   // quadratic constraints: d'P_k d / 2 per row and the s^2 term of the dual residual (or NULL)
   // iterate to write
   double *xo, *lamo, *nuo;
+  // objectives whose gradient at a trial point needs a matrix-vector product (one CTA does it: these are the reduced
+  // and dual problems, small next to the primal ones):
+  //   CVXB_OBJ_COMPOSED  grad = F' grad f_inner(xf + s dxf)      M = F (mrows x n), vin = xf, dvin = dxf, inner family mkind
+  //   CVXB_OBJ_KLDUAL    grad = w - B (y o exp(-s v))            M = B (n x mcols), vin = y,  dvin = v
+  const double *M, *vin, *dvin;
+  int ldM, mrows, mcols, mkind;
+  double *tmp, *gf;         // scratch: length max(mrows, mcols) and n
 };
+
+// gf := gradient of the objective at the trial point for the two matrix-backed families (all threads of the CTA)
+__device__ void pd_trial_gradient(const PdLs& A, double s) {
+  if (A.kind == CVXB_OBJ_COMPOSED) {
+    for (int i = threadIdx.x; i < A.mrows; i += VT) {
+      const double xi = A.vin[i] + s * A.dvin[i];
+      A.tmp[i] = grad_f0(A.mkind, A.mrows, xi, 0.0, 0.0, A.pw);      // NaN for KL outside its domain: the trial then fails
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = warp; j < A.n; j += VT / 32) {                       // one warp per column of F, coalesced down the column
+      double acc = 0.0;
+      for (int i = lane; i < A.mrows; i += 32) acc = fma(A.M[(size_t)j * A.ldM + i], A.tmp[i], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) A.gf[j] = acc;
+    }
+  } else {
+    for (int i = threadIdx.x; i < A.mcols; i += VT) A.tmp[i] = A.vin[i] * exp(-s * A.dvin[i]);
+    __syncthreads();
+    for (int j = threadIdx.x; j < A.n; j += VT) {                     // thread j owns row j of B: consecutive threads, consecutive rows
+      double acc = 0.0;
+      for (int i = 0; i < A.mcols; ++i) acc = fma(A.M[(size_t)i * A.ldM + j], A.tmp[i], acc);
+      A.gf[j] = A.a[j] - acc;
+    }
+  }
+  __syncthreads();
+}
+
 
 // ||r(t, u + s du)||^2 and strict feasibility of x_s; lam_s > 0 asserted via *lamneg
 __device__ double pd_trial(const PdLs& A, double s, double* buf, int* ibuf, int* feas, int* lamneg, double* rdual2,
@@ -140,9 +181,12 @@ __device__ double pd_trial(const PdLs& A, double s, double* buf, int* ibuf, int*
   infeas = block_or(infeas, ibuf);
   ln = block_or(ln, ibuf);
   double sd = 0.0;
+  const bool matrix_backed = A.kind == CVXB_OBJ_COMPOSED || A.kind == CVXB_OBJ_KLDUAL;
+  if (matrix_backed) pd_trial_gradient(A, s);
   for (int j = threadIdx.x; j < A.n; j += VT) {
     double gf;
-    if (A.kind == CVXB_OBJ_LINEAR) gf = A.a[j];
+    if (matrix_backed) gf = A.gf[j];
+    else if (A.kind == CVXB_OBJ_LINEAR) gf = A.a[j];
     else if (A.kind == CVXB_OBJ_QUADRATIC) gf = A.a[j] + A.Px[j] + s * A.Pd[j];
     else if (A.kind == CVXB_OBJ_PNORM) gf = grad_f0(A.kind, A.n, A.x[j] + s * A.dx[j], 0.0, 0.0, A.pw);
     else {
@@ -217,13 +261,16 @@ __global__ void __launch_bounds__(VT) pd_linesearch_kernel(PdLs A, double* scal,
 // objective value at x
 __global__ void __launch_bounds__(VT) pd_objective_kernel(int n, int kind, double obj_r, const double* __restrict__ x,
                                                           const double* __restrict__ a, const double* __restrict__ Px,
-                                                          double pw, double* scal) {
+                                                          double pw, double* scal, const double* __restrict__ dual_y = nullptr,
+                                                          int kd = 0) {
   __shared__ double buf[33];
   double f0 = 0.0;
+  if (kind == CVXB_OBJ_KLDUAL)
+    for (int j = threadIdx.x; j < kd; j += VT) f0 += dual_y[j];          // + R'exp(-B'z)   (Dist_KL.scala:143-147)
   for (int j = threadIdx.x; j < n; j += VT) {
     double xj = x[j];
     if (kind == CVXB_OBJ_PNORM) f0 += pow(fabs(xj), pw);
-    else if (kind == CVXB_OBJ_LINEAR) f0 += a[j] * xj;
+    else if (kind == CVXB_OBJ_LINEAR || kind == CVXB_OBJ_KLDUAL) f0 += a[j] * xj;
     else if (kind == CVXB_OBJ_QUADRATIC) f0 += a[j] * xj + 0.5 * xj * Px[j];
     else f0 += xj * log(xj * (double)n);
   }
@@ -273,6 +320,8 @@ int pd_assemble(cvxb_problem_s* P, const cvxb_params& pars, double t) {
   CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->x, 0.0, P->gx));
   CVXB_TRY(prof_end(h, PROF_GEMV, 8.0 * m * n));
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->Px));
+  if (P->objective == CVXB_OBJ_COMPOSED) CVXB_TRY(composed_refresh(P));
+  if (P->objective == CVXB_OBJ_KLDUAL) CVXB_TRY(dual_refresh(P));
   CVXB_LAUNCH(h, pd_cnt_kernel, 1, VT, 0, m, t, P->gr, P->ub, P->gx, P->lam, P->tmpm, P->wts, P->inv, P->qcorr, h.d_scal, h.d_flag);
   CVXB_TRY(prof_begin(h, PROF_GEMV));
   CVXB_TRY(gemv_t(h, m, n, 1.0, P->G, P->ldm, P->inv, 0.0, P->gt));
@@ -290,6 +339,8 @@ int pd_assemble(cvxb_problem_s* P, const cvxb_params& pars, double t) {
   else if (P->objective == CVXB_OBJ_KL) CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, 1.0, P->H, P->ldn));
   else if (P->objective == CVXB_OBJ_PNORM)
     CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, P->obj_pow * (P->obj_pow - 1.0), P->H, P->ldn, nullptr, P->obj_pow - 2.0));
+  else if (P->objective == CVXB_OBJ_COMPOSED) CVXB_TRY(composed_hessian(P, 1.0, nullptr));
+  else if (P->objective == CVXB_OBJ_KLDUAL) CVXB_TRY(dual_hessian(P, 1.0, nullptr));
   else CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, nullptr, 0.0, P->H, P->ldn));
   CVXB_TRY(quad_hessian_terms(P, P->lam));     // + lam_k hess g_k   (PrimalDualSolver.scala:230-236)
   GemmArgs g{n, n, m, P->Gs, P->ldm, true, P->Gs, P->ldm, true, P->H, P->ldn, 1.0, 1.0, 2};
@@ -324,6 +375,8 @@ int pd_after_solve(cvxb_problem_s* P, const cvxb_params& pars, double t, bool us
   const int n = P->n, m = P->m, p = P->p;
   CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->dir, 0.0, P->Gd));
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->dir, 0.0, P->Pd));
+  if (P->objective == CVXB_OBJ_COMPOSED) CVXB_TRY(gemv_n(h, P->cmp_n, n, 1.0, P->cmpF, P->cmp_ld, P->dir, 0.0, P->cmpd));   // F du
+  if (P->objective == CVXB_OBJ_KLDUAL) CVXB_TRY(gemv_t(h, n, P->kd, 1.0, P->obj_P, P->ldn, P->dir, 0.0, P->dv));           // B'dz
   CVXB_LAUNCH(h, pd_dlam_kernel, 1, VT, 0, m, t, P->lam, P->tmpm, P->Gd, P->dlam);
   CVXB_TRY(gemv_t(h, m, n, 1.0, P->G, P->ldm, P->dlam, 0.0, P->rd1));
   if (p > 0) {
@@ -349,6 +402,13 @@ int pd_after_solve(cvxb_problem_s* P, const cvxb_params& pars, double t, bool us
   A.Gd = P->Gd; A.dlam = P->dlam; A.dx = P->dir; A.dnu = P->dnu; A.rd1 = P->rd1; A.Adx = P->Adx; A.Pd = P->Pd;
   A.xo = P->x; A.lamo = P->lam; A.nuo = P->nu;
   A.qq = P->mq > 0 ? P->qq : nullptr; A.rd2 = P->mq > 0 ? P->rd2 : nullptr;
+  A.M = nullptr; A.vin = A.dvin = nullptr; A.ldM = A.mrows = A.mcols = A.mkind = 0; A.tmp = A.gf = nullptr;
+  if (P->objective == CVXB_OBJ_COMPOSED) {
+    A.M = P->cmpF; A.ldM = P->cmp_ld; A.mrows = P->cmp_n; A.mcols = n; A.mkind = P->cmp_kind;
+    A.vin = P->cmpx; A.dvin = P->cmpd; A.tmp = P->cmpg; A.gf = P->cmpgf;
+  } else if (P->objective == CVXB_OBJ_KLDUAL) {
+    A.M = P->obj_P; A.ldM = P->ldn; A.mrows = n; A.mcols = P->kd; A.vin = P->dy; A.dvin = P->dv; A.tmp = P->du; A.gf = P->Pd;
+  }
   CVXB_LAUNCH(h, pd_linesearch_kernel, 1, VT, 0, A, h.d_scal, h.d_flag);
   return CVXB_OK;
 }
@@ -392,11 +452,6 @@ int pd_loop(cvxb_problem_s* P, const cvxb_params& pars, cvxb_solution* out) {
   const bool withEqs = p > 0;
   const bool bug = pars.bugCompat && withEqs;
   const double mu = pars.mu, tol = pars.tolSolver;
-  if (P->objective == CVXB_OBJ_KLDUAL) {
-    set_last_error("PrimalDualSolver on the dual KL objective is not built on the device: the residual line search needs "
-                   "grad f(z + s dz) = w - B (R o exp(-B'(z + s dz))), a GEMV per trial; use the barrier solver");
-    return CVXB_ENOTIMPL;
-  }
   CVXB_TRY(pd_alloc(P));
   // lam0 = -1/(g(x0)-ub), nu0 = 0
   CVXB_TRY(quad_refresh(P));
@@ -475,7 +530,14 @@ int pd_loop(cvxb_problem_s* P, const cvxb_params& pars, cvxb_solution* out) {
     it++;
   }
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->Px));
-  CVXB_LAUNCH(h, pd_objective_kernel, 1, VT, 0, n, P->objective, P->obj_r, P->x, P->obj_a, P->Px, P->obj_pow, h.d_scal);
+  if (P->objective == CVXB_OBJ_COMPOSED) {       // f(u) = f_inner(z0 + F u)
+    CVXB_TRY(composed_refresh(P));
+    CVXB_LAUNCH(h, pd_objective_kernel, 1, VT, 0, P->cmp_n, P->cmp_kind, P->obj_r, P->cmpx, nullptr, nullptr, P->obj_pow, h.d_scal);
+  } else {
+    if (P->objective == CVXB_OBJ_KLDUAL) CVXB_TRY(dual_refresh(P));
+    CVXB_LAUNCH(h, pd_objective_kernel, 1, VT, 0, n, P->objective, P->obj_r, P->x, P->obj_a, P->Px, P->obj_pow, h.d_scal, P->dy,
+                P->kd);
+  }
   CVXB_TRY(fetch_status(h));
   out->has_lambda = 1; out->has_nu = withEqs ? 1 : 0;
   out->has_newtonDecrement = 0; out->newtonDecrement = 0;

@@ -36,6 +36,7 @@ __device__ __forceinline__ double obj_term(int kind, int n, int j, double xj, co
 __device__ __forceinline__ double obj_grad(int kind, int n, int j, double xj, const double* a, const double* Px,
                                            double pw = 2.0) {
   if (kind == CVXB_OBJ_PNORM) { const double sg = pnorm_sgn(xj); return sg * pw * pow(sg * xj, pw - 1.0); }   // :77-78
+  if (kind == CVXB_OBJ_COMPOSED) return Px[j];           // F' grad f_inner(z0 + F u), computed by barrier_eval
   if (kind == CVXB_OBJ_LINEAR) return a[j];
   if (kind == CVXB_OBJ_KLDUAL) return a[j] - Px[j];      // w - B y   (Px holds B y)
   if (kind == CVXB_OBJ_QUADRATIC) return a[j] + Px[j];
@@ -122,6 +123,9 @@ struct LsArgs {
   int kd;
   double pw;             // CVXB_OBJ_PNORM exponent
   double *x, *dir;
+  // the vectors the KL / p-norm objective is evaluated on: (x, dir, n), or (z0 + F u, F du, dim x) for a composed objective
+  const double *xobj, *dobj;
+  int nobj;
 };
 
 __device__ bool ls_in_set(const LsArgs& A, double s, int* ibuf) {
@@ -154,14 +158,14 @@ __device__ double ls_value(const LsArgs& A, double s, double f0, double c1, doub
   double f0s;
   if (A.kind == CVXB_OBJ_KL) {
     double v = 0.0;
-    for (int j = threadIdx.x; j < A.n; j += VT) {
-      double xj = A.x[j] + s * A.dir[j];
-      v += xj * log(xj * (double)A.n);
+    for (int j = threadIdx.x; j < A.nobj; j += VT) {
+      double xj = A.xobj[j] + s * A.dobj[j];
+      v += xj * log(xj * (double)A.nobj);
     }
     f0s = block_sum(v, buf);
   } else if (A.kind == CVXB_OBJ_PNORM) {
     double v = 0.0;
-    for (int j = threadIdx.x; j < A.n; j += VT) v += pow(fabs(A.x[j] + s * A.dir[j]), A.pw);
+    for (int j = threadIdx.x; j < A.nobj; j += VT) v += pow(fabs(A.xobj[j] + s * A.dobj[j]), A.pw);
     f0s = block_sum(v, buf);
   } else if (A.kind == CVXB_OBJ_KLDUAL) {
     double v = 0.0;
@@ -267,6 +271,21 @@ __global__ void dual_scale_cols_kernel(int D, int kd, const double* __restrict__
   if (i >= D) return;
   if (t_dev) t = *t_dev;
   for (int j = blockIdx.y; j < kd; j += gridDim.y) Bs[(size_t)j * ldbs + i] = B[(size_t)j * ldb + i] * sqrt(t * y[j]);
+}
+
+// ---- objective composed with x = z0 + F u (reduced KL / p-norm problems) ----------------------------------
+// g = grad f_inner(x) elementwise (Dist_KL.scala:229-233, ObjectiveFunctions.scala:77-78)
+__global__ void cmp_grad_kernel(int n, int kind, double pw, const double* __restrict__ x, double* __restrict__ g) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) g[j] = obj_grad(kind, n, j, x[j], nullptr, nullptr, pw);
+}
+// w = t * diag hess f_inner(x): t / x (Dist_KL.scala:236-239), t p (p-1) |x|^(p-2) (ObjectiveFunctions.scala:79-82)
+__global__ void cmp_weights_kernel(int n, int kind, double pw, double t, const double* __restrict__ t_dev,
+                                   const double* __restrict__ x, double* __restrict__ w) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  if (t_dev) t = *t_dev;
+  w[j] = kind == CVXB_OBJ_KL ? t / x[j] : t * pw * (pw - 1.0) * pow(fabs(x[j]), pw - 2.0);
 }
 
 // ---- quadratic constraints ------------------------------------------------------------------------
@@ -483,19 +502,56 @@ int quad_hessian_terms(cvxb_problem_s* P, const double* c) {
   return CVXB_OK;
 }
 
+// composed objective at P->x: x_full = z0 + F u, g = grad f_inner(x_full), Px := F'g   (ObjectiveFunction.scala:26-40)
+int composed_refresh(cvxb_problem_s* P) {
+  Handle& h = *P->h;
+  CVXB_CUDA_OK(cudaMemcpyAsync(P->cmpx, P->cmpz0, (size_t)P->cmp_n * sizeof(double), cudaMemcpyDeviceToDevice, h.stream));
+  CVXB_TRY(gemv_n(h, P->cmp_n, P->n, 1.0, P->cmpF, P->cmp_ld, P->x, 1.0, P->cmpx));
+  CVXB_LAUNCH(h, cmp_grad_kernel, (P->cmp_n + 255) / 256, 256, 0, P->cmp_n, P->cmp_kind, P->obj_pow, P->cmpx, P->cmpg);
+  CVXB_TRY(gemv_t(h, P->cmp_n, P->n, 1.0, P->cmpF, P->cmp_ld, P->cmpg, 0.0, P->Px));
+  return CVXB_OK;
+}
+// H := t F' diag(hess f_inner(x_full)) F as one weighted SYRK, mirrored (exactly symmetric)
+int composed_hessian(cvxb_problem_s* P, double t, const double* t_dev) {
+  Handle& h = *P->h;
+  CVXB_LAUNCH(h, cmp_weights_kernel, (P->cmp_n + 255) / 256, 256, 0, P->cmp_n, P->cmp_kind, P->obj_pow, t, t_dev, P->cmpx, P->cmpw);
+  CVXB_TRY(scale_rows(h, P->cmp_n, P->n, P->cmpF, P->cmp_ld, P->cmpw, P->cmpFs, P->cmp_ld, true));
+  GemmArgs g{P->n, P->n, P->cmp_n, P->cmpFs, P->cmp_ld, true, P->cmpFs, P->cmp_ld, true, P->H, P->ldn, 1.0, 0.0, 2};
+  g.streamk = true;
+  return gemm_dmma(h, g);
+}
+
+// dual KL objective at P->x = z: u = B'z, y = R o exp(-u), Px := B y   (Dist_KL.scala:143-151)
+int dual_refresh(cvxb_problem_s* P) {
+  Handle& h = *P->h;
+  CVXB_TRY(gemv_t(h, P->n, P->kd, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->du));
+  CVXB_LAUNCH(h, dual_y_kernel, (P->kd + 255) / 256, 256, 0, P->kd, P->objR, P->du, P->dy);
+  return gemv_n(h, P->n, P->kd, 1.0, P->obj_P, P->ldn, P->dy, 0.0, P->Px);
+}
+// H := t * B diag(y) B' as one more weighted SYRK (contraction length = the primal dimension), mirrored: exactly
+// symmetric   (Dist_KL.scala:152-159)
+int dual_hessian(cvxb_problem_s* P, double t, const double* t_dev) {
+  Handle& h = *P->h;
+  const int n = P->n;
+  CVXB_LAUNCH(h, dual_scale_cols_kernel, dim3((n + 127) / 128, P->kd > 1024 ? 1024 : P->kd), 128, 0, n, P->kd, P->obj_P,
+              P->ldn, P->dy, t, t_dev, P->Bs, P->ldn);
+  GemmArgs gd{n, n, P->kd, P->Bs, P->ldn, false, P->Bs, P->ldn, false, P->H, P->ldn, 1.0, 0.0, 2};
+  gd.streamk = true;
+  return gemm_dmma(h, gd);
+}
+
 int barrier_eval(cvxb_problem_s* P, double t, const double* t_dev = nullptr) {
   Handle& h = *P->h;
   const int n = P->n, m = P->m, p = P->p;
   CVXB_TRY(quad_refresh(P));
   CVXB_TRY(gemv_n(h, m, n, 1.0, P->G, P->ldm, P->x, 0.0, P->gx));
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->Px));
-  if (P->objective == CVXB_OBJ_KLDUAL) {     // u = B'z, y = R o exp(-u), Px := B y
-    CVXB_TRY(gemv_t(h, n, P->kd, 1.0, P->obj_P, P->ldn, P->x, 0.0, P->du));
-    CVXB_LAUNCH(h, dual_y_kernel, (P->kd + 255) / 256, 256, 0, P->kd, P->objR, P->du, P->dy);
-    CVXB_TRY(gemv_n(h, n, P->kd, 1.0, P->obj_P, P->ldn, P->dy, 0.0, P->Px));
-  }
-  CVXB_LAUNCH(h, eval_cnt_kernel, 1, VT, 0, m, n, P->objective, P->obj_r, t, t_dev, P->gr, P->ub, P->gx, P->inv, P->x,
-              P->obj_a, P->Px, P->qcorr, P->dy, P->kd, P->obj_pow, h.d_scal, h.d_flag);
+  if (P->objective == CVXB_OBJ_KLDUAL) CVXB_TRY(dual_refresh(P));           // u = B'z, y = R o exp(-u), Px := B y
+  if (P->objective == CVXB_OBJ_COMPOSED) CVXB_TRY(composed_refresh(P));     // x_full = z0 + F u, Px := F' grad f(x_full)
+  const bool cmp = P->objective == CVXB_OBJ_COMPOSED;
+  CVXB_LAUNCH(h, eval_cnt_kernel, 1, VT, 0, m, cmp ? P->cmp_n : n, cmp ? P->cmp_kind : P->objective, P->obj_r, t, t_dev, P->gr,
+              P->ub, P->gx, P->inv, cmp ? P->cmpx : P->x, P->obj_a, P->Px, P->qcorr, P->dy, P->kd, P->obj_pow, h.d_scal,
+              h.d_flag);
   CVXB_TRY(gemv_t(h, m, n, 1.0, P->G, P->ldm, P->inv, 0.0, P->gt));
   if (p > 0) CVXB_TRY(gemv_n(h, p, n, 1.0, P->A, P->ldp, P->x, 0.0, P->axv));
   CVXB_LAUNCH(h, eval_grad_kernel, 1, VT, 0, n, p, P->objective, t, t_dev, P->x, P->obj_a, P->Px, P->gt, P->y, P->b, P->axv,
@@ -513,14 +569,8 @@ int barrier_hessian(cvxb_problem_s* P, double t, const double* t_dev = nullptr) 
   else if (P->objective == CVXB_OBJ_KL) CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, tv, P->H, P->ldn, t_dev));
   else if (P->objective == CVXB_OBJ_PNORM)      // t p (p-1) |x|^(p-2) on the diagonal
     CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, P->x, tv * P->obj_pow * (P->obj_pow - 1.0), P->H, P->ldn, t_dev, P->obj_pow - 2.0));
-  else if (P->objective == CVXB_OBJ_KLDUAL) {
-    // t * B diag(y) B'  as one more weighted SYRK (contraction length = primal dimension), mirrored: exactly symmetric
-    CVXB_LAUNCH(h, dual_scale_cols_kernel, dim3((n + 127) / 128, P->kd > 1024 ? 1024 : P->kd), 128, 0, n, P->kd, P->obj_P,
-                P->ldn, P->dy, t, t_dev, P->Bs, P->ldn);
-    GemmArgs gd{n, n, P->kd, P->Bs, P->ldn, false, P->Bs, P->ldn, false, P->H, P->ldn, 1.0, 0.0, 2};
-    gd.streamk = true;
-    CVXB_TRY(gemm_dmma(h, gd));
-  }
+  else if (P->objective == CVXB_OBJ_KLDUAL) CVXB_TRY(dual_hessian(P, t, t_dev));
+  else if (P->objective == CVXB_OBJ_COMPOSED) CVXB_TRY(composed_hessian(P, t, t_dev));
   else CVXB_TRY(fill_matrix(h, n, 0.0, nullptr, 0, nullptr, 0.0, P->H, P->ldn));
   CVXB_TRY(quad_hessian_terms(P, P->inv));     // + hess g_k / d_k   (BarrierSolver.scala:313)
   GemmArgs g{n, n, m, P->Gs, P->ldm, true, P->Gs, P->ldm, true, P->H, P->ldn, 1.0, 1.0, 2};
@@ -536,8 +586,11 @@ int enqueue_linesearch(cvxb_problem_s* P, const cvxb_params& pars, double t, int
   if (P->objective == CVXB_OBJ_QUADRATIC) CVXB_TRY(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, P->dir, 0.0, P->Pd));
   CVXB_TRY(quad_direction(P, P->dir));
   if (P->objective == CVXB_OBJ_KLDUAL) CVXB_TRY(gemv_t(h, n, P->kd, 1.0, P->obj_P, P->ldn, P->dir, 0.0, P->dv));
+  const bool cmp = P->objective == CVXB_OBJ_COMPOSED;
+  if (cmp) CVXB_TRY(gemv_n(h, P->cmp_n, n, 1.0, P->cmpF, P->cmp_ld, P->dir, 0.0, P->cmpd));     // F du
   LsArgs A;
-  A.m = m; A.n = n; A.kind = P->objective; A.mode = mode; A.iter0 = iter0;
+  A.m = m; A.n = n; A.kind = cmp ? P->cmp_kind : P->objective; A.mode = mode; A.iter0 = iter0;
+  A.xobj = cmp ? P->cmpx : P->x; A.dobj = cmp ? P->cmpd : P->dir; A.nobj = cmp ? P->cmp_n : n;
   A.t = t; A.alpha = pars.alpha; A.beta = pars.beta; A.tol = pars.tolSolver;
   A.gx = P->gx; A.ub = P->ub; A.Gd = P->Gd; A.a = P->obj_a; A.Px = P->Px; A.Pd = P->Pd; A.y = P->y;
   A.x = P->x; A.dir = P->dir; A.qq = P->mq > 0 ? P->qq : nullptr; A.t_dev = t_dev;
@@ -981,12 +1034,30 @@ static int problem_reduce(cvxb_problem_s* P, cvxb::SolutionSpaceDev* S, double t
                          "a 0 = 0 system); build the solver without them");
     return CVXB_ENOTIMPL;
   }
-  if (P->objective != CVXB_OBJ_LINEAR && P->objective != CVXB_OBJ_QUADRATIC) {
-    cvxb::set_last_error("reduced: only linear and quadratic objectives have a closed-form affine transform on the device");
+  const bool compose = P->objective == CVXB_OBJ_KL || P->objective == CVXB_OBJ_PNORM;
+  if (P->objective != CVXB_OBJ_LINEAR && P->objective != CVXB_OBJ_QUADRATIC && !compose) {
+    cvxb::set_last_error("reduced: the affine transform of this objective family (kind %d) is not built on the device", P->objective);
     return CVXB_ENOTIMPL;
   }
   cvxb_problem_s* R = nullptr;
-  CVXB_TRY(problem_alloc(h, k, ml, 0, P->objective, &R, mq, 0));
+  CVXB_TRY(problem_alloc(h, k, ml, 0, compose ? (int)CVXB_OBJ_COMPOSED : P->objective, &R, mq, 0));
+  if (compose) {
+    // f(u) = f_inner(z0 + F u): keep F and z0 with the reduced problem (ObjectiveFunction.affineTransformed,
+    // ObjectiveFunction.scala:26-40); value, gradient F'grad f and Hessian F' hess f F are evaluated per step
+    R->cmp_n = n; R->cmp_ld = pad_ld(n); R->cmp_kind = P->objective;
+    const size_t ldc = (size_t)R->cmp_ld;
+    double* blk = nullptr;
+    cudaError_t e = cudaMalloc((void**)&blk, sizeof(double) * (2 * ldc * k + 5 * ldc + (size_t)pad_ld(k)));
+    if (e != cudaSuccess) { cvxb::set_last_error("CUDA error %s in reduced", cudaGetErrorString(e)); problem_free(R); return CVXB_ECUDA; }
+    R->owned.push_back(blk);
+    cudaMemsetAsync(blk, 0, sizeof(double) * (2 * ldc * k + 5 * ldc + (size_t)pad_ld(k)), h.stream);
+    R->cmpF = blk; R->cmpFs = blk + ldc * k;
+    double* v = blk + 2 * ldc * k;
+    R->cmpz0 = v; R->cmpx = v + ldc; R->cmpd = v + 2 * ldc; R->cmpg = v + 3 * ldc; R->cmpw = v + 4 * ldc; R->cmpgf = v + 5 * ldc;
+    cudaMemcpy2DAsync(R->cmpF, ldc * sizeof(double), S->F(), (size_t)S->ldq * sizeof(double), (size_t)n * sizeof(double), k,
+                      cudaMemcpyDeviceToDevice, h.stream);
+    cudaMemcpyAsync(R->cmpz0, S->z0, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h.stream);
+  }
   double* T1 = nullptr;        // n x k scratch, then vectors
   double* vec = nullptr;       // 2 * ldn + (mq + 2) scalars
   int st = CVXB_OK;
@@ -1015,7 +1086,7 @@ static int problem_reduce(cvxb_problem_s* P, cvxb::SolutionSpaceDev* S, double t
       T(gemm_dmma(h, g2));
       T(gemv_n(h, n, n, 1.0, P->obj_P, P->ldn, S->z0, 0.0, Pz));
     }
-    if (st == CVXB_OK) {
+    if (st == CVXB_OK && !compose) {
       CVXB_LAUNCH(h, affine_shift_kernel, 1, VT, 0, n, P->obj_a, P->objective == CVXB_OBJ_QUADRATIC ? Pz : nullptr, S->z0, shifted, scal);
       T(gemv_t(h, n, k, 1.0, F, S->ldq, shifted, 0.0, R->obj_a));
     }

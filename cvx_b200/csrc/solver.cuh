@@ -2,6 +2,8 @@
 #pragma once
 #include "kkt.cuh"
 
+enum { CVXB_OBJ_COMPOSED = 100 };     // internal: not part of cvxb_objective_kind
+
 struct cvxb_problem_s {
   cvxb_handle_s* h = nullptr;
   int n = 0, m = 0, p = 0, objective = 0;
@@ -31,6 +33,17 @@ struct cvxb_problem_s {
   // CVXB_OBJ_KLDUAL: f(z) = w'z + sum_j R_j exp(-(B'z)_j); obj_P holds B (n x kd), obj_a holds w
   int kd = 0, ldk = 0;
   double *objR = nullptr, *du = nullptr, *dy = nullptr, *dv = nullptr, *Bs = nullptr;   // B'z, R o exp(-B'z), B'd, B diag(sqrt(t y))
+  // objective composed with an affine map, f(u) = f_inner(z0 + F u) (ObjectiveFunction.affineTransformed,
+  // ObjectiveFunction.scala:26-40, for the KL and p-norm objectives of a reduced problem): objective ==
+  // CVXB_OBJ_COMPOSED, cmp_kind the inner family, cmp_n its dimension; F is cmp_n x n (leading dimension cmp_ld)
+  int cmp_n = 0, cmp_ld = 0, cmp_kind = 0;
+  double *cmpF = nullptr, *cmpz0 = nullptr;
+  double *cmpx = nullptr;     // z0 + F u
+  double *cmpd = nullptr;     // F du (line searches)
+  double *cmpg = nullptr;     // grad f_inner(z0 + F u); scratch of the primal-dual line search afterwards
+  double *cmpw = nullptr;     // t * diag hess f_inner
+  double *cmpFs = nullptr;    // diag(sqrt(cmpw)) F
+  double *cmpgf = nullptr;    // n: F' grad f_inner at a line-search trial point
   // matrices
   double *Gs = nullptr, *H = nullptr, *Hreg = nullptr;
   cvxb::KktWork kw;

@@ -138,6 +138,23 @@ class SolutionSpace:
         self.n, self.p = n, p
         self._z0 = self._F = None
 
+    @classmethod
+    def from_basis(cls, z0, F, handle=None) -> "SolutionSpace":
+        """The affine map x = z0 + F u handed in explicitly (Solver.affineTransformed(z0, F, u0), Solver.scala:33-46):
+        cvxb_solution_space_from_basis.  F is n x k; `parameter` computes F'(x - z0)."""
+        self = object.__new__(cls)
+        F, z0 = fmat(F), fvec(z0)
+        n, k = F.shape
+        if z0.shape[0] != n:
+            raise _lib.DimensionMismatch("affineTransformed: z0.length != F.rows")
+        self.A = self.b = None
+        self.handle = _h(handle)
+        self._s = C.c_void_p()
+        check(self.handle.lib.cvxb_solution_space_from_basis(self.handle._h, n, k, ptr(z0), ptr(F), n, C.byref(self._s)))
+        self.n, self.p = n, n - k
+        self._z0, self._F = z0, F
+        return self
+
     def _fetch(self):
         if self._z0 is None:
             z0 = np.empty(self.n)

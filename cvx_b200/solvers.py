@@ -209,6 +209,59 @@ class ConstraintSet:
         rep.solution = ph
         return rep
 
+    # ---- phase I with the equalities eliminated (ConstraintSet.scala:424-477)
+    def phase_I_Constraints_noEqs(self) -> "ConstraintSet":
+        """g_j(x) - s <= ub_j in dimension n + 1 with the feasible point (x0, 1 + max_j(g_j(x0) - ub_j)),
+        x0 = pointWhereDefined (ConstraintSet.scala:153-168; Constraint.phase_I, Constraint.scala:64-89)."""
+        n, ml = self.dim, self.H.shape[0]
+        G1 = np.empty((ml, n + 1), order="F")
+        G1[:, :n] = self.H
+        G1[:, n] = -1.0
+        quad = []
+        for q in self.quadratic:
+            P1 = np.zeros((n + 1, n + 1))
+            P1[:n, :n] = q.P
+            quad.append(QuadraticConstraint(str(q.id) + "_phase_I", n + 1, q.ub, q.r, np.concatenate([q.a, [-1.0]]), P1))
+        x0 = self.pointWhereDefined
+        assert x0 is not None, "phase I needs pointWhereDefined"
+        s0 = 1.0 + float(np.max(self.valuesAt(x0) - self.ub_all()))
+        fp = np.concatenate([x0, [s0]])
+        return ConstraintSet(G1, self.u, fp, self.r, quad).addFeasiblePoint(fp)
+
+    def phase_I_Analysis_by_reduction(self, eqs, pars=None, debugLevel=0, handle=None, corrected=False) -> "FeasibilityReport":
+        """ConstraintSet.phase_I_Analysis_by_reduction (ConstraintSet.scala:424-477): phase I with Ax = b parameterised
+        as x = z0 + F u.  AS WRITTEN THE REFERENCE CANNOT COMPLETE THIS CALL: it reduces the (n+1)-dimensional phase-I
+        solver with the n-dimensional solution space of Ax = b (`solverNoEqs.reduced(solEqs)`, :447-449), and
+        BarrierSolver.reduced -> SolutionSpace.parameter subtracts z0 (length n) from the starting point (length
+        n + 1) -- a Breeze dimension error.  Mirrored: the device call refuses with the dimension error
+        (CVXB_EDIM -> DimensionMismatch, an AssertionError).  corrected=True does what the method's doc comment
+        describes: the map (x, s) = (z0, 0) + blockdiag(F, 1)(u, s), the barrier solve of min s in (u, s), and the
+        report in x = z0 + F u with the reference's strictness test (s < 0 and ||Ax - b|| < tolSolver, :461-462)."""
+        from .linalg import SolutionSpace
+        pars = pars if pars is not None else SolverParams.standardParams()
+        n = self.dim
+        a = np.zeros(n + 1)
+        a[n] = 1.0
+        solverNoEqs = BarrierSolver(LinearObjectiveFunction(n + 1, 0.0, a), self.phase_I_Constraints_noEqs(), None, pars, None, handle)
+        solEqs = eqs.solutionSpace if handle is None or eqs.solutionSpace.handle is solverNoEqs.handle else SolutionSpace(eqs.A, eqs.b, solverNoEqs.handle)
+        if not corrected:
+            solver = solverNoEqs.reduced(solEqs)          # raises DimensionMismatch: F.rows = n, dim(problem) = n + 1
+            raise AssertionError("unreachable: the reference's call cannot succeed")      # pragma: no cover
+        F, z0 = solEqs.F, solEqs.z0
+        k = F.shape[1]
+        F1 = np.zeros((n + 1, k + 1), order="F")
+        F1[:n, :k] = F
+        F1[n, k] = 1.0
+        ext = SolutionSpace.from_basis(np.concatenate([z0, [0.0]]), F1, solverNoEqs.handle)
+        solver = solverNoEqs.reduced(ext)
+        sol = solver.solve(debugLevel)
+        u_feas, s_feas = sol.x[:k], float(sol.x[k])
+        x_feas = z0 + F @ u_feas
+        eqError = eqs.errorAt(x_feas)
+        rep = FeasibilityReport(x_feas, np.array([s_feas]), s_feas < 0.0 and eqError < pars.tolSolver, self, eqError)
+        rep.solution = sol
+        return rep
+
     # ---- phase I, sum of infeasibilities (ConstraintSet.scala:233-282, 488-545; Constraint.scala:101-159)
     def phase_I_SOI_ObjectiveFunction(self):
         """f(x, s) = s_1 + ... + s_p in dimension n + p (ConstraintSet.scala:233-249)."""

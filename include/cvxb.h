@@ -129,6 +129,31 @@ int cvxb_cholesky_solve(cvxb_handle h, int n, const double* H, int ldh, const do
 int cvxb_symmetric_solve(cvxb_handle h, int n, const double* H, int ldh, const double* r, double tol,
                          double* x, cvxb_kkt_info* info);
 
+/* ---- seam B with pinned, double-buffered staging: general (non-closed-form) objectives ---------------------------
+ * An objective given only as closures (ObjectiveFunction.valueAt / gradientAt / hessianAt, ObjectiveFunction.scala:12-14;
+ * e.g. the reference's Type1Function power problems, src/test/scala/cvx/Type1Function.scala:67-78) has its Hessian
+ * assembled on the HOST every Newton step.  A stage owns the device copy of H (n x n) and A (p x n), two pinned host
+ * buffers of block_cols columns each, and a copy stream: the caller fills buffer 0 with columns [0, c), pushes it, fills
+ * buffer 1 with [c, 2c) while the first block is in flight, waits for buffer 0, ... -- assembly and upload overlap -- and
+ * then solves on the device-resident matrix:
+ *   cvxb_stage_cholesky_solve   MatrixUtils.choleskySolve(H, b)       (UnconstrainedSolver.scala:50-66)
+ *   cvxb_stage_kkt_solve        KKTSystem(H, A, q, b).solve           (EqualityConstrainedSolver.scala:52-58)
+ * Vectors are plain host pointers.  Host pointers only (no CVXB_FLAG_DEVICE_PTRS). */
+typedef struct cvxb_stage_s* cvxb_stage;
+int cvxb_stage_create(cvxb_handle h, int n, int p, int block_cols /* 0 = default */, cvxb_stage* out);
+int cvxb_stage_destroy(cvxb_stage stage);
+/* pinned host buffer `which` (0 or 1): n x block_cols column-major with leading dimension n */
+int cvxb_stage_buffer(cvxb_stage stage, int which, double** host_buffer, int* block_cols);
+/* start the upload of buffer `which` into columns [col0, col0 + ncols) of H; returns at once */
+int cvxb_stage_push(cvxb_stage stage, int which, int col0, int ncols);
+/* block until buffer `which` may be overwritten (its last push has left the host) */
+int cvxb_stage_wait(cvxb_stage stage, int which);
+/* A (p x n, leading dimension lda): uploaded once, it does not change between Newton steps */
+int cvxb_stage_set_equalities(cvxb_stage stage, const double* A, int lda);
+int cvxb_stage_cholesky_solve(cvxb_stage stage, const double* b, double tol, double* x, cvxb_kkt_info* info);
+int cvxb_stage_kkt_solve(cvxb_stage stage, const double* q, const double* b, double tol, double* x, double* w,
+                         cvxb_kkt_info* info);
+
 /* MatrixUtils.ruizEquilibrate(H): (d, Q)                         MatrixUtils.scala:240-268 */
 int cvxb_ruiz_equilibrate(cvxb_handle h, int n, const double* H, int ldh, double* d, double* Q,
                           int ldq, int* sweeps);
@@ -305,6 +330,7 @@ typedef struct cvxb_batch_desc {
   const double* x0;        /* B*n   */
 } cvxb_batch_desc;
 
+enum { CVXB_BATCH_STAGES = 16 };
 typedef struct cvxb_batch_result {
   double* x;               /* B*n */
   int* status;             /* B: cvxb_status per problem */
@@ -314,6 +340,8 @@ typedef struct cvxb_batch_result {
   double* duality_gap;     /* B */
   double* equality_gap;    /* B */
   double solve_ms;
+  int* stage_newton_steps; /* B * CVXB_BATCH_STAGES or NULL: Newton steps of each of the first 16 outer stages (0 beyond
+                              the last stage), as cvxb_solution.stage_newton_steps */
 } cvxb_batch_result;
 
 typedef struct cvxb_batch_s* cvxb_batch;

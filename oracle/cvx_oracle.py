@@ -412,7 +412,7 @@ def affineTransformedProblem(objF, cnts, z0, F):
         o = QuadraticObjective((Pu + Pu.T) / 2, F.T @ (objF.a + objF.P @ z0),
                                objF.r + float(objF.a @ z0) + float(z0 @ (objF.P @ z0)) / 2)
     else:
-        raise NotImplementedError("affine transform of objective kind %s" % objF.kind)
+        o = ComposedObjective(objF, z0, F)
     return o, c
 
 
@@ -579,6 +579,30 @@ class DualKLObjective(Objective):
     def primalOptimum(self, z):
         """Dist_KL.primalOptimum (:163)."""
         return self._y(z)
+
+
+class ComposedObjective(Objective):
+    """ObjectiveFunction.affineTransformed(z, F) (ObjectiveFunction.scala:26-40): h(u) = f(z + F u), gradient
+    F' grad f, Hessian F' hess f F -- the generic transform every objective without a closed form of its own goes
+    through (KL, p-norm).  (The reference gives the transformed function the dimension `dim - F.cols` instead of F.cols,
+    ObjectiveFunction.scala:28; BarrierSolver's constructor assert objF.dim == startingPoint.length, BarrierSolver.scala:32,
+    therefore only passes when n = 2p -- defect D11.  The restatement uses F.cols.)"""
+    kind = "composed"
+
+    def __init__(self, inner, z0, F):
+        self.inner, self.z0, self.F = inner, np.asarray(z0, float), np.asarray(F, float)
+        self.dim = self.F.shape[1]
+        self.reference_dim = inner.dim - self.F.shape[1]      # what ObjectiveFunction.scala:28 computes
+
+    def valueAt(self, u):
+        return self.inner.valueAt(self.z0 + self.F @ u)
+
+    def gradientAt(self, u):
+        return self.F.T @ self.inner.gradientAt(self.z0 + self.F @ u)
+
+    def hessianAt(self, u):
+        H = self.F.T @ self.inner.hessianAt(self.z0 + self.F @ u) @ self.F
+        return (H + H.T) / 2          # Breeze's cholesky insists on exact symmetry (see affineTransformedProblem)
 
 
 @dataclass

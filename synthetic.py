@@ -313,3 +313,76 @@ def newton_step_inputs(n, m_half, p, seed=0):
     smax = float(np.min(np.where(Gd > 0, slack / np.where(Gd > 0, Gd, 1.0), np.inf)))
     x = prob["x0"] + 0.5 * smax * d
     return prob, x, 10.0
+
+
+# ---------------- objectives given as closures (seam B: Hessian assembled on the host) ----------------
+
+
+class PowerFunction:
+    """Type1Function.powerFunction(A, alpha, q) (src/test/scala/cvx/Type1Function.scala:25-78, docs/cvx_notes example 3.1):
+    f(x) = sum_j alpha_j ((a_j . x)^2)^q, a_j = row_j(A), q > 1; global minimum 0 on ker(A).  Plain numpy closures --
+    value, gradient, Hessian -- as an objective without a closed-form family looks to the solvers; `hessianColumns`
+    produces a block of columns of  A' diag(alpha o phi''(Ax)) A  so that its upload can overlap the next block."""
+
+    def __init__(self, A, alpha, q):
+        self.A, self.alpha, self.q = np.asarray(A, float), np.asarray(alpha, float), float(q)
+        assert self.q > 1, "q=%s is not > 1." % q
+        assert self.A.shape[0] <= self.A.shape[1] and self.alpha.shape[0] == self.A.shape[0] and np.all(self.alpha > 0)
+        self.dim = self.A.shape[1]
+        self._w_at, self._w = None, None
+
+    def _u(self, x):
+        u = self.A @ x
+        return np.where(np.abs(u) < 1e-14, 0.0, u)
+
+    def valueAt(self, x):
+        u = self._u(x)
+        return float(self.alpha @ np.power(u * u, self.q))
+
+    def gradientAt(self, x):
+        u = self._u(x)
+        d = np.where(u == 0.0, 0.0, (2 * self.q) * np.power(u * u, self.q - 0.5)) * np.sign(u)
+        return self.A.T @ (self.alpha * d)
+
+    def _weights(self, x):
+        if self._w_at is None or not np.array_equal(self._w_at, x):
+            u = self._u(x)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                d2 = np.where(u == 0.0, 0.0, (2 * self.q) * (2 * self.q - 1) * np.power(u * u, self.q - 1))
+            self._w_at, self._w = np.array(x, copy=True), self.alpha * d2
+        return self._w
+
+    def hessianAt(self, x):
+        w = self._weights(x)
+        H = self.A.T @ (self.A * w[:, None])
+        return (H + H.T) / 2
+
+    def hessianColumns(self, x, j0, j1, out):
+        w = self._weights(x)
+        np.matmul(self.A.T, self.A[:, j0:j1] * w[:, None], out=out)
+
+    def isMinimizer(self, x, tol):
+        return float(np.linalg.norm(self.A @ x)) < tol
+
+
+def power_problem(A, alpha, q):
+    """OptimizationProblems.powerProblem (src/test/scala/cvx/OptimizationProblems.scala:61-90): unconstrained, start
+    x_j = -10 + j sqrt(n), known minimum value 0 on ker(A)."""
+    f = PowerFunction(A, alpha, q)
+    n = f.dim
+    return f, np.array([-10.0 + j * np.sqrt(n) for j in range(n)])
+
+
+def power_problems():
+    """OptimizationProblems.powerProblems (:112-125): A = I_2 and A = [[1,0],[1,1]], alpha = (1,1), q = 2."""
+    return [power_problem(np.eye(2), np.ones(2), 2.0), power_problem(np.array([[1.0, 0.0], [1.0, 1.0]]), np.ones(2), 2.0)]
+
+
+def random_power_problem(dim, m, q, seed=0):
+    """Type1Function.randomPowerFunction (Type1Function.scala:85-95) with a seed: A = U(0,1)^{m x dim} + I, alpha ~ U(0,1)."""
+    rng = np.random.default_rng(seed)
+    A = rng.uniform(0, 1, (m, dim))
+    A[np.arange(m), np.arange(m)] += 1.0
+    alpha = rng.uniform(0.05, 1.0, m)
+    f = PowerFunction(A, alpha, q)
+    return f, rng.uniform(-1.0, 1.0, dim)

@@ -45,17 +45,30 @@ def test_newton_direction_parity(handle, n, mh, p, seed):
     assert info.path == 0
 
 
+def _band():
+    """Allowed deviation of the Newton count of outer stage k from the oracle's (tests/golden/iteration_noise.json,
+    produced by tools/iteration_noise_experiment.py): +-1 -- north_star's bar -- for as long as the CPU oracle itself
+    reproduces its counts under rounding-level changes (BLAS threads, literal Hessian accumulation, half-ulp input
+    changes): stages 0-3, t <= 1e3.  Beyond that the oracle's own variants disagree (by up to 3 steps at t = 1e6, 5 at
+    t = 1e8, 27 at t = 1e11, and on whether a stage spins to maxIter at all); the band there is twice the largest
+    deviation observed between two CPU variants."""
+    import json
+    import os
+    f = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "iteration_noise.json")
+    return json.load(open(f))["summary"]["band_by_stage"]
+
+
 def _check_solve(sol, sol0, obj0, ph0=None):
-    """Stage counts: identical number of outer stages; Newton steps per stage within +-1 while the stage is in
-    the deterministic regime (t <= 1e3).  Later stages stop on `newtonDecrement <= 1e-8` / `||b-Ax|| <= 1e-8`
-    tests that sit at the rounding-noise floor of t*f0 - sum log d (t >= 1e4): there two LAPACK builds differ
-    by a few steps too, so the bar is a loose band and the objective (1e-8 relative) is the real check."""
+    """Identical number of outer stages; Newton steps per stage within the measured band (see _band); objective within
+    1e-8 relative; duality gap m/t identical."""
+    band = _band()
     assert sol.outer_stages == sol0.outer_stages
     assert len(sol.stage_newton_steps) == len(sol0.stage_newton_steps)
     for k, (a, b) in enumerate(zip(sol.stage_newton_steps, sol0.stage_newton_steps)):
         if a >= 1000 or b >= 1000:
-            continue      # equality-gap spin until maxIter: decided by whether ||b-Ax|| rounds above 1e-8
-        tol = 1 if k <= 3 else max(3, (6 * b) // 10)
+            assert k >= 4, (k, sol.stage_newton_steps, sol0.stage_newton_steps)
+            continue      # equality-gap spin until maxIter: decided by whether ||b-Ax|| rounds above 1e-8 (15 flips between CPU variants)
+        tol = band[k] if k < len(band) else band[-1]
         assert abs(a - b) <= tol, (k, sol.stage_newton_steps, sol0.stage_newton_steps)
     assert abs(sol.objective - obj0) <= 1e-8 * max(1.0, abs(obj0))
     assert abs(sol.dualityGap - sol0.dualityGap) <= 1e-12 * sol0.dualityGap

