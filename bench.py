@@ -290,6 +290,37 @@ def cpu_reference_leg(workload, steps, warmup, seed=0):
     return done / dt, done, dt, " + ".join(sample), cores
 
 
+def cpu_modes_leg():
+    """the CPU baseline in its two modes on the configs where the literal one is feasible --
+    `literal` = the reference's actual per-constraint foldLeft Hessian (BarrierSolver.scala:303-315: m rank-one updates
+    with fresh n x n temporaries), `vectorised` = one dgemm.  C1 (n=100, m=200, p=20, barrier) as Newton steps/s, C3
+    (n=64, m=128 batched mix, 8 problems) as solves/s.  At C4 / C5 the literal loop would move ~44 TB per Hessian."""
+    from oracle import cvx_oracle as O
+    from oracle import problems as P
+    _blas_threads()
+    out = {}
+    pr = make_problem("c1", 0)
+    objF, cnts, eqs = P.to_oracle(pr)
+    for mode, lit in (("literal", True), ("vectorised", False)):
+        t0 = time.perf_counter()
+        # maxIter 100 instead of 1000: this instance has a stage in which the reference repeats one identical step until
+        # maxIter (||b-Ax|| stays above tol, EqualityConstrainedSolver.scala:49); every repeat is a full Newton step on the CPU
+        sol, _ = O.solveProblem(objF, cnts, eqs, "BR", pars=O.SolverParams(maxIter=100), literal=lit)
+        dt = time.perf_counter() - t0
+        steps = int(sol.newton_steps)
+        out["c1_" + mode] = {"value": steps / dt, "unit": "steps/s", "steps": steps, "seconds": dt}
+    import synthetic as S
+    probs = [S.batched_problem(i, 64, 128, 1000) for i in range(8)]
+    for mode, lit in (("literal", True), ("vectorised", False)):
+        t0 = time.perf_counter()
+        for q in probs:
+            o_, c_, e_ = P.to_oracle(q)
+            O.solveProblem(o_, c_, e_, "BR", literal=lit)
+        dt = time.perf_counter() - t0
+        out["c3_" + mode] = {"value": len(probs) / dt, "unit": "solves/s", "problems": len(probs), "seconds": dt}
+    return out
+
+
 def pinned_problem(prob):
     """The problem's matrices as column-major (Breeze layout) views on pinned host memory: what a long-running caller
     hands to the C ABI.  Returns (problem dict, bytes uploaded per cvxb_problem_create, keep-alive list)."""
@@ -372,7 +403,7 @@ def main():
     ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--no-legs", action="store_true", help="skip the extra single-GPU legs (c2, c5)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--legs", default="c2,c5", help="comma-separated extra workloads run at N=1 after the headline")
+    ap.add_argument("--legs", default="c1,c2,c5", help="comma-separated extra workloads run at N=1 after the headline")
     ap.add_argument("--batch", type=int, default=8192, help="problems in the batched leg (configs[2])")
     ap.add_argument("--cpu-steps", type=int, default=0, help="Newton steps of the CPU-baseline sample (0 = auto)")
     args = ap.parse_args()
@@ -632,6 +663,12 @@ def main():
                                  "this image lacks)" % (done, sample, dt, cores)}
             except Exception as e:      # never lose the GPU line to a CPU-side problem
                 cpu = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+        cpu_modes = None
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                cpu_modes = cpu_modes_leg()
+            except Exception as e:
+                cpu_modes = {"failed": repr(e)}
         line = {"metric": "newton_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dev_ms_max / max(steps_done, 1), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -647,7 +684,7 @@ def main():
                 "flops_per_step": f_step(n, m, p), "tflops": f_step(n, m, p) * value / world / 1e12,
                 "tflops_frac_of_fp64_tensor_peak": f_step(n, m, p) * value / world / 1e12 / fp64_peak if fp64_peak else None,
                 "e2e": e2e, "gpu_launches": int(total_launches), "roofline": roofline, "roofline_chol_trailing": chol,
-                "step_breakdown": breakdown, "hbm_kernels": hbm, "cpu_baseline": cpu, "batched": batched, "legs": legs,
+                "step_breakdown": breakdown, "hbm_kernels": hbm, "cpu_baseline": cpu, "cpu_baseline_modes": cpu_modes, "batched": batched, "legs": legs,
                 "last_solution": {"objective": last.objective, "outer_stages": last.outer_stages,
                                   "newton_steps": last.newton_steps, "phase1_newton_steps": last.phase1_newton_steps}}
         print(json.dumps(line))

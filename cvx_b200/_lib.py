@@ -115,7 +115,8 @@ class BatchDesc(C.Structure):
 
 class BatchResult(C.Structure):
     _fields_ = [("x", _dp), ("status", _ip), ("newton_steps", _ip), ("outer_stages", _ip), ("objective", _dp),
-                ("duality_gap", _dp), ("equality_gap", _dp), ("solve_ms", C.c_double), ("stage_newton_steps", _ip)]
+                ("duality_gap", _dp), ("equality_gap", _dp), ("solve_ms", C.c_double), ("stage_newton_steps", _ip),
+                ("cycles", C.POINTER(C.c_longlong))]
 
 
 # every symbol include/cvxb.h declares: name -> (restype, argtypes)
@@ -127,6 +128,7 @@ SYMBOLS = {
     "cvxb_last_error": (C.c_char_p, []),
     "cvxb_version": (C.c_char_p, []),
     "cvxb_launch_count": (C.c_longlong, [_vp]),
+    "cvxb_status_read_count": (C.c_longlong, [_vp]),
     "cvxb_default_params": (C.c_int, [C.POINTER(Params)]),
     "cvxb_profile_enable": (C.c_int, [_vp, C.c_int]),
     "cvxb_profile_read": (C.c_int, [_vp, C.POINTER(C.c_longlong), _dp, _dp]),
@@ -241,6 +243,11 @@ class Handle:
     @property
     def launches(self) -> int:
         return int(self.lib.cvxb_launch_count(self._h))
+
+    @property
+    def status_reads(self) -> int:
+        """Host round trips so far (status block read + stream synchronisation)."""
+        return int(self.lib.cvxb_status_read_count(self._h))
 
     def synchronize(self):
         check(self.lib.cvxb_synchronize(self._h))

@@ -28,6 +28,7 @@ class BatchSolution:
     equalityGap: np.ndarray    # B
     solve_ms: float
     stage_newton_steps: Optional[np.ndarray] = None    # B x 16: Newton steps per outer stage
+    cycles: Optional[np.ndarray] = None                # B: SM clock cycles each problem occupied its CTA
 
 
 def pack_problems(probs: Sequence[dict]):
@@ -106,8 +107,10 @@ class BatchedBarrierSolver:
         r.objective, r.duality_gap, r.equality_gap = dptr(objv), dptr(gap), dptr(eqg)
         stage_steps = np.zeros((B, 16), dtype=np.int32)
         r.stage_newton_steps = ip(stage_steps)
+        cycles = np.zeros(B, dtype=np.int64)
+        r.cycles = cycles.ctypes.data_as(C.POINTER(C.c_longlong))
         check(self.handle.lib.cvxb_batch_barrier_solve(self.handle._h, self._b, C.byref(cp), C.byref(r)))
-        return BatchSolution(x, status, steps, stages, objv, gap, eqg, float(r.solve_ms), stage_steps)
+        return BatchSolution(x, status, steps, stages, objv, gap, eqg, float(r.solve_ms), stage_steps, cycles)
 
     def device_records(self):
         """(device pointer, doubles per row) of the packed results of the last solve:

@@ -215,6 +215,8 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
       CVXB_CUDA_OK(cudaMemset(h->sk_flags, 0, (size_t)h->sm_count * sizeof(int)));
     }
   }
+  CVXB_CUDA_OK(cudaMalloc((void**)&h->d_prof, 4 * sizeof(unsigned long long)));
+  CVXB_CUDA_OK(cudaMemset(h->d_prof, 0, 4 * sizeof(unsigned long long)));
   CVXB_CUDA_OK(cudaMallocHost((void**)&h->h_scal, NSCAL * sizeof(double)));
   CVXB_CUDA_OK(cudaMallocHost((void**)&h->h_flag, NFLAG * sizeof(int)));
   CVXB_CUDA_OK(cudaEventCreate(&h->ev0));
@@ -241,6 +243,8 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
   CVXB_CUDA_OK(cudaEventCreate(&h->gev0));
   CVXB_CUDA_OK(cudaEventCreate(&h->gev1));
   if (const char* e = getenv("CVXB_NO_GRAPHS")) h->use_graphs = (e[0] == '0' || e[0] == 0) ? 1 : 0;
+  if (const char* e = getenv("CVXB_NO_LOOP")) h->use_loop = (e[0] == '0' || e[0] == 0) ? 1 : 0;
+  if (!h->use_graphs) h->use_loop = 0;
   CVXB_TRY(gemm_dmma_init());
   CVXB_TRY(factor_init());
   *out = h;
@@ -253,6 +257,7 @@ int cvxb_destroy(cvxb_handle h) {
   cudaStreamSynchronize(h->stream);
   if (h->kkt_cache) { KktWork* W = (KktWork*)h->kkt_cache; kkt_work_free(*W); delete W; }
   cudaFree(h->sk_ws); cudaFree(h->sk_flags);
+  cudaFree(h->d_prof);
   cudaFree(h->wave_ready); cudaFree(h->d_scal); cudaFree(h->d_flag); cudaFree(h->d_part); cudaFree(h->d_ticket);
   cudaFreeHost(h->h_scal); cudaFreeHost(h->h_flag);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->gev0); cudaEventDestroy(h->gev1);
@@ -272,6 +277,7 @@ int cvxb_synchronize(cvxb_handle h) {
 }
 
 long long cvxb_launch_count(cvxb_handle h) { return h ? h->launches : 0; }
+long long cvxb_status_read_count(cvxb_handle h) { return h ? h->status_reads : 0; }
 
 int cvxb_profile_enable(cvxb_handle h, int on) {
   CHECK_HANDLE(h);
@@ -281,6 +287,7 @@ int cvxb_profile_enable(cvxb_handle h, int on) {
   h->prof_flops = 0.0;
   h->prof_ms_graph = 0.0;
   h->prof_launches_graph = 0;
+  CVXB_CUDA_OK(cudaMemsetAsync(h->d_prof, 0, 4 * sizeof(unsigned long long), h->stream));
   for (auto& R : h->prof_range) { R.used = 0; R.work = 0.0; }
   return CVXB_OK;
 }
@@ -312,8 +319,10 @@ int cvxb_profile_read(cvxb_handle h, long long* launches, double* ms_total, doub
     CVXB_CUDA_OK(cudaEventElapsedTime(&t, h->prof_events[i], h->prof_events[i + 1]));
     ms += t;
   }
-  if (launches) *launches = (long long)(h->prof_used / 2) + h->prof_launches_graph;
-  if (ms_total) *ms_total = ms + h->prof_ms_graph;
+  unsigned long long dp[4] = {0, 0, 0, 0};       // SYRKs timed inside device-driven stage loops
+  CVXB_CUDA_OK(cudaMemcpy(dp, h->d_prof, sizeof(dp), cudaMemcpyDeviceToHost));
+  if (launches) *launches = (long long)(h->prof_used / 2) + h->prof_launches_graph + (long long)dp[2];
+  if (ms_total) *ms_total = ms + h->prof_ms_graph + (double)dp[1] * 1e-6;
   if (flops_total) *flops_total = h->prof_flops;
   return CVXB_OK;
 }

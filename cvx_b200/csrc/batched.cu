@@ -27,6 +27,8 @@ struct cvxb_batch_s {
   double *x = nullptr, *objval = nullptr, *gap = nullptr, *eqgap = nullptr;
   int *status = nullptr, *steps = nullptr, *stages = nullptr;
   int* stage_steps = nullptr;    // B x CVXB_BATCH_STAGES: Newton steps of each of the first outer stages
+  int* order = nullptr;          // pickup order of the problems (longest expected first), or NULL = index order
+  long long* cycles = nullptr;   // B: SM clock cycles each problem spent in its CTA
   double* records = nullptr;     // B x (n + CVXB_BATCH_RECORD_EXTRA): [x, objective, gap, status, steps, stages] per problem
   double* scratch = nullptr;     // per-CTA copy of H (n x n)
   unsigned* counter = nullptr;
@@ -52,6 +54,8 @@ struct BatchArgs {
   double *x, *objval, *gap, *eqgap;
   int *status, *steps, *stages;
   int* stage_steps;
+  const int* order;
+  long long* cycles;
   double* records;
   double* scratch;
   unsigned* counter;
@@ -536,8 +540,10 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
     __syncthreads();
     if (tid == 0) s_pid = (int)atomicAdd(A.counter, 1u);
     __syncthreads();
-    const int pid = s_pid;
-    if (pid >= A.B) break;
+    if (s_pid >= A.B) break;
+    // longest-expected-first pickup (cvxb_batch_create): the tail of the batch is then made of the short problems
+    const int pid = A.order ? A.order[s_pid] : s_pid;
+    const long long clk0 = clock64();
     // ---- load the problem
     const int kind = A.objective[pid];
     const int p = A.pcount ? A.pcount[pid] : A.p;
@@ -682,6 +688,7 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
     __syncthreads();
     if (tid < CVXB_BATCH_STAGES) A.stage_steps[(size_t)pid * CVXB_BATCH_STAGES + tid] = S.stage_steps[tid];
     if (tid == 0) {
+      A.cycles[pid] = clock64() - clk0;
       A.status[pid] = status;
       A.steps[pid] = total_steps;
       A.stages[pid] = stage;
@@ -769,6 +776,20 @@ int cvxb_batch_create(cvxb_handle h, const cvxb_batch_desc* d, cvxb_batch* out) 
   T(balloc(Bt, &Bt->status, B)); T(balloc(Bt, &Bt->steps, B)); T(balloc(Bt, &Bt->stages, B));
   T(balloc(Bt, &Bt->records, B * (n + CVXB_BATCH_RECORD_EXTRA)));
   T(balloc(Bt, &Bt->stage_steps, B * CVXB_BATCH_STAGES));
+  T(balloc(Bt, &Bt->cycles, B));
+  if (!(h->flags & CVXB_FLAG_DEVICE_PTRS) && !getenv("CVXB_BATCH_INDEX_ORDER")) {
+    // Pickup order: problems are handed to the CTAs through one atomic ticket counter; dealing out the long ones
+    // first (quadratic objectives: ~100 Newton steps each on the BASELINE mix, against ~70 for the KL problems, and a
+    // P x product per evaluation) leaves only short problems for the last, partly filled wave.
+    std::vector<int> ord((size_t)d->B);
+    size_t k = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+      const int want = pass == 0 ? CVXB_OBJ_QUADRATIC : (pass == 1 ? CVXB_OBJ_LINEAR : CVXB_OBJ_KL);
+      for (int i = 0; i < d->B; ++i)
+        if (d->objective[i] == want) ord[k++] = i;
+    }
+    T(bupload(Bt, &Bt->order, ord.data(), B));
+  }
   Bt->grid = h->sm_count * 2;
   if (Bt->grid > d->B) Bt->grid = d->B;
   T(balloc(Bt, &Bt->scratch, (size_t)Bt->grid * BN * BN));
@@ -817,7 +838,9 @@ int cvxb_batch_barrier_solve(cvxb_handle h, cvxb_batch Bt, const cvxb_params* pa
   A.A = Bt->A; A.b = Bt->b; A.x0 = Bt->x0;
   A.x = Bt->x; A.objval = Bt->objval; A.gap = Bt->gap; A.eqgap = Bt->eqgap;
   A.status = Bt->status; A.steps = Bt->steps; A.stages = Bt->stages; A.records = Bt->records; A.stage_steps = Bt->stage_steps;
+  A.order = Bt->order; A.cycles = Bt->cycles;
   A.scratch = Bt->scratch; A.counter = Bt->counter; A.P = *pars;
+  cvxb::NvtxRange nvtx("cvxb batched barrier solve");
   CVXB_CUDA_OK(cudaMemsetAsync(Bt->counter, 0, sizeof(unsigned), h->stream));
   CVXB_CUDA_OK(cudaEventRecord(h->ev0, h->stream));
   batched_barrier_kernel<<<Bt->grid, BT, sizeof(Smem), h->stream>>>(A);
@@ -831,6 +854,7 @@ int cvxb_batch_barrier_solve(cvxb_handle h, cvxb_batch Bt, const cvxb_params* pa
   if (out->status) CVXB_CUDA_OK(cudaMemcpyAsync(out->status, Bt->status, B * sizeof(int), k, h->stream));
   if (out->newton_steps) CVXB_CUDA_OK(cudaMemcpyAsync(out->newton_steps, Bt->steps, B * sizeof(int), k, h->stream));
   if (out->outer_stages) CVXB_CUDA_OK(cudaMemcpyAsync(out->outer_stages, Bt->stages, B * sizeof(int), k, h->stream));
+  if (out->cycles) CVXB_CUDA_OK(cudaMemcpyAsync(out->cycles, Bt->cycles, B * sizeof(long long), k, h->stream));
   if (out->stage_newton_steps)
     CVXB_CUDA_OK(cudaMemcpyAsync(out->stage_newton_steps, Bt->stage_steps, B * CVXB_BATCH_STAGES * sizeof(int), k, h->stream));
   if (out->objective) CVXB_CUDA_OK(cudaMemcpyAsync(out->objective, Bt->objval, B * sizeof(double), k, h->stream));

@@ -11,6 +11,7 @@
 #include <vector>
 #include <string>
 #include "../../include/cvxb.h"
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges cost a pointer test when no tool is attached
 
 namespace cvxb {
 
@@ -46,6 +47,7 @@ struct cvxb_handle_s {
   bool own_stream = false;
   unsigned flags = 0;
   long long launches = 0;
+  long long status_reads = 0;     // host round trips: copies of the status block followed by a stream synchronisation
   int sm_count = 148;
   // device scalar / flag blocks shared by all kernels of this handle, and their pinned mirrors
   double* d_scal = nullptr;   // cvxb::NSCAL doubles
@@ -69,6 +71,9 @@ struct cvxb_handle_s {
   double prof_ms_graph = 0.0;
   long long prof_launches_graph = 0;
   int use_graphs = 1;
+  int use_loop = 1;                             // centering stages driven from the device (WHILE node); 0 = one graph launch per step
+  bool capture_plain = false;                   // capturing into a WHILE body: no event-record nodes allowed there
+  unsigned long long* d_prof = nullptr;         // [0] start stamp, [1] summed ns, [2] count: SYRK timing inside WHILE bodies (%globaltimer)
   int prof_on = 0;
   std::vector<cudaEvent_t> prof_events;   // start/stop pairs (range PROF_HESSIAN)
   size_t prof_used = 0;
@@ -108,6 +113,13 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// NVTX range for the scope (SURVEY.md section 5 "tracing"): solves, outer stages, Newton steps and the factorisation show
+// up as nested ranges in Nsight Systems / Compute timelines
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 // timed ranges (cvxb_profile_read_range): CUDA events on the handle's stream around a piece of the step
 enum ProfId {
   PROF_HESSIAN = 0,      // Hessian-assembly SYRK G' diag(w) G (kept in prof_events for the captured-step path)
@@ -140,6 +152,8 @@ enum Scal {
   S_TMP0, S_TMP1, S_TMP2, S_TMP3,
   S_PD_GAP, S_PD_RNORM, S_PD_SMAX, S_PD_RDUAL, S_PD_EQGAP, S_PD_T, S_OBJ,
   S_MINSLACK,
+  // device-driven centering stage (solver.cu: stage loop as a CUDA-graph WHILE node): loop state the host seeds and reads back
+  S_L_ND, S_L_NORMGRAD, S_L_EQGAP, S_L_TOL,
   S_COUNT
 };
 // ---- device flag slots (h.d_flag) --------------------------------------------------------------
@@ -149,6 +163,9 @@ enum Flag {
   F_STEP_TAKEN, F_BAD /* any failure upstream: gates the x update */, F_ZERO_DIAG,
   F_PD_LS_FAIL, F_PD_NOTNEG, F_PD_LAMNEG, F_ITER0 /* first Newton step of an unconstrained stage */,
   F_WAVE_ABORT /* a wavefront solve gave up waiting (never expected) */,
+  // stage-loop state (see S_L_*): Newton iterations counted as the reference counts them, steps executed, line-search
+  // trials, remaining step budget, and why the loop stopped
+  F_L_ITER, F_L_EXEC, F_L_TRIALS, F_L_BUDGET, F_L_LIMITED, F_L_MAXITER, F_L_MODE, F_L_REASON,
   F_COUNT
 };
 

@@ -460,6 +460,13 @@ __global__ void __launch_bounds__(NT, 1) dmma_peak_kernel(int iters, double* sin
 
 }  // namespace
 
+__global__ void prof_stamp_kernel(int which, unsigned long long* slots) {
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  if (which == 0) slots[0] = now;
+  else { slots[1] += now - slots[0]; slots[2] += 1ull; }
+}
+
 int dmma_peak_probe(Handle& h, int iters, double* ms, double* flops) {
   cudaEvent_t e0, e1;
   CVXB_CUDA_OK(cudaEventCreate(&e0));
@@ -492,6 +499,16 @@ int gemm_dmma_init() {
 }
 
 int gemm_dmma_timed(Handle& h, const GemmArgs& g, double flops) {
+  if (h.capturing && h.capture_plain) {
+    // WHILE body: event-record nodes are not allowed there; two one-thread kernels stamp %globaltimer around the SYRK
+    // and accumulate on the device (cvxb_profile_read adds the sums)
+    prof_stamp_kernel<<<1, 1, 0, h.stream>>>(0, h.d_prof);
+    int st = gemm_dmma(h, g);
+    prof_stamp_kernel<<<1, 1, 0, h.stream>>>(1, h.d_prof);
+    h.launches += 2;
+    h.capture_flops += flops;
+    return st;
+  }
   if (h.capturing) {   // inside a captured Newton step: external event nodes, read back after each replay
     CVXB_CUDA_OK(cudaEventRecordWithFlags(h.gev0, h.stream, cudaEventRecordExternal));
     int st = gemm_dmma(h, g);

@@ -199,6 +199,7 @@ int fetch_status(Handle& h) {
   CVXB_CUDA_OK(cudaMemcpyAsync(h.h_flag, h.d_flag, NFLAG * sizeof(int), cudaMemcpyDeviceToHost, h.stream));
   CVXB_CUDA_OK(cudaMemcpyAsync(h.h_scal, h.d_scal, NSCAL * sizeof(double), cudaMemcpyDeviceToHost, h.stream));
   CVXB_CUDA_OK(cudaStreamSynchronize(h.stream));
+  h.status_reads++;
   if (h.h_flag[F_WAVE_ABORT]) {
     // a wavefront triangular solve gave up waiting for a predecessor block (its CTAs were not co-resident):
     // never expected under a cooperative launch; switch to the per-block kernels and report
@@ -226,6 +227,7 @@ void fill_info(Handle& h, cvxb_kkt_info* info, int path, int regularized) {
 int kkt_enqueue(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, int ldh, const double* A, int lda,
                 const double* q, const double* b, double tol, bool regularize, bool skip_ruiz, double* x, double* w,
                 bool prefactored) {
+  NvtxRange nvtx("cvxb KKTSystem.solvePD (Ruiz, Cholesky + forward substitution, Schur complement)");
   const int n = W.n, p = W.p;
   if (prefactored) {
     // KKTSystem.solveWithCholFactor (KKTSystem.scala:99-167): the caller's factor L is used as is (d = 1, no

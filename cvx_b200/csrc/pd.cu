@@ -447,6 +447,7 @@ int pd_solve_direction(cvxb_problem_s* P, const cvxb_params& pars, cvxb_kkt_info
 }  // namespace
 
 int pd_loop(cvxb_problem_s* P, const cvxb_params& pars, cvxb_solution* out) {
+  NvtxRange nvtx("cvxb PrimalDualSolver.solve");
   Handle& h = *P->h;
   const int n = P->n, m = P->m, p = P->p;
   const bool withEqs = p > 0;
@@ -477,6 +478,7 @@ int pd_loop(cvxb_problem_s* P, const cvxb_params& pars, cvxb_solution* out) {
     CVXB_CUDA_OK(cudaMemsetAsync(P->nu0s, 0, (size_t)P->ldp * sizeof(double), h.stream));
   }
   while (!(gap < tol && rnorm < tol) && it < maxIter && it < limit) {
+    NvtxRange nvtx_step("cvxb primal-dual iteration");
     CVXB_TRY(pd_assemble(P, pars, t));
     if (bug && it == 0) {
       CVXB_CUDA_OK(cudaMemcpyAsync(P->gx0s, P->gx, m * sizeof(double), cudaMemcpyDeviceToDevice, h.stream));

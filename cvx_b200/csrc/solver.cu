@@ -384,6 +384,56 @@ __global__ void set_stage_kernel(double t, double* scal, int* flag) {
   flag[F_ITER0] = 1;
 }
 
+// ---- device-driven centering stage ----------------------------------------------------------------------------------
+struct LoopSeed {
+  int iter, budget, limited, maxIter, mode;
+  double nd, normGrad, eqGap, tol;
+};
+__global__ void loop_seed_kernel(LoopSeed v, double* scal, int* flag) {
+  flag[F_L_ITER] = v.iter; flag[F_L_EXEC] = 0; flag[F_L_TRIALS] = 0; flag[F_L_BUDGET] = v.budget; flag[F_L_LIMITED] = v.limited;
+  flag[F_L_MAXITER] = v.maxIter; flag[F_L_MODE] = v.mode; flag[F_L_REASON] = 0;
+  scal[S_L_ND] = v.nd; scal[S_L_NORMGRAD] = v.normGrad; scal[S_L_EQGAP] = v.eqGap; scal[S_L_TOL] = v.tol;
+}
+enum LoopReason { LOOP_DONE = 0, LOOP_NEEDS_HOST = 1, LOOP_LS_FAILED = 2, LOOP_INFEASIBLE = 3, LOOP_BUDGET = 4, LOOP_SPIN = 5 };
+// After one Newton step: the bookkeeping and the loop test of EqualityConstrainedSolver.solve (:49, mode 0) /
+// UnconstrainedSolver.solve (:45, mode 1), exactly as inner_solve_eq / inner_solve_uncon apply them on the host.
+// Anything the device cannot finish by itself (a refused linear solve: the host walks the fallback chain; a failed
+// line search; an infeasible iterate) stops the loop with the step left uncounted.
+__global__ void loop_decide_kernel(cudaGraphConditionalHandle handle, double* scal, int* flag) {
+  const double tol = scal[S_L_TOL];
+  int go = 0, reason = LOOP_DONE;
+  if (flag[F_BAD]) reason = LOOP_NEEDS_HOST;
+  else if (flag[F_LS_STATUS]) reason = LOOP_LS_FAILED;
+  else if (flag[F_INFEAS]) reason = LOOP_INFEASIBLE;
+  else {
+    const int mode = flag[F_L_MODE];
+    const double nd = scal[S_ND];
+    double normGrad = scal[S_L_NORMGRAD], eqGap = scal[S_L_EQGAP];
+    int iter = flag[F_L_ITER] + 1;
+    flag[F_L_EXEC] += 1;
+    if (flag[F_L_LIMITED]) flag[F_L_BUDGET] -= 1;
+    bool spin = false;
+    if (flag[F_STEP_TAKEN]) {
+      flag[F_L_TRIALS] += flag[F_LS_TRIALS];
+      normGrad = scal[S_NORMGRAD];
+      if (mode == 0) eqGap = scal[S_EQNORM];
+    } else if (mode == 0 && ((nd > tol && normGrad > tol) || eqGap > tol) && !(nd > tol)) {
+      // no step taken, so x, H and d repeat exactly: the reference spins here until maxIter (inner_solve_eq)
+      iter = flag[F_L_MAXITER];
+      spin = true;
+    }
+    const bool cond = mode == 0 ? ((nd > tol && normGrad > tol) || eqGap > tol) : (nd > tol && normGrad > tol);
+    const bool budget_out = flag[F_L_LIMITED] && flag[F_L_BUDGET] <= 0;
+    go = (!spin && iter < flag[F_L_MAXITER] && cond && !budget_out) ? 1 : 0;
+    if (spin) reason = LOOP_SPIN;
+    else if (!go && budget_out && cond && iter < flag[F_L_MAXITER]) reason = LOOP_BUDGET;
+    flag[F_L_ITER] = iter;
+    scal[S_L_ND] = nd; scal[S_L_NORMGRAD] = normGrad; scal[S_L_EQGAP] = eqGap;
+  }
+  flag[F_L_REASON] = reason;
+  cudaGraphSetConditional(handle, go ? 1u : 0u);
+}
+
 __global__ void set_unit_kernel(int n, int k, double* a) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = (i == k) ? 1.0 : 0.0;
@@ -465,8 +515,10 @@ int problem_alloc(Handle& h, int n, int m, int p, int objective, cvxb_problem_s*
 void problem_free(cvxb_problem_s* P) {
   if (!P) return;
   if (P->phase1) problem_free(P->phase1);
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < 2; ++k) {
     if (P->step_graph[k]) cudaGraphExecDestroy(P->step_graph[k]);
+    if (P->loop_graph[k]) cudaGraphExecDestroy(P->loop_graph[k]);
+  }
   for (size_t i = 0; i < P->owned.size(); ++i) {
     if (i == 0 && P->arena_async) cudaFreeAsync(P->owned[i], P->h->stream); else cudaFree(P->owned[i]);
   }
@@ -622,12 +674,16 @@ static bool same_step_pars(const cvxb_params& a, const cvxb_params& b) {
 }
 
 int run_step(cvxb_problem_s* P, const cvxb_params& pars, double t, int mode, int iter0) {
+  NvtxRange nvtx("cvxb Newton step");
   Handle& h = *P->h;
   if (!h.use_graphs) return enqueue_step(P, pars, t, mode, iter0, nullptr);
   cudaGraphExec_t& exec = P->step_graph[mode];
   if (!exec || !same_step_pars(P->graph_pars, pars)) {
     if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
     if (P->step_graph[1 - mode]) { cudaGraphExecDestroy(P->step_graph[1 - mode]); P->step_graph[1 - mode] = nullptr; }
+    if (!same_step_pars(P->graph_pars, pars))
+      for (int k = 0; k < 2; ++k)
+        if (P->loop_graph[k]) { cudaGraphExecDestroy(P->loop_graph[k]); P->loop_graph[k] = nullptr; }
     P->graph_pars = pars;
     const long long l0 = h.launches;
     cudaGraph_t graph = nullptr;
@@ -674,6 +730,62 @@ static void graph_profile_tick(Handle& h, double flops) {
   }
 }
 
+// The whole centering stage as one graph launch.  Built once per problem and mode: WHILE node, body = the captured
+// Newton step + loop_decide_kernel.  Returns false when the device-driven loop is not available here (then the
+// caller drives the stage step by step as before).
+static bool stage_loop_build(cvxb_problem_s* P, const cvxb_params& pars, double t, int mode) {
+  Handle& h = *P->h;
+  if (!h.use_loop || !h.use_graphs || P->loop_failed) return false;
+  if (P->loop_graph[mode] && same_step_pars(P->graph_pars, pars)) return true;
+  if (!same_step_pars(P->graph_pars, pars)) {
+    for (int k = 0; k < 2; ++k) {
+      if (P->loop_graph[k]) { cudaGraphExecDestroy(P->loop_graph[k]); P->loop_graph[k] = nullptr; }
+      if (P->step_graph[k]) { cudaGraphExecDestroy(P->step_graph[k]); P->step_graph[k] = nullptr; }
+    }
+    P->graph_pars = pars;
+  }
+  cudaGraph_t graph = nullptr;
+  auto fail = [&]() {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    P->loop_failed = true;
+    return false;
+  };
+  if (cudaGraphCreate(&graph, 0) != cudaSuccess) return fail();
+  cudaGraphConditionalHandle handle;
+  if (cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault) != cudaSuccess) return fail();
+  cudaGraphNodeParams np = {};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = handle;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t node;
+  if (cudaGraphAddNode(&node, graph, nullptr, 0, &np) != cudaSuccess) return fail();
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  const long long l0 = h.launches;
+  if (cudaStreamBeginCaptureToGraph(h.stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return fail();
+  h.capturing = true;
+  h.capture_plain = true;
+  h.capture_flops = 0.0;
+  int st = enqueue_step(P, pars, t, mode, 0, h.d_scal + S_T);
+  P->loop_flops[mode] = h.capture_flops;
+  if (st == CVXB_OK) {
+    loop_decide_kernel<<<1, 1, 0, h.stream>>>(handle, h.d_scal, h.d_flag);
+    h.launches++;
+    if (cudaGetLastError() != cudaSuccess) st = CVXB_ECUDA;
+  }
+  h.capturing = false;
+  h.capture_plain = false;
+  cudaGraph_t out = nullptr;
+  cudaError_t e = cudaStreamEndCapture(h.stream, &out);
+  P->loop_step_launches[mode] = h.launches - l0;
+  h.launches = l0;
+  if (st != CVXB_OK || e != cudaSuccess) return fail();
+  if (cudaGraphInstantiate(&P->loop_graph[mode], graph, 0) != cudaSuccess) { P->loop_graph[mode] = nullptr; return fail(); }
+  cudaGraphDestroy(graph);
+  return true;
+}
+
 struct InnerResult {
   double nd = 0, normGrad = 0, eqGap = 0;
   int iter = 0;
@@ -700,8 +812,42 @@ static int ls_status_to_error(Handle& h, const char* who) {
   return CVXB_ELINESEARCH;
 }
 
-// EqualityConstrainedSolver.solve (EqualityConstrainedSolver.scala:37-107) at barrier parameter t, from P->x
+// One launch of the device-driven stage loop from the state in R / rs; updates them from the loop's state block.
+// *reason = why the loop stopped (LoopReason).
+static int stage_loop_run(cvxb_problem_s* P, const cvxb_params& pars, int mode, RunStats& rs, InnerResult& R, int* reason) {
+  Handle& h = *P->h;
+  LoopSeed seed;
+  seed.iter = R.iter;
+  seed.budget = (int)(rs.budget > 2000000000ll ? 2000000000ll : rs.budget);
+  seed.limited = rs.limited ? 1 : 0;
+  seed.maxIter = pars.maxIter;
+  seed.mode = mode;
+  seed.nd = R.nd; seed.normGrad = R.normGrad; seed.eqGap = R.eqGap; seed.tol = pars.tolSolver;
+  CVXB_LAUNCH(h, loop_seed_kernel, 1, 1, 0, seed, h.d_scal, h.d_flag);
+  CVXB_CUDA_OK(cudaGraphLaunch(P->loop_graph[mode], h.stream));
+  CVXB_TRY(fetch_status(h));
+  *reason = h.h_flag[F_L_REASON];
+  const int exec = h.h_flag[F_L_EXEC];
+  const bool aborted = *reason == LOOP_NEEDS_HOST || *reason == LOOP_LS_FAILED || *reason == LOOP_INFEASIBLE;
+  h.launches += (long long)(exec + (aborted ? 1 : 0)) * P->loop_step_launches[mode];
+  h.prof_flops += (double)(exec + (aborted ? 1 : 0)) * P->loop_flops[mode];      // SYRKs stamped inside the loop
+  R.iter = h.h_flag[F_L_ITER];
+  R.executed += exec;
+  R.trials += h.h_flag[F_L_TRIALS];
+  if (rs.limited) rs.budget -= exec;
+  R.nd = h.h_scal[S_L_ND];
+  R.normGrad = h.h_scal[S_L_NORMGRAD];
+  if (mode == 0) R.eqGap = h.h_scal[S_L_EQGAP];
+  return CVXB_OK;
+}
+
+// EqualityConstrainedSolver.solve (EqualityConstrainedSolver.scala:37-107) at barrier parameter t, from P->x.
+// The stage runs as ONE graph launch (WHILE node, loop test on the device): the host reads the status block once when
+// the loop ends and only takes part in a step when the device refused its linear solve (fallback chain of
+// KKTSystem.solve).  Without that facility (CVXB_NO_LOOP, profiling on, graph build refused) it drives the stage step
+// by step: one graph launch and one status read per Newton step.
 int inner_solve_eq(cvxb_problem_s* P, const cvxb_params& pars, double t, RunStats& rs, InnerResult& R) {
+  NvtxRange nvtx("cvxb EqualityConstrainedSolver.solve (one barrier stage)");
   Handle& h = *P->h;
   const double tol = pars.tolSolver;
   R = InnerResult();
@@ -712,11 +858,23 @@ int inner_solve_eq(cvxb_problem_s* P, const cvxb_params& pars, double t, RunStat
   if (h.h_flag[F_INFEAS]) { set_last_error("gradientBarrierFunction: x not strictly feasible"); return CVXB_ENOTFEASIBLE; }
   R.normGrad = h.h_scal[S_NORMGRAD];
   R.eqGap = h.h_scal[S_EQNORM];
+  bool pending = false;      // a step whose status block is already on the host (the device loop stopped inside it)
   while (R.iter < pars.maxIter && ((R.nd > tol && R.normGrad > tol) || R.eqGap > tol)) {
     if (rs.limited && rs.budget <= 0) break;
-    CVXB_TRY(run_step(P, pars, t, 0, 0));
-    CVXB_TRY(fetch_status(h));
-    graph_profile_tick(h, P->graph_flops[0]);
+    if (!pending && stage_loop_build(P, pars, t, 0)) {
+      int reason = LOOP_DONE;
+      CVXB_TRY(stage_loop_run(P, pars, 0, rs, R, &reason));
+      if (reason == LOOP_LS_FAILED) return ls_status_to_error(h, "EqualityConstrainedSolver");
+      if (reason == LOOP_INFEASIBLE) { set_last_error("gradientBarrierFunction: x not strictly feasible"); return CVXB_ENOTFEASIBLE; }
+      if (reason != LOOP_NEEDS_HOST) continue;       // the loop test above decides (done / budget / spin: iter == maxIter)
+      pending = true;
+    }
+    if (!pending) {
+      CVXB_TRY(run_step(P, pars, t, 0, 0));
+      CVXB_TRY(fetch_status(h));
+      graph_profile_tick(h, P->graph_flops[0]);
+    }
+    pending = false;
     if (h.h_flag[F_BAD]) {
       // optimistic attempt refused on the device (x untouched): walk the reference's fallback chain
       cvxb_kkt_info info;
@@ -748,8 +906,9 @@ int inner_solve_eq(cvxb_problem_s* P, const cvxb_params& pars, double t, RunStat
   return CVXB_OK;
 }
 
-// UnconstrainedSolver.solve (UnconstrainedSolver.scala:34-125)
+// UnconstrainedSolver.solve (UnconstrainedSolver.scala:34-125); device-driven like inner_solve_eq
 int inner_solve_uncon(cvxb_problem_s* P, const cvxb_params& pars, double t, RunStats& rs, InnerResult& R) {
+  NvtxRange nvtx("cvxb UnconstrainedSolver.solve (one barrier stage)");
   Handle& h = *P->h;
   const double tol = pars.tolSolver;
   const int n = P->n;
@@ -760,11 +919,25 @@ int inner_solve_uncon(cvxb_problem_s* P, const cvxb_params& pars, double t, RunS
   CVXB_TRY(fetch_status(h));
   if (h.h_flag[F_INFEAS]) { set_last_error("gradientBarrierFunction: x not strictly feasible"); return CVXB_ENOTFEASIBLE; }
   R.normGrad = h.h_scal[S_NORMGRAD];
+  bool pending = false;
   while (R.iter < pars.maxIter && R.nd > tol && R.normGrad > tol) {
     if (rs.limited && rs.budget <= 0) break;
-    CVXB_TRY(run_step(P, pars, t, 1, R.iter == 0));
-    CVXB_TRY(fetch_status(h));
-    graph_profile_tick(h, P->graph_flops[1]);
+    const bool first = R.iter == 0;
+    if (!pending && stage_loop_build(P, pars, t, 1)) {
+      int reason = LOOP_DONE;
+      CVXB_TRY(stage_loop_run(P, pars, 1, rs, R, &reason));
+      if (reason == LOOP_LS_FAILED) return ls_status_to_error(h, "UnconstrainedSolver");
+      if (reason == LOOP_INFEASIBLE) { set_last_error("gradientBarrierFunction: x not strictly feasible"); return CVXB_ENOTFEASIBLE; }
+      if (reason != LOOP_NEEDS_HOST) continue;
+      pending = true;
+    }
+    const bool iter0 = pending ? (R.iter == 0) : first;
+    if (!pending) {
+      CVXB_TRY(run_step(P, pars, t, 1, iter0));
+      CVXB_TRY(fetch_status(h));
+      graph_profile_tick(h, P->graph_flops[1]);
+    }
+    pending = false;
     if (h.h_flag[F_BAD]) {
       cvxb_kkt_info info;
       int st = chol_solve_retry(h, P->kw, pars, P->H, P->ldn, P->y, -1.0, pars.tolEqSolve, P->dir, &info);
@@ -780,7 +953,7 @@ int inner_solve_uncon(cvxb_problem_s* P, const cvxb_params& pars, double t, RunS
       }
       if (st != CVXB_OK) return st;
       if (info.regularized) R.regularized++;
-      CVXB_TRY(enqueue_linesearch(P, pars, t, 1, R.iter == 0));
+      CVXB_TRY(enqueue_linesearch(P, pars, t, 1, iter0));
       CVXB_TRY(barrier_eval(P, t));
       CVXB_TRY(fetch_status(h));
     }
@@ -803,6 +976,7 @@ enum Termination { TERM_STANDARD = 0, TERM_PHASE1 = 1 };
 
 // BarrierSolver.solveWithEQs / solveWithoutEQs (BarrierSolver.scala:70-177), from P->x
 int barrier_loop(cvxb_problem_s* P, const cvxb_params& pars, int term, RunStats& rs, cvxb_solution* out) {
+  NvtxRange nvtx(term == TERM_PHASE1 ? "cvxb phase I barrier loop" : "cvxb BarrierSolver.solve");
   Handle& h = *P->h;
   const double mu = pars.mu;
   double t = pars.t0;

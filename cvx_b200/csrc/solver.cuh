@@ -51,6 +51,12 @@ struct cvxb_problem_s {
   long long graph_launches[2] = {0, 0};
   double graph_flops[2] = {0.0, 0.0};
   cvxb_params graph_pars;
+  // a whole centering stage as ONE graph launch: a WHILE node whose body is the Newton step followed by a kernel that
+  // applies the reference's loop test on the device (EqualityConstrainedSolver.scala:49, UnconstrainedSolver.scala:45)
+  cudaGraphExec_t loop_graph[2] = {nullptr, nullptr};
+  long long loop_step_launches[2] = {0, 0};
+  double loop_flops[2] = {0.0, 0.0};          // algorithmic flops of the timed SYRK of one step of the loop
+  bool loop_failed = false;
   cvxb_problem_s* phase1 = nullptr;   // the n+1 dimensional feasibility problem (built on demand)
   std::vector<void*> owned;
   cvxb::Arena arena;

