@@ -498,7 +498,8 @@ def main():
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches = h.launches - l0
     n_syrk, syrk_ms, syrk_flops = h.profile_read()
-    ranges = {k_: h.profile_read_range(k_) for k_ in ("chol_trailing_update", "factor_h_with_trsm", "schur_syrk", "ruiz", "gemv_g")}
+    ranges = {k_: h.profile_read_range(k_) for k_ in ("chol_trailing_update", "factor_h_with_trsm", "schur_syrk", "ruiz", "gemv_g",
+                                                         "chol_lookahead_phases", "chol_trsm_right")}
     h.profile_enable(False)
     barrier()
     clk = clocks.stop()

@@ -273,7 +273,7 @@ class Handle:
         return n.value, ms.value, fl.value
 
     PROF_RANGES = {"hessian_syrk": 0, "chol_trailing_update": 1, "factor_h_with_trsm": 2, "schur_syrk": 3, "ruiz": 4,
-                   "gemv_g": 5}
+                   "gemv_g": 5, "chol_lookahead_phases": 6, "chol_trsm_right": 7}
 
     def profile_read_range(self, which):
         """(count, total ms, total algorithmic work) of one timed range of the step (cvxb_profile_read_range)."""

@@ -128,6 +128,8 @@ enum ProfId {
   PROF_SCHUR = 3,        // Schur complement S = Y'Y (TN SYRK, mirrored)
   PROF_RUIZ = 4,         // ruizEquilibrate(H)
   PROF_GEMV = 5,         // the HBM-bound GEMVs over G of one step (bytes instead of flops)
+  PROF_LOOKAHEAD = 6,    // chain-bound phases of the factorisation: the look-ahead schedule on diagonal blocks <= 2560..4608 columns
+  PROF_TRSM_RIGHT = 7,   // A21 := A21 L11^-T at the recursive levels
   PROF_COUNT = 8
 };
 int prof_begin(cvxb_handle_s& h, int id);

@@ -750,8 +750,11 @@ int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot,
   // look-ahead schedule up to 4608 against 54.3 ms with the switch at 2560)
   static const int la_wide = getenv("CVXB_LA_WIDE") ? atoi(getenv("CVXB_LA_WIDE")) : 2560;
   const int la_max = (r > 1024 && rl_max_n() > la_wide) ? la_wide : rl_max_n();
-  if (!plain && n > NB && n <= la_max && h.stream2)
-    return potrf_lookahead(h, n, A, lda, invD, flag_slot, mindiag_slot, col0, B, ldb, r);
+  if (!plain && n > NB && n <= la_max && h.stream2) {
+    CVXB_TRY(prof_begin(h, PROF_LOOKAHEAD));
+    CVXB_TRY(potrf_lookahead(h, n, A, lda, invD, flag_slot, mindiag_slot, col0, B, ldb, r));
+    return prof_end(h, PROF_LOOKAHEAD, (double)n * n * n / 3.0 + (double)n * n * r);
+  }
   if (n <= NB) {
     CVXB_LAUNCH(h, leaf_kernel<true>, 1, LEAF_THREADS, LEAF_SMEM, n, n, A, lda, invD, h.d_flag, h.d_scal, flag_slot,
                 mindiag_slot, col0);
@@ -762,7 +765,9 @@ int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot,
   CVXB_TRY(potrf_rec(h, a, A, lda, invD, flag_slot, mindiag_slot, col0, plain, B, ldb, r));
   double* A21 = A + a;
   double* A22 = A + (size_t)a * lda + a;
+  CVXB_TRY(prof_begin(h, PROF_TRSM_RIGHT));
   CVXB_TRY(trsm_right_lt(h, b, a, A, lda, invD, A21, lda));
+  CVXB_TRY(prof_end(h, PROF_TRSM_RIGHT, (double)b * a * a));
   // A22 -= A21 A21'  lower: A(m,k) = A21[k*lda + m] (M contiguous), B(k,n) = A21(n,k) (N contiguous)
   GemmArgs g{b, b, a, A21, lda, false, A21, lda, false, A22, lda, -1.0, 1.0, 1};
   g.streamk = true;      // main stream only (the look-ahead schedule has joined)

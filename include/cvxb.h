@@ -65,7 +65,9 @@ int cvxb_profile_read(cvxb_handle h, long long* launches, double* ms_total, doub
  * seam-B calls, not the captured barrier step): {count, total ms, total algorithmic work}.  range: 0 = Hessian SYRK
  * (same as cvxb_profile_read), 1 = Cholesky trailing updates A22 -= A21 A21' of the recursive levels (flops),
  * 2 = factorisation of H with the forward substitution of [DA', Dq] riding along (flops), 3 = Schur complement SYRK
- * (flops), 4 = ruizEquilibrate (bytes of ONE sweep over H per call), 5 = the GEMVs G x and G'(1/f) (bytes). */
+ * (flops), 4 = ruizEquilibrate (bytes of ONE sweep over H per call), 5 = the GEMVs G x and G'(1/f) (bytes),
+ * 6 = the chain-bound look-ahead phases of the factorisations (flops), 7 = the A21 L11^-T solves of the recursive
+ * levels (flops). */
 int cvxb_profile_read_range(cvxb_handle h, int range, long long* count, double* ms_total, double* work_total);
 
 /* ---- parameters: SolverParams.scala:24-46 plus the constants hard-coded in the solvers ------- */
