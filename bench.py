@@ -618,11 +618,14 @@ def main():
                     "peak_source": peak_source, "share_of_step": syrk_ms / dev_ms if dev_ms > 0 else None}
         chol = roofline_from_range(
             ranges["chol_trailing_update"],
-            "gemm_dmma_streamk_kernel<NT> (Cholesky trailing update A22 -= A21 A21', lower triangle, K = 2048..4096 at the "
-            "recursive levels of the n = %d factorisation)" % n, fp64_peak, peak_source, dev_ms)
-        # the same kernel timed alone at the two extreme shapes of the n = 8192 factorisation
+            "gemm_dmma_persist_kernel<NT> (Cholesky trailing updates A22 -= A21 A21' of the tile-DAG schedule, lower triangle, "
+            "K = 1024..2048, n = %d: persistent grid on 140 of 148 SMs, timed on the bulk stream WHILE the chain of the next "
+            "diagonal block runs on the other SMs; recursive schedule below n = 5120: gemm_dmma_streamk_kernel<NT>)" % n,
+            fp64_peak, peak_source, dev_ms)
+        # the same contraction timed alone on the whole machine at three shapes of the n = 8192 factorisation
         alone = {}
-        for tag, (nn_, kk_) in (("top_level_4096x4096_K4096", (4096, 4096)), ("rank128_update_8064x8064_K128", (8064, 128))):
+        for tag, (nn_, kk_) in (("trailing_6144x6144_K2048", (6144, 2048)), ("top_level_4096x4096_K4096", (4096, 4096)),
+                                ("rank128_update_8064x8064_K128", (8064, 128))):
             try:
                 ms_k, fl_k = h.bench_kernel(2, nn_, kk_, 5)
                 alone[tag] = {"ms": ms_k, "tflops": fl_k / ms_k / 1e9, "frac": fl_k / ms_k / 1e9 / fp64_peak}

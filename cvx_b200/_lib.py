@@ -178,6 +178,7 @@ SYMBOLS = {
     "cvxb_test_dgemm": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, C.c_int, _vp,
                                   C.c_int, C.c_double, _vp, C.c_int, C.c_int]),
     "cvxb_bench_kernel": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]),
+    "cvxb_debug_set_schedule": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
 }
 
 _lib = None
@@ -281,6 +282,10 @@ class Handle:
         n, ms, wk = C.c_longlong(), C.c_double(), C.c_double()
         check(self.lib.cvxb_profile_read_range(self._h, rid, C.byref(n), C.byref(ms), C.byref(wk)))
         return n.value, ms.value, wk.value
+
+    def set_schedule(self, dag_block: int = -1, dag_min_n: int = -1, dag_reserve: int = -1):
+        """Tile-DAG schedule of the big factorisations (cvxb_debug_set_schedule); negative = keep, dag_block 0 = off."""
+        check(self.lib.cvxb_debug_set_schedule(self._h, dag_block, dag_min_n, dag_reserve))
 
     # measurement helper (bench.py)
     def bench_kernel(self, which: int, n: int, k: int, reps: int):

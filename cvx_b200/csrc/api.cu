@@ -233,7 +233,23 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
   {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    CVXB_CUDA_OK(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, lo));
+    // three lanes: the handle's stream (critical chain, highest priority), stream2 (the look-ahead schedule's own bulk
+    // updates, which the chain waits for two leaves later) and stream3 (bulk updates of the tile-DAG schedule, lowest)
+    const int mid = (lo - 1 >= hi) ? lo - 1 : lo;
+    CVXB_CUDA_OK(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, mid));
+    if (!getenv("CVXB_NO_DAG")) {
+      CVXB_CUDA_OK(cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, lo));
+      for (int i = 0; i < 3; ++i) CVXB_CUDA_OK(cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, lo));
+      CVXB_CUDA_OK(cudaMalloc((void**)&h->d_part3, DAG_LANES * PART3_DOUBLES * sizeof(double)));
+      for (int i = 0; i < 130; ++i) {
+        cudaEvent_t e;
+        CVXB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->dag_events.push_back(e);
+      }
+      if (const char* e = getenv("CVXB_DAG_BLOCK")) h->dag_block = atoi(e) / NB * NB;
+      if (const char* e = getenv("CVXB_DAG_MIN_N")) h->dag_min_n = atoi(e);
+      if (const char* e = getenv("CVXB_DAG_RESERVE")) h->dag_reserve = atoi(e);
+    }
   }
   for (int i = 0; i < 600; ++i) {
     cudaEvent_t e;
@@ -264,7 +280,11 @@ int cvxb_destroy(cvxb_handle h) {
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   for (auto& R : h->prof_range) for (cudaEvent_t e : R.ev) cudaEventDestroy(e);
   for (cudaEvent_t e : h->la_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->dag_events) cudaEventDestroy(e);
   if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->stream3) cudaStreamDestroy(h->stream3);
+  for (int i = 0; i < 3; ++i) if (h->side[i]) cudaStreamDestroy(h->side[i]);
+  cudaFree(h->d_part3);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return CVXB_OK;
@@ -911,6 +931,15 @@ __global__ void copy_kernel(size_t count, const double2* __restrict__ a, double2
 
 int cvxb_debug_leaf_clocks(long long* out, int reset) { return cvxb::leaf_clocks(out, reset != 0); }
 
+int cvxb_debug_set_schedule(cvxb_handle h, int dag_block, int dag_min_n, int dag_reserve) {
+  CHECK_HANDLE(h);
+  CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (dag_block >= 0) h->dag_block = dag_block / NB * NB;       // 0 switches the tile-DAG schedule off
+  if (dag_min_n >= 0) h->dag_min_n = dag_min_n;
+  if (dag_reserve >= 0) h->dag_reserve = dag_reserve < h->sm_count ? dag_reserve : h->sm_count - 1;
+  return CVXB_OK;
+}
+
 int cvxb_bench_kernel(cvxb_handle h, int which, int n, int k, int reps, double* ms_per_launch,
                       double* flops_or_bytes_per_launch) {
   CHECK_HANDLE(h);
@@ -971,6 +1000,30 @@ int cvxb_bench_kernel(cvxb_handle h, int which, int n, int k, int reps, double* 
     }
     *ms_per_launch = total / reps;
     *flops_or_bytes_per_launch = (double)n * n * n / 3.0;
+  } else if (which == 9) {
+    // blocked Cholesky of an n x n matrix with the forward substitution of k right-hand sides riding along
+    // (the factor_h_with_trsm range of the KKT step: C4 n = 8192, k = 2049)
+    double* Bm = nullptr;
+    CVXB_CUDA_OK(cudaMalloc((void**)&G, (size_t)ldn * n * sizeof(double)));
+    CVXB_CUDA_OK(cudaMalloc((void**)&C, (size_t)ldn * n * sizeof(double)));
+    CVXB_CUDA_OK(cudaMalloc((void**)&Bm, (size_t)ldn * (k > 0 ? k : 1) * sizeof(double)));
+    CVXB_CUDA_OK(cudaMalloc((void**)&invD, (size_t)((n + NB - 1) / NB) * NB * NB * sizeof(double)));
+    fill_random_kernel<<<1024, 256, 0, H.stream>>>((size_t)ldn * n, G, 777ull, -1.0, 1.0);
+    CVXB_TRY(add_diag(H, n, (double)n + 1.0, G, ldn));
+    double total = 0;
+    for (int r = -1; r < reps; ++r) {
+      CVXB_TRY(copy_matrix(H, n, n, G, ldn, C, ldn));
+      fill_random_kernel<<<1024, 256, 0, H.stream>>>((size_t)ldn * (k > 0 ? k : 1), Bm, 31ull, -1.0, 1.0);
+      CVXB_CUDA_OK(cudaEventRecord(H.ev0, H.stream));
+      CVXB_TRY(potrf_lower_rhs(H, n, C, ldn, invD, F_CHOL_H, S_MINDIAG_H, Bm, ldn, k));
+      CVXB_CUDA_OK(cudaEventRecord(H.ev1, H.stream));
+      CVXB_CUDA_OK(cudaEventSynchronize(H.ev1));
+      CVXB_CUDA_OK(cudaEventElapsedTime(&t, H.ev0, H.ev1));
+      if (r >= 0) total += t;
+    }
+    cudaFree(Bm);
+    *ms_per_launch = total / reps;
+    *flops_or_bytes_per_launch = (double)n * n * n / 3.0 + (double)n * n * k;
   } else if (which == 5 || which == 6) {
     // 5: forward + backward single-RHS solves with a factor of size n; 6: Ruiz equilibration (20 enqueued sweeps)
     CVXB_CUDA_OK(cudaMalloc((void**)&G, (size_t)ldn * n * sizeof(double)));

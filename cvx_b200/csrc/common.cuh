@@ -85,8 +85,16 @@ struct cvxb_handle_s {
     double work = 0.0;
   };
   ProfRange prof_range[8];
-  // a stream-K grid may be asked to leave some SMs to the kernels of a concurrent critical chain
-  int sk_reserve = 0;
+  // tile-DAG schedule of the big factorisations (factor.cu: potrf_dag): a third stream carries the bulk updates through
+  // persistent GEMM grids that leave `sk_reserve` SMs to the kernels of the concurrent critical chain
+  cudaStream_t stream3 = nullptr;
+  double* d_part3 = nullptr;                 // scratch of the bulk lanes' triangular-solve leaves (DAG_LANES x PART3_DOUBLES)
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // side lanes: latency-bound triangular-solve recursions run beside each other
+  size_t part_cap = (size_t)1 << 22;         // doubles usable at d_part (switched together with d_part)
+  std::vector<cudaEvent_t> dag_events;
+  int sk_reserve = 0;                        // != 0 only while bulk work is being enqueued
+  bool in_dag = false;                       // potrf_dag is enqueuing (its diagonal blocks use the look-ahead / recursive schedules)
+  int dag_block = 2048, dag_min_n = 5120, dag_reserve = 12;   // cvxb_debug_set_schedule
 };
 
 namespace cvxb {
@@ -135,6 +143,8 @@ enum ProfId {
 int prof_begin(cvxb_handle_s& h, int id);
 int prof_end(cvxb_handle_s& h, int id, double work);
 constexpr size_t PART_DOUBLES = (size_t)1 << 22;   // 32 MiB of split-K partials for gemv_n
+constexpr size_t PART3_DOUBLES = (size_t)1 << 21;  // scratch per bulk lane (out-of-place leaf solves of up to 15872 rows)
+constexpr int DAG_LANES = 4;                       // stream3 + three side lanes
 
 // count + launch + error check
 #define CVXB_LAUNCH(h, kernel, grid, block, smem, ...)                                       \
@@ -189,6 +199,7 @@ struct GemmArgs {
   int tile = 0;   // 0 = choose 128 / 64 / 32 by grid size; in-place callers (C aliases A or B) must pin 128
   bool lower_only = false;   // rectangular C whose rows and columns share an origin: never write elements with m < n
   bool streamk = false;      // tri != 0, 128x128 tiles, handle's own stream: persistent stream-K grid (no partial last wave)
+  int tri_skip = 0;          // tri != 0 on the bulk stream: leave out the leading tri_skip x tri_skip block of tiles (done elsewhere)
 };
 int gemm_dmma(Handle& h, const GemmArgs& g);
 int gemm_dmma_on(Handle& h, const GemmArgs& g, cudaStream_t st);   // same, on another stream of the handle

@@ -720,7 +720,7 @@ int trsm_right_lt(Handle& h, int M, int n1, const double* L, int ldl, const doub
     // X = A21 * invL11' through a scratch panel (the product cannot alias its operand once the grid has
     // more than one tile column), so that small tiles can spread M x 128 outputs over all SMs
     const int lds = pad_ld(M);
-    if ((size_t)lds * n1 <= PART_DOUBLES - 65536) {
+    if ((size_t)lds * n1 + 65536 <= h.part_cap) {
       double* Xs = h.d_part;
       GemmArgs g{M, n1, n1, A21, lda, false, invD, NB, false, Xs, lds, 1.0, 0.0, 0};
       CVXB_TRY(gemm_dmma(h, g));
@@ -739,12 +739,226 @@ int trsm_right_lt(Handle& h, int M, int n1, const double* L, int ldl, const doub
                        lda);
 }
 
+int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0, bool plain,
+              double* B, int ldb, int r);
+
+// While alive, everything enqueued through the handle goes to one of the bulk lanes: lane 0 = stream3, where GEMMs of at
+// least half a wave of tiles run as persistent grids that leave `dag_reserve` SMs free; lanes 1..3 = side streams with
+// plain launches.  Every lane has its own scratch for the out-of-place leaf solves.
+struct BulkScope {
+  Handle& h;
+  cudaStream_t keep_stream;
+  double* keep_part;
+  size_t keep_cap;
+  int keep_reserve;
+  BulkScope(Handle& h_, int lane) : h(h_), keep_stream(h_.stream), keep_part(h_.d_part), keep_cap(h_.part_cap),
+                                    keep_reserve(h_.sk_reserve) {
+    h.stream = lane == 0 ? h.stream3 : h.side[lane - 1];
+    h.d_part = h.d_part3 + (size_t)lane * PART3_DOUBLES;
+    h.part_cap = PART3_DOUBLES;
+    h.sk_reserve = lane == 0 ? h.dag_reserve : -1;      // -1: inside the DAG schedule (no nesting), plain launches
+  }
+  ~BulkScope() {
+    h.stream = keep_stream;
+    h.d_part = keep_part;
+    h.part_cap = keep_cap;
+    h.sk_reserve = keep_reserve;
+  }
+};
+
+// Tile-DAG schedule for matrices beyond the L2-resident regime (n >= dag_min_n; C4: n = 8192 with the 2049 columns of
+// [DA', Dq] riding along, C5: n = 16385).  Right-looking over diagonal blocks of `dag_block` columns with a look-ahead of
+// one block, on two lanes:
+//   chain (the handle's stream, + stream2 inside):  P(k) = look-ahead Cholesky of the diagonal block A_kk -- a serial chain
+//       of 128-column leaves (~60 us each) that keeps only a handful of SMs busy;
+//   bulk (stream3, persistent GEMM grids on SMs - dag_reserve CTAs), per level k once P(k) is done:
+//       A[k+1.., k] := A[k+1.., k] L_kk^-T;  A_{k+1,k+1} -= L_{k+1,k} L_{k+1,k}'  -> P(k+1) may start;
+//       rest of the trailing update (one lower-triangular SYRK over all remaining blocks, minus that first block);
+//       Y_k := L_kk^-1 B_k;  B[k+1..] -= L[k+1.., k] Y_k.
+// P(k+1) runs in the shadow of level k's bulk work (4.4 / 2.3 / 0.8 ms of GEMMs against a chain of ~1 ms at C4), so of the
+// four block chains only the first and the tail of the last are exposed; the recursive schedule ran all of them, and the
+// forward substitution's rank-128 pieces, with the machine mostly idle.  Every dependency is an event between the two
+// lanes, so the schedule is capturable into the per-step CUDA graph like the look-ahead schedule.
+// Diagonal blocks of the tile-DAG schedule: `nbk` columns in the middle, where a block's chain hides behind the bulk work
+// of the level before; half a block first (nothing can overlap the first chain) and geometrically shrinking blocks at the
+// end (the last chain and the last triangular solve of the right-hand sides are exposed too, and the bulk work left to
+// hide a chain behind shrinks with the trailing matrix).  All starts are multiples of 128.
+static void dag_blocks(int n, int nbk, std::vector<int>& start) {
+  start.clear();
+  int pos = 0;
+  static const bool flat = getenv("CVXB_DAG_FLAT") != nullptr;
+  while (pos < n) {
+    const int rem = n - pos;
+    int b;
+    if (flat) b = nbk;
+    else if (pos == 0 && n >= 3 * nbk) b = (nbk / 2) / NB * NB < NB ? NB : (nbk / 2) / NB * NB;
+    else if (rem >= 2 * nbk) b = nbk;
+    else if (rem <= 5 * NB) b = rem;
+    else b = ((rem + 1) / 2 + NB - 1) / NB * NB;
+    if (b > rem) b = rem;
+    start.push_back(pos);
+    pos += b;
+  }
+  start.push_back(n);
+}
+
+int potrf_dag(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0, double* B,
+              int ldb, int r) {
+  const int nbk = h.dag_block;
+  std::vector<int> bstart;
+  dag_blocks(n, nbk, bstart);
+  const int T = (int)bstart.size() - 1;
+  if (2 * T + 10 > (int)h.dag_events.size()) {
+    set_last_error("potrf_dag: %d diagonal blocks exceed the event pool", T);
+    return CVXB_EINVAL;
+  }
+  cudaStream_t sa = h.stream, sc = h.stream3;
+  // CVXB_DAG_TRACE=1: time stamps (CUDA events) at every piece boundary of both lanes, printed after the factorisation
+  static const bool trace_env = getenv("CVXB_DAG_TRACE") != nullptr;
+  const bool trace = trace_env && !h.capturing;
+  struct Mark { const char* what; int k; int lane; cudaEvent_t ev; };
+  std::vector<Mark> marks;
+  auto mark = [&](const char* what, int k, int lane) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, lane ? sc : sa);
+    marks.push_back(Mark{what, k, lane, e});
+  };
+  mark("start", 0, 0);
+  for (int k = 0; k < T; ++k) {
+    const int k0 = bstart[k], kb = bstart[k + 1] - k0;
+    const int rem = n - k0 - kb;
+    double* Akk = A + (size_t)k0 * lda + k0;
+    double* invDk = invD + (size_t)(k0 / NB) * NB * NB;
+    cudaEvent_t evP = h.dag_events[2 * k], evR = h.dag_events[2 * k + 1];
+    if (k > 0) CVXB_CUDA_OK(cudaStreamWaitEvent(sa, h.dag_events[2 * (k - 1) + 1], 0));       // A_kk fully updated
+    mark("P begin", k, 0);
+    CVXB_TRY(potrf_rec(h, kb, Akk, lda, invDk, flag_slot, mindiag_slot, col0 + k0, false, nullptr, 0, 0));
+    CVXB_CUDA_OK(cudaEventRecord(evP, sa));
+    mark("P end", k, 0);
+    double* A21 = Akk + kb;                                     // rows below the diagonal block, this block column
+    const int kn = k + 1 < T ? bstart[k + 2] - bstart[k + 1] : 0;      // next diagonal block
+    // The triangular solves are recursions of ~47 dependent launches per 2048 columns, most of them small (K = 128..512)
+    // and bound by launch + pipeline-fill latency (~12 us each), not by their flops.  Independent pieces -- row groups of
+    // A21 L_kk^-T, column groups of L_kk^-1 B_k -- therefore run beside each other on the side lanes: their latencies
+    // overlap instead of adding up.  Lane 0 keeps the rows of the next diagonal block (the critical path to P(k+1)).
+    int nside = 0;                                              // side lanes used at this level
+    cudaEvent_t evS[3];
+    // a side lane needs P(k) and everything level k-1 wrote below / beside it (its trailing update and right-hand-side
+    // update end lane 0's work of that level)
+    auto side_begin = [&](int lane) {
+      cudaError_t e = cudaStreamWaitEvent(h.side[lane - 1], evP, 0);
+      if (e == cudaSuccess && k > 0) e = cudaStreamWaitEvent(h.side[lane - 1], h.dag_events[2 * T + 7 + ((k - 1) & 1)], 0);
+      return e;
+    };
+    auto side_end = [&](int lane) {
+      evS[nside] = h.dag_events[2 * T + 1 + 3 * (k & 1) + nside];
+      cudaError_t e = cudaEventRecord(evS[nside], h.side[lane - 1]);
+      ++nside;
+      return e;
+    };
+    double* Anext = A + (size_t)(k0 + kb) * lda + (k0 + kb);
+    // lane 0 first (host enqueue order = the order the critical path needs): rows of the next diagonal block, its update
+    CVXB_CUDA_OK(cudaStreamWaitEvent(sc, evP, 0));
+    if (rem > 0) {
+      BulkScope bulk(h, 0);
+      mark("bulk level begin", k, 1);
+      CVXB_TRY(trsm_right_lt(h, kn, kb, Akk, lda, invDk, A21, lda));
+      mark("trsm right (next block rows) done", k, 1);
+      GemmArgs gn{kn, kn, kb, A21, lda, false, A21, lda, false, Anext, lda, -1.0, 1.0, 1};
+      CVXB_TRY(gemm_dmma(h, gn));
+      CVXB_CUDA_OK(cudaEventRecord(evR, sc));
+      mark("next block updated", k, 1);
+    }
+    const int rows_rest = rem - kn;                             // rows of A21 below the next diagonal block
+    int lane_next = 1;
+    if (rows_rest > 0) {
+      // up to two side lanes for the remaining rows of the TRSM (three without a right-hand-side block)
+      int groups = rows_rest >= 4096 ? 2 : 1;
+      if (!B && rows_rest >= 6144) groups = 3;
+      const int per = ((rows_rest + groups - 1) / groups + NB - 1) / NB * NB;
+      for (int gI = 0; gI < groups; ++gI) {
+        const int r0 = kn + gI * per, rr = rem - r0 < per ? rem - r0 : per;
+        if (rr <= 0) break;
+        CVXB_CUDA_OK(side_begin(lane_next));
+        {
+          BulkScope lane(h, lane_next);
+          CVXB_TRY(trsm_right_lt(h, rr, kb, Akk, lda, invDk, A21 + r0, lda));
+        }
+        CVXB_CUDA_OK(side_end(lane_next));
+        ++lane_next;
+      }
+    }
+    cudaEvent_t evY = nullptr;
+    if (B && lane_next <= 3) {
+      // Y_k = L_kk^-1 B_k on a side lane
+      CVXB_CUDA_OK(side_begin(lane_next));
+      {
+        BulkScope lane(h, lane_next);
+        CVXB_TRY(trsm_rec(h, kb, r, Akk, lda, invDk, B + k0, ldb, false));
+      }
+      evY = h.dag_events[2 * T + 1 + 3 * (k & 1) + nside];
+      CVXB_CUDA_OK(cudaEventRecord(evY, h.side[lane_next - 1]));
+      ++lane_next;
+    }
+    {
+      BulkScope bulk(h, 0);
+      for (int i = 0; i < nside; ++i) CVXB_CUDA_OK(cudaStreamWaitEvent(sc, evS[i], 0));
+      if (rem > kn) {                                           // kn is a whole number of 128-tiles here
+        mark("trsm right (all rows) done", k, 1);
+        GemmArgs gt{rem, rem, kb, A21, lda, false, A21, lda, false, Anext, lda, -1.0, 1.0, 1};
+        gt.tri_skip = kn / NB;
+        // timed on the bulk lane (events on stream3): the update shares the machine with the chain of P(k+1)
+        const bool timed = kb >= 1024 && rem >= 2048;
+        if (timed) CVXB_TRY(prof_begin(h, PROF_CHOL_TRAIL));
+        CVXB_TRY(gemm_dmma(h, gt));
+        if (timed) CVXB_TRY(prof_end(h, PROF_CHOL_TRAIL, (double)kb * ((double)rem * (rem + 1.0) - (double)kn * (kn + 1.0))));
+        mark("trailing syrk done", k, 1);
+      }
+      if (B) {
+        if (evY) CVXB_CUDA_OK(cudaStreamWaitEvent(sc, evY, 0));
+        else CVXB_TRY(trsm_rec(h, kb, r, Akk, lda, invDk, B + k0, ldb, false));                // Y_k
+        mark("Y_k done", k, 1);
+        if (rem > 0) {
+          GemmArgs gb{rem, r, kb, A21, lda, false, B + k0, ldb, true, B + k0 + kb, ldb, -1.0, 1.0, 0};
+          CVXB_TRY(gemm_dmma(h, gb));
+          mark("rhs update done", k, 1);
+        }
+      }
+    }
+    CVXB_CUDA_OK(cudaEventRecord(h.dag_events[2 * T + 7 + (k & 1)], sc));      // level k complete on lane 0
+  }
+  cudaEvent_t evJ = h.dag_events[2 * T];
+  CVXB_CUDA_OK(cudaEventRecord(evJ, sc));
+  CVXB_CUDA_OK(cudaStreamWaitEvent(sa, evJ, 0));
+  mark("joined", T, 0);
+  if (trace) {
+    cudaStreamSynchronize(sa);
+    fprintf(stderr, "potrf_dag n=%d r=%d block=%d reserve=%d\n", n, r, nbk, h.dag_reserve);
+    for (const Mark& m : marks) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, marks[0].ev, m.ev);
+      fprintf(stderr, "  %8.3f ms  %s  k=%d  %s\n", ms, m.lane ? "bulk " : "chain", m.k, m.what);
+    }
+    for (const Mark& m : marks) cudaEventDestroy(m.ev);
+  }
+  return CVXB_OK;
+}
+
 // Recursive halving; sub-problems that fit the L2-resident regime switch to the look-ahead schedule.
 // With a right-hand-side block B (n x r) the forward substitution B := L^-1 B rides along: every piece of it is
 // issued as soon as the columns of L it needs exist (in the look-ahead regime on the second stream, in the shadow
 // of the leaf chain), instead of as a separate sweep over L after the factorisation.
 int potrf_rec(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0, bool plain = false,
               double* B = nullptr, int ldb = 0, int r = 0) {
+  if (!plain && h.stream3 && h.stream2 && h.dag_block >= NB && n >= h.dag_min_n && n > h.dag_block &&
+      n / h.dag_block < 48 && h.sk_reserve == 0 && !h.in_dag) {
+    h.in_dag = true;
+    const int st = potrf_dag(h, n, A, lda, invD, flag_slot, mindiag_slot, col0, B, ldb, r);
+    h.in_dag = false;
+    return st;
+  }
   // a wide right-hand-side block adds (rem x r x 128) of rank-128 GEMM work per step to the second stream: beyond
   // ~2560 columns that no longer fits in the shadow of the leaf chain (C4, r = 2049: 57.1 ms per step with the
   // look-ahead schedule up to 4608 against 54.3 ms with the switch at 2560)
@@ -789,7 +1003,7 @@ int potrf_rec_plain(Handle& h, int n, double* A, int lda, double* invD, int flag
 int trsm_rec(Handle& h, int n, int r, const double* L, int ldl, const double* invD, double* B, int ldb, bool trans) {
   if (n <= NB) {
     const int lds = pad_ld(n);
-    if ((size_t)lds * r <= PART_DOUBLES - 65536) {      // out of place through the scratch panel (see above)
+    if ((size_t)lds * r + 65536 <= h.part_cap) {      // out of place through the scratch panel (see above)
       double* Ys = h.d_part;
       GemmArgs g{n, r, n, invD, NB, trans, B, ldb, true, Ys, lds, 1.0, 0.0, 0};
       CVXB_TRY(gemm_dmma(h, g));

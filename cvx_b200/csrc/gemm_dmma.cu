@@ -385,6 +385,39 @@ gemm_dmma_streamk_kernel(int M, int N, int K, const double* __restrict__ A, int 
   }
 }
 
+// Persistent tile loop on a RESTRICTED grid: G = (SMs - reserve) CTAs of one per SM (216 KB of shared memory each) walk
+// the 128x128 tiles id0 + cta, id0 + cta + G, ... of one GEMM.  The tile-DAG schedule of the big factorisations
+// (factor.cu: potrf_dag) runs its bulk updates through this kernel on a low-priority stream: the grid never takes more
+// than G SMs, so the kernels of the concurrent critical chain (leaf -> panel solve -> look-ahead update of the next
+// diagonal block) always find a free SM instead of waiting a whole tile time (0.13-0.27 ms at K = 1024..2048) behind a
+// full wave of bulk tiles.  No inter-CTA dependency (no cooperative launch needed); `id0` lets a triangular update skip
+// the leading tile rows the critical path has already updated (ids are row-major over the lower triangle).
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(256, 1)
+gemm_dmma_persist_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                         double* __restrict__ C, int ldc, double alpha, double beta, int tri, int tiles_m, int id0, int id1,
+                         int lower_only) {
+  typedef CtaTile<128, 128, 2, 4, A_KC, B_KC> T;
+  extern __shared__ __align__(16) double smem[];
+  const int KT = (K + BK - 1) / BK;
+  double acc[T::MT][T::NTL][2];
+  for (int id = id0 + (int)blockIdx.x; id < id1; id += (int)gridDim.x) {
+    int bm, bn;
+    if (tri) {
+      tri_tile(id, bm, bn);
+    } else {
+      bm = id % tiles_m;
+      bn = id / tiles_m;
+    }
+    const int m0 = bm * 128, n0 = bn * 128;
+    if (lower_only && m0 + 128 <= n0) continue;
+    T::zero(acc);
+    __syncthreads();          // every warp is done with the previous tile's stages
+    T::mainloop(acc, smem, M, N, K, A, lda, B, ldb, m0, n0, 0, KT);
+    T::template epilogue<2>(acc, M, N, C, ldc, alpha, beta, tri, (tri && bm == bn) || lower_only, m0, n0);
+  }
+}
+
 template <int BM, int WARPS_M, int WARPS_N>
 constexpr int smem_bytes() { return StagesFor<BM>::value * 2 * TileElems<BM>::value * (int)sizeof(double); }
 
@@ -492,6 +525,10 @@ int gemm_dmma_init() {
                                     smem_bytes<128, 2, 4>()));
   CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_streamk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     smem_bytes<128, 2, 4>()));
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_persist_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<128, 2, 4>()));
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_persist_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<128, 2, 4>()));
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_persist_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<128, 2, 4>()));
+  CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_persist_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<128, 2, 4>()));
   CVXB_TRY((set_attr<128, 2, 4>()));
   CVXB_TRY((set_attr<64, 2, 2>()));
   CVXB_TRY((set_attr<32, 2, 2>()));
@@ -588,6 +625,37 @@ int gemm_dmma(Handle& h, const GemmArgs& g) {
       }
       cudaGetLastError();       // not launchable cooperatively here: the plain grid below
     }
+  }
+  if (h.sk_reserve > 0 && g.tile == 0 && (tile == 128 || (g.tri && g.tri_skip > 0))) {
+    // bulk stream of the tile-DAG factorisation: persistent loop on (SMs - reserve) CTAs when the GEMM is long enough to
+    // keep the chain's kernels waiting (at least half a wave of tiles; shorter ones finish within a chain step anyway)
+    const int tm = (g.M + 127) / 128;
+    const long long T = ntiles(128);
+    long long id0 = 0;
+    if (g.tri && g.tri_skip > 0) id0 = (long long)g.tri_skip * (g.tri_skip + 1) / 2;
+    const int G = h.sm_count - h.sk_reserve;
+    if (G > 0 && T > id0 && (T - id0 >= G / 2 || g.tri_skip > 0) && T < (1ll << 30)) {
+      cudaStream_t st = g_gemm_stream ? g_gemm_stream : h.stream;
+      const int grid = (int)(T - id0 < G ? T - id0 : G);
+      const int lo = g.lower_only ? 1 : 0;
+#define CVXB_PERSIST(AK, BKC)                                                                                              \
+  gemm_dmma_persist_kernel<AK, BKC><<<grid, 256, smem_bytes<128, 2, 4>(), st>>>(g.M, g.N, g.K, g.A, g.lda, g.B, g.ldb, g.C, \
+                                                                               g.ldc, g.alpha, g.beta, g.tri, tm, (int)id0, \
+                                                                               (int)T, lo)
+      if (g.a_kc && g.b_kc) CVXB_PERSIST(true, true);
+      else if (!g.a_kc && g.b_kc) CVXB_PERSIST(false, true);
+      else if (!g.a_kc && !g.b_kc) CVXB_PERSIST(false, false);
+      else CVXB_PERSIST(true, false);
+#undef CVXB_PERSIST
+      h.launches++;
+      CVXB_CUDA_OK(cudaGetLastError());
+      return CVXB_OK;
+    }
+  }
+  if (g.tri && g.tri_skip > 0) {
+    if ((long long)g.tri_skip * 128 >= g.M) return CVXB_OK;      // nothing left below the skipped block
+    set_last_error("gemm_dmma: tri_skip is only served on the bulk stream (persistent 128x128 grid)");
+    return CVXB_EINVAL;
   }
   if (tile == 128) return launch_layout<128, 2, 4>(h, g);    // (a 16-warp 4x4 layout measured 7% slower)
   if (tile == 64) return launch_layout<64, 2, 2>(h, g);

@@ -373,6 +373,12 @@ int cvxb_test_dgemm(cvxb_handle h, int a_kc, int b_kc, int M, int N, int K, doub
 int cvxb_bench_kernel(cvxb_handle h, int which, int n, int k, int reps, double* ms_per_launch,
                       double* flops_or_bytes_per_launch);
 
+/* Schedule of the big factorisations (tests and tuning; defaults: blocks of 2048 columns from n = 5120 on, 12 SMs left to
+ * the critical chain): the tile-DAG schedule runs the bulk updates of a right-looking blocked Cholesky on a third stream
+ * beside the chain of diagonal-block factorisations.  A negative argument keeps the current value;
+ * dag_block = 0 switches the schedule off (recursive halving + look-ahead only). */
+int cvxb_debug_set_schedule(cvxb_handle h, int dag_block, int dag_min_n, int dag_reserve);
+
 #ifdef __cplusplus
 }
 #endif

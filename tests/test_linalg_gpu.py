@@ -177,6 +177,38 @@ def test_kkt_fused_forward_substitution(handle, n, p, seed, monkeypatch):
     assert rel(s["H"] @ c, s["q"]) < 1e-9
 
 
+@pytest.mark.parametrize("n,p,block,seed", [(1000, 100, 256, 11), (1537, 200, 384, 12), (2049, 129, 512, 13),
+                                            (1300, 0, 256, 14)])
+def test_tile_dag_schedule_equals_recursive(handle, n, p, block, seed):
+    """The tile-DAG schedule of the big factorisations (potrf_dag: chain of diagonal-block factorisations beside the bulk
+    updates on a third stream, persistent GEMM grids on a restricted number of SMs) is the same right-looking blocked
+    Cholesky in another order: factor, KKT solution and choleskySolve agree with the recursive schedule to rounding and
+    meet the planted-solution bar.  Small blocks bring the schedule (default: n >= 5120, blocks of 2048) down to test
+    sizes, with ragged last blocks (1537 = 4*384 + 1, 2049 = 4*512 + 1)."""
+    from cvx_b200 import KKTSystem, MatrixUtils
+    H = spd(n, seed)
+    try:
+        handle.set_schedule(0, -1, -1)
+        L0 = MatrixUtils.regularizedCholesky(H, handle)
+        handle.set_schedule(block, block + 1, 8)
+        L1 = MatrixUtils.regularizedCholesky(H, handle)
+        assert np.array_equal(np.triu(L1, 1), np.zeros((n, n)))
+        assert rel(L1, L0) < 1e-12 and rel(L1 @ L1.T, H) < 1e-13
+        if p:
+            s = P.kkt_planted_pd(n, p, seed)
+            handle.set_schedule(0, -1, -1)
+            x0, w0 = KKTSystem(s["H"], s["A"], s["q"], s["b"], handle).solve(1e-6, None, 1e-7, 0)
+            c0 = MatrixUtils.choleskySolve(s["H"], s["q"], None, 1e-7, 0, handle)
+            handle.set_schedule(block, block + 1, 8)
+            x1, w1 = KKTSystem(s["H"], s["A"], s["q"], s["b"], handle).solve(1e-6, None, 1e-7, 0)
+            c1 = MatrixUtils.choleskySolve(s["H"], s["q"], None, 1e-7, 0, handle)
+            assert rel(x1, x0) < 1e-7 and rel(w1, w0) < 1e-7 and rel(c1, c0) < 1e-7
+            assert rel(x1, s["x"]) < 1e-5 and rel(w1, s["w"]) < 1e-5
+            assert rel(s["H"] @ c1, s["q"]) < 1e-9
+    finally:
+        handle.set_schedule(2048, 5120, 12)
+
+
 @pytest.mark.parametrize("n,p,seed", [(50, 5, 0), (400, 60, 1)])
 def test_solve_with_chol_factor(handle, n, p, seed):
     """KktTest.testSolutionWithCholFactor (:117-184)."""
