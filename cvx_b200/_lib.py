@@ -110,13 +110,14 @@ class SolutionC(C.Structure):
 
 class BatchDesc(C.Structure):
     _fields_ = [("B", C.c_int), ("n", C.c_int), ("m", C.c_int), ("p", C.c_int), ("objective", _ip), ("pcount", _ip),
-                ("obj_a", _dp), ("obj_r", _dp), ("obj_P", _dp), ("G", _dp), ("ub", _dp), ("A", _dp), ("b", _dp), ("x0", _dp)]
+                ("obj_a", _dp), ("obj_r", _dp), ("obj_P", _dp), ("G", _dp), ("ub", _dp), ("A", _dp), ("b", _dp), ("x0", _dp),
+                ("phase1", _ip)]
 
 
 class BatchResult(C.Structure):
     _fields_ = [("x", _dp), ("status", _ip), ("newton_steps", _ip), ("outer_stages", _ip), ("objective", _dp),
                 ("duality_gap", _dp), ("equality_gap", _dp), ("solve_ms", C.c_double), ("stage_newton_steps", _ip),
-                ("cycles", C.POINTER(C.c_longlong))]
+                ("cycles", C.POINTER(C.c_longlong)), ("phase1_newton_steps", _ip), ("phase1_stages", _ip), ("phase1_s", _dp)]
 
 
 # every symbol include/cvxb.h declares: name -> (restype, argtypes)

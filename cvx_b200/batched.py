@@ -29,11 +29,15 @@ class BatchSolution:
     solve_ms: float
     stage_newton_steps: Optional[np.ndarray] = None    # B x 16: Newton steps per outer stage
     cycles: Optional[np.ndarray] = None                # B: SM clock cycles each problem occupied its CTA
+    phase1_newton_steps: Optional[np.ndarray] = None   # B: Newton steps / stages / final slack of the phase-I analysis
+    phase1_stages: Optional[np.ndarray] = None
+    phase1_s: Optional[np.ndarray] = None
 
 
 def pack_problems(probs: Sequence[dict]):
     """Problem dictionaries (oracle/problems.py layout) -> packed column-major arrays of cvxb_batch_desc.
-    Every problem must have the same n and m, a strictly feasible x0 and at most one equality."""
+    Every problem must have the same n and m and at most one equality.  A problem without a strictly feasible x0 is
+    started from its `xdef` (ConstraintSet.pointWhereDefined) and flagged for the phase-I analysis."""
     B = len(probs)
     n = probs[0]["n"]
     m = probs[0]["G"].shape[0]
@@ -48,9 +52,10 @@ def pack_problems(probs: Sequence[dict]):
     A = np.zeros((B, n))
     b = np.zeros(B)
     x0 = np.empty((B, n))
+    phase1 = np.zeros(B, dtype=np.int32)
     for k, pr in enumerate(probs):
         assert pr["n"] == n and pr["G"].shape == (m, n), "batched problems must share n and m"
-        assert pr.get("x0") is not None, "batched solver needs a strictly feasible start (no phase I)"
+        assert pr.get("x0") is not None or pr.get("xdef") is not None, "need a feasible start x0 or a point xdef"
         obj[k] = _KIND[pr["kind"]]
         if pr["kind"] != "kl":
             obj_a[k] = pr["a"]
@@ -65,8 +70,13 @@ def pack_problems(probs: Sequence[dict]):
             pcount[k] = 1
             A[k] = pr["A"][0]
             b[k] = pr["b"][0]
-        x0[k] = pr["x0"]
-    return dict(B=B, n=n, m=m, objective=obj, pcount=pcount, obj_a=obj_a, obj_r=obj_r, obj_P=obj_P, G=G, ub=ub, A=A, b=b, x0=x0)
+        if pr.get("x0") is not None:
+            x0[k] = pr["x0"]
+        else:
+            x0[k] = pr["xdef"]
+            phase1[k] = 1
+    return dict(B=B, n=n, m=m, objective=obj, pcount=pcount, obj_a=obj_a, obj_r=obj_r, obj_P=obj_P, G=G, ub=ub, A=A, b=b, x0=x0,
+                phase1=phase1 if phase1.any() else None)
 
 
 class BatchedBarrierSolver:
@@ -84,6 +94,8 @@ class BatchedBarrierSolver:
         d.obj_P = dptr(packed["obj_P"]) if packed["obj_P"] is not None else None
         d.G, d.ub, d.x0 = dptr(packed["G"]), dptr(packed["ub"]), dptr(packed["x0"])
         d.A, d.b = dptr(packed["A"]), dptr(packed["b"])
+        ph = packed.get("phase1")
+        d.phase1 = ph.ctypes.data_as(C.POINTER(C.c_int)) if ph is not None else None
         self.B, self.n = d.B, d.n
         self._b = C.c_void_p()
         check(self.handle.lib.cvxb_batch_create(self.handle._h, C.byref(d), C.byref(self._b)))
@@ -109,8 +121,11 @@ class BatchedBarrierSolver:
         r.stage_newton_steps = ip(stage_steps)
         cycles = np.zeros(B, dtype=np.int64)
         r.cycles = cycles.ctypes.data_as(C.POINTER(C.c_longlong))
+        ph_steps, ph_stages, ph_s = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32), np.zeros(B)
+        r.phase1_newton_steps, r.phase1_stages, r.phase1_s = ip(ph_steps), ip(ph_stages), dptr(ph_s)
         check(self.handle.lib.cvxb_batch_barrier_solve(self.handle._h, self._b, C.byref(cp), C.byref(r)))
-        return BatchSolution(x, status, steps, stages, objv, gap, eqg, float(r.solve_ms), stage_steps, cycles)
+        return BatchSolution(x, status, steps, stages, objv, gap, eqg, float(r.solve_ms), stage_steps, cycles, ph_steps,
+                             ph_stages, ph_s)
 
     def device_records(self):
         """(device pointer, doubles per row) of the packed results of the last solve:

@@ -10,7 +10,10 @@
 // Semantics are those of the large path (solver.cu / kkt.cu), i.e. of BarrierSolver.scala:70-188,
 // EqualityConstrainedSolver.scala:37-107, UnconstrainedSolver.scala:34-125 (incl. D4, D7),
 // KKTSystem.scala:43-246 (path 0, regularised retry, path 1 = H + A'A) and MatrixUtils.scala:240-516.
-// The eigendecomposition last resorts (kktSymSolve / symSolve) are reported as CVXB_ELINSOLVE.
+// The decomposition last resort kktSymSolve (KKTSystem.scala:283-310) runs inside the CTA as well (one-sided Jacobi SVD
+// of the (n+1)^2 KKT matrix in the shared-memory block of G, which is reloaded afterwards).
+// Problems flagged `phase1` start from a point where they are merely defined: the CTA first runs the reference's phase-I
+// feasibility analysis (ConstraintSet.scala:326-395, 556-575) on the (n+1) x (m+2p) problem it builds in place.
 #include "kkt.cuh"
 #include "vecops.cuh"
 
@@ -28,6 +31,9 @@ struct cvxb_batch_s {
   int *status = nullptr, *steps = nullptr, *stages = nullptr;
   int* stage_steps = nullptr;    // B x CVXB_BATCH_STAGES: Newton steps of each of the first outer stages
   int* order = nullptr;          // pickup order of the problems (longest expected first), or NULL = index order
+  int* phase1 = nullptr;         // B or NULL
+  int *ph_steps = nullptr, *ph_stages = nullptr;
+  double* ph_s = nullptr;
   long long* cycles = nullptr;   // B: SM clock cycles each problem spent in its CTA
   double* records = nullptr;     // B x (n + CVXB_BATCH_RECORD_EXTRA): [x, objective, gap, status, steps, stages] per problem
   double* scratch = nullptr;     // per-CTA copy of H (n x n)
@@ -59,6 +65,10 @@ struct BatchArgs {
   double* records;
   double* scratch;
   unsigned* counter;
+  const int* phase1;       // B or NULL: 1 = x0 is only a point where the problem is defined, run phase I first
+  int* ph_steps;           // phase-I Newton steps / outer stages / final slack s (NULL when no problem asks for phase I)
+  int* ph_stages;
+  double* ph_s;
   cvxb_params P;
 };
 
@@ -73,6 +83,7 @@ struct Smem {
   double sc[16];
   int fl[8];
   int pcur;                 // equalities of the current problem (0 or 1)
+  int ncur, mcur;           // dimensions of the problem the CTA is working on (the phase-I pass: n + 1, m + 2p)
   int stage_steps[CVXB_BATCH_STAGES];
 };
 #define S_T1 (S.work)
@@ -106,7 +117,7 @@ __device__ long long g_batch_clk[12];
 // returns false when x is not strictly feasible (slack <= 0)
 __device__ bool b_eval(Smem& S, const BatchArgs& A, int kind, double obj_r, const double* Pg, double beq, double t,
                        double* fval, double* f0out, double* normGrad, double* eqdiff) {
-  const int tid = threadIdx.x, n = A.n, m = A.m;
+  const int tid = threadIdx.x, n = S.ncur, m = S.mcur;
   if (tid < m) {
     double s = 0.0;
     for (int j = 0; j < n; ++j) s = fma(GG(tid, j), S.x[j], s);
@@ -170,7 +181,7 @@ __device__ bool b_eval(Smem& S, const BatchArgs& A, int kind, double obj_r, cons
 
 // ---- H = t hess f0 + G' diag(inv^2) G, full symmetric in S.L, via DMMA out of shared memory --------------
 __device__ void b_hessian(Smem& S, const BatchArgs& A, int kind, const double* Pg, double t) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = A.n, m = A.m;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = S.ncur, m = S.mcur;
   const int g = lane >> 2, tq = lane & 3;
   const int nt = (n + 7) >> 3;
   const int ntiles = nt * (nt + 1) / 2;
@@ -213,7 +224,7 @@ __device__ void b_hessian(Smem& S, const BatchArgs& A, int kind, const double* P
 
 // ---- Ruiz equilibration of the full symmetric H in S.L -> S.dr  (MatrixUtils.scala:240-268) ---------------
 __device__ void b_ruiz(Smem& S, const BatchArgs& A) {
-  const int tid = threadIdx.x, n = A.n, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, n = S.ncur, lane = tid & 31, warp = tid >> 5;
   if (tid < n) S.dr[tid] = 1.0;
   __syncthreads();
   for (int sweep = 0; sweep < A.P.ruizMaxSweeps; ++sweep) {
@@ -412,7 +423,7 @@ __device__ void b_scale_H(Smem& S, int n, double delta) {
 // returns true when the attempt chain (plain, then regularised) produced an accepted solution.
 __device__ bool b_linear_solve(Smem& S, const BatchArgs& A, const double* Hs, double diag_add, bool rank1,
                                const double* q, double brhs, double tol, int* regularized) {
-  const int tid = threadIdx.x, n = A.n;
+  const int tid = threadIdx.x, n = S.ncur;
   bool have_dr = false;
   for (int attempt = 0; attempt < 2; ++attempt) {
     b_load_H(S, n, Hs, diag_add, rank1);
@@ -491,6 +502,122 @@ __device__ bool b_linear_solve(Smem& S, const BatchArgs& A, const double* Hs, do
   return false;
 }
 
+// ---- KKTSystem.kktSymSolve (KKTSystem.scala:63, 283-310): last resort of the fallback chain for p == 1 -------------------
+// M = [H a; a' 0] ((n+1)^2), rhs = (-q, b): symSolve = MatrixUtils.diagonalizationSolve (MatrixUtils.scala:603-751) through
+// a one-sided (Hestenes) Jacobi SVD inside the CTA -- the in-CTA twin of eig.cu: svd_solve_device, same pairing order,
+// same threshold, same two acceptance tests (range test, residual test; defect D3: no recovery once they fail).
+// W = M V and V live in the shared-memory block of G and L (G is reloaded by the caller afterwards; L is scratch here).
+__device__ __noinline__ bool b_kkt_sym_solve(Smem& S, int n, const double* Hs, const double* q, double brhs, double tol) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = n + 1, ld = BN + 1;
+  double* W = S.G;
+  double* V = S.G + ld * ld;
+  double* vec = S.L + 8;                 // V ends two entries into L
+  double *z = vec, *b0 = vec + 72, *xs = vec + 144, *aw = vec + 216, *rhs = vec + 288;
+  __syncthreads();
+  for (int idx = tid; idx < N * N; idx += BT) {
+    const int i = idx % N, j = idx / N;
+    double v;
+    if (i < n && j < n) v = Hs[i + (size_t)j * n];
+    else if (i == n && j == n) v = 0.0;
+    else v = S.aeq[i < n ? i : j];
+    W[i + j * ld] = v;
+    V[i + j * ld] = (i == j) ? 1.0 : 0.0;
+  }
+  if (tid < N) rhs[tid] = tid < n ? -q[tid] : brhs;
+  __syncthreads();
+  const int np = N + (N & 1), mrr = np - 1;
+  for (int sweep = 0; sweep < 60 && N > 1; ++sweep) {
+    if (tid == 0) S.fl[1] = 0;
+    __syncthreads();
+    for (int r = 0; r < np - 1; ++r) {
+      for (int k = warp; k < np / 2; k += BT / 32) {
+        const int ci = (r + k) % mrr;
+        const int cj = (k == 0) ? mrr : (r + mrr - k) % mrr;
+        if (ci >= N || cj >= N) continue;            // dummy column of an odd-sized problem
+        double* wi = W + ci * ld;
+        double* wj = W + cj * ld;
+        double a = 0.0, b = 0.0, g = 0.0;
+        for (int t = lane; t < N; t += 32) {
+          const double x = wi[t], y = wj[t];
+          a = fma(x, x, a); b = fma(y, y, b); g = fma(x, y, g);
+        }
+        a = warp_sum(a); b = warp_sum(b); g = warp_sum(g);
+        if (!(fabs(g) > 1e-15 * sqrt(a * b))) continue;     // already orthogonal (also when a column is zero); warp-uniform
+        const double zeta = (b - a) / (2.0 * g);
+        const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + tt * tt), sn = c * tt;
+        double* vi = V + ci * ld;
+        double* vj = V + cj * ld;
+        for (int t = lane; t < N; t += 32) {
+          double x = wi[t], y = wj[t];
+          wi[t] = c * x - sn * y;
+          wj[t] = sn * x + c * y;
+          x = vi[t]; y = vj[t];
+          vi[t] = c * x - sn * y;
+          vj[t] = sn * x + c * y;
+        }
+        if (lane == 0) atomicAdd(&S.fl[1], 1);
+      }
+      __syncthreads();
+    }
+    if (S.fl[1] == 0) break;
+    __syncthreads();
+  }
+  __syncthreads();
+  // z_j = (u_j . rhs) / s_j with u_j = w_j / s_j; exact-zero singular values are skipped as the reference skips them
+  for (int j = warp; j < N; j += BT / 32) {
+    const double* w = W + j * ld;
+    double s2 = 0.0, wb = 0.0;
+    for (int t = lane; t < N; t += 32) { s2 = fma(w[t], w[t], s2); wb = fma(w[t], rhs[t], wb); }
+    s2 = warp_sum(s2); wb = warp_sum(wb);
+    if (lane == 0) {
+      const double sg = sqrt(s2);
+      z[j] = (sg > 0.0) ? (wb / sg) / sg : 0.0;
+    }
+  }
+  __syncthreads();
+  if (tid < N) {
+    double sb = 0.0, sx = 0.0;
+    for (int j = 0; j < N; ++j) { sb = fma(W[tid + j * ld], z[j], sb); sx = fma(V[tid + j * ld], z[j], sx); }
+    b0[tid] = sb;        // U (U' rhs): projection of rhs onto the range
+    xs[tid] = sx;        // V S^-1 U' rhs
+  }
+  __syncthreads();
+  if (tid < N) {
+    double sa = 0.0;
+    if (tid < n) {
+      for (int j = 0; j < n; ++j) sa = fma(Hs[tid + (size_t)j * n], xs[j], sa);
+      sa = fma(S.aeq[tid], xs[n], sa);
+    } else {
+      for (int j = 0; j < n; ++j) sa = fma(S.aeq[j], xs[j], sa);
+    }
+    aw[tid] = sa;
+  }
+  __syncthreads();
+  double nb = 0.0, d0 = 0.0, d1 = 0.0;
+  if (tid < N) {
+    const double bi = rhs[tid], r0 = bi - b0[tid], r1 = aw[tid] - bi;
+    nb = bi * bi; d0 = r0 * r0; d1 = r1 * r1;
+  }
+  nb = block_sum(nb, S.red);
+  d0 = block_sum(d0, S.red);
+  d1 = block_sum(d1, S.red);
+  const double relDist = relative_size(sqrt(d0), sqrt(nb), tol), relErr = relative_size(sqrt(d1), sqrt(nb), tol);
+  if (tid < n) S.dir[tid] = xs[tid];
+  if (tid == 0) S.sc[1] = xs[n];
+  __syncthreads();
+  return (relDist <= tol) && (relErr <= tol);
+}
+
+// G of the current problem back into shared memory (after b_kkt_sym_solve used its space)
+__device__ __noinline__ void b_reload_G(Smem& S, const double* Gg, int n, int m) {
+  for (int idx = threadIdx.x; idx < BN * LDG; idx += BT) S.G[idx] = 0.0;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < m * n; idx += BT) GG(idx % m, idx / m) = Gg[idx];
+  __syncthreads();
+}
+
 __device__ bool b_in_set(Smem& S, int m, double s) {
   int out = 0;
   if (threadIdx.x < m) {
@@ -507,7 +634,7 @@ __device__ double b_value(Smem& S, const BatchArgs& A, int kind, double t, doubl
   const int tid = threadIdx.x;
   double ls = 0.0;
   int bad = 0;
-  if (tid < A.m) {
+  if (tid < S.mcur) {
     double d = S.ub[tid] - (S.gx[tid] + s * S.Gd[tid]);
     if (!(d > 0.0)) bad = 1;
     ls = log(d);
@@ -518,9 +645,9 @@ __device__ double b_value(Smem& S, const BatchArgs& A, int kind, double t, doubl
   double f0s;
   if (kind == CVXB_OBJ_KL) {
     double v = 0.0;
-    if (tid < A.n) {
+    if (tid < S.ncur) {
       double xj = S.x[tid] + s * S.dir[tid];
-      v = xj * log(xj * (double)A.n);
+      v = xj * log(xj * (double)S.ncur);
     }
     f0s = block_sum(v, S.red);
   } else {
@@ -529,13 +656,148 @@ __device__ double b_value(Smem& S, const BatchArgs& A, int kind, double t, doubl
   return t * f0s - ls;
 }
 
-__global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
+struct LoopOut {
+  int status, stage, total_steps;
+  double objv, gap, eqgap;
+};
+
+// BarrierSolver.solveWithEQs / solveWithoutEQs (BarrierSolver.scala:70-177) on the problem currently in shared memory
+// (S.ncur, S.mcur are ITS dimensions: the phase-I pass runs with n + 1 variables and m + 2p rows), from S.x.
+//   term 0: standard termination (duality gap and equality gap below tolSolver);
+//   term 1: phase I (CvxUtils.scala:78-87): objective value below zero -- a strictly feasible point has been found.
+__device__ __noinline__ void b_barrier_loop(Smem& S, const BatchArgs& A, int kind, double obj_r, const double* Pg, double beq,
+                                            int p, int term, double* Hs, const double* Gg, bool record_stages, LoopOut& out) {
+  const int tid = threadIdx.x, n = S.ncur, m = S.mcur;
+  const double tol = A.P.tolSolver, tolEq = A.P.tolEqSolve;
+  int status = CVXB_OK, stage = 0, total_steps = 0;
+  double t = A.P.t0, gap = 1.7976931348623157e308, eqgap = 1.7976931348623157e308;
+  double objv = term ? 1.7976931348623157e308 : 0.0;
+  const double maxStage = 1000.0 / A.P.mu;
+  while (!(term ? (objv < 0.0 && eqgap < A.P.phase1EqTol) : (gap < tol && eqgap < tol)) && stage < maxStage &&
+         status == CVXB_OK) {
+    // ---------------- inner Newton solve at parameter t
+    int iter = 0;
+    double nd = tol + 1, fval, f0, normGrad, eqd, trust = 0.0;
+    if (!b_eval(S, A, kind, obj_r, Pg, beq, t, &fval, &f0, &normGrad, &eqd)) { status = CVXB_ENOTFEASIBLE; break; }
+    double eqnorm = fabs(eqd);
+    while (iter < A.P.maxIter && (p ? ((nd > tol && normGrad > tol) || eqnorm > tol) : (nd > tol && normGrad > tol))) {
+      BCLK(0);
+      b_hessian(S, A, kind, Pg, t);
+      BCLK(1);
+      b_store_H(S, n, Hs);
+      BCLK(2);
+      int reg = 0;
+      bool ok = b_linear_solve(S, A, Hs, 0.0, false, S.y, eqd, tolEq, &reg);
+      if (!ok) {
+        if (p) {
+          // path 1: K = H + a a', z = q - a' b   (KKTSystem.scala:57-59)
+          if (tid < n) S.zrhs[tid] = S.y[tid] - S.aeq[tid] * eqd;
+          __syncthreads();
+          ok = b_linear_solve(S, A, Hs, 0.0, true, S.zrhs, eqd, tolEq, &reg);
+          if (!ok) {
+            // path 2: decomposition of the full KKT matrix  (KKTSystem.scala:63, 283-310)
+            ok = b_kkt_sym_solve(S, n, Hs, S.y, eqd, tolEq);
+            b_reload_G(S, Gg, n, m);
+            if (!ok) { status = CVXB_EUNSOLVABLE; break; }
+          }
+        } else {
+          ok = b_linear_solve(S, A, Hs, A.P.newtonRegDelta, false, S.y, 0.0, tolEq, &reg);   // H + 1e-9 I
+        }
+        if (!ok) { status = CVXB_ELINSOLVE; break; }
+      }
+      BCLK(7);
+      // q = d . grad
+      double q = 0.0, c1 = 0.0, c2 = 0.0;
+      if (kind == CVXB_OBJ_QUADRATIC && tid >= 128 && tid < 128 + n) {
+        const int i = tid - 128;
+        double s = 0.0;
+        for (int j = 0; j < n; ++j) s = fma(Pg[i + (size_t)j * n], S.dir[j], s);
+        S.Pd[i] = s;
+      }
+      if (tid < m) {
+        double s = 0.0;
+        for (int j = 0; j < n; ++j) s = fma(GG(tid, j), S.dir[j], s);
+        S.Gd[tid] = s;
+      }
+      __syncthreads();
+      if (tid < n) {
+        double dj = S.dir[tid];
+        q = dj * S.y[tid];
+        if (kind == CVXB_OBJ_LINEAR) c1 = S.oa[tid] * dj;
+        else if (kind == CVXB_OBJ_QUADRATIC) { c1 = (S.oa[tid] + S.Px[tid]) * dj; c2 = dj * S.Pd[tid]; }
+      }
+      q = block_sum(q, S.red);
+      c1 = block_sum(c1, S.red);
+      c2 = block_sum(c2, S.red);
+      nd = -q / 2;
+      bool moved = false;
+      if (nd > tol) {
+        int it = 0, thr = 0;
+        double step;
+        if (p) {
+          double s = 1.0;
+          while (!b_in_set(S, m, s) && it < 100) { s *= A.P.beta; ++it; }
+          if (it == 100) { status = CVXB_ELINESEARCH; break; }
+          while (it < 100) {
+            double v = b_value(S, A, kind, t, s, f0, c1, c2, &thr);
+            if (thr) break;
+            if (!(v > fval + A.P.alpha * s * q)) break;
+            s *= A.P.beta; ++it;
+          }
+          if (thr) { status = CVXB_ENOTFEASIBLE; break; }
+          if (it == 100) { status = CVXB_ELINESEARCH; break; }
+          step = s;
+        } else {
+          const double hnorm = sqrt(-q);
+          if (iter == 0) trust = hnorm;
+          const double scl = (iter == 0 || hnorm <= trust) ? 1.0 : trust / hnorm;
+          double tt = 1.0;
+          while (!b_in_set(S, m, scl * tt) && it < 200) { tt *= A.P.beta; ++it; }
+          if (it == 100) { status = CVXB_ELINESEARCH; break; }
+          if (b_in_set(S, m, scl)) {
+            (void)b_value(S, A, kind, t, scl * tt, f0, c1, c2, &thr);
+            if (thr) { status = CVXB_ENOTFEASIBLE; break; }
+          }
+          while (it < 200) {
+            double v = b_value(S, A, kind, t, scl * tt, f0, c1, c2, &thr);
+            if (thr) break;
+            if (!(v > fval + A.P.alpha * tt * q)) break;
+            tt *= A.P.beta; ++it;
+          }
+          if (thr) { status = CVXB_ENOTFEASIBLE; break; }
+          if (it == 100) { status = CVXB_ELINESEARCH; break; }
+          step = scl * tt;
+        }
+        BCLK(8);
+        if (tid < n) S.x[tid] = S.x[tid] + S.dir[tid] * step;
+        __syncthreads();
+        if (!b_eval(S, A, kind, obj_r, Pg, beq, t, &fval, &f0, &normGrad, &eqd)) { status = CVXB_ENOTFEASIBLE; break; }
+        eqnorm = fabs(eqd);
+        moved = true;
+        BCLK(9);
+      }
+      ++iter;
+      if (!moved && p && ((nd > tol && normGrad > tol) || eqnorm > tol)) { iter = A.P.maxIter; break; }   // identical repeats
+    }
+    if (status != CVXB_OK) break;
+    total_steps += iter;
+    if (record_stages && tid == 0 && stage < CVXB_BATCH_STAGES) S.stage_steps[stage] = iter;
+    objv = f0;
+    gap = (double)m / t;
+    eqgap = p ? eqnorm : 0.0;
+    t *= A.P.mu;
+    ++stage;
+  }
+  out.status = status; out.stage = stage; out.total_steps = total_steps;
+  out.objv = objv; out.gap = gap; out.eqgap = eqgap;
+}
+
+__global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(const __grid_constant__ BatchArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   __shared__ int s_pid;
   const int tid = threadIdx.x, n = A.n, m = A.m;
   double* Hs = A.scratch + (size_t)blockIdx.x * BN * BN;
-  const double tol = A.P.tolSolver, tolEq = A.P.tolEqSolve;
   for (;;) {
     __syncthreads();
     if (tid == 0) s_pid = (int)atomicAdd(A.counter, 1u);
@@ -547,7 +809,7 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
     // ---- load the problem
     const int kind = A.objective[pid];
     const int p = A.pcount ? A.pcount[pid] : A.p;
-    if (tid == 0) S.pcur = p;
+    if (tid == 0) { S.pcur = p; S.ncur = n; S.mcur = m; }
     const double obj_r = A.obj_r ? A.obj_r[pid] : 0.0;
     const double* Pg = A.obj_P ? A.obj_P + (size_t)pid * n * n : nullptr;
     const double* Gg = A.G + (size_t)pid * m * n;
@@ -563,119 +825,68 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
     }
     const double beq = p ? A.b[pid] : 0.0;
     __syncthreads();
-
     if (tid < CVXB_BATCH_STAGES) S.stage_steps[tid] = 0;
-    int status = CVXB_OK, stage = 0, total_steps = 0;
-    double t = A.P.t0, gap = 1.7976931348623157e308, eqgap = 1.7976931348623157e308, objv = 0.0;
-    const double maxStage = 1000.0 / A.P.mu;
-    while (!(gap < tol && eqgap < tol) && stage < maxStage && status == CVXB_OK) {
-      // ---------------- inner Newton solve at parameter t
-      int iter = 0;
-      double nd = tol + 1, fval, f0, normGrad, eqd, trust = 0.0;
-      if (!b_eval(S, A, kind, obj_r, Pg, beq, t, &fval, &f0, &normGrad, &eqd)) { status = CVXB_ENOTFEASIBLE; break; }
-      double eqnorm = fabs(eqd);
-      while (iter < A.P.maxIter && (p ? ((nd > tol && normGrad > tol) || eqnorm > tol) : (nd > tol && normGrad > tol))) {
-        BCLK(0);
-        b_hessian(S, A, kind, Pg, t);
-        BCLK(1);
-        b_store_H(S, n, Hs);
-        BCLK(2);
-        int reg = 0;
-        bool ok = b_linear_solve(S, A, Hs, 0.0, false, S.y, eqd, tolEq, &reg);
-        if (!ok) {
-          if (p) {
-            // path 1: K = H + a a', z = q - a' b   (KKTSystem.scala:57-59)
-            if (tid < n) S.zrhs[tid] = S.y[tid] - S.aeq[tid] * eqd;
-            __syncthreads();
-            ok = b_linear_solve(S, A, Hs, 0.0, true, S.zrhs, eqd, tolEq, &reg);
-          } else {
-            ok = b_linear_solve(S, A, Hs, A.P.newtonRegDelta, false, S.y, 0.0, tolEq, &reg);   // H + 1e-9 I
-          }
-          if (!ok) { status = CVXB_ELINSOLVE; break; }
-        }
-        BCLK(7);
-        // q = d . grad
-        double q = 0.0, c1 = 0.0, c2 = 0.0;
-        if (kind == CVXB_OBJ_QUADRATIC && tid >= 128 && tid < 128 + n) {
-          const int i = tid - 128;
-          double s = 0.0;
-          for (int j = 0; j < n; ++j) s = fma(Pg[i + (size_t)j * n], S.dir[j], s);
-          S.Pd[i] = s;
-        }
-        if (tid < m) {
-          double s = 0.0;
-          for (int j = 0; j < n; ++j) s = fma(GG(tid, j), S.dir[j], s);
-          S.Gd[tid] = s;
-        }
-        __syncthreads();
-        if (tid < n) {
-          double dj = S.dir[tid];
-          q = dj * S.y[tid];
-          if (kind == CVXB_OBJ_LINEAR) c1 = S.oa[tid] * dj;
-          else if (kind == CVXB_OBJ_QUADRATIC) { c1 = (S.oa[tid] + S.Px[tid]) * dj; c2 = dj * S.Pd[tid]; }
-        }
-        q = block_sum(q, S.red);
-        c1 = block_sum(c1, S.red);
-        c2 = block_sum(c2, S.red);
-        nd = -q / 2;
-        bool moved = false;
-        if (nd > tol) {
-          int it = 0, thr = 0;
-          double step;
-          if (p) {
-            double s = 1.0;
-            while (!b_in_set(S, m, s) && it < 100) { s *= A.P.beta; ++it; }
-            if (it == 100) { status = CVXB_ELINESEARCH; break; }
-            while (it < 100) {
-              double v = b_value(S, A, kind, t, s, f0, c1, c2, &thr);
-              if (thr) break;
-              if (!(v > fval + A.P.alpha * s * q)) break;
-              s *= A.P.beta; ++it;
-            }
-            if (thr) { status = CVXB_ENOTFEASIBLE; break; }
-            if (it == 100) { status = CVXB_ELINESEARCH; break; }
-            step = s;
-          } else {
-            const double hnorm = sqrt(-q);
-            if (iter == 0) trust = hnorm;
-            const double scl = (iter == 0 || hnorm <= trust) ? 1.0 : trust / hnorm;
-            double tt = 1.0;
-            while (!b_in_set(S, m, scl * tt) && it < 200) { tt *= A.P.beta; ++it; }
-            if (it == 100) { status = CVXB_ELINESEARCH; break; }
-            if (b_in_set(S, m, scl)) {
-              (void)b_value(S, A, kind, t, scl * tt, f0, c1, c2, &thr);
-              if (thr) { status = CVXB_ENOTFEASIBLE; break; }
-            }
-            while (it < 200) {
-              double v = b_value(S, A, kind, t, scl * tt, f0, c1, c2, &thr);
-              if (thr) break;
-              if (!(v > fval + A.P.alpha * tt * q)) break;
-              tt *= A.P.beta; ++it;
-            }
-            if (thr) { status = CVXB_ENOTFEASIBLE; break; }
-            if (it == 100) { status = CVXB_ELINESEARCH; break; }
-            step = scl * tt;
-          }
-          BCLK(8);
-          if (tid < n) S.x[tid] = S.x[tid] + S.dir[tid] * step;
-          __syncthreads();
-          if (!b_eval(S, A, kind, obj_r, Pg, beq, t, &fval, &f0, &normGrad, &eqd)) { status = CVXB_ENOTFEASIBLE; break; }
-          eqnorm = fabs(eqd);
-          moved = true;
-          BCLK(9);
-        }
-        ++iter;
-        if (!moved && p && ((nd > tol && normGrad > tol) || eqnorm > tol)) { iter = A.P.maxIter; break; }   // identical repeats
+
+    LoopOut ph;
+    ph.status = CVXB_OK; ph.stage = 0; ph.total_steps = 0; ph.objv = 0.0; ph.gap = 0.0; ph.eqgap = 0.0;
+    double ph_s = 0.0;
+    const bool need_phase1 = A.phase1 && A.phase1[pid];
+    if (need_phase1) {
+      // ---- phase I (ConstraintSet.phase_I_Analysis, ConstraintSet.scala:326-395, 556-575; Constraint.phase_I
+      // Constraint.scala:64-89; EqualityConstraint.scala:84-100): minimise s over (x, s) subject to
+      // g_i(x) - s <= ub_i and +-(a.x - b) - s <= phase1EqTol, built in place: one more column (-1) and two more rows
+      // (+-a) of G, no equalities, linear objective s; start (x0, 1 + max_i (g_i(x0) - ub_i)).
+      const int n1 = n + 1, m1 = m + 2 * p;
+      if (tid < m1) GG(tid, n) = -1.0;
+      if (p && tid < n) { GG(m, tid) = S.aeq[tid]; GG(m + 1, tid) = -S.aeq[tid]; }
+      if (tid == 0) {
+        if (p) { S.ub[m] = beq + A.P.phase1EqTol; S.ub[m + 1] = -beq + A.P.phase1EqTol; }
+        S.x[n] = 0.0;
+        S.pcur = 0;
+        S.ncur = n1;
+        S.mcur = m1;
       }
-      if (status != CVXB_OK) break;
-      total_steps += iter;
-      if (tid == 0 && stage < CVXB_BATCH_STAGES) S.stage_steps[stage] = iter;
-      objv = f0;
-      gap = (double)m / t;
-      eqgap = p ? eqnorm : 0.0;
-      t *= A.P.mu;
-      ++stage;
+      if (tid < n1) S.oa[tid] = (tid == n) ? 1.0 : 0.0;
+      __syncthreads();
+      double viol = -1e308;
+      if (tid < m1) {
+        double sx = 0.0;
+        for (int j = 0; j < n; ++j) sx = fma(GG(tid, j), S.x[j], sx);
+        viol = sx - S.ub[tid];
+      }
+      viol = -block_min(-viol, S.red);
+      if (tid == 0) S.x[n] = 1.0 + viol;
+      __syncthreads();
+      b_barrier_loop(S, A, CVXB_OBJ_LINEAR, 0.0, nullptr, 0.0, 0, 1, Hs, Gg, false, ph);
+      __syncthreads();
+      ph_s = S.x[n];
+      if (ph.status == CVXB_OK && !(ph_s < A.P.tolSolver)) ph.status = CVXB_EINFEASIBLE;   // FeasibilityReport.isFeasible(tol)
+      __syncthreads();
+      // back to the problem itself, from the feasible point found
+      if (tid < m1) GG(tid, n) = 0.0;
+      if (p && tid < n1) { GG(m, tid) = 0.0; GG(m + 1, tid) = 0.0; }
+      if (tid == 0) {
+        if (p) { S.ub[m] = 1.0; S.ub[m + 1] = 1.0; }
+        S.pcur = p;
+        S.ncur = n;
+        S.mcur = m;
+        S.x[n] = 0.0;
+      }
+      if (tid < n1) S.oa[tid] = (tid < n && kind != CVXB_OBJ_KL && A.obj_a) ? A.obj_a[(size_t)pid * n + tid] : 0.0;
+      if (tid < BN) { S.Px[tid] = 0.0; S.Pd[tid] = 0.0; }
+      __syncthreads();
     }
+    LoopOut r;
+    if (ph.status == CVXB_OK) {
+      b_barrier_loop(S, A, kind, obj_r, Pg, beq, p, 0, Hs, Gg, true, r);
+    } else {
+      r = ph;
+      r.stage = 0; r.total_steps = 0; r.objv = 0.0;
+      r.gap = 1.7976931348623157e308; r.eqgap = 1.7976931348623157e308;
+    }
+    __syncthreads();
+    const int status = r.status, total_steps = r.total_steps, stage = r.stage;
+    const double objv = r.objv, gap = r.gap, eqgap = r.eqgap;
     if (tid < n) A.x[(size_t)pid * n + tid] = S.x[tid];
     {   // the packed record the multi-GPU gather ships (one all-gather, no host staging)
       double* rec = A.records + (size_t)pid * (n + CVXB_BATCH_RECORD_EXTRA);
@@ -695,6 +906,7 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(BatchArgs A) {
       A.objval[pid] = objv;
       A.gap[pid] = gap;
       A.eqgap[pid] = p ? eqgap : 0.0;
+      if (A.ph_steps) { A.ph_steps[pid] = ph.total_steps; A.ph_stages[pid] = ph.stage; A.ph_s[pid] = ph_s; }
     }
   }
 }
@@ -755,7 +967,18 @@ int cvxb_batch_create(cvxb_handle h, const cvxb_batch_desc* d, cvxb_batch* out) 
         cvxb::set_last_error("cvxb_batch_create: pcount[%d] = %d outside 0..p = %d", i, d->pcount[i], d->p);
         return CVXB_EDIM;
       }
+      if (d->phase1 && d->phase1[i]) {
+        const int pi = d->pcount ? d->pcount[i] : d->p;
+        if (d->n + 1 > BN || d->m + 2 * pi > BM_) {
+          cvxb::set_last_error("cvxb_batch_create: problem %d asks for phase I, whose feasibility problem has n + 1 = %d variables "
+                               "and m + 2p = %d rows; the kernel holds 64 x 128", i, d->n + 1, d->m + 2 * pi);
+          return CVXB_EDIM;
+        }
+      }
     }
+  } else if (d->phase1 && (d->n + 1 > BN || d->m + 2 * d->p > BM_)) {
+    cvxb::set_last_error("cvxb_batch_create: phase I needs n <= 63 and m + 2p <= 128");
+    return CVXB_EDIM;
   }
   cvxb::DeviceGuard _guard(h->device);
   cvxb_batch_s* Bt = new cvxb_batch_s();
@@ -777,6 +1000,10 @@ int cvxb_batch_create(cvxb_handle h, const cvxb_batch_desc* d, cvxb_batch* out) 
   T(balloc(Bt, &Bt->records, B * (n + CVXB_BATCH_RECORD_EXTRA)));
   T(balloc(Bt, &Bt->stage_steps, B * CVXB_BATCH_STAGES));
   T(balloc(Bt, &Bt->cycles, B));
+  if (d->phase1) {
+    T(bupload(Bt, &Bt->phase1, d->phase1, B));
+    T(balloc(Bt, &Bt->ph_steps, B)); T(balloc(Bt, &Bt->ph_stages, B)); T(balloc(Bt, &Bt->ph_s, B));
+  }
   if (!(h->flags & CVXB_FLAG_DEVICE_PTRS) && !getenv("CVXB_BATCH_INDEX_ORDER")) {
     // Pickup order: problems are handed to the CTAs through one atomic ticket counter; dealing out the long ones
     // first (quadratic objectives: ~100 Newton steps each on the BASELINE mix, against ~70 for the KL problems, and a
@@ -839,6 +1066,7 @@ int cvxb_batch_barrier_solve(cvxb_handle h, cvxb_batch Bt, const cvxb_params* pa
   A.x = Bt->x; A.objval = Bt->objval; A.gap = Bt->gap; A.eqgap = Bt->eqgap;
   A.status = Bt->status; A.steps = Bt->steps; A.stages = Bt->stages; A.records = Bt->records; A.stage_steps = Bt->stage_steps;
   A.order = Bt->order; A.cycles = Bt->cycles;
+  A.phase1 = Bt->phase1; A.ph_steps = Bt->ph_steps; A.ph_stages = Bt->ph_stages; A.ph_s = Bt->ph_s;
   A.scratch = Bt->scratch; A.counter = Bt->counter; A.P = *pars;
   cvxb::NvtxRange nvtx("cvxb batched barrier solve");
   CVXB_CUDA_OK(cudaMemsetAsync(Bt->counter, 0, sizeof(unsigned), h->stream));
@@ -860,6 +1088,15 @@ int cvxb_batch_barrier_solve(cvxb_handle h, cvxb_batch Bt, const cvxb_params* pa
   if (out->objective) CVXB_CUDA_OK(cudaMemcpyAsync(out->objective, Bt->objval, B * sizeof(double), k, h->stream));
   if (out->duality_gap) CVXB_CUDA_OK(cudaMemcpyAsync(out->duality_gap, Bt->gap, B * sizeof(double), k, h->stream));
   if (out->equality_gap) CVXB_CUDA_OK(cudaMemcpyAsync(out->equality_gap, Bt->eqgap, B * sizeof(double), k, h->stream));
+  if (Bt->ph_steps) {
+    if (out->phase1_newton_steps) CVXB_CUDA_OK(cudaMemcpyAsync(out->phase1_newton_steps, Bt->ph_steps, B * sizeof(int), k, h->stream));
+    if (out->phase1_stages) CVXB_CUDA_OK(cudaMemcpyAsync(out->phase1_stages, Bt->ph_stages, B * sizeof(int), k, h->stream));
+    if (out->phase1_s) CVXB_CUDA_OK(cudaMemcpyAsync(out->phase1_s, Bt->ph_s, B * sizeof(double), k, h->stream));
+  } else if (!dev) {
+    if (out->phase1_newton_steps) memset(out->phase1_newton_steps, 0, B * sizeof(int));
+    if (out->phase1_stages) memset(out->phase1_stages, 0, B * sizeof(int));
+    if (out->phase1_s) memset(out->phase1_s, 0, B * sizeof(double));
+  }
   CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
   float ms = 0;
   CVXB_CUDA_OK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));

@@ -94,7 +94,7 @@ struct cvxb_handle_s {
   std::vector<cudaEvent_t> dag_events;
   int sk_reserve = 0;                        // != 0 only while bulk work is being enqueued
   bool in_dag = false;                       // potrf_dag is enqueuing (its diagonal blocks use the look-ahead / recursive schedules)
-  int dag_block = 2048, dag_min_n = 5120, dag_reserve = 12;   // cvxb_debug_set_schedule
+  int dag_block = 2048, dag_min_n = 5120, dag_reserve = 8;   // cvxb_debug_set_schedule
 };
 
 namespace cvxb {

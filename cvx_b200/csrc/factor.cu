@@ -791,7 +791,11 @@ static void dag_blocks(int n, int nbk, std::vector<int>& start) {
     const int rem = n - pos;
     int b;
     if (flat) b = nbk;
-    else if (pos == 0 && n >= 3 * nbk) b = (nbk / 2) / NB * NB < NB ? NB : (nbk / 2) / NB * NB;
+    else if (pos == 0 && n >= 3 * nbk) {
+      static const int first_div = getenv("CVXB_DAG_FIRST_DIV") ? atoi(getenv("CVXB_DAG_FIRST_DIV")) : 2;
+      b = (nbk / (first_div > 0 ? first_div : 2)) / NB * NB;
+      if (b < NB) b = NB;
+    }
     else if (rem >= 2 * nbk) b = nbk;
     else if (rem <= 5 * NB) b = rem;
     else b = ((rem + 1) / 2 + NB - 1) / NB * NB;

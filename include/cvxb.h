@@ -319,8 +319,13 @@ int cvxb_pd_newton_direction(cvxb_handle h, cvxb_problem prob, const cvxb_params
 /* ---- batched small problems (one CTA per problem) ------------------------------ */
 /* B independent problems of identical shape (n <= 64, m <= 128, p in {0,1}); arrays are packed
  * problem after problem, each matrix column-major with ld = its row count.  objective[i] is a
- * cvxb_objective_kind; x0 must be strictly feasible (no phase I).  Outputs: x (B*n), per-problem
- * status, Newton step and outer-stage counts. */
+ * cvxb_objective_kind; x0 must be strictly feasible unless phase1[i] is set.  Outputs: x (B*n), per-problem
+ * status, Newton step and outer-stage counts.
+ * phase1[i] != 0: x0 of problem i is only a point where the problem is defined (ConstraintSet.pointWhereDefined); the CTA
+ * first runs the reference's phase-I analysis (ConstraintSet.phase_I_Analysis, ConstraintSet.scala:326-395, 556-575:
+ * minimise s subject to g_i(x) - s <= ub_i, +-(a.x - b) - s <= phase1EqTol, from (x0, 1 + max(g(x0) - ub)), until the
+ * objective is negative), fails the problem with CVXB_EINFEASIBLE unless s < tolSolver, and then solves from the feasible
+ * point found.  The feasibility problem must fit the kernel too: n + 1 <= 64 and m + 2p <= 128. */
 typedef struct cvxb_batch_desc {
   int B, n, m, p;
   const int* objective;    /* B */
@@ -333,6 +338,7 @@ typedef struct cvxb_batch_desc {
   const double* A;         /* B*p*n */
   const double* b;         /* B*p   */
   const double* x0;        /* B*n   */
+  const int* phase1;       /* B or NULL (= no problem needs phase I) */
 } cvxb_batch_desc;
 
 enum { CVXB_BATCH_STAGES = 16 };
@@ -348,6 +354,9 @@ typedef struct cvxb_batch_result {
   int* stage_newton_steps; /* B * CVXB_BATCH_STAGES or NULL: Newton steps of each of the first 16 outer stages (0 beyond
                               the last stage), as cvxb_solution.stage_newton_steps */
   long long* cycles;       /* B or NULL: SM clock cycles each problem occupied its CTA (load balance / roofline evidence) */
+  int* phase1_newton_steps; /* B or NULL: Newton steps / outer stages of the phase-I analysis (0 where none ran) */
+  int* phase1_stages;
+  double* phase1_s;        /* B or NULL: final phase-I slack s (negative: strictly feasible point found) */
 } cvxb_batch_result;
 
 typedef struct cvxb_batch_s* cvxb_batch;
@@ -373,7 +382,7 @@ int cvxb_test_dgemm(cvxb_handle h, int a_kc, int b_kc, int M, int N, int K, doub
 int cvxb_bench_kernel(cvxb_handle h, int which, int n, int k, int reps, double* ms_per_launch,
                       double* flops_or_bytes_per_launch);
 
-/* Schedule of the big factorisations (tests and tuning; defaults: blocks of 2048 columns from n = 5120 on, 12 SMs left to
+/* Schedule of the big factorisations (tests and tuning; defaults: blocks of 2048 columns from n = 5120 on, 8 SMs left to
  * the critical chain): the tile-DAG schedule runs the bulk updates of a right-looking blocked Cholesky on a third stream
  * beside the chain of diagonal-block factorisations.  A negative argument keeps the current value;
  * dag_block = 0 switches the schedule off (recursive halving + look-ahead only). */

@@ -120,6 +120,134 @@ def test_batched_infeasible_start_is_flagged(handle):
     assert np.all(sol.status[[0, 1, 3]] == 0)
 
 
+def _phase1_problem(i, n, m):
+    """Phase-I variant of the batch shapes: even i -> KL problem of Dist_KL.apply form (start 1/n is defined but violates the
+    H x <= u rows, one equality: the feasibility problem has n + 1 variables and m + 2 rows), odd i -> slab QP started
+    outside its slab (no equality)."""
+    if i % 2 == 0:
+        return P.kl_random(n, m - n, 0, 700 + i)          # x0 = None, xdef = 1/n
+    pr = P.slab_qp(n, m // 2, 0, 700 + i, scale=True)
+    rng = np.random.default_rng(900 + i)
+    pr["xdef"] = pr["x0"] + rng.uniform(0.5, 1.0, n)
+    pr["x0"] = None
+    return pr
+
+
+@pytest.mark.parametrize("n,m,B", [(63, 126, 12), (20, 40, 8)])
+def test_batched_phase1_variant_matches_oracle(handle, n, m, B):
+    """SURVEY 8d C3 "and a phase-I variant": problems without a feasible start run ConstraintSet.phase_I_Analysis
+    (ConstraintSet.scala:326-395, 556-575) inside their CTA first.  Phase-I stage and Newton-step counts and the main
+    solve agree with the oracle's withFeasiblePoint + barrierSolve, problem by problem; problems that do have a
+    feasible start (mixed into the same batch) are untouched."""
+    import cvx_b200 as cb
+    probs = [_phase1_problem(i, n, m) for i in range(B)]
+    probs.append(P.slab_qp(n, m // 2, 0, 990, scale=True))          # feasible start: no phase I for this one
+    packed = cb.pack_problems(probs)
+    assert packed["phase1"] is not None and packed["phase1"].sum() == B
+    sol = cb.BatchedBarrierSolver(packed, None, handle).solve()
+    assert np.all(sol.status == 0), sol.status
+    assert sol.phase1_newton_steps[B] == 0 and sol.phase1_stages[B] == 0
+    for i, pr in enumerate(probs):
+        objF, cnts, eqs = P.to_oracle(pr)
+        s0, ph0 = O.solveProblem(objF, cnts, eqs, "BR")
+        o0 = objF.valueAt(s0.x)
+        assert abs(sol.objective[i] - o0) <= 1e-8 * max(1.0, abs(o0)), (i, sol.objective[i], o0)
+        assert np.linalg.norm(sol.x[i] - s0.x) <= 1e-6 * np.linalg.norm(s0.x)
+        assert sol.outer_stages[i] == s0.outer_stages
+        if i < B:
+            assert sol.phase1_stages[i] == ph0.outer_stages, (i, sol.phase1_stages[i], ph0.outer_stages)
+            assert abs(int(sol.phase1_newton_steps[i]) - int(ph0.newton_steps)) <= ph0.outer_stages, \
+                (i, sol.phase1_newton_steps[i], ph0.newton_steps)
+            assert sol.phase1_s[i] < 0.0 and abs(sol.phase1_s[i] - ph0.x[-1]) <= 1e-6 * max(1.0, abs(ph0.x[-1]))
+        # the point reached is strictly feasible
+        assert np.all(pr["G"] @ sol.x[i] * (1 + 3e-16) < pr["ub"]), i
+
+
+def test_batched_phase1_agrees_with_large_path(handle):
+    """The same problems through the one-problem-at-a-time device path (run_phase1 + barrier_loop in solver.cu)."""
+    import cvx_b200 as cb
+    probs = [_phase1_problem(i, 63, 126) for i in range(4)]
+    sol = cb.BatchedBarrierSolver(cb.pack_problems(probs), None, handle).solve()
+    for i, pr in enumerate(probs):
+        s1 = cb.from_dict(pr, "BR", None, handle).solve()
+        assert abs(sol.objective[i] - s1.objective) <= 1e-9 * max(1.0, abs(s1.objective))
+        assert sol.outer_stages[i] == s1.outer_stages
+        assert sol.phase1_stages[i] == s1.phase1_stages
+        assert abs(int(sol.phase1_newton_steps[i]) - int(s1.phase1_newton_steps)) <= s1.phase1_stages
+
+
+def test_batched_phase1_infeasible_problems_are_refused(handle):
+    """Problems with an empty feasible set end inside or after phase I as the reference does: either the barrier
+    function is asked for a point that is no longer strictly feasible (IllegalArgumentException, BarrierSolver.scala:284
+    -> CVXB_ENOTFEASIBLE), the line search breaks down (NotConvergedException -> CVXB_ELINESEARCH) or phase I ends with
+    s >= tol (InfeasibleProblemException, ConstraintSet.scala:556-575 ->
+    CVXB_EINFEASIBLE); the other problems of the batch are solved."""
+    import cvx_b200 as cb
+    n, m = 20, 40
+    probs = [_phase1_problem(i, n, m) for i in range(3)]
+    bad = P.slab_qp(n, m // 2, 0, 5, scale=True)
+    bad["ub"] = bad["ub"].copy()
+    bad["ub"][m // 2] = -(bad["ub"][0] + 1.0)          # rows 0 and m/2 are +r.x <= u0 and -r.x <= -(u0 + 1): empty
+    bad["xdef"], bad["x0"] = bad["x0"], None
+    kl = P.infeasible_kl_1(n)                           # the reference's own infeasible problem (n + 2 rows: pad to m)
+    pad = m - kl["G"].shape[0]
+    kl["G"] = np.vstack([kl["G"], np.zeros((pad, n))])
+    kl["ub"] = np.concatenate([kl["ub"], np.ones(pad)])
+    kl["rvec"] = np.zeros(m)
+    probs.insert(1, bad)
+    probs.append(kl)
+    sol = cb.BatchedBarrierSolver(cb.pack_problems(probs), None, handle).solve()
+    refused = (cb._lib.EINFEASIBLE, cb._lib.ENOTFEASIBLE, cb._lib.ELINESEARCH)
+    for i in (1, len(probs) - 1):
+        objF, cnts, eqs = P.to_oracle(probs[i])
+        with pytest.raises((O.InfeasibleProblemException, O.NotStrictlyFeasible, O.NotConvergedException)):
+            O.solveProblem(objF, cnts, eqs, "BR")
+        # which of the three the iteration runs into at the edge of the barrier's domain is decided by rounding (as in
+        # tests/test_feasibility_gpu.py for the one-problem path); no solution may come out
+        assert sol.status[i] in refused, (i, sol.status)
+    assert np.all(sol.status[[0, 2, 3]] == 0)
+
+
+@pytest.mark.parametrize("n,m", [(12, 28), (64, 128)])
+def test_batched_decomposition_last_resort(handle, n, m):
+    """KKTSystem.kktSymSolve inside the batched kernel (KKTSystem.scala:63, 283-310): an indefinite objective Hessian
+    (P - cI) makes the Cholesky factorisations of H and of H + a a' fail at most Newton steps, so the direction comes from
+    the decomposition of the full (n+1)^2 KKT matrix -- in the oracle (path 2 recorded in its KKT statistics) and in
+    the CTA (one-sided Jacobi SVD in shared memory).  Whole solves agree: same outer stages, objective 1e-8, x 1e-6."""
+    import cvx_b200 as cb
+    probs = []
+    for i, c in enumerate((10.0, 50.0, 2.0)):
+        pr = P.slab_qp(n, m // 2, 1, 40 + i, scale=True)
+        pr["P"] = pr["P"] - c * np.eye(n)
+        probs.append(pr)
+    probs.append(P.slab_qp(n, m // 2, 1, 77, scale=True))            # a convex one beside them
+    sol = cb.BatchedBarrierSolver(cb.pack_problems(probs), None, handle).solve()
+    used_path2 = 0
+    for i, pr in enumerate(probs):
+        objF, cnts, eqs = P.to_oracle(pr)
+        stats = []
+        try:
+            s0 = O.barrierSolve(objF, cnts, eqs, O.SolverParams.standardParams(), None, False, kkt_stats=stats)
+        except O.UnsolvableSystemException:
+            assert sol.status[i] == cb._lib.EUNSOLVABLE, (i, sol.status)
+            continue
+        used_path2 += any(s_.path == 2 for s_ in stats)
+        assert sol.status[i] == 0, (i, sol.status)
+        o0 = objF.valueAt(s0.x)
+        assert abs(sol.objective[i] - o0) <= 1e-8 * max(1.0, abs(o0)), (i, sol.objective[i], o0)
+        assert np.linalg.norm(sol.x[i] - s0.x) <= 1e-6 * np.linalg.norm(s0.x), i
+        assert sol.outer_stages[i] == s0.outer_stages
+        assert abs(int(sol.newton_steps[i]) - int(s0.newton_steps)) <= s0.outer_stages
+    assert used_path2 >= 2
+
+
+def test_batch_phase1_dimension_limits(handle):
+    import cvx_b200 as cb
+    pr = P.kl_random(64, 64, 0, 1)           # phase I would need 65 variables
+    with pytest.raises(AssertionError):
+        cb.BatchedBarrierSolver(cb.pack_problems([pr]), None, handle)
+
+
 def test_batch_dimension_limits(handle):
     import cvx_b200 as cb
     with pytest.raises(AssertionError):
