@@ -110,6 +110,16 @@ __device__ long long g_batch_clk[12];
     }                                                                           \
   } while (0)
 
+__device__ long long g_potrf_clk[8];      // CVXB_BATCH_TIMING: diag / panel / update / barriers inside b_potrf
+#define PCLK(slot)                                                              \
+  do {                                                                          \
+    if (CVXB_BATCH_TIMING && blockIdx.x == 0 && threadIdx.x == 0) {             \
+      long long _c = clock64();                                                 \
+      g_potrf_clk[slot] += _c - g_potrf_clk[7];                                 \
+      g_potrf_clk[7] = _c;                                                      \
+    }                                                                           \
+  } while (0)
+
 #define HL(i, j) S.L[(i) + (j) * LDH]
 #define GG(i, j) S.G[(i) + (j) * LDG]
 
@@ -267,9 +277,11 @@ __device__ int b_potrf(Smem& S, int n, double* mind_out) {
   if (tid == 0) { S.fl[0] = 0; S.sc[0] = 1e300; }
   __syncthreads();
   const int nblk = (n + BSUB - 1) / BSUB;
+  PCLK(0);
   for (int kb = 0; kb < nblk; ++kb) {
     const int o = kb * BSUB;
     const int bs = (n - o) < BSUB ? (n - o) : BSUB;
+    PCLK(4);
     if (warp == 0) {
       // branch-free in-warp sweep (factor.cu: warp_diag_factor): selects only, updates unpredicated
       double a[BSUB], rr[BSUB];
@@ -311,6 +323,7 @@ __device__ int b_potrf(Smem& S, int n, double* mind_out) {
         if (lane == c) S.rdiag[o + c] = rr[c];
       }
     }
+    PCLK(1);
     __syncthreads();
     const int r0 = o + BSUB;
     const int nrows = n - r0;
@@ -329,6 +342,7 @@ __device__ int b_potrf(Smem& S, int n, double* mind_out) {
       for (int c = 0; c < BSUB; ++c) HL(r, o + c) = xr[c];
     }
     __syncthreads();
+    PCLK(2);
     for (int c = r0 + warp; c < n; c += BT / 32) {
       for (int r = c - ((c - r0) & 31) + lane; r < n; r += 32) {
         if (r < c) continue;
@@ -339,6 +353,7 @@ __device__ int b_potrf(Smem& S, int n, double* mind_out) {
       }
     }
     __syncthreads();
+    PCLK(3);
   }
   *mind_out = S.sc[0];
   return S.fl[0];
@@ -390,29 +405,37 @@ __device__ void b_llt_apply(Smem& S, int n, const double* v, double* out) {
   __syncthreads();
 }
 
-// restore H (full) from the per-CTA scratch, optionally adding delta*I and a rank-one term aa'
+// restore H (full) from the per-CTA scratch, optionally adding delta*I and a rank-one term aa'.
+// The scratch copy has the fixed column stride BN (= 64): thread t walks rows t & 63 of columns t >> 6, +4, ... -- no
+// integer division by the runtime n in these whole-matrix passes (it was a fifth of the kernel's instructions).
 __device__ void b_load_H(Smem& S, int n, const double* Hs, double diag_add, bool rank1) {
-  for (int idx = threadIdx.x; idx < n * n; idx += BT) {
-    int i = idx % n, j = idx / n;
-    double v = Hs[idx];
-    if (i == j) v += diag_add;
-    if (rank1) v += S.aeq[i] * S.aeq[j];
-    HL(i, j) = v;
-  }
+  const int i = threadIdx.x & (BN - 1);
+  if (i < n)
+    for (int j = threadIdx.x >> 6; j < n; j += BT / BN) {
+      double v = Hs[i + j * BN];
+      if (i == j) v += diag_add;
+      if (rank1) v += S.aeq[i] * S.aeq[j];
+      HL(i, j) = v;
+    }
   __syncthreads();
 }
 __device__ void b_store_H(Smem& S, int n, double* Hs) {
-  for (int idx = threadIdx.x; idx < n * n; idx += BT) Hs[idx] = HL(idx % n, idx / n);
+  const int i = threadIdx.x & (BN - 1);
+  if (i < n)
+    for (int j = threadIdx.x >> 6; j < n; j += BT / BN) Hs[i + j * BN] = HL(i, j);
   __syncthreads();
 }
 
 // (d d') o H in place, + delta on the diagonal
 __device__ void b_scale_H(Smem& S, int n, double delta) {
-  for (int idx = threadIdx.x; idx < n * n; idx += BT) {
-    int i = idx % n, j = idx / n;
-    double v = (S.dr[i] * S.dr[j]) * HL(i, j);
-    if (i == j) v += delta;
-    HL(i, j) = v;
+  const int i = threadIdx.x & (BN - 1);
+  if (i < n) {
+    const double di = S.dr[i];
+    for (int j = threadIdx.x >> 6; j < n; j += BT / BN) {
+      double v = (di * S.dr[j]) * HL(i, j);
+      if (i == j) v += delta;
+      HL(i, j) = v;
+    }
   }
   __syncthreads();
 }
@@ -422,11 +445,11 @@ __device__ void b_scale_H(Smem& S, int n, double delta) {
 //   p == 1: KKT  Hmod dir + a' w = -q, a.dir = beq_rhs
 // returns true when the attempt chain (plain, then regularised) produced an accepted solution.
 __device__ bool b_linear_solve(Smem& S, const BatchArgs& A, const double* Hs, double diag_add, bool rank1,
-                               const double* q, double brhs, double tol, int* regularized) {
+                               const double* q, double brhs, double tol, int* regularized, bool h_in_smem = false) {
   const int tid = threadIdx.x, n = S.ncur;
   bool have_dr = false;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    b_load_H(S, n, Hs, diag_add, rank1);
+    if (!(h_in_smem && attempt == 0)) b_load_H(S, n, Hs, diag_add, rank1);     // (the plain H is still in S.L on the first try)
     BCLK(3);
     if (!have_dr) { b_ruiz(S, A); have_dr = true; }
     BCLK(4);
@@ -449,7 +472,7 @@ __device__ bool b_linear_solve(Smem& S, const BatchArgs& A, const double* Hs, do
       if (tid < n) {
         double s = 0.0;
         for (int j = 0; j < n; ++j) {
-          double hij = Hs[tid + (size_t)j * n];
+          double hij = Hs[tid + j * BN];
           if (tid == j) hij += diag_add;
           s = fma(hij, S.dir[j], s);
         }
@@ -518,7 +541,7 @@ __device__ __noinline__ bool b_kkt_sym_solve(Smem& S, int n, const double* Hs, c
   for (int idx = tid; idx < N * N; idx += BT) {
     const int i = idx % N, j = idx / N;
     double v;
-    if (i < n && j < n) v = Hs[i + (size_t)j * n];
+    if (i < n && j < n) v = Hs[i + j * BN];
     else if (i == n && j == n) v = 0.0;
     else v = S.aeq[i < n ? i : j];
     W[i + j * ld] = v;
@@ -587,7 +610,7 @@ __device__ __noinline__ bool b_kkt_sym_solve(Smem& S, int n, const double* Hs, c
   if (tid < N) {
     double sa = 0.0;
     if (tid < n) {
-      for (int j = 0; j < n; ++j) sa = fma(Hs[tid + (size_t)j * n], xs[j], sa);
+      for (int j = 0; j < n; ++j) sa = fma(Hs[tid + j * BN], xs[j], sa);
       sa = fma(S.aeq[tid], xs[n], sa);
     } else {
       for (int j = 0; j < n; ++j) sa = fma(S.aeq[j], xs[j], sa);
@@ -687,7 +710,7 @@ __device__ __noinline__ void b_barrier_loop(Smem& S, const BatchArgs& A, int kin
       b_store_H(S, n, Hs);
       BCLK(2);
       int reg = 0;
-      bool ok = b_linear_solve(S, A, Hs, 0.0, false, S.y, eqd, tolEq, &reg);
+      bool ok = b_linear_solve(S, A, Hs, 0.0, false, S.y, eqd, tolEq, &reg, true);
       if (!ok) {
         if (p) {
           // path 1: K = H + a a', z = q - a' b   (KKTSystem.scala:57-59)
@@ -1029,9 +1052,11 @@ int cvxb_batch_create(cvxb_handle h, const cvxb_batch_desc* d, cvxb_batch* out) 
 
 int cvxb_debug_batch_clocks(long long* out, int reset) {
   if (out) CVXB_CUDA_OK(cudaMemcpyFromSymbol(out, g_batch_clk, 12 * sizeof(long long)));
+  if (out && getenv("CVXB_POTRF_CLOCKS")) CVXB_CUDA_OK(cudaMemcpyFromSymbol(out, g_potrf_clk, 8 * sizeof(long long)));
   if (reset) {
     long long z[12] = {0};
     CVXB_CUDA_OK(cudaMemcpyToSymbol(g_batch_clk, z, sizeof(z)));
+    CVXB_CUDA_OK(cudaMemcpyToSymbol(g_potrf_clk, z, 8 * sizeof(long long)));
   }
   return CVXB_OK;
 }
