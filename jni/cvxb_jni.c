@@ -453,25 +453,30 @@ JNIEXPORT jdouble JNICALL Java_cvx_CvxbNative_batchSolve(JNIEnv* env, jclass c, 
                                                          jdoubleArray params, jdoubleArray x, jintArray status,
                                                          jintArray newtonSteps, jintArray outerStages,
                                                          jdoubleArray objectiveOut, jdoubleArray dualityGap,
-                                                         jdoubleArray equalityGap) {
+                                                         jdoubleArray equalityGap, jintArray phase1,
+                                                         jintArray phase1NewtonSteps) {
   (void)c;
   cvxb_params P;
   params_from(env, params, &P);
   jint *po = IGET(objective), *pc = IGET(pcount), *pst = IGET(status), *pns = IGET(newtonSteps), *pos = IGET(outerStages);
+  /* phase1 (may be null): problems whose x0 is only a point where they are defined run the phase-I analysis first
+   * (ConstraintSet.withFeasiblePoint, ConstraintSet.scala:556-575); phase1NewtonSteps (may be null) receives its steps */
+  jint *pp1 = IGET(phase1), *pp1n = IGET(phase1NewtonSteps);
   jdouble *pa = DGET(objA), *pr = DGET(objR), *pP = DGET(objP), *pG = DGET(G), *pub = DGET(ub), *pA = DGET(A), *pb = DGET(b),
           *px0 = DGET(x0), *px = DGET(x), *pov = DGET(objectiveOut), *pgap = DGET(dualityGap), *peq = DGET(equalityGap);
   int ok = !(MISSING(objective, po) || MISSING(pcount, pc) || MISSING(status, pst) || MISSING(newtonSteps, pns) ||
              MISSING(outerStages, pos) || MISSING(objA, pa) || MISSING(objR, pr) || MISSING(objP, pP) || MISSING(G, pG) ||
              MISSING(ub, pub) || MISSING(A, pA) || MISSING(b, pb) || MISSING(x0, px0) || MISSING(x, px) ||
-             MISSING(objectiveOut, pov) || MISSING(dualityGap, pgap) || MISSING(equalityGap, peq));
+             MISSING(objectiveOut, pov) || MISSING(dualityGap, pgap) || MISSING(equalityGap, peq) || MISSING(phase1, pp1) ||
+             MISSING(phase1NewtonSteps, pp1n));
   cvxb_batch_desc d;
   memset(&d, 0, sizeof d);
   d.B = B; d.n = n; d.m = m; d.p = p; d.objective = (const int*)po; d.pcount = (const int*)pc; d.obj_a = pa; d.obj_r = pr;
-  d.obj_P = pP; d.G = pG; d.ub = pub; d.A = pA; d.b = pb; d.x0 = px0;
+  d.obj_P = pP; d.G = pG; d.ub = pub; d.A = pA; d.b = pb; d.x0 = px0; d.phase1 = (const int*)pp1;
   cvxb_batch_result r;
   memset(&r, 0, sizeof r);
   r.x = px; r.status = (int*)pst; r.newton_steps = (int*)pns; r.outer_stages = (int*)pos; r.objective = pov;
-  r.duality_gap = pgap; r.equality_gap = peq;
+  r.duality_gap = pgap; r.equality_gap = peq; r.phase1_newton_steps = (int*)pp1n;
   cvxb_batch bt = 0;
   int st = CVXB_EINVAL;
   if (ok) {
@@ -479,6 +484,7 @@ JNIEXPORT jdouble JNICALL Java_cvx_CvxbNative_batchSolve(JNIEnv* env, jclass c, 
     if (st == CVXB_OK) st = cvxb_batch_barrier_solve(HND(h), bt, &P, &r);
     cvxb_batch_destroy(bt);
   }
+  IPUT(phase1NewtonSteps, pp1n, 0); IPUT(phase1, pp1, JNI_ABORT);
   IPUT(outerStages, pos, 0); IPUT(newtonSteps, pns, 0); IPUT(status, pst, 0);
   DPUT(equalityGap, peq, 0); DPUT(dualityGap, pgap, 0); DPUT(objectiveOut, pov, 0); DPUT(x, px, 0);
   IPUT(pcount, pc, JNI_ABORT); IPUT(objective, po, JNI_ABORT);

@@ -84,7 +84,10 @@ object CvxbNative {
                          objA: Array[Double], objR: Array[Double], objP: Array[Double], G: Array[Double],
                          ub: Array[Double], A: Array[Double], b: Array[Double], x0: Array[Double], params: Array[Double],
                          x: Array[Double], status: Array[Int], newtonSteps: Array[Int], outerStages: Array[Int],
-                         objectiveOut: Array[Double], dualityGap: Array[Double], equalityGap: Array[Double]): Double
+                         objectiveOut: Array[Double], dualityGap: Array[Double], equalityGap: Array[Double],
+                         phase1: Array[Int], phase1NewtonSteps: Array[Int]): Double
+  // phase1 (or null): 1 = x0 of that problem is only ConstraintSet.pointWhereDefined, run phase_I_Analysis first
+  // (ConstraintSet.scala:326-395, 556-575; needs n <= 63, m + 2p <= 128); phase1NewtonSteps (or null) receives its steps
 
   lazy val defaultHandle: Long = create(0)
 

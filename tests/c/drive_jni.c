@@ -27,7 +27,7 @@ jlong Java_cvx_CvxbNative_problemReduce(JNIEnv*, jclass, jlong, jlong, jlong, jd
 jdouble Java_cvx_CvxbNative_batchSolve(JNIEnv*, jclass, jlong, jint, jint, jint, jint, jintArray, jintArray, jdoubleArray,
                                        jdoubleArray, jdoubleArray, jdoubleArray, jdoubleArray, jdoubleArray, jdoubleArray,
                                        jdoubleArray, jdoubleArray, jdoubleArray, jintArray, jintArray, jintArray, jdoubleArray,
-                                       jdoubleArray, jdoubleArray);
+                                       jdoubleArray, jdoubleArray, jintArray, jintArray);
 
 static unsigned long long g_seed = 1234567891011ull;
 static double urand(double lo, double hi) {
@@ -169,12 +169,27 @@ int main(void) {
                jbub = fake_new_double_array(B * bm, bub), jbx0 = fake_new_double_array(B * bn, bx0), jbx = fake_new_double_array(B * bn, 0),
                jbov = fake_new_double_array(B, 0), jbg = fake_new_double_array(B, 0), jbe = fake_new_double_array(B, 0);
   double ms = Java_cvx_CvxbNative_batchSolve(env, 0, h, B, bn, bm, 0, jk, jpc, joa, jor, 0, jbG, jbub, 0, 0, jbx0, jprm, jbx, jbs, jbn, jbo,
-                                             jbov, jbg, jbe);
+                                             jbov, jbg, jbe, 0, 0);
   CHECK(!fake_pending_class()[0] && ms > 0, "batchSolve threw");
   for (int k = 0; k < B; ++k)
     CHECK(fake_ints(jbs)[k] == 0 && fabs(fake_doubles(jbov)[k] + 4.0 * (1.0 + k)) < 1e-6, "batch problem %d: status %d objective %.9g", k,
           fake_ints(jbs)[k], fake_doubles(jbov)[k]);
   printf("batchSolve via JNI: objectives %.9f %.9f in %.3f ms\n", fake_doubles(jbov)[0], fake_doubles(jbov)[1], ms);
+  /* the same two problems started outside the box: phase I inside the kernel first (phase1 flags), same optima */
+  int ph[2] = {1, 1};
+  double bx1[8];
+  for (int j = 0; j < B * bn; ++j) bx1[j] = 2.0 + 0.1 * j;
+  jintArray jph = fake_new_int_array(B, ph), jphn = fake_new_int_array(B, 0);
+  jdoubleArray jbx1 = fake_new_double_array(B * bn, bx1);
+  ms = Java_cvx_CvxbNative_batchSolve(env, 0, h, B, bn, bm, 0, jk, jpc, joa, jor, 0, jbG, jbub, 0, 0, jbx1, jprm, jbx, jbs, jbn, jbo, jbov, jbg,
+                                      jbe, jph, jphn);
+  CHECK(!fake_pending_class()[0] && ms > 0, "batchSolve (phase I) threw");
+  for (int k = 0; k < B; ++k)
+    CHECK(fake_ints(jbs)[k] == 0 && fake_ints(jphn)[k] > 0 && fabs(fake_doubles(jbov)[k] + 4.0 * (1.0 + k)) < 1e-6,
+          "batch problem %d with phase I: status %d, %d phase-I steps, objective %.9g", k, fake_ints(jbs)[k], fake_ints(jphn)[k],
+          fake_doubles(jbov)[k]);
+  printf("batchSolve via JNI with phase I: %d + %d phase-I Newton steps, objectives %.9f %.9f\n", fake_ints(jphn)[0], fake_ints(jphn)[1],
+         fake_doubles(jbov)[0], fake_doubles(jbov)[1]);
 
   CHECK(fake_outstanding_arrays() == 0, "%d array accesses were never released", fake_outstanding_arrays());
   Java_cvx_CvxbNative_destroy(env, 0, h);
