@@ -610,10 +610,12 @@ def main():
         roofline = {"bound": "tensor",
                     "kernel": "gemm_dmma_streamk_kernel<TN> (Hessian assembly G' diag(w) G, FP64 DMMA m8n8k4, persistent stream-K grid)",
                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                    "traffic": 13.2e9 + 0.55e9 if big else (111.9e6 if args.workload == "c2" else None),
-                    "traffic_source": ("dram__bytes_read+write per launch, ncu --set full, profiles/r1_ncu_full_syrk_hessian_c4_n8192_m16384.txt "
-                                       "(algorithmic: 1.07 GB read of G + 0.54 GB write of H; the rest is tile rows re-reading G through "
-                                       "L2, 5 % of DRAM peak: the kernel is tensor-bound)") if big else None,
+                    "traffic": 7.54e9 + 0.54e9 if big else (111.9e6 if args.workload == "c2" else None),
+                    "traffic_source": ("dram__bytes_read+write per launch, ncu --set full, profiles/r2_ncu_full_syrk_hessian_c4_tile_order.txt "
+                                       "(algorithmic: 1.07 GB read of G + 0.54 GB write of H; the rest: every wave of 148 tiles streams its "
+                                       "24 operand panels of 16.8 MB once -- K = 16384 is far longer than L2 can keep across waves; 13.7 GB "
+                                       "before the supertile order and the short stream-K tail; 3 % of DRAM peak: the kernel is "
+                                       "tensor-bound)") if big else None,
                     "launches": n_syrk, "avg_launch_ms": syrk_ms / max(n_syrk, 1), "flops_per_launch": syrk_flops / max(n_syrk, 1),
                     "peak_source": peak_source, "share_of_step": syrk_ms / dev_ms if dev_ms > 0 else None}
         chol = roofline_from_range(

@@ -262,6 +262,7 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
   if (const char* e = getenv("CVXB_NO_LOOP")) h->use_loop = (e[0] == '0' || e[0] == 0) ? 1 : 0;
   if (!h->use_graphs) h->use_loop = 0;
   CVXB_TRY(gemm_dmma_init());
+  CVXB_TRY(gemm_dmma_build_tile_orders(*h));
   CVXB_TRY(factor_init());
   *out = h;
   return CVXB_OK;
@@ -272,7 +273,7 @@ int cvxb_destroy(cvxb_handle h) {
   cvxb::DeviceGuard guard(h->device);
   cudaStreamSynchronize(h->stream);
   if (h->kkt_cache) { KktWork* W = (KktWork*)h->kkt_cache; kkt_work_free(*W); delete W; }
-  cudaFree(h->sk_ws); cudaFree(h->sk_flags);
+  cudaFree(h->sk_ws); cudaFree(h->sk_flags); cudaFree(h->tile_order);
   cudaFree(h->d_prof);
   cudaFree(h->wave_ready); cudaFree(h->d_scal); cudaFree(h->d_flag); cudaFree(h->d_part); cudaFree(h->d_ticket);
   cudaFreeHost(h->h_scal); cudaFreeHost(h->h_flag);

@@ -58,6 +58,8 @@ struct cvxb_handle_s {
   unsigned* d_ticket = nullptr;  // last-block-done counters
   cudaStream_t stream2 = nullptr;            // look-ahead stream of the blocked Cholesky
   std::vector<cudaEvent_t> la_events;        // fork / join events of the look-ahead schedule
+  unsigned* tile_order = nullptr;            // L2-aware tile orders of the triangular stream-K grids (gemm_dmma.cu)
+  std::vector<size_t> tile_order_off;        // offset of the table for tm tiles per dimension, (size_t)-1 = none
   double* sk_ws = nullptr;       // stream-K partial tiles: one 128x128 slot per SM
   int* sk_flags = nullptr;       // "slot c holds a partial" flags (self-cleaning)
   int* wave_ready = nullptr;     // per-block "y_k published" flags of the wavefront triangular solves
@@ -209,6 +211,7 @@ int gemm_dmma_pdl(Handle& h, const GemmArgs& g);
 // gemm_dmma bracketed by CUDA events when the handle's profiling is on (flops = algorithmic flops)
 int gemm_dmma_timed(Handle& h, const GemmArgs& g, double flops);
 int gemm_dmma_init();   // sets the dynamic-smem attribute on all instantiations (once per device)
+int gemm_dmma_build_tile_orders(Handle& h);   // per handle: device tables of the L2-aware tile orders
 int dmma_peak_probe(Handle& h, int iters, double* ms, double* flops);   // register-only DMMA issue rate
 
 // ---------------------------------------------------------------- BLAS-2 (blas2.cu)

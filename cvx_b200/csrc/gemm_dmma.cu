@@ -293,8 +293,9 @@ gemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, con
 
 // Stream-K variant of the 128x128 triangular (SYRK) grid: ONE persistent CTA per SM.  With T tiles and G CTAs the
 // plain grid runs ceil(T/G) waves and leaves the last one partly empty (C2: 136 tiles on 148 SMs; C4: 2080 =
-// 14 waves + 8 tiles).  Here the first T - (G + T%G) tiles are dealt out whole (CTA i takes tiles i, i+G, ...) and
-// the k-slabs of the remaining G + T%G tiles are cut into G equal contiguous shares.  A share starts with the tail
+// 14 waves + 8 tiles).  Here the tiles of the full waves are dealt out whole (CTA i takes tiles i, i+G, ...) and the
+// k-slabs of the remaining T%G tiles (of G + T%G tiles when that would leave shares shorter than 8 slabs, or when there is
+// no full wave) are cut into G equal contiguous shares.  A share starts with the tail
 // (or a middle piece) of a tile -- written as a partial to the CTA's workspace slot and flagged -- and ends with the
 // head of another tile, whose CTA is that tile's owner: it adds the partials of CTAs i+1, i+2, ... in index order
 // (fixed order: results are deterministic and tri=2 stays bitwise symmetric) and runs the epilogue.  The partials
@@ -304,7 +305,8 @@ template <bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(256, 1)
 gemm_dmma_streamk_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const double* __restrict__ B,
                          int ldb, double* __restrict__ C, int ldc, double alpha, double beta, int tri, int tiles_total,
-                         int tiles_whole, double* __restrict__ ws, int* flags, int* abort_flag) {
+                         int tiles_whole, double* __restrict__ ws, int* flags, int* abort_flag,
+                         const unsigned* __restrict__ order) {
   typedef CtaTile<128, 128, 2, 4, A_KC, B_KC> T;
   constexpr int PER_THREAD = T::MT * T::NTL * 2;       // 64 accumulators
   extern __shared__ __align__(16) double smem[];
@@ -312,9 +314,20 @@ gemm_dmma_streamk_kernel(int M, int N, int K, const double* __restrict__ A, int 
   const int KT = (K + BK - 1) / BK;
   double acc[T::MT][T::NTL][2];
   // whole tiles
+  // tile id -> (bm, bn): through the L2-aware order table when there is one (supertiles of 12 x 12 tiles: the ~148 tiles in
+  // flight at any time then share 24 operand panels instead of ~67), else row-major over the lower triangle
+  auto tile_of = [&](int id, int& bm, int& bn) {
+    if (order) {
+      const unsigned v = __ldg(order + id);
+      bm = (int)(v >> 16);
+      bn = (int)(v & 0xffffu);
+    } else {
+      tri_tile(id, bm, bn);
+    }
+  };
   for (int id = cta; id < tiles_whole; id += G) {
     int bm, bn;
-    tri_tile(id, bm, bn);
+    tile_of(id, bm, bn);
     T::zero(acc);
     __syncthreads();          // every warp is done with the previous tile's stages
     T::mainloop(acc, smem, M, N, K, A, lda, B, ldb, bm * 128, bn * 128, 0, KT);
@@ -329,7 +342,7 @@ gemm_dmma_streamk_kernel(int M, int N, int K, const double* __restrict__ A, int 
     const int kb = (int)(pos - (long long)tl * KT);
     const int ke = (end - pos < KT - kb) ? kb + (int)(end - pos) : KT;
     int bm, bn;
-    tri_tile(tiles_whole + tl, bm, bn);
+    tile_of(tiles_whole + tl, bm, bn);
     T::zero(acc);
     __syncthreads();
     T::mainloop(acc, smem, M, N, K, A, lda, B, ldb, bm * 128, bn * 128, kb, ke);
@@ -520,6 +533,33 @@ int dmma_peak_probe(Handle& h, int iters, double* ms, double* flops) {
   return CVXB_OK;
 }
 
+// L2-aware tile orders for the triangular stream-K grids, one per tile count per dimension tm = 13..256 (n <= 32768):
+// supertiles of 12 x 12 tiles, row-major over the lower triangle of supertiles, row-major inside.  With the plain
+// row-major order the ~148 tiles in flight span two to three tile rows, i.e. up to 64 + 3 operand panels -- at the C4
+// Hessian SYRK (K = 16384: 16.8 MB per panel, far beyond what L2 can keep across waves) all of G was re-read in every one
+// of the 14 waves (ncu: 13.2 GB of DRAM reads for a 1.07 GB operand).  A 12 x 12 supertile needs 24 panels.
+int gemm_dmma_build_tile_orders(Handle& h) {
+  if (getenv("CVXB_NO_TILE_ORDER")) return CVXB_OK;
+  constexpr int S = 12, TM_MAX = 256;
+  std::vector<unsigned> table;
+  h.tile_order_off.assign(TM_MAX + 1, (size_t)-1);
+  for (int tm = S + 1; tm <= TM_MAX; ++tm) {
+    h.tile_order_off[tm] = table.size();
+    const int SR = (tm + S - 1) / S;
+    for (int sr = 0; sr < SR; ++sr)
+      for (int sc = 0; sc <= sr; ++sc)
+        for (int bm = sr * S; bm < tm && bm < (sr + 1) * S; ++bm)
+          for (int bn = sc * S; bn <= bm && bn < (sc + 1) * S; ++bn) table.push_back(((unsigned)bm << 16) | (unsigned)bn);
+    if (table.size() - h.tile_order_off[tm] != (size_t)tm * (tm + 1) / 2) {
+      set_last_error("gemm_dmma_build_tile_orders: internal error at tm = %d", tm);
+      return CVXB_EINVAL;
+    }
+  }
+  CVXB_CUDA_OK(cudaMalloc((void**)&h.tile_order, table.size() * sizeof(unsigned)));
+  CVXB_CUDA_OK(cudaMemcpy(h.tile_order, table.data(), table.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  return CVXB_OK;
+}
+
 int gemm_dmma_init() {
   CVXB_CUDA_OK(cudaFuncSetAttribute(gemm_dmma_streamk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     smem_bytes<128, 2, 4>()));
@@ -601,13 +641,23 @@ int gemm_dmma(Handle& h, const GemmArgs& g) {
   const long long want = (long long)h.sm_count * 3 / 4;
   int tile = g.tile;
   if (tile == 0) tile = ntiles(128) >= want ? 128 : (ntiles(64) >= want ? 64 : 32);
+  // short contractions (rank-128 / rank-256 updates): the 64x64 tile runs two CTAs per SM, so one CTA's epilogue (read,
+  // update and write of C: as long as the mainloop itself at K = 128) overlaps the other's mainloop
+  static const int smallk = getenv("CVXB_SMALLK") ? atoi(getenv("CVXB_SMALLK")) : 256;
+  if (g.tile == 0 && tile == 128 && g.K <= smallk && g.beta != 0.0) tile = 64;
   if (tile == 128 && g.streamk && g.tri && h.sk_ws && g_gemm_stream == nullptr && g.a_kc == g.b_kc) {
     // stream-K for the big SYRKs on the handle's own stream (see gemm_dmma_streamk_kernel)
     const long long T = ntiles(128);
     const int G = h.sm_count, KT = (g.K + BK - 1) / BK;
     const int r = (int)(T % G);
     if (r != 0 && KT >= 16 && T >= G / 2 && T < (1ll << 30)) {
-      const int whole = T >= G + r ? (int)(T - (G + r)) : 0;
+      // tiles cut along K: only the r tiles of the partial last wave when their K-shares are long enough (>= 8 slabs per
+      // CTA), else one more full wave with them.  Cutting few tiles keeps the CTAs of every full wave aligned in k, so
+      // the panels they share are read from HBM once per wave; a cut wave's CTAs sit at staggered k offsets and re-read
+      // each panel (ncu at C4: 5 of the 10.7 GB of DRAM reads came from a cut wave of 156 tiles).
+      static const bool short_tail = getenv("CVXB_SK_LONG_TAIL") == nullptr;
+      const long long tail = (short_tail && T >= G && (long long)r * KT / G >= 8) ? r : (long long)G + r;
+      const int whole = T >= tail ? (int)(T - tail) : 0;
       int M = g.M, N = g.N, K = g.K, lda = g.lda, ldb = g.ldb, ldc = g.ldc, tri = g.tri, tt = (int)T, tw = whole;
       const double *A = g.A, *B = g.B;
       double* C = g.C;
@@ -615,7 +665,10 @@ int gemm_dmma(Handle& h, const GemmArgs& g) {
       double* ws = h.sk_ws;
       int* fl = h.sk_flags;
       int* ab = h.d_flag + F_WAVE_ABORT;
-      void* args[] = {&M, &N, &K, &A, &lda, &B, &ldb, &C, &ldc, &alpha, &beta, &tri, &tt, &tw, &ws, &fl, &ab};
+      const int tm = (g.M + 127) / 128;
+      const unsigned* ord = (h.tile_order && tm < (int)h.tile_order_off.size() && h.tile_order_off[tm] != (size_t)-1)
+                                ? h.tile_order + h.tile_order_off[tm] : nullptr;
+      void* args[] = {&M, &N, &K, &A, &lda, &B, &ldb, &C, &ldc, &alpha, &beta, &tri, &tt, &tw, &ws, &fl, &ab, &ord};
       const void* fn = g.a_kc ? (const void*)gemm_dmma_streamk_kernel<true, true>
                               : (const void*)gemm_dmma_streamk_kernel<false, false>;
       cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(G), dim3(256), args, smem_bytes<128, 2, 4>(), h.stream);
