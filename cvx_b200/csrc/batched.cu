@@ -1041,6 +1041,7 @@ int cvxb_batch_create(cvxb_handle h, const cvxb_batch_desc* d, cvxb_batch* out) 
     T(bupload(Bt, &Bt->order, ord.data(), B));
   }
   Bt->grid = h->sm_count * 2;
+  if (const char* e = getenv("CVXB_BATCH_CTAS_PER_SM")) Bt->grid = h->sm_count * (atoi(e) > 0 ? atoi(e) : 2);   // residency experiments
   if (Bt->grid > d->B) Bt->grid = d->B;
   T(balloc(Bt, &Bt->scratch, (size_t)Bt->grid * BN * BN));
   T(balloc(Bt, &Bt->counter, 1));
