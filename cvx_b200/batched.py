@@ -180,6 +180,19 @@ def pack_records(local: BatchSolution) -> np.ndarray:
     return rec
 
 
+_PINNED = {}
+
+
+def _pinned_buffer(rows: int, cols: int):
+    """Pinned host staging buffer for the gathered records, kept between calls (pinning memory costs more than the copy)."""
+    import torch
+    key = (rows, cols)
+    if key not in _PINNED:
+        _PINNED.clear()
+        _PINNED[key] = torch.empty(rows, cols, dtype=torch.float64).pin_memory()
+    return _PINNED[key]
+
+
 def gather_solutions(local, B: int, n: int, group=None):
     """Final exchange of the sharded batch: ONE all-gather of the packed per-problem records
     [x(n), objective, gap, status, newton steps, outer stages]; the global convergence figures (converged count, max
@@ -207,10 +220,20 @@ def gather_solutions(local, B: int, n: int, group=None):
         rec = pad
     out = torch.empty(world * per, row, dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
-    # drop the padding rows of short shards, keep problem order
-    keep = torch.cat([torch.arange(r_ * per, r_ * per + (shard_range(B, r_, world)[1] - shard_range(B, r_, world)[0]))
-                      for r_ in range(world)]).to(dev)
-    g = out.index_select(0, keep).cpu().numpy()
+    if world * per == B:
+        # even split (the BASELINE shapes): the gathered block IS the result, one copy into a pinned host buffer
+        if dev.type == "cuda":
+            host = _pinned_buffer(world * per, row)
+            host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            g = host.numpy()
+        else:
+            g = out.numpy()
+    else:
+        # drop the padding rows of short shards, keep problem order
+        keep = torch.cat([torch.arange(r_ * per, r_ * per + (shard_range(B, r_, world)[1] - shard_range(B, r_, world)[0]))
+                          for r_ in range(world)]).to(dev)
+        g = out.index_select(0, keep).cpu().numpy()
     status = g[:, n + 2].astype(np.int32)
     steps = g[:, n + 3].astype(np.int32)
     return dict(x=np.ascontiguousarray(g[:, :n]), objective=g[:, n].copy(), dualityGap=g[:, n + 1].copy(), status=status,
