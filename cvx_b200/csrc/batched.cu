@@ -190,42 +190,55 @@ __device__ bool b_eval(Smem& S, const BatchArgs& A, int kind, double obj_r, cons
 }
 
 // ---- H = t hess f0 + G' diag(inv^2) G, full symmetric in S.L, via DMMA out of shared memory --------------
+// The 8 x 8 output tiles of the lower triangle are dealt out in PAIRS of neighbours in a tile row: both share the
+// A-operand fragment (rows of G' scaled by inv^2), and their four independent accumulator chains double the DMMAs in
+// flight per warp -- the phase is bound by the latency of LDS -> DMMA chains, not by the tensor pipe (20 work items in
+// 3 rounds over the 8 warps instead of 36 tiles in 5).  inv^2 is staged once in S.Gd (dead until the line search).
 __device__ void b_hessian(Smem& S, const BatchArgs& A, int kind, const double* Pg, double t) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = S.ncur, m = S.mcur;
   const int g = lane >> 2, tq = lane & 3;
   const int nt = (n + 7) >> 3;
-  const int ntiles = nt * (nt + 1) / 2;
   const int m4 = (m + 3) & ~3;
-  for (int tl = warp; tl < ntiles; tl += BT / 32) {
-    int r = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
-    while ((r + 1) * (r + 2) / 2 <= tl) ++r;
-    while (r * (r + 1) / 2 > tl) --r;
-    const int ti = r, tj = tl - r * (r + 1) / 2;
-    const int i0 = ti * 8, j0 = tj * 8;
-    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
-    for (int kk = 0; kk < m4; kk += 8) {
-      const double w0 = (kk + tq < m) ? S.inv[kk + tq] : 0.0;
-      double a = GG(kk + tq, i0 + g) * (w0 * w0);
-      double b = GG(kk + tq, j0 + g);
-      dmma884b(c0, c1, a, b);
-      if (kk + 4 < m4) {
-        const double w1 = (kk + 4 + tq < m) ? S.inv[kk + 4 + tq] : 0.0;
-        double a2 = GG(kk + 4 + tq, i0 + g) * (w1 * w1);
-        double b2 = GG(kk + 4 + tq, j0 + g);
-        dmma884b(e0, e1, a2, b2);
+  if (tid < BM_) S.Gd[tid] = (tid < m) ? S.inv[tid] * S.inv[tid] : 0.0;
+  __syncthreads();
+  int item = 0;
+  for (int ti = 0; ti < nt; ++ti) {
+    for (int tj = 0; tj <= ti; tj += 2, ++item) {
+      if ((item & (BT / 32 - 1)) != warp) continue;
+      const bool two = tj + 1 <= ti;
+      const int i0 = ti * 8, j0 = tj * 8, j1 = two ? j0 + 8 : j0;
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, h0 = 0.0, h1 = 0.0;
+      for (int kk = 0; kk < m4; kk += 8) {
+        {
+          const int r = kk + tq;
+          const double a = GG(r, i0 + g) * S.Gd[r];
+          dmma884b(c0, c1, a, GG(r, j0 + g));
+          if (two) dmma884b(f0, f1, a, GG(r, j1 + g));
+        }
+        if (kk + 4 < m4) {
+          const int r = kk + 4 + tq;
+          const double a = GG(r, i0 + g) * S.Gd[r];
+          dmma884b(e0, e1, a, GG(r, j0 + g));
+          if (two) dmma884b(h0, h1, a, GG(r, j1 + g));
+        }
       }
-    }
-    c0 += e0; c1 += e1;
-    const int i = i0 + g;
+      c0 += e0; c1 += e1; f0 += h0; f1 += h1;
+      const int i = i0 + g;
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int j = j0 + 2 * tq + e;
-      if (i < n && j < n && j <= i) {
-        double v = e ? c1 : c0;
-        if (kind == CVXB_OBJ_QUADRATIC) v += t * Pg[i + (size_t)j * n];
-        else if (kind == CVXB_OBJ_KL && i == j) v += t / S.x[i];
-        HL(i, j) = v;
-        HL(j, i) = v;
+      for (int half = 0; half < 2; ++half) {
+        if (half && !two) break;
+        const int jb = half ? j1 : j0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = jb + 2 * tq + e;
+          if (i < n && j < n && j <= i) {
+            double v = half ? (e ? f1 : f0) : (e ? c1 : c0);
+            if (kind == CVXB_OBJ_QUADRATIC) v += t * Pg[i + (size_t)j * n];
+            else if (kind == CVXB_OBJ_KL && i == j) v += t / S.x[i];
+            HL(i, j) = v;
+            HL(j, i) = v;
+          }
+        }
       }
     }
   }
@@ -250,7 +263,9 @@ __device__ void b_ruiz(Smem& S, const BatchArgs& A) {
     S_COLSQ[part * BN + j] = s;
     __syncthreads();
     // two barriers per sweep: the 64 column owners live in warps 0 and 1, so rho = max|1-u| needs one
-    // shuffle reduction per warp and a two-entry exchange
+    // shuffle reduction per warp and a two-entry exchange.  (A one-barrier variant -- every warp owning 8 columns and
+    // computing u_j itself -- measured 38 % slower: the sqrt / divide sequences then issue in all 8 warps of both
+    // resident CTAs instead of in 2.)
     if (warp < 2) {
       double dev = 0.0;
       if (tid < n) {
@@ -329,27 +344,44 @@ __device__ int b_potrf(Smem& S, int n, double* mind_out) {
     const int nrows = n - r0;
     if (nrows <= 0) continue;
     if (tid < nrows) {
+      // right-looking substitution (factor.cu: leaf panel): once x[c] is known it is folded into all later columns, so the
+      // dependent chain is 16 x (multiply + one FMA) instead of the 136 in-order FMAs of the dot-product form
       const int r = r0 + tid;
       double xr[BSUB];
 #pragma unroll
-      for (int c = 0; c < BSUB; ++c) {
-        double v = HL(r, o + c);
+      for (int c = 0; c < BSUB; ++c) xr[c] = HL(r, o + c);
 #pragma unroll
-        for (int k = 0; k < c; ++k) v = fma(-xr[k], HL(o + c, o + k), v);
-        xr[c] = v * S.rdiag[o + c];
+      for (int c = 0; c < BSUB; ++c) {
+        xr[c] *= S.rdiag[o + c];
+#pragma unroll
+        for (int c2 = c + 1; c2 < BSUB; ++c2) xr[c2] = fma(-xr[c], HL(o + c2, o + c), xr[c2]);
       }
 #pragma unroll
       for (int c = 0; c < BSUB; ++c) HL(r, o + c) = xr[c];
     }
     __syncthreads();
     PCLK(2);
-    for (int c = r0 + warp; c < n; c += BT / 32) {
-      for (int r = c - ((c - r0) & 31) + lane; r < n; r += 32) {
-        if (r < c) continue;
-        double v = HL(r, c);
+    {
+      // trailing update A(r,c) -= sum_k L(r,o+k) L(c,o+k), r >= c >= r0, as 8 x 8 DMMA tiles of the lower triangle
+      // (rows past n only feed discarded outputs and are read as zero)
+      const int g = lane >> 2, tq = lane & 3;
+      const int T = (nrows + 7) >> 3;
+      const int ntile = T * (T + 1) / 2;
+      for (int tl = warp; tl < ntile; tl += BT / 32) {
+        int ti = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= tl) ++ti;
+        while (ti * (ti + 1) / 2 > tl) --ti;
+        const int tj = tl - ti * (ti + 1) / 2;
+        const int rr = r0 + 8 * ti + g, cr = r0 + 8 * tj + g;
+        double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-        for (int k = 0; k < BSUB; ++k) v = fma(-HL(r, o + k), HL(c, o + k), v);
-        HL(r, c) = v;
+        for (int kk = 0; kk < BSUB; kk += 4)
+          dmma884b(c0, c1, rr < n ? HL(rr, o + kk + tq) : 0.0, cr < n ? HL(cr, o + kk + tq) : 0.0);
+        const int cc = r0 + 8 * tj + 2 * tq;
+        if (rr < n) {
+          if (cc <= rr) HL(rr, cc) -= c0;
+          if (cc + 1 <= rr) HL(rr, cc + 1) -= c1;
+        }
       }
     }
     __syncthreads();
