@@ -123,6 +123,30 @@ __device__ long long g_potrf_clk[8];      // CVXB_BATCH_TIMING: diag / panel / u
 #define HL(i, j) S.L[(i) + (j) * LDH]
 #define GG(i, j) S.G[(i) + (j) * LDG]
 
+// Three block sums behind ONE set of barriers (a block_sum costs three __syncthreads; a Newton step had ~18 of them).  The
+// additions of each sum happen in the same order as in vecops.cuh: block_sum (xor tree inside the warp, then the xor tree
+// over the 8 warp totals), so the results are bit-identical to three separate calls.  `buf` >= 35 doubles.
+__device__ __forceinline__ void b_sum3(double& a, double& b, double& c, double* buf) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  c = warp_sum(c);
+  __syncthreads();
+  if (lane == 0) { buf[warp] = a; buf[8 + warp] = b; buf[16 + warp] = c; }
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < 24 ? buf[lane] : 0.0;
+    t += __shfl_xor_sync(0xffffffffu, t, 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    if (lane < 24 && (lane & 7) == 0) buf[32 + (lane >> 3)] = t;
+  }
+  __syncthreads();
+  a = buf[32];
+  b = buf[33];
+  c = buf[34];
+}
+
 // ---- evaluation at S.x for parameter t: gx, 1/slack, barrier value, gradient, eq residual -----------------
 // returns false when x is not strictly feasible (slack <= 0)
 __device__ bool b_eval(Smem& S, const BatchArgs& A, int kind, double obj_r, const double* Pg, double beq, double t,
@@ -148,8 +172,6 @@ __device__ bool b_eval(Smem& S, const BatchArgs& A, int kind, double obj_r, cons
     S.inv[tid] = 1.0 / d;
     ls = log(d);
   }
-  ls = block_sum(ls, S.red);
-  bad = block_or(bad, S.ired);
   double f0 = 0.0;
   if (tid < n) {
     double xj = S.x[tid];
@@ -157,7 +179,10 @@ __device__ bool b_eval(Smem& S, const BatchArgs& A, int kind, double obj_r, cons
     else if (kind == CVXB_OBJ_QUADRATIC) f0 = S.oa[tid] * xj + 0.5 * xj * S.Px[tid];
     else f0 = xj * log(xj * (double)n);
   }
-  f0 = block_sum(f0, S.red) + obj_r;
+  double nbad = (double)bad;
+  b_sum3(ls, nbad, f0, S.red);          // (writes of S.inv above are ordered before the gradient's reads by its barriers)
+  bad = nbad != 0.0;
+  f0 += obj_r;
   // gradient: y_j = t grad f0_j + sum_i G(i,j)/d_i ; 4 threads per column
   {
     const int j = tid >> 2, part = tid & 3;
@@ -180,8 +205,8 @@ __device__ bool b_eval(Smem& S, const BatchArgs& A, int kind, double obj_r, cons
     g2 = S.y[tid] * S.y[tid];
     if (S.pcur) ax = S.aeq[tid] * S.x[tid];
   }
-  g2 = block_sum(g2, S.red);
-  ax = block_sum(ax, S.red);
+  double dummy = 0.0;
+  b_sum3(g2, ax, dummy, S.red);
   *fval = t * f0 - ls;
   *f0out = f0;
   *normGrad = sqrt(g2);
@@ -512,8 +537,8 @@ __device__ bool b_linear_solve(Smem& S, const BatchArgs& A, const double* Hs, do
         r2 = r * r;
         q2 = q[tid] * q[tid];
       }
-      r2 = block_sum(r2, S.red);
-      q2 = block_sum(q2, S.red);
+      double dummy = 0.0;
+      b_sum3(r2, q2, dummy, S.red);
       double e1 = relative_size(sqrt(r2), sqrt(q2), tol);
       return e1 <= tol;
     }
@@ -525,9 +550,7 @@ __device__ bool b_linear_solve(Smem& S, const BatchArgs& A, const double* Hs, do
     __syncthreads();
     double sa = 0.0, saq = 0.0, nq = 0.0;
     if (tid < n) { sa = S.ya[tid] * S.ya[tid]; saq = S.ya[tid] * S.yq[tid]; nq = S.qs[tid] * S.qs[tid]; }
-    sa = block_sum(sa, S.red);
-    saq = block_sum(saq, S.red);
-    nq = block_sum(nq, S.red);
+    b_sum3(sa, saq, nq, S.red);
     if (!(sa > 0.0)) return false;               // cholesky(S) of the 1 x 1 Schur complement fails
     const double K = sqrt(sa);
     const double z = -(brhs + saq);
@@ -546,8 +569,8 @@ __device__ bool b_linear_solve(Smem& S, const BatchArgs& A, const double* Hs, do
       S.dir[tid] = S.dr[tid] * S_T2[tid];
       axs = S.aeq[tid] * S.dir[tid];
     }
-    r2 = block_sum(r2, S.red);
-    axs = block_sum(axs, S.red);
+    double dummy = 0.0;
+    b_sum3(r2, axs, dummy, S.red);
     double e1 = relative_size(sqrt(r2), sqrt(nq), tol);
     double e2 = relative_size(fabs(axs - brhs), fabs(brhs), tol);
     if (tid == 0) S.sc[1] = w;
@@ -694,20 +717,15 @@ __device__ double b_value(Smem& S, const BatchArgs& A, int kind, double t, doubl
     if (!(d > 0.0)) bad = 1;
     ls = log(d);
   }
-  ls = block_sum(ls, S.red);
-  bad = block_or(bad, S.ired);
-  *throws = bad;
-  double f0s;
-  if (kind == CVXB_OBJ_KL) {
-    double v = 0.0;
-    if (tid < S.ncur) {
-      double xj = S.x[tid] + s * S.dir[tid];
-      v = xj * log(xj * (double)S.ncur);
-    }
-    f0s = block_sum(v, S.red);
-  } else {
-    f0s = f0 + s * c1 + 0.5 * s * s * c2;
+  double v = 0.0;
+  if (kind == CVXB_OBJ_KL && tid < S.ncur) {
+    double xj = S.x[tid] + s * S.dir[tid];
+    v = xj * log(xj * (double)S.ncur);
   }
+  double nbad = (double)bad;
+  b_sum3(ls, nbad, v, S.red);
+  *throws = nbad != 0.0;
+  const double f0s = (kind == CVXB_OBJ_KL) ? v : f0 + s * c1 + 0.5 * s * s * c2;
   return t * f0s - ls;
 }
 
@@ -781,9 +799,7 @@ __device__ __noinline__ void b_barrier_loop(Smem& S, const BatchArgs& A, int kin
         if (kind == CVXB_OBJ_LINEAR) c1 = S.oa[tid] * dj;
         else if (kind == CVXB_OBJ_QUADRATIC) { c1 = (S.oa[tid] + S.Px[tid]) * dj; c2 = dj * S.Pd[tid]; }
       }
-      q = block_sum(q, S.red);
-      c1 = block_sum(c1, S.red);
-      c2 = block_sum(c2, S.red);
+      b_sum3(q, c1, c2, S.red);
       nd = -q / 2;
       bool moved = false;
       if (nd > tol) {
