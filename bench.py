@@ -589,6 +589,25 @@ def main():
                    "includes": "kernel + ONE NCCL all-gather of the packed device records + one device-to-host copy"
                                if world > 1 else "kernel + device-to-host of the results"}
         solver.close()
+        if world == 1:
+            # the phase-I variant: no feasible starts, ConstraintSet.phase_I_Analysis runs inside each CTA first
+            try:
+                Bp = min(Bt, 2048)
+                pprobs = [P.batched_problem_phase1(i, 63, 126) for i in range(Bp)]
+                psolver = cb.BatchedBarrierSolver(cb.pack_problems(pprobs), cb.SolverParams(), h)
+                psolver.solve(download=False)
+                t0 = time.perf_counter()
+                psol = psolver.solve()
+                pwall = time.perf_counter() - t0
+                batched["phase1_variant"] = {
+                    "B": Bp, "n": 63, "m": 126, "value": Bp / pwall, "unit": "solves/s", "device_only_value": Bp / (psol.solve_ms / 1e3),
+                    "converged": int((psol.status == 0).sum()), "phase1_newton_steps_mean": float(psol.phase1_newton_steps.mean()),
+                    "newton_steps_mean": float(psol.newton_steps.mean()),
+                    "what": "problems without a feasible start: phase I (n + 1 = 64 variables, m + 2p <= 128 rows) then the barrier "
+                            "solve, all inside the problem's CTA"}
+                psolver.close()
+            except Exception as e:      # never lose the headline to a leg
+                batched["phase1_variant"] = {"failed": repr(e)}
 
     # ---- the other single-GPU configs as extra legs (N = 1 only) -------------------------------------------------------
     legs = {}

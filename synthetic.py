@@ -236,6 +236,20 @@ def batched_problem(i, n=64, m=128, base_seed=1000):
     return slab_qp(n, m // 2, 0, base_seed + i, scale=True)
 
 
+def batched_problem_phase1(i, n=63, m=126, base_seed=7000):
+    """Phase-I variant of C3: the same two families without a feasible start -- even i: KL problem of
+    Dist_KL.apply form (start 1/n is defined but violates the H x <= u rows; one equality: the feasibility problem has n + 1
+    variables and m + 2 rows), odd i: slab QP started outside its slab.  n = 63, m = 126 is the largest shape whose
+    feasibility problem still fits the batched kernel's 64 x 128 layout."""
+    if i % 2 == 0:
+        return kl_random(n, m - n, 0, base_seed + i)          # x0 = None, xdef = 1/n
+    pr = slab_qp(n, m // 2, 0, base_seed + i, scale=True)
+    rng = np.random.default_rng(base_seed + 100000 + i)
+    pr["xdef"] = pr["x0"] + rng.uniform(0.5, 1.0, n)
+    pr["x0"] = None
+    return pr
+
+
 def lin_quad_set(n, m_lin, m_quad, p=0, seed=0, objective="quadratic", feasible_start=True):
     """FeasibilityTests / ConstraintSets.randomConstraintSet design (src/test/scala/cvx/FeasibilityTests.scala:105-117,
     ConstraintSets.scala:67-89; Constraints.randomLinearIneqConstraint / randomQuadraticConstraint,

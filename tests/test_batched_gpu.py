@@ -121,16 +121,8 @@ def test_batched_infeasible_start_is_flagged(handle):
 
 
 def _phase1_problem(i, n, m):
-    """Phase-I variant of the batch shapes: even i -> KL problem of Dist_KL.apply form (start 1/n is defined but violates the
-    H x <= u rows, one equality: the feasibility problem has n + 1 variables and m + 2 rows), odd i -> slab QP started
-    outside its slab (no equality)."""
-    if i % 2 == 0:
-        return P.kl_random(n, m - n, 0, 700 + i)          # x0 = None, xdef = 1/n
-    pr = P.slab_qp(n, m // 2, 0, 700 + i, scale=True)
-    rng = np.random.default_rng(900 + i)
-    pr["xdef"] = pr["x0"] + rng.uniform(0.5, 1.0, n)
-    pr["x0"] = None
-    return pr
+    """Phase-I variant of the batch shapes (synthetic.batched_problem_phase1)."""
+    return P.batched_problem_phase1(i, n, m, 700)
 
 
 @pytest.mark.parametrize("n,m,B", [(63, 126, 12), (20, 40, 8)])
