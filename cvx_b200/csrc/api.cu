@@ -762,7 +762,7 @@ int cvxb_ruiz_equilibrate(cvxb_handle h, int n, const double* H, int ldh, double
   if (!W) return st;
   Staged dH, dQ;
   CVXB_TRY(stage_in(*h, n, n, H, ldh, dH));
-  CVXB_TRY(ruiz_equilibrate(*h, n, dH.d, dH.ld, W->dr, W->colsq, P.ruizMaxSweeps, P.ruizTol));
+  CVXB_TRY(ruiz_equilibrate(*h, n, dH.d, dH.ld, W->dr, W->colsq, P.ruizMaxSweeps, P.ruizTol, W->L, (size_t)W->ldn * n));
   if (Q) {
     CVXB_TRY(stage_out_alloc(*h, n, n, dQ));
     CVXB_TRY(scaled_full(*h, n, dH.d, dH.ld, W->dr, dQ.d, dQ.ld));
@@ -854,7 +854,7 @@ int cvxb_symmetric_solve(cvxb_handle h, int n, const double* Hm, int ldh, const 
   CVXB_TRY(stage_out_alloc(*h, n, 1, dx));
   CVXB_TRY(stage_out_alloc(*h, n, 1, du));
   CVXB_TRY(stage_out_alloc(*h, n, n, dQ));
-  CVXB_TRY(ruiz_equilibrate(*h, n, dH.d, dH.ld, W->dr2, W->colsq, P.ruizMaxSweeps, P.ruizTol));
+  CVXB_TRY(ruiz_equilibrate(*h, n, dH.d, dH.ld, W->dr2, W->colsq, P.ruizMaxSweeps, P.ruizTol, W->L, (size_t)W->ldn * n));
   CVXB_TRY(scaled_full(*h, n, dH.d, dH.ld, W->dr2, dQ.d, dQ.ld));
   // checkSymmetric(Q, 1e-13)  (SymmetricLinearSystem.scala:28)
   CVXB_LAUNCH(*h, check_symmetric_kernel, n, 256, 0, n, dQ.d, dQ.ld, W->t3);
@@ -1043,7 +1043,7 @@ int cvxb_bench_kernel(cvxb_handle h, int which, int n, int k, int reps, double* 
         CVXB_TRY(trsm_lower(H, n, 1, G, ldn, invD, C, ldn, false));
         CVXB_TRY(trsm_lower(H, n, 1, G, ldn, invD, C, ldn, true));
       } else {
-        CVXB_TRY(ruiz_equilibrate(H, n, G, ldn, C, C + ldn, 20, 1e-6));
+        CVXB_TRY(ruiz_equilibrate(H, n, G, ldn, C, C + ldn, 20, 1e-6, invD, (size_t)((n + NB - 1) / NB) * NB * NB));
       }
       CVXB_CUDA_OK(cudaEventRecord(H.ev1, H.stream));
       CVXB_CUDA_OK(cudaEventSynchronize(H.ev1));

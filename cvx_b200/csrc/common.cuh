@@ -233,8 +233,9 @@ int copy_matrix(Handle& h, int m, int n, const double* A, int lda, double* B, in
 
 // ---------------------------------------------------------------- factorisations (factor.cu)
 // MatrixUtils.ruizEquilibrate: leaves d in `d` (n), sweeps in flag F_RUIZ_SWEEPS.  No host sync.
+// big_scratch (optional): >= 2 * ceil(n/128) * pad_ld(n) doubles -- enables the symmetric-half sweeps for n >= 4096
 int ruiz_equilibrate(Handle& h, int n, const double* Hm, int ldh, double* d, double* colnorm_scratch,
-                     int max_sweeps, double tol);
+                     int max_sweeps, double tol, double* big_scratch = nullptr, size_t big_doubles = 0);
 // L := lower((d d') o H) + delta*I, zeros above the diagonal
 int scaled_lower(Handle& h, int n, const double* Hm, int ldh, const double* d, double delta, double* L, int ldl);
 // full Q = (d d') o H

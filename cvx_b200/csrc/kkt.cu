@@ -239,7 +239,7 @@ int kkt_enqueue(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, i
   } else {
     if (!skip_ruiz) {
       CVXB_TRY(prof_begin(h, PROF_RUIZ));
-      CVXB_TRY(ruiz_equilibrate(h, n, Hm, ldh, W.dr, W.colsq, P.ruizMaxSweeps, P.ruizTol));
+      CVXB_TRY(ruiz_equilibrate(h, n, Hm, ldh, W.dr, W.colsq, P.ruizMaxSweeps, P.ruizTol, W.L, (size_t)W.ldn * n));
       CVXB_TRY(prof_end(h, PROF_RUIZ, 8.0 * n * n));       // bytes per sweep; sweeps taken are in F_RUIZ_SWEEPS
     }
     CVXB_TRY(scaled_lower(h, n, Hm, ldh, W.dr, regularize ? P.cholRegDelta : 0.0, W.L, W.ldn));
@@ -343,7 +343,7 @@ int kkt_solve_device(Handle& h, KktWork& W, const cvxb_params& P, const double* 
 int chol_enqueue(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, int ldh, const double* b,
                  double rhs_sign, double tol, bool regularize, bool skip_ruiz, double* x) {
   const int n = W.n;
-  if (!skip_ruiz) CVXB_TRY(ruiz_equilibrate(h, n, Hm, ldh, W.dr, W.colsq, P.ruizMaxSweeps, P.ruizTol));
+  if (!skip_ruiz) CVXB_TRY(ruiz_equilibrate(h, n, Hm, ldh, W.dr, W.colsq, P.ruizMaxSweeps, P.ruizTol, W.L, (size_t)W.ldn * n));
   CVXB_TRY(scaled_lower(h, n, Hm, ldh, W.dr, regularize ? P.cholRegDelta : 0.0, W.L, W.ldn));
   CVXB_LAUNCH(h, chol_rhs_kernel, 1, VT, 0, n, rhs_sign, W.dr, b, W.qs, h.d_scal, h.d_flag);
   CVXB_TRY(potrf_lower_rhs(h, n, W.L, W.ldn, W.invD, F_CHOL_H, S_MINDIAG_H, W.qs, W.ldn, 1));     // w = L^-1 (d o b) rides along

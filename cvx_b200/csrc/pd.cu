@@ -353,7 +353,8 @@ int pd_symmetric_enqueue(cvxb_problem_s* P, const cvxb_params& pars, bool regula
   Handle& h = *P->h;
   const int n = P->n;
   if (!skip_outer) {
-    CVXB_TRY(ruiz_equilibrate(h, n, P->H, P->ldn, P->kw.dr2, P->kw.colsq, pars.ruizMaxSweeps, pars.ruizTol));
+    CVXB_TRY(ruiz_equilibrate(h, n, P->H, P->ldn, P->kw.dr2, P->kw.colsq, pars.ruizMaxSweeps, pars.ruizTol, P->kw.L,
+                              (size_t)P->kw.ldn * n));
     CVXB_TRY(scaled_full(h, n, P->H, P->ldn, P->kw.dr2, P->Hreg, P->ldn));
     CVXB_LAUNCH(h, mul_kernel, 1, VT, 0, n, P->kw.dr2, P->vvec, P->kw.qk);
   }

@@ -46,6 +46,31 @@ def test_ruiz_matches_oracle(handle, n, cond_pow):
     assert np.array_equal(Q, Q.T)
 
 
+@pytest.mark.parametrize("n,cond_pow", [(4096, 1), (4229, 2)])
+def test_ruiz_symmetric_half_sweeps(handle, n, cond_pow, monkeypatch):
+    """Beyond L2 (n >= 4096) the sweeps read only the lower triangle (ruiz_sym_kernel: tile-wise column and row partials,
+    deterministic order): same d, same scaled matrix and the same number of sweeps as the oracle (MatrixUtils.scala:240-268)
+    and as the full-column kernel, with a ragged last tile (4229 = 33 * 128 + 5) and a zero row."""
+    from cvx_b200 import MatrixUtils
+    rng = np.random.default_rng(n)
+    M = rng.uniform(-1, 1, (n, 64))
+    H = M @ M.T + 1e-3 * n * np.eye(n)
+    sc = 10.0 ** rng.uniform(-cond_pow, cond_pow, n)
+    H = H * np.outer(sc, sc)
+    H = (H + H.T) * 0.5
+    H[7, :] = 0.0
+    H[:, 7] = 0.0
+    d, Q, sweeps = MatrixUtils.ruizEquilibrate(H, handle, return_sweeps=True)
+    d0, Q0 = O.ruizEquilibrate(H)
+    assert d[7] == 1.0
+    assert abs(sweeps - O.ruizEquilibrate.last_sweeps) <= 1
+    if sweeps == O.ruizEquilibrate.last_sweeps:
+        assert rel(d, d0) < 1e-12 and rel(Q, Q0) < 1e-12
+    assert np.array_equal(Q, Q.T)
+    d_a, _, sweeps_a = MatrixUtils.ruizEquilibrate(H, handle, return_sweeps=True)
+    assert np.array_equal(d, d_a) and sweeps == sweeps_a            # deterministic: no floating-point atomics
+
+
 @pytest.mark.parametrize("n", [1, 7, 128, 129, 300, 1025])
 def test_regularized_cholesky(handle, n):
     from cvx_b200 import MatrixUtils
