@@ -246,6 +246,7 @@ int cvxb_create(int device, void* stream, unsigned flags, cvxb_handle* out) {
         CVXB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         h->dag_events.push_back(e);
       }
+      if (getenv("CVXB_DAG_BLOCK") || getenv("CVXB_DAG_RESERVE")) h->dag_auto = false;
       if (const char* e = getenv("CVXB_DAG_BLOCK")) h->dag_block = atoi(e) / NB * NB;
       if (const char* e = getenv("CVXB_DAG_MIN_N")) h->dag_min_n = atoi(e);
       if (const char* e = getenv("CVXB_DAG_RESERVE")) h->dag_reserve = atoi(e);
@@ -935,6 +936,11 @@ int cvxb_debug_leaf_clocks(long long* out, int reset) { return cvxb::leaf_clocks
 int cvxb_debug_set_schedule(cvxb_handle h, int dag_block, int dag_min_n, int dag_reserve) {
   CHECK_HANDLE(h);
   CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (dag_block < 0 && dag_min_n < 0 && dag_reserve < 0) {      // all three "keep": back to the library's defaults
+    h->dag_block = 2048; h->dag_min_n = 5120; h->dag_reserve = 8; h->dag_auto = true;
+    return CVXB_OK;
+  }
+  h->dag_auto = false;                                          // explicit settings are taken as given
   if (dag_block >= 0) h->dag_block = dag_block / NB * NB;       // 0 switches the tile-DAG schedule off
   if (dag_min_n >= 0) h->dag_min_n = dag_min_n;
   if (dag_reserve >= 0) h->dag_reserve = dag_reserve < h->sm_count ? dag_reserve : h->sm_count - 1;

@@ -97,6 +97,7 @@ struct cvxb_handle_s {
   int sk_reserve = 0;                        // != 0 only while bulk work is being enqueued
   bool in_dag = false;                       // potrf_dag is enqueuing (its diagonal blocks use the look-ahead / recursive schedules)
   int dag_block = 2048, dag_min_n = 5120, dag_reserve = 8;   // cvxb_debug_set_schedule
+  bool dag_auto = true;                      // potrf_dag may narrow the blocks / the reserve for narrow right-hand sides
 };
 
 namespace cvxb {

@@ -926,7 +926,20 @@ static void dag_blocks(int n, int nbk, std::vector<int>& start) {
 
 int potrf_dag(Handle& h, int n, double* A, int lda, double* invD, int flag_slot, int mindiag_slot, int col0, double* B,
               int ldb, int r) {
-  const int nbk = h.dag_block;
+  // Without a wide right-hand-side block there is less bulk work to hide a chain behind: narrower blocks (shorter chains,
+  // shorter exposed first and last block) win below n = 12288 (n = 8192: 8.7 ms with 1024 columns against 9.2 ms with
+  // 2048), and from there on the chain lane has so much slack that 4 reserved SMs are enough (n = 16385: 52.4 against
+  // 53.0 ms).  cvxb_debug_set_schedule switches these defaults off.
+  int nbk = h.dag_block;
+  const int keep_reserve = h.dag_reserve;
+  if (h.dag_auto && r <= 1024) {
+    if (n < 12288) nbk = nbk / 2 >= 4 * NB ? (nbk / 2) / NB * NB : nbk;
+    else h.dag_reserve = h.dag_reserve > 4 ? 4 : h.dag_reserve;
+  }
+  struct RestoreReserve {
+    Handle& h; int v;
+    ~RestoreReserve() { h.dag_reserve = v; }
+  } restore_reserve{h, keep_reserve};
   std::vector<int> bstart;
   dag_blocks(n, nbk, bstart);
   const int T = (int)bstart.size() - 1;

@@ -385,7 +385,8 @@ int cvxb_bench_kernel(cvxb_handle h, int which, int n, int k, int reps, double* 
 /* Schedule of the big factorisations (tests and tuning; defaults: blocks of 2048 columns from n = 5120 on, 8 SMs left to
  * the critical chain): the tile-DAG schedule runs the bulk updates of a right-looking blocked Cholesky on a third stream
  * beside the chain of diagonal-block factorisations.  A negative argument keeps the current value;
- * dag_block = 0 switches the schedule off (recursive halving + look-ahead only). */
+ * dag_block = 0 switches the schedule off (recursive halving + look-ahead only); all three negative restore the defaults,
+ * including the automatic choice of narrower blocks / a smaller reserve when no wide right-hand-side block rides along. */
 int cvxb_debug_set_schedule(cvxb_handle h, int dag_block, int dag_min_n, int dag_reserve);
 
 #ifdef __cplusplus

@@ -231,7 +231,7 @@ def test_tile_dag_schedule_equals_recursive(handle, n, p, block, seed):
             assert rel(x1, s["x"]) < 1e-5 and rel(w1, s["w"]) < 1e-5
             assert rel(s["H"] @ c1, s["q"]) < 1e-9
     finally:
-        handle.set_schedule(2048, 5120, 8)
+        handle.set_schedule()          # back to the defaults
 
 
 @pytest.mark.parametrize("n,p,seed", [(50, 5, 0), (400, 60, 1)])
