@@ -586,6 +586,12 @@ def main():
                    "m": 128, "scaling": "strong", "device_only_value": Bt / dev_s, "converged": conv,
                    "max_newton_steps": mxs, "newton_steps_per_sec": nsteps / wall_s,
                    "tflops_algorithmic": fl_b / dev_s / 1e12,
+                   "roofline": {"bound": "latency (FP64 dependent-issue chains inside one CTA per problem; not tensor- or HBM-bound)",
+                                "achieved": fl_b / dev_s / 1e12, "unit": "TFLOP/s",
+                                "note": "fraction of the FP64 tensor peak is filled in below; per-phase clock64 split (in-CTA Cholesky "
+                                        "36 %, of it the 64 sequential pivots 67 %; Ruiz 19 %; Hessian DMMA 15 %; triangular solves 15 %), "
+                                        "residency scaling and the ncu capture (issue slots 28 % busy, top stall barrier): "
+                                        "profiles/r2_batched_phase_split.txt, profiles/r2_ncu_full_batched_1024.txt"},
                    "includes": "kernel + ONE NCCL all-gather of the packed device records + one device-to-host copy"
                                if world > 1 else "kernel + device-to-host of the results"}
         solver.close()
@@ -655,6 +661,9 @@ def main():
             except Exception as e:
                 alone[tag] = {"failed": repr(e)}
         chol["timed_alone"] = alone
+        if batched and "roofline" in batched:
+            batched["roofline"]["peak"] = fp64_peak
+            batched["roofline"]["frac"] = batched["roofline"]["achieved"] / fp64_peak if fp64_peak else None
         fcnt, fms, fwk = ranges["factor_h_with_trsm"]
         breakdown = {"hessian_syrk": syrk_ms / dev_ms if dev_ms > 0 else None}
         for k_, (c_, ms_, wk_) in ranges.items():
