@@ -99,6 +99,20 @@ def test_pack_problems_layout():
     assert cb.shard_range(10, 0, 4) == (0, 3) and cb.shard_range(10, 3, 4) == (9, 10) and cb.shard_range(2, 3, 4) == (2, 2)
 
 
+def test_pack_problems_flags_phase1_for_problems_without_a_feasible_start():
+    """A problem that only has a point where it is defined (ConstraintSet.pointWhereDefined) is started there and flagged
+    for the in-kernel phase-I analysis; a batch of feasible starts carries no flag array at all."""
+    import cvx_b200 as cb
+    from oracle import problems as P
+    probs = [P.batched_problem_phase1(i, 7, 14, 3) for i in range(3)] + [P.slab_qp(7, 7, 0, 9)]
+    pk = cb.pack_problems(probs)
+    assert pk["phase1"].tolist() == [1, 1, 1, 0]
+    assert np.array_equal(pk["x0"][0], probs[0]["xdef"]) and np.array_equal(pk["x0"][3], probs[3]["x0"])
+    assert cb.pack_problems([P.slab_qp(7, 7, 0, 9)])["phase1"] is None
+    from cvx_b200 import _lib
+    assert _lib.BatchDesc.phase1.offset == C.sizeof(_lib.BatchDesc) - C.sizeof(C.c_void_p)      # appended: old callers stay valid
+
+
 def test_bench_gpu_arm_never_imports_the_oracle():
     """bench.py may execute oracle/ only in its CPU legs (cpu_baseline, --impl reference): every import of it sits
     inside cpu_reference_leg / cpu_modes_leg; synthetic.py (input generation for both arms) does not import it at all."""
