@@ -155,6 +155,31 @@ def test_batched_phase1_variant_matches_oracle(handle, n, m, B):
         assert np.all(pr["G"] @ sol.x[i] * (1 + 3e-16) < pr["ub"]), i
 
 
+def test_batched_phase1_variant_at_batch_scale(handle):
+    """The phase-I variant at batch scale (bench.py's `batched.phase1_variant`: n = 63, m = 126, the largest shape whose
+    feasibility problem fits the kernel): every problem finds a strictly feasible point and converges; size-independent
+    properties on the whole batch, oracle parity on a sample."""
+    import cvx_b200 as cb
+    B = 512
+    probs = [P.batched_problem_phase1(i, 63, 126) for i in range(B)]
+    sol = cb.BatchedBarrierSolver(cb.pack_problems(probs), None, handle).solve()
+    assert np.all(sol.status == 0), np.nonzero(sol.status)[0][:10]
+    assert np.all(sol.phase1_s < 0.0) and np.all(sol.phase1_newton_steps > 0) and np.all(sol.phase1_stages >= 1)
+    assert np.all(sol.outer_stages == 12) and np.all(sol.stage_newton_steps[:, :12].sum(1) == sol.newton_steps)
+    for i in range(0, B, 7):
+        pr = probs[i]
+        assert np.all(pr["G"] @ sol.x[i] * (1 + 3e-16) < pr["ub"]), i
+        if pr.get("A") is not None:
+            assert abs(float(pr["A"][0] @ sol.x[i]) - pr["b"][0]) < 1e-8, i
+    for i in (0, 1, 254, 255, 510, 511):
+        objF, cnts, eqs = P.to_oracle(probs[i])
+        s0, ph0 = O.solveProblem(objF, cnts, eqs, "BR")
+        o0 = objF.valueAt(s0.x)
+        assert abs(sol.objective[i] - o0) <= 1e-8 * max(1.0, abs(o0)), (i, sol.objective[i], o0)
+        assert sol.phase1_stages[i] == ph0.outer_stages and sol.outer_stages[i] == s0.outer_stages
+        assert abs(int(sol.phase1_newton_steps[i]) - int(ph0.newton_steps)) <= ph0.outer_stages
+
+
 def test_batched_phase1_agrees_with_large_path(handle):
     """The same problems through the one-problem-at-a-time device path (run_phase1 + barrier_loop in solver.cu)."""
     import cvx_b200 as cb
