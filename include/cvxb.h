@@ -89,7 +89,9 @@ typedef struct cvxb_params {
   double phase1EqTol;   /* 1e-6  ConstraintSet.scala:342, CvxUtils.scala:86 */
   double pdStepFraction;/* 0.99  PrimalDualSolver.scala:339,509 */
   int bugCompat;        /* 1: reproduce reference defects D1/D2 of PrimalDualSolver.solve_withEQs */
-  long long stepLimit;  /* >0: stop after this many Newton steps in total (bench.py --steps) */
+  long long stepLimit;  /* 0 (reference behaviour): no budget.  >0: a budget of Newton steps for the whole call (phase I
+                         * included) -- the solve returns its current iterate with status OK when it is used up; not a
+                         * SolverParams field of the reference (callers with a time budget, and bench.py --steps) */
 } cvxb_params;
 int cvxb_default_params(cvxb_params* p);
 
