@@ -587,9 +587,12 @@ __device__ bool b_linear_solve(Smem& S, const BatchArgs& A, const double* Hs, do
 // a one-sided (Hestenes) Jacobi SVD inside the CTA -- the in-CTA twin of eig.cu: svd_solve_device, same pairing order,
 // same threshold, same two acceptance tests (range test, residual test; defect D3: no recovery once they fail).
 // W = M V and V live in the shared-memory block of G and L (G is reloaded by the caller afterwards; L is scratch here).
-__device__ __noinline__ bool b_kkt_sym_solve(Smem& S, int n, const double* Hs, const double* q, double brhs, double tol) {
+// With with_eq = false the same routine is MatrixUtils.symSolve(H, -q), the last resort of UnconstrainedSolver.solve
+// (UnconstrainedSolver.scala:58-65) after choleskySolve(H) and choleskySolve(H + 1e-9 I) have failed.
+__device__ __noinline__ bool b_kkt_sym_solve(Smem& S, int n, bool with_eq, const double* Hs, const double* q, double brhs,
+                                             double tol) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int N = n + 1, ld = BN + 1;
+  const int N = n + (with_eq ? 1 : 0), ld = BN + 1;
   double* W = S.G;
   double* V = S.G + ld * ld;
   double* vec = S.L + 8;                 // V ends two entries into L
@@ -668,7 +671,7 @@ __device__ __noinline__ bool b_kkt_sym_solve(Smem& S, int n, const double* Hs, c
     double sa = 0.0;
     if (tid < n) {
       for (int j = 0; j < n; ++j) sa = fma(Hs[tid + j * BN], xs[j], sa);
-      sa = fma(S.aeq[tid], xs[n], sa);
+      if (with_eq) sa = fma(S.aeq[tid], xs[n], sa);
     } else {
       for (int j = 0; j < n; ++j) sa = fma(S.aeq[j], xs[j], sa);
     }
@@ -685,17 +688,27 @@ __device__ __noinline__ bool b_kkt_sym_solve(Smem& S, int n, const double* Hs, c
   d1 = block_sum(d1, S.red);
   const double relDist = relative_size(sqrt(d0), sqrt(nb), tol), relErr = relative_size(sqrt(d1), sqrt(nb), tol);
   if (tid < n) S.dir[tid] = xs[tid];
-  if (tid == 0) S.sc[1] = xs[n];
+  if (tid == 0 && with_eq) S.sc[1] = xs[n];
   __syncthreads();
   return (relDist <= tol) && (relErr <= tol);
 }
 
-// G of the current problem back into shared memory (after b_kkt_sym_solve used its space)
-__device__ __noinline__ void b_reload_G(Smem& S, const double* Gg, int n, int m) {
+// Phase-I form of G (ConstraintSet.phase_I_Analysis): one more column of -1 and, for an equality, the two rows +-a
+// (n, m, p: the dimensions of the problem itself)
+__device__ void b_phase1_G(Smem& S, int n, int m, int p) {
+  const int tid = threadIdx.x;
+  if (tid < m + 2 * p) GG(tid, n) = -1.0;
+  if (p && tid < n) { GG(m, tid) = S.aeq[tid]; GG(m + 1, tid) = -S.aeq[tid]; }
+  __syncthreads();
+}
+
+// G of the current problem back into shared memory (after b_kkt_sym_solve used its space); phase1: in its phase-I form
+__device__ __noinline__ void b_reload_G(Smem& S, const double* Gg, int n, int m, int p, bool phase1) {
   for (int idx = threadIdx.x; idx < BN * LDG; idx += BT) S.G[idx] = 0.0;
   __syncthreads();
   for (int idx = threadIdx.x; idx < m * n; idx += BT) GG(idx % m, idx / m) = Gg[idx];
   __syncthreads();
+  if (phase1) b_phase1_G(S, n, m, p);
 }
 
 __device__ bool b_in_set(Smem& S, int m, double s) {
@@ -741,7 +754,8 @@ struct LoopOut {
 //   term 0: standard termination (duality gap and equality gap below tolSolver);
 //   term 1: phase I (CvxUtils.scala:78-87): objective value below zero -- a strictly feasible point has been found.
 __device__ __noinline__ void b_barrier_loop(Smem& S, const BatchArgs& A, int kind, double obj_r, const double* Pg, double beq,
-                                            int p, int term, double* Hs, const double* Gg, bool record_stages, LoopOut& out) {
+                                            int p, int term, double* Hs, const double* Gg, int p_orig, bool record_stages,
+                                            LoopOut& out) {
   const int tid = threadIdx.x, n = S.ncur, m = S.mcur;
   const double tol = A.P.tolSolver, tolEq = A.P.tolEqSolve;
   int status = CVXB_OK, stage = 0, total_steps = 0;
@@ -771,12 +785,18 @@ __device__ __noinline__ void b_barrier_loop(Smem& S, const BatchArgs& A, int kin
           ok = b_linear_solve(S, A, Hs, 0.0, true, S.zrhs, eqd, tolEq, &reg);
           if (!ok) {
             // path 2: decomposition of the full KKT matrix  (KKTSystem.scala:63, 283-310)
-            ok = b_kkt_sym_solve(S, n, Hs, S.y, eqd, tolEq);
-            b_reload_G(S, Gg, n, m);
+            ok = b_kkt_sym_solve(S, n, true, Hs, S.y, eqd, tolEq);
+            b_reload_G(S, Gg, A.n, A.m, p_orig, false);
             if (!ok) { status = CVXB_EUNSOLVABLE; break; }
           }
         } else {
           ok = b_linear_solve(S, A, Hs, A.P.newtonRegDelta, false, S.y, 0.0, tolEq, &reg);   // H + 1e-9 I
+          if (!ok) {
+            // MatrixUtils.symSolve(H, -y)   (UnconstrainedSolver.scala:65)
+            ok = b_kkt_sym_solve(S, n, false, Hs, S.y, 0.0, tolEq);
+            b_reload_G(S, Gg, A.n, A.m, p_orig, term == 1);       // (the phase-I pass works on the widened G)
+            if (!ok) { status = CVXB_EUNSOLVABLE; break; }
+          }
         }
         if (!ok) { status = CVXB_ELINSOLVE; break; }
       }
@@ -910,8 +930,7 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(const __grid_con
       // g_i(x) - s <= ub_i and +-(a.x - b) - s <= phase1EqTol, built in place: one more column (-1) and two more rows
       // (+-a) of G, no equalities, linear objective s; start (x0, 1 + max_i (g_i(x0) - ub_i)).
       const int n1 = n + 1, m1 = m + 2 * p;
-      if (tid < m1) GG(tid, n) = -1.0;
-      if (p && tid < n) { GG(m, tid) = S.aeq[tid]; GG(m + 1, tid) = -S.aeq[tid]; }
+      b_phase1_G(S, n, m, p);
       if (tid == 0) {
         if (p) { S.ub[m] = beq + A.P.phase1EqTol; S.ub[m + 1] = -beq + A.P.phase1EqTol; }
         S.x[n] = 0.0;
@@ -930,7 +949,7 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(const __grid_con
       viol = -block_min(-viol, S.red);
       if (tid == 0) S.x[n] = 1.0 + viol;
       __syncthreads();
-      b_barrier_loop(S, A, CVXB_OBJ_LINEAR, 0.0, nullptr, 0.0, 0, 1, Hs, Gg, false, ph);
+      b_barrier_loop(S, A, CVXB_OBJ_LINEAR, 0.0, nullptr, 0.0, 0, 1, Hs, Gg, p, false, ph);
       __syncthreads();
       ph_s = S.x[n];
       if (ph.status == CVXB_OK && !(ph_s < A.P.tolSolver)) ph.status = CVXB_EINFEASIBLE;   // FeasibilityReport.isFeasible(tol)
@@ -951,7 +970,7 @@ __global__ void __launch_bounds__(BT, 2) batched_barrier_kernel(const __grid_con
     }
     LoopOut r;
     if (ph.status == CVXB_OK) {
-      b_barrier_loop(S, A, kind, obj_r, Pg, beq, p, 0, Hs, Gg, true, r);
+      b_barrier_loop(S, A, kind, obj_r, Pg, beq, p, 0, Hs, Gg, p, true, r);
     } else {
       r = ph;
       r.stage = 0; r.total_steps = 0; r.objv = 0.0;

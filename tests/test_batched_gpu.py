@@ -258,6 +258,28 @@ def test_batched_decomposition_last_resort(handle, n, m):
     assert used_path2 >= 2
 
 
+def test_batched_symsolve_last_resort_without_equalities(handle):
+    """UnconstrainedSolver's last resort MatrixUtils.symSolve(H, -y) (UnconstrainedSolver.scala:58-65) inside the batched
+    kernel: with an indefinite objective Hessian and no equality, choleskySolve(H) and choleskySolve(H + 1e-9 I) fail and
+    the direction comes from the decomposition of H -- as in the oracle; whole solves agree."""
+    import cvx_b200 as cb
+    n, m = 12, 28
+    probs = []
+    for i, c in enumerate((10.0, 50.0)):
+        pr = P.slab_qp(n, m // 2, 0, 60 + i, scale=True)
+        pr["P"] = pr["P"] - c * np.eye(n)
+        probs.append(pr)
+    sol = cb.BatchedBarrierSolver(cb.pack_problems(probs), None, handle).solve()
+    for i, pr in enumerate(probs):
+        objF, cnts, eqs = P.to_oracle(pr)
+        s0 = O.barrierSolve(objF, cnts, eqs, O.SolverParams.standardParams(), None, False)
+        o0 = objF.valueAt(s0.x)
+        assert sol.status[i] == 0, (i, sol.status)
+        assert abs(sol.objective[i] - o0) <= 1e-8 * max(1.0, abs(o0)), (i, sol.objective[i], o0)
+        assert np.linalg.norm(sol.x[i] - s0.x) <= 1e-6 * np.linalg.norm(s0.x), i
+        assert sol.outer_stages[i] == s0.outer_stages
+
+
 def test_batch_phase1_dimension_limits(handle):
     import cvx_b200 as cb
     pr = P.kl_random(64, 64, 0, 1)           # phase I would need 65 variables
