@@ -870,12 +870,12 @@ int cvxb_symmetric_solve(cvxb_handle h, int n, const double* Hm, int ldh, const 
   CVXB_TRY(stage_out_alloc(*h, n, 1, ds));
   CVXB_TRY(scale_rows(*h, n, 1, dr.d, pad_ld(n), W->dr2, ds.d, ds.ld, false));
   if (!symmetric) {
-    st = svd_solve_device(*h, n, dQ.d, dQ.ld, ds.d, 1.0, tol, du.d, nullptr);     // svdSolve branch (:29)
+    st = svd_solve_device(*h, n, dQ.d, dQ.ld, ds.d, 1.0, tol, du.d, nullptr, false);     // svdSolve branch (:29)
     if (info) { memset(info, 0, sizeof(*info)); info->path = 3; }
   } else {
     st = chol_solve_device(*h, *W, P, dQ.d, dQ.ld, ds.d, 1.0, tol, du.d, info);
     if (st == CVXB_ELINSOLVE) {                                                    // symSolve fallback (:33)
-      st = svd_solve_device(*h, n, dQ.d, dQ.ld, ds.d, 1.0, tol, du.d, nullptr);
+      st = svd_solve_device(*h, n, dQ.d, dQ.ld, ds.d, 1.0, tol, du.d, nullptr, true);
       if (info) info->path = 2;
     }
   }

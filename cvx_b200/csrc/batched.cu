@@ -648,23 +648,39 @@ __device__ __noinline__ bool b_kkt_sym_solve(Smem& S, int n, bool with_eq, const
     __syncthreads();
   }
   __syncthreads();
-  // z_j = (u_j . rhs) / s_j with u_j = w_j / s_j; exact-zero singular values are skipped as the reference skips them
+  // The matrix is symmetric: eigen-decomposition semantics with U = V (orthonormal by construction) and the Rayleigh
+  // quotient lambda_j = v_j . w_j (eig.cu: sym_coeff_kernel):  c_j = v_j . rhs, a_j = c_j where lambda_j != 0 (exact-zero
+  // test as in the reference), z_j = c_j / lambda_j.  aw doubles as the coefficient vector a until it is overwritten.
   for (int j = warp; j < N; j += BT / 32) {
     const double* w = W + j * ld;
-    double s2 = 0.0, wb = 0.0;
-    for (int t = lane; t < N; t += 32) { s2 = fma(w[t], w[t], s2); wb = fma(w[t], rhs[t], wb); }
-    s2 = warp_sum(s2); wb = warp_sum(wb);
-    if (lane == 0) {
-      const double sg = sqrt(s2);
-      z[j] = (sg > 0.0) ? (wb / sg) / sg : 0.0;
+    const double* v = V + j * ld;
+    double lam = 0.0, vb = 0.0;
+    for (int t = lane; t < N; t += 32) { lam = fma(v[t], w[t], lam); vb = fma(v[t], rhs[t], vb); }
+    lam = warp_sum(lam); vb = warp_sum(vb);
+    if (lane == 0) { z[j] = vb; aw[j] = lam; }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // eigenvalues at the rounding level of the largest one are solved as zeros (eig.cu: sym_finish_kernel)
+    double mx = 0.0;
+    for (int j = lane; j < N; j += 32) mx = fmax(mx, fabs(aw[j]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const double thr = 64.0 * 2.220446049250313e-16 * (double)N * mx;
+    for (int j = lane; j < N; j += 32) {
+      const double lam = aw[j], c = z[j];
+      z[j] = (fabs(lam) > thr) ? c / lam : 0.0;
+      aw[j] = (lam != 0.0) ? c : 0.0;
     }
   }
   __syncthreads();
+  double sb = 0.0, sx = 0.0;
+  if (tid < N)
+    for (int j = 0; j < N; ++j) { sb = fma(V[tid + j * ld], aw[j], sb); sx = fma(V[tid + j * ld], z[j], sx); }
+  __syncthreads();
   if (tid < N) {
-    double sb = 0.0, sx = 0.0;
-    for (int j = 0; j < N; ++j) { sb = fma(W[tid + j * ld], z[j], sb); sx = fma(V[tid + j * ld], z[j], sx); }
-    b0[tid] = sb;        // U (U' rhs): projection of rhs onto the range
-    xs[tid] = sx;        // V S^-1 U' rhs
+    b0[tid] = sb;        // V (V' rhs) over the nonzero eigenvalues: projection of rhs onto the range
+    xs[tid] = sx;        // V Lambda^-1 V' rhs
   }
   __syncthreads();
   if (tid < N) {

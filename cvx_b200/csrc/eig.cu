@@ -86,6 +86,65 @@ __global__ void __launch_bounds__(256) svd_coeff_kernel(int n, const double* __r
   }
 }
 
+// Symmetric matrices (symSolve / kktSymSolve, MatrixUtils.scala:734-751: eigSym, U = V = eigenvectors, d = eigenvalues): the
+// coefficients are taken from V, which is orthonormal to rounding by construction (a product of rotations), and from the
+// Rayleigh quotient lambda_j = v_j . (A v_j) = v_j . w_j.  The left vectors u_j = w_j / s_j of a one-sided Jacobi SVD are
+// only orthonormal for singular values well above rounding: for a (numerically) singular matrix -- dependent equality rows
+// make the KKT matrix singular -- u_null is a unit vector of pure noise, not orthogonal to the range, and the projection
+// U U'b of a perfectly consistent right-hand side missed it by percents (found by tools/gpu_fuzz_kkt.py).
+//   c_j = v_j . b ;  a_j = c_j (lambda_j != 0, exact-zero test as in the reference) ;  z_j = c_j / lambda_j (sym_finish_kernel)
+__global__ void __launch_bounds__(256) sym_coeff_kernel(int n, const double* __restrict__ W, int ldw, const double* __restrict__ V,
+                                                        int ldv, const double* __restrict__ b, double sign,
+                                                        double* __restrict__ z, double* __restrict__ a) {
+  __shared__ double buf[33];
+  const int j = blockIdx.x;
+  const double* w = W + (size_t)j * ldw;
+  const double* v = V + (size_t)j * ldv;
+  double lam = 0.0, vb = 0.0;
+  for (int k = threadIdx.x; k < n; k += 256) {
+    lam = fma(v[k], w[k], lam);
+    vb = fma(v[k], sign * b[k], vb);
+  }
+  lam = block_sum(lam, buf);
+  vb = block_sum(vb, buf);
+  if (threadIdx.x == 0) {
+    z[j] = vb;        // c_j, finished by sym_finish_kernel
+    a[j] = lam;
+  }
+}
+
+// LAPACK's dsyev returns the eigenvalues of a singular matrix as noise of size eps * ||A||, and the reference divides by
+// them: the component c_j / lambda_j v_j it adds lies in the null space and is harmless.  The Rayleigh quotient of a Jacobi
+// null column is noise too, but of ANY size down to 1e-150 (a column that small keeps shrinking under the rotations), and
+// c_j / lambda_j then overflows the solution.  Eigenvalues at the rounding level of the largest one are therefore solved
+// as the zeros they stand for (z_j = 0: the minimum-norm solution; the x-part of a KKT solution with dependent equality
+// rows is the same); they stay in the projection of the range test as in the reference unless exactly zero.
+__global__ void __launch_bounds__(1024) sym_finish_kernel(int n, double* __restrict__ z, double* __restrict__ a) {
+  __shared__ double buf[33];
+  double mx = 0.0;
+  for (int j = threadIdx.x; j < n; j += 1024) mx = fmax(mx, fabs(a[j]));
+  mx = -block_min(-mx, buf);
+  const double thr = 64.0 * 2.220446049250313e-16 * (double)n * mx;
+  for (int j = threadIdx.x; j < n; j += 1024) {
+    const double lam = a[j], c = z[j];
+    z[j] = (fabs(lam) > thr) ? c / lam : 0.0;
+    a[j] = (lam != 0.0) ? c : 0.0;
+  }
+}
+
+// General matrices (svdSolve): singular values at the rounding level of the largest one are treated as the zeros they
+// stand for (their left vectors w_j / s_j are noise, see above; LAPACK's U is orthonormal there, the reference then
+// divides rounding noise by rounding noise)
+__global__ void __launch_bounds__(1024) svd_threshold_kernel(int n, const double* __restrict__ sig, double* __restrict__ z) {
+  __shared__ double buf[33];
+  double mx = 0.0;
+  for (int j = threadIdx.x; j < n; j += 1024) mx = fmax(mx, sig[j]);
+  mx = -block_min(-mx, buf);
+  const double thr = 64.0 * 2.220446049250313e-16 * (double)n * mx;
+  for (int j = threadIdx.x; j < n; j += 1024)
+    if (!(sig[j] > thr)) z[j] = 0.0;
+}
+
 // relative sizes  ||b - b0|| / relsize(b)  and  ||A w - b|| / relsize(b)
 __global__ void __launch_bounds__(VT) svd_check_kernel(int n, double sign, const double* __restrict__ b,
                                                        const double* __restrict__ b0, const double* __restrict__ aw,
@@ -134,7 +193,7 @@ __global__ void kkt_rhs2_kernel(int n, int p, const double* __restrict__ q, cons
 // x = pseudo-inverse solve of A x = sign*b through the Jacobi SVD, with the reference's two acceptance
 // tests.  Returns CVXB_EUNSOLVABLE (UnsolvableSystemException) when either fails.
 int svd_solve_device(Handle& h, int n, const double* A, int lda, const double* b, double sign, double tol, double* x,
-                     int* sweeps_out) {
+                     int* sweeps_out, bool symmetric) {
   const int ld = pad_ld(n);
   const int np = n + (n & 1);
   double *W = nullptr, *V = nullptr, *vec = nullptr;
@@ -164,9 +223,17 @@ int svd_solve_device(Handle& h, int n, const double* A, int lda, const double* b
   if (sweeps_out) *sweeps_out = sweeps;
   if (st != CVXB_OK) { cleanup(); if (st == CVXB_ECUDA) set_last_error("svd_solve_device: CUDA failure"); return st; }
   double *z = vec, *sig = vec + ld, *b0 = vec + 2 * ld, *aw = vec + 3 * ld;
-  svd_coeff_kernel<<<n, 256, 0, h.stream>>>(n, W, ld, b, sign, z, sig);
-  h.launches++;
-  st = gemv_n(h, n, n, 1.0, W, ld, z, 0.0, b0);            // U a = W (c / s)
+  if (symmetric) {
+    sym_coeff_kernel<<<n, 256, 0, h.stream>>>(n, W, ld, V, ld, b, sign, z, sig);      // sig := a (projection coefficients)
+    sym_finish_kernel<<<1, 1024, 0, h.stream>>>(n, z, sig);
+    h.launches += 2;
+    st = gemv_n(h, n, n, 1.0, V, ld, sig, 0.0, b0);        // U a with U = V
+  } else {
+    svd_coeff_kernel<<<n, 256, 0, h.stream>>>(n, W, ld, b, sign, z, sig);
+    svd_threshold_kernel<<<1, 1024, 0, h.stream>>>(n, sig, z);
+    h.launches += 2;
+    st = gemv_n(h, n, n, 1.0, W, ld, z, 0.0, b0);          // U a = W (c / s)
+  }
   if (st == CVXB_OK) st = gemv_n(h, n, n, 1.0, V, ld, z, 0.0, x);       // w = V z
   if (st == CVXB_OK) st = gemv_n(h, n, n, 1.0, A, lda, x, 0.0, aw);     // A w
   if (st == CVXB_OK) {
@@ -200,7 +267,7 @@ int kkt_sym_solve_device(Handle& h, int n, int p, const double* Hm, int ldh, con
   kkt_matrix_kernel<<<dim3((N + 127) / 128, N > 1024 ? 1024 : N), 128, 0, h.stream>>>(n, p, Hm, ldh, A, lda, M, ld);
   kkt_rhs2_kernel<<<(N + 255) / 256, 256, 0, h.stream>>>(n, p, q, b, rhs);
   h.launches += 2;
-  int st = svd_solve_device(h, N, M, ld, rhs, 1.0, tol, sol, nullptr);
+  int st = svd_solve_device(h, N, M, ld, rhs, 1.0, tol, sol, nullptr, true);
   if (st == CVXB_OK) {
     if (cudaMemcpyAsync(x, sol, n * sizeof(double), cudaMemcpyDeviceToDevice, h.stream) != cudaSuccess ||
         cudaMemcpyAsync(w, sol + n, p * sizeof(double), cudaMemcpyDeviceToDevice, h.stream) != cudaSuccess ||

@@ -70,8 +70,9 @@ int chol_solve_retry(Handle& h, KktWork& W, const cvxb_params& P, const double* 
 
 // MatrixUtils.symSolve / svdSolve (eig.cu): pseudo-inverse solve of A x = sign*b by one-sided Jacobi SVD with the
 // reference's acceptance tests; CVXB_EUNSOLVABLE = UnsolvableSystemException
+// symmetric: A is symmetric (symSolve / kktSymSolve: eigen-decomposition semantics, coefficients from V); else svdSolve
 int svd_solve_device(Handle& h, int n, const double* A, int lda, const double* b, double sign, double tol, double* x,
-                     int* sweeps_out);
+                     int* sweeps_out, bool symmetric);
 // KKTSystem.kktSymSolve on the (n+p)^2 KKT matrix
 int kkt_sym_solve_device(Handle& h, int n, int p, const double* Hm, int ldh, const double* A, int lda, const double* q,
                          const double* b, double tol, double* x, double* w);

@@ -366,7 +366,7 @@ int pd_symmetric_enqueue(cvxb_problem_s* P, const cvxb_params& pars, bool regula
 // symSolve(Q, d o v) then x = d o u   (SymmetricLinearSystem.scala:33, 51-55); Q and d o v are still in place
 int pd_symmetric_eigen(cvxb_problem_s* P, const cvxb_params& pars) {
   Handle& h = *P->h;
-  CVXB_TRY(svd_solve_device(h, P->n, P->Hreg, P->ldn, P->kw.qk, 1.0, pars.tolEqSolve, P->kw.t2, nullptr));
+  CVXB_TRY(svd_solve_device(h, P->n, P->Hreg, P->ldn, P->kw.qk, 1.0, pars.tolEqSolve, P->kw.t2, nullptr, true));
   CVXB_LAUNCH(h, mul_kernel, 1, VT, 0, P->n, P->kw.dr2, P->kw.t2, P->dir);
   return CVXB_OK;
 }

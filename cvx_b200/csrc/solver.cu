@@ -949,7 +949,7 @@ int inner_solve_uncon(cvxb_problem_s* P, const cvxb_params& pars, double t, RunS
         st = chol_solve_device(h, P->kw, pars, P->Hreg, P->ldn, P->y, -1.0, pars.tolEqSolve, P->dir, &info);
         R.fallbacks++;
         if (st == CVXB_ELINSOLVE)    // MatrixUtils.symSolve(H, -y)   UnconstrainedSolver.scala:65
-          st = svd_solve_device(h, n, P->H, P->ldn, P->y, -1.0, pars.tolEqSolve, P->dir, nullptr);
+          st = svd_solve_device(h, n, P->H, P->ldn, P->y, -1.0, pars.tolEqSolve, P->dir, nullptr, true);
       }
       if (st != CVXB_OK) return st;
       if (info.regularized) R.regularized++;

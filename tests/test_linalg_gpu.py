@@ -307,6 +307,30 @@ def test_kkt_fallback_path2_eigen(handle):
     assert rel(x1, x0) < 1e-9 and rel(w1, w0) < 1e-9
 
 
+@pytest.mark.parametrize("n,p,seed", [(103, 20, 1003), (164, 35, 1006), (119, 18, 1008), (40, 6, 5)])
+def test_kkt_dependent_equality_rows(handle, n, p, seed):
+    """Two identical rows in A make the Schur complement -- and the KKT matrix -- singular, the system stays consistent.
+    Wherever the fallback chain ends (a Cholesky that gets through on a pivot of rounding noise, or kktSymSolve,
+    KKTSystem.scala:283-310, on the singular KKT matrix), the reference answers; so does the device: the decomposition
+    solve takes its coefficients from the orthonormal V and solves eigenvalues at rounding level as zeros (found by
+    tools/gpu_fuzz_kkt.py: the left vectors w_j / s_j of a one-sided Jacobi SVD are noise for a zero singular value)."""
+    from cvx_b200 import KKTSystem
+    rng = np.random.default_rng(seed)
+    Qm, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    H = (Qm * rng.uniform(0.5, 5.0, n)) @ Qm.T
+    H = (H + H.T) * 0.5
+    A = rng.uniform(-1, 1, (p, n))
+    A[-1] = A[0]
+    x, w = rng.uniform(-1, 1, n), rng.uniform(-1, 1, p)
+    q, b = -(H @ x + A.T @ w), A @ x
+    x0, w0 = O.kkt_solve(H, A, q, b, 1e-6)
+    x1, w1 = KKTSystem(H, A, q, b, handle).solve(1e-6, None, 1e-6, 0)
+    res = lambda xx, ww: np.linalg.norm(np.concatenate([H @ xx + A.T @ ww + q, A @ xx - b])) / np.linalg.norm(np.concatenate([q, b]))
+    assert res(x1, w1) < max(RTOL, 10 * res(x0, w0))
+    assert rel(x1, x) < 1e-8 and rel(x1, x0) < 1e-8          # x is unique; w is not (the two equal rows share their multiplier)
+    assert abs((w1[0] + w1[-1]) - (w[0] + w[-1])) < 1e-6
+
+
 @pytest.mark.parametrize("n", [9, 130])
 def test_symmetric_system_indefinite_uses_symsolve(handle, n):
     """Symmetric indefinite, nonsingular: choleskySolve throws, symSolve answers (SymmetricLinearSystem.scala:31-34)."""
