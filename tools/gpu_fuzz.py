@@ -7,12 +7,14 @@ from oracle import cvx_oracle as O, problems as P
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 150
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+NMIN = int(sys.argv[3]) if len(sys.argv) > 3 else 2          # python tools/gpu_fuzz.py cases seed [nmin nmax]: medium sizes
+NMAX = int(sys.argv[4]) if len(sys.argv) > 4 else 45         # exercise the multi-leaf Cholesky schedules and the wavefront solves
 h = cb.default_handle()
 bad = 0
 t0 = time.time()
 for it in range(N):
     fam = rng.choice(["slab_lp", "slab_qp", "kl", "quad", "pnorm", "lp_phase1", "kl_phase1"])
-    n = int(rng.integers(2, 45))
+    n = int(rng.integers(NMIN, NMAX))
     seed = int(rng.integers(0, 10**6))
     solver = str(rng.choice(["BR", "PD"]))
     try:
