@@ -180,6 +180,7 @@ SYMBOLS = {
                                   C.c_int, C.c_double, _vp, C.c_int, C.c_int]),
     "cvxb_bench_kernel": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]),
     "cvxb_debug_set_schedule": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "cvxb_debug_dag_blocks": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
 }
 
 _lib = None

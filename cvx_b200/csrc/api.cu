@@ -933,6 +933,8 @@ __global__ void copy_kernel(size_t count, const double2* __restrict__ a, double2
 
 int cvxb_debug_leaf_clocks(long long* out, int reset) { return cvxb::leaf_clocks(out, reset != 0); }
 
+int cvxb_debug_dag_blocks(int n, int dag_block, int* starts, int cap) { return cvxb::dag_block_starts(n, dag_block, starts, cap); }
+
 int cvxb_debug_set_schedule(cvxb_handle h, int dag_block, int dag_min_n, int dag_reserve) {
   CHECK_HANDLE(h);
   CVXB_CUDA_OK(cudaStreamSynchronize(h->stream));

@@ -252,6 +252,7 @@ int trsm_lower(Handle& h, int n, int r, const double* L, int ldl, const double* 
 // inverse diagonal blocks of a given lower-triangular matrix (for cvxb_triangular_solve and
 // solveWithCholFactor); zero diagonal -> F_ZERO_DIAG
 int factor_init();   // kernel attributes (once per process, outside any stream capture)
+int dag_block_starts(int n, int nbk, int* out, int cap);   // block starts of the tile-DAG schedule (+ n as the last entry)
 int leaf_clocks(long long* out, bool reset);   // per-phase clock64 sums of the leaf kernel (debug builds)
 int invert_diag_blocks(Handle& h, int n, const double* L, int ldl, double* invD);
 

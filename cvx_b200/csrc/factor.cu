@@ -1482,6 +1482,15 @@ int leaf_init(bool force = false) {
 
 int factor_init() { return leaf_init(true); }     // per handle: attributes belong to the current device
 
+// the diagonal-block starts of the tile-DAG schedule for an n x n matrix (host logic only; tests/test_abi_cpu.py)
+int dag_block_starts(int n, int nbk, int* out, int cap) {
+  if (n < 1 || nbk < NB) return -1;
+  std::vector<int> st;
+  dag_blocks(n, nbk / NB * NB, st);
+  for (int i = 0; i < (int)st.size() && i < cap; ++i) out[i] = st[i];
+  return (int)st.size();
+}
+
 int ruiz_equilibrate(Handle& h, int n, const double* Hm, int ldh, double* d, double* colsq, int max_sweeps, double tol,
                      double* big_scratch, size_t big_doubles) {
   if (n <= 0) return CVXB_OK;

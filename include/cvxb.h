@@ -390,6 +390,9 @@ int cvxb_bench_kernel(cvxb_handle h, int which, int n, int k, int reps, double* 
  * dag_block = 0 switches the schedule off (recursive halving + look-ahead only); all three negative restore the defaults,
  * including the automatic choice of narrower blocks / a smaller reserve when no wide right-hand-side block rides along. */
 int cvxb_debug_set_schedule(cvxb_handle h, int dag_block, int dag_min_n, int dag_reserve);
+/* The diagonal-block starts that schedule uses for an n x n matrix with blocks of dag_block columns, followed by n itself;
+ * returns their number (host logic only: needs no GPU and no handle), -1 on bad arguments. */
+int cvxb_debug_dag_blocks(int n, int dag_block, int* starts, int cap);
 
 #ifdef __cplusplus
 }

@@ -113,6 +113,36 @@ def test_pack_problems_flags_phase1_for_problems_without_a_feasible_start():
     assert _lib.BatchDesc.phase1.offset == C.sizeof(_lib.BatchDesc) - C.sizeof(C.c_void_p)      # appended: old callers stay valid
 
 
+def test_tile_dag_block_schedule():
+    """Host logic of the tile-DAG factorisation schedule (factor.cu: dag_blocks): the diagonal blocks tile [0, n) in order,
+    every start is a multiple of the 128-column leaf, the first block is half a block when there are at least three
+    (nothing can overlap the first chain), the blocks shrink geometrically at the end down to <= 5 leaves, and no block is
+    wider than the nominal width (or than the 5-leaf tail).  C4 (n = 8192, 2048): 1024, 2048, 2048, 1536, 768, 384, 384."""
+    from cvx_b200 import _lib
+    lib = _lib.load()
+    buf = (C.c_int * 256)()
+
+    def blocks(n, nbk):
+        k = lib.cvxb_debug_dag_blocks(n, nbk, buf, 256)
+        assert 2 <= k <= 256
+        st = list(buf[:k])
+        assert st[0] == 0 and st[-1] == n and all(b > a for a, b in zip(st, st[1:]))
+        assert all(s_ % 128 == 0 for s_ in st[:-1])
+        return [b - a for a, b in zip(st, st[1:])]
+
+    assert blocks(8192, 2048) == [1024, 2048, 2048, 1536, 768, 384, 384]
+    for n, nbk in [(5120, 2048), (5121, 2048), (16385, 2048), (16385, 1024), (12289, 2048), (1000, 256), (1537, 384), (2049, 512),
+                   (32768, 2048), (6145, 1024)]:
+        sz = blocks(n, nbk)
+        assert sum(sz) == n and max(sz) <= max(nbk, 5 * 128 + 1) and sz[-1] <= 5 * 128 + 1      # (a tail of <= 5 leaves is one block)
+        if n >= 3 * nbk:
+            assert sz[0] == max(128, nbk // 2 // 128 * 128)
+        if nbk >= 1024:                                              # (with test-sized blocks the 5-leaf tail exceeds a block)
+            tail = sz[1:]
+            assert all(b <= a for a, b in zip(tail, tail[1:]))      # non-increasing after the first block
+    assert lib.cvxb_debug_dag_blocks(0, 2048, buf, 256) == -1 and lib.cvxb_debug_dag_blocks(100, 64, buf, 256) == -1
+
+
 def test_bench_gpu_arm_never_imports_the_oracle():
     """bench.py may execute oracle/ only in its CPU legs (cpu_baseline, --impl reference): every import of it sits
     inside cpu_reference_leg / cpu_modes_leg; synthetic.py (input generation for both arms) does not import it at all."""
