@@ -294,8 +294,44 @@ class KKTInfo:
     err2: float = 0.0
 
 
+# "reference": KKTSystem.solveWithCholFactor as written.  "one_trsm": the device's as-if variant of the block elimination
+#  -- NOT the reference's arithmetic; it exists only so that tests and tools can show that a
+# disagreement between device and oracle is exactly this deviation (tools/gpu_fuzz.py, tests/test_oracle_cpu.py).
+BLOCK_ELIMINATION = "reference"
+
+
+def _solveWithCholFactor_one_trsm(L, A, q, b, tol, info=None):
+    """The device's formulation (kkt.cu): Y = L^-1 [A', q], S = Yp'Yp (positive semidefinite by construction), z = -(b + Yp'yq),
+    x = -L^-T (yq + Yp w).  Same quantities as KKTSystem.scala:116-139 in exact arithmetic; the reference forms
+    R = A (L^-T L^-1 A') and symmetrises it, which loses definiteness in floating point once cond(H) reaches ~1e20."""
+    n = L.shape[1]
+    p = A.shape[0]
+    B = np.zeros((n, p + 1))
+    B[:, :p] = A.T
+    B[:, p] = q
+    Y = triangularSolve(L, "L", B)
+    Yp, yq = Y[:, :p], Y[:, p]
+    S = Yp.T @ Yp
+    S = (S + S.T) * 0.5
+    K = breeze_cholesky(S)
+    z = -(b + Yp.T @ yq)
+    u = forwardSolve(K, z)
+    w = backSolve(K.T, u)
+    x = -triangularSolve(L.T, "U", (yq + Yp @ w)[:, None])[:, 0]
+    Hx = L @ (L.T @ x)
+    err1 = relativeSize(Hx + A.T @ w + q, -q, tol)
+    err2 = relativeSize(A @ x - b, b, tol)
+    if info is not None:
+        info.err1, info.err2 = err1, err2
+    if err1 > tol or err2 > tol:
+        raise LinSolveException("Error in solution exceeds tolerance.")
+    return x, w
+
+
 def solveWithCholFactor(L, A, q, b, tol, info: Optional[KKTInfo] = None):
     """KKTSystem.scala:99-167."""
+    if BLOCK_ELIMINATION == "one_trsm":
+        return _solveWithCholFactor_one_trsm(L, A, q, b, tol, info)
     n = L.shape[1]
     assert L.shape[0] == n and A.shape[1] == n
     p = A.shape[0]

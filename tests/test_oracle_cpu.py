@@ -442,3 +442,34 @@ def test_iteration_noise_fixture_supports_the_band():
     from tools.iteration_noise_experiment import problems, run
     pr = problems()["kl_1A"]
     assert run(pr)["stages"][:4] == d["runs"]["kl_1A"]["base"]["stages"][:4]
+
+
+def test_block_elimination_formulations_differ_only_at_extreme_conditioning():
+    """The one as-if deviation of the device path with a numerical consequence: the reference forms
+    the Schur complement as R = A (L^-T L^-1 A'), symmetrised (KKTSystem.scala:116-139); the device forms S = Y'Y with
+    Y = L^-1 A', positive semidefinite by construction.  On well-conditioned systems the two agree to the conditioning of the system.  In the
+    last barrier stages of an LP (cond(H) ~ 1e20) the reference's R loses definiteness, its whole fallback chain fails and
+    it throws (defect D3) -- under every rounding-level variation tried (tests/golden/outcome_noise.json) -- while the
+    one-TRSM formulation solves the problem: the oracle restates both, and with the device's formulation it reaches the
+    optimum the device reports (tools/gpu_fuzz.py, profiles/r2_fuzz_large_path.log)."""
+    s = P.kkt_planted_pd(120, 20, 3)
+    L = O.regularizedCholesky(s["H"])
+    x0, w0 = O.solveWithCholFactor(L, s["A"], s["q"], s["b"], 1e-10)
+    x1, w1 = O._solveWithCholFactor_one_trsm(L, s["A"], s["q"], s["b"], 1e-10)
+    assert np.linalg.norm(x1 - x0) < 1e-9 * np.linalg.norm(x0) and np.linalg.norm(w1 - w0) < 1e-9 * np.linalg.norm(w0)
+    assert np.linalg.norm(x1 - s["x"]) < 1e-8 * np.linalg.norm(s["x"])
+    prob = P.slab_lp(27, 54, 1, 20152)
+    objF, cnts, eqs = P.to_oracle(prob)
+    with pytest.raises(O.UnsolvableSystemException):
+        O.solveProblem(objF, cnts, eqs, "BR")
+    O.BLOCK_ELIMINATION = "one_trsm"
+    try:
+        sol, _ = O.solveProblem(objF, cnts, eqs, "BR")
+    finally:
+        O.BLOCK_ELIMINATION = "reference"
+    assert sol.outer_stages == 12 and abs(objF.valueAt(sol.x) - (-0.5643950053)) < 1e-8
+    import json
+    import os
+    noise = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "outcome_noise.json")))
+    assert noise["summary"]["outcomes_seen_per_problem"]["fuzz11_it18"] == ["UnsolvableSystemException"]
+
