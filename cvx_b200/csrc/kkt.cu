@@ -150,6 +150,17 @@ __global__ void __launch_bounds__(VT) sub_kernel(int n, const double* __restrict
   for (int i = threadIdx.x; i < n; i += VT) out[i] = a[i] - b[i];
 }
 
+// S := (R + R') / 2 in place, exactly symmetric   (KKTSystem.scala:139)
+__global__ void symmetrize_kernel(int p, double* __restrict__ S, int lds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p) return;
+  for (int j = blockIdx.y; j < i; j += gridDim.y) {
+    const double v = (S[(size_t)j * lds + i] + S[(size_t)i * lds + j]) * 0.5;
+    S[(size_t)j * lds + i] = v;
+    S[(size_t)i * lds + j] = v;
+  }
+}
+
 template <typename T>
 int dev_alloc(KktWork& W, T** ptr, size_t count) {
   void* q = W.arena ? W.arena->take((count ? count : 1) * sizeof(T)) : nullptr;
@@ -166,6 +177,7 @@ size_t kkt_work_bytes(int n, int p) {
   const size_t ldn = pad_ld(n), ldp = pad_ld(p);
   const size_t nblk = (n + NB - 1) / NB, pblk = (p + NB - 1) / NB;
   size_t d = ldn * n + nblk * NB * NB + ldn * (p + 1) + ldp * (p > 0 ? p : 1) + (pblk ? pblk : 1) * NB * NB + 9 * ldn + 3 * ldp;
+  if (p > 0) d += 2 * ldn * (p + 1) + 128;       // Xlit, Blit
   return d * sizeof(double) + 32 * 256;
 }
 
@@ -180,6 +192,10 @@ int kkt_work_alloc(Handle& h, KktWork& W, int n, int p, Arena* arena) {
   CVXB_TRY(dev_alloc(W, &W.L, (size_t)W.ldn * n));
   CVXB_TRY(dev_alloc(W, &W.invD, (size_t)nblk * NB * NB));
   CVXB_TRY(dev_alloc(W, &W.Y, (size_t)W.ldn * (p + 1)));
+  if (p > 0) {
+    CVXB_TRY(dev_alloc(W, &W.Xlit, (size_t)W.ldn * (p + 1)));
+    CVXB_TRY(dev_alloc(W, &W.Blit, (size_t)W.ldn * (p + 1)));
+  }
   CVXB_TRY(dev_alloc(W, &W.S, (size_t)W.ldp * (p > 0 ? p : 1)));
   CVXB_TRY(dev_alloc(W, &W.invDs, (size_t)(pblk ? pblk : 1) * NB * NB));
   double** nv[] = {&W.dr, &W.colsq, &W.qs, &W.xs, &W.t1, &W.t2, &W.t3, &W.qk, &W.dr2};
@@ -248,12 +264,32 @@ int kkt_enqueue(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, i
   CVXB_TRY(transpose_scale(h, p, n, A, lda, W.dr, W.Y, W.ldn));
   double* yq = W.Y + (size_t)p * W.ldn;
   CVXB_LAUNCH(h, kkt_rhs_kernel, 1, VT, 0, n, p, W.dr, q, b, W.qs, yq, h.d_scal, h.d_flag);
+  // bugCompat & 2: the block elimination literally as the reference writes it (KKTSystem.scala:116-139): X = H^-1 [DA', Dq]
+  // by two triangular solves, R = (DA')' X_p by a full GEMM, S = (R + R')/2 -- instead of S = Y'Y.  The two agree to rounding
+  // until cond(H) ~ 1e20 (last barrier stages of LPs), where R loses positive definiteness and the reference gives up
+  // (DESIGN.md section 2); this switch reproduces that.
+  const bool literal = (P.bugCompat & 2) != 0 && p > 0 && W.Xlit && W.Blit;
+  if (literal) CVXB_TRY(copy_matrix(h, n, p + 1, W.Y, W.ldn, W.Blit, W.ldn));
   if (prefactored) CVXB_TRY(trsm_lower(h, n, p + 1, W.L, W.ldn, W.invD, W.Y, W.ldn, false));
   else {  // factorisation with Y = L^-1 [DA', Dq] riding along
     CVXB_TRY(prof_begin(h, PROF_FACTOR));
     CVXB_TRY(potrf_lower_rhs(h, n, W.L, W.ldn, W.invD, F_CHOL_H, S_MINDIAG_H, W.Y, W.ldn, p + 1));
     CVXB_TRY(prof_end(h, PROF_FACTOR, (double)n * n * n / 3.0 + (double)n * n * (p + 1)));
   }
+  if (literal) {
+    double* xq = W.Xlit + (size_t)p * W.ldn;
+    CVXB_TRY(copy_matrix(h, n, p + 1, W.Y, W.ldn, W.Xlit, W.ldn));
+    CVXB_TRY(trsm_lower(h, n, p + 1, W.L, W.ldn, W.invD, W.Xlit, W.ldn, true));            // X = L^-T L^-1 [DA', Dq]
+    GemmArgs gr{p, p, n, W.Blit, W.ldn, true, W.Xlit, W.ldn, true, W.S, W.ldp, 1.0, 0.0, 0};   // R = (DA')' X_p
+    CVXB_TRY(gemm_dmma(h, gr));
+    CVXB_LAUNCH(h, symmetrize_kernel, dim3((p + 127) / 128, p > 1024 ? 1024 : p), 128, 0, p, W.S, W.ldp);
+    CVXB_TRY(gemv_t(h, n, p, 1.0, W.Blit, W.ldn, xq, 0.0, W.tp));                            // (DA')' H^-1 Dq
+    CVXB_LAUNCH(h, kkt_z_kernel, 1, VT, 0, p, b, W.tp, w);
+    CVXB_TRY(potrf_lower_rhs(h, p, W.S, W.ldp, W.invDs, F_CHOL_S, S_MINDIAG_S, w, W.ldp, 1));
+    CVXB_TRY(trsm_lower(h, p, 1, W.S, W.ldp, W.invDs, w, W.ldp, true));
+    CVXB_TRY(gemv_n(h, n, p, 1.0, W.Xlit, W.ldn, w, 1.0, xq));                               // H^-1 Dq + H^-1 DA' w
+    CVXB_LAUNCH(h, kkt_unscale_kernel, 1, VT, 0, n, -1.0, xq, W.dr, W.xs, x);
+  } else {
   // Schur complement S = Yp'Yp and its (plain, unregularised) Cholesky  KKTSystem.scala:126-140
   GemmArgs g{p, p, n, W.Y, W.ldn, true, W.Y, W.ldn, true, W.S, W.ldp, 1.0, 0.0, 2};
   g.streamk = true;
@@ -269,6 +305,7 @@ int kkt_enqueue(Handle& h, KktWork& W, const cvxb_params& P, const double* Hm, i
   CVXB_TRY(gemv_n(h, n, p, 1.0, W.Y, W.ldn, w, 1.0, yq));
   CVXB_TRY(trsm_lower(h, n, 1, W.L, W.ldn, W.invD, yq, W.ldn, true));
   CVXB_LAUNCH(h, kkt_unscale_kernel, 1, VT, 0, n, -1.0, yq, W.dr, W.xs, x);
+  }
   // residuals on the equilibrated system, with L L' in place of Q  (KKTSystem.scala:148-154)
   CVXB_TRY(gemv_t(h, n, n, 1.0, W.L, W.ldn, W.xs, 0.0, W.t1));
   CVXB_TRY(gemv_n(h, n, n, 1.0, W.L, W.ldn, W.t1, 0.0, W.t2));

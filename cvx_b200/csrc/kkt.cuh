@@ -11,6 +11,8 @@ struct KktWork {
   double* Y = nullptr;      // n x (p+1): [d o A', d o q] -> L^-1 [..]
   double* S = nullptr;      // p x p Schur complement -> its factor
   double* invDs = nullptr;
+  double* Xlit = nullptr;   // n x (p+1): H^-1 [DA', Dq]   } the reference's literal block elimination (bugCompat & 2),
+  double* Blit = nullptr;   // n x (p+1): copy of [DA', Dq]  } allocated with the rest when p > 0
   double* Hk = nullptr;     // path 1: H + A'A (allocated on first use)
   double* Q = nullptr;      // symmetric-solve scratch (allocated on first use)
   double *dr = nullptr, *colsq = nullptr, *qs = nullptr, *xs = nullptr, *t1 = nullptr, *t2 = nullptr, *t3 = nullptr,

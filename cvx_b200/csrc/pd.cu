@@ -331,7 +331,7 @@ int pd_assemble(cvxb_problem_s* P, const cvxb_params& pars, double t) {
     CVXB_TRY(gemv_t(h, p, n, 1.0, P->A, P->ldp, P->nu, 0.0, P->atnu));
     CVXB_TRY(gemv_n(h, p, n, 1.0, P->A, P->ldp, P->x, 0.0, P->axv));
   }
-  CVXB_LAUNCH(h, pd_rhs_kernel, 1, VT, 0, n, p, P->objective, pars.bugCompat && p > 0 ? 1 : 0, P->x, P->obj_a, P->Px, P->gt,
+  CVXB_LAUNCH(h, pd_rhs_kernel, 1, VT, 0, n, p, P->objective, (pars.bugCompat & 1) && p > 0 ? 1 : 0, P->x, P->obj_a, P->Px, P->gt,
               P->atnu, P->rd0, P->vvec, P->qvec, P->axv, P->b, P->pres, P->negpres, P->obj_pow);
   // H_pd = hess f + G' diag(-lam/f) G
   CVXB_TRY(scale_rows(h, m, n, P->G, P->ldm, P->wts, P->Gs, P->ldm, true));
@@ -452,7 +452,7 @@ int pd_loop(cvxb_problem_s* P, const cvxb_params& pars, cvxb_solution* out) {
   Handle& h = *P->h;
   const int n = P->n, m = P->m, p = P->p;
   const bool withEqs = p > 0;
-  const bool bug = pars.bugCompat && withEqs;
+  const bool bug = (pars.bugCompat & 1) && withEqs;
   const double mu = pars.mu, tol = pars.tolSolver;
   CVXB_TRY(pd_alloc(P));
   // lam0 = -1/(g(x0)-ub), nu0 = 0

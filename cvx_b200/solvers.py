@@ -39,7 +39,7 @@ class SolverParams:
     tolFeas: float = 1e-7
     delta: float = 1e-6
     # not in the reference record: PrimalDualSolver.solve_withEQs defects D1/D2 reproduced when True
-    bugCompat: bool = False
+    bugCompat: int = 0         # bit 0: PD defects D1/D2; bit 1: the reference's literal block elimination (cvxb.h)
     # benchmark aid: stop after this many Newton steps in total (0 = run to termination)
     stepLimit: int = 0
 

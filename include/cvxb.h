@@ -88,7 +88,10 @@ typedef struct cvxb_params {
   double newtonRegDelta;/* 1e-9  UnconstrainedSolver.scala:60 */
   double phase1EqTol;   /* 1e-6  ConstraintSet.scala:342, CvxUtils.scala:86 */
   double pdStepFraction;/* 0.99  PrimalDualSolver.scala:339,509 */
-  int bugCompat;        /* 1: reproduce reference defects D1/D2 of PrimalDualSolver.solve_withEQs */
+  int bugCompat;        /* bit 0: reproduce reference defects D1/D2 of PrimalDualSolver.solve_withEQs;
+                         * bit 1: form the Schur complement literally as KKTSystem.scala:116-139 does (H^-1 A' by two
+                         * triangular solves, A (H^-1 A') by a GEMM, symmetrised) instead of Y'Y with Y = L^-1 A': twice
+                         * the flops, and the reference's loss of definiteness at cond(H) ~ 1e20 */
   long long stepLimit;  /* 0 (reference behaviour): no budget.  >0: a budget of Newton steps for the whole call (phase I
                          * included) -- the solve returns its current iterate with status OK when it is used up; not a
                          * SolverParams field of the reference (callers with a time budget, and bench.py --steps) */

@@ -180,3 +180,33 @@ def test_min_pnorm_known_minimiser(handle, pw, solver):
         assert sol.outer_stages == sol0.outer_stages
     else:
         assert abs(sol.newton_steps - sol0.newton_steps) <= 1
+
+
+def test_literal_block_elimination_switch(handle):
+    """bugCompat bit 1: the Schur complement formed literally as the reference writes it (KKTSystem.scala:116-139: H^-1 A' by two
+    triangular solves, A (H^-1 A') by a GEMM, symmetrised) instead of Y'Y.  On an ordinary problem both give the same solve;
+    on the slab LP found by tools/gpu_fuzz.py the literal form loses positive definiteness in the last stages and the solve
+    ends as the reference's does -- UnsolvableSystemException at the end of KKTSystem.solve's fallback chain (defect D3) --
+    while the default form reaches the optimum (the oracle restates both)."""
+    import cvx_b200 as cb
+    lit = cb.SolverParams()
+    lit.bugCompat = 2
+    pr = P.slab_qp(48, 60, 6, 3)
+    a = cb.from_dict(pr, "BR", None, handle).solve()
+    b = cb.from_dict(pr, "BR", lit, handle).solve()
+    assert abs(a.objective - b.objective) <= 1e-9 * max(1.0, abs(a.objective))
+    assert np.linalg.norm(a.x - b.x) <= 1e-7 * np.linalg.norm(a.x) and a.outer_stages == b.outer_stages
+    lp = P.slab_lp(27, 54, 1, 20152)
+    objF, cnts, eqs = P.to_oracle(lp)
+    with pytest.raises(O.UnsolvableSystemException):
+        O.solveProblem(objF, cnts, eqs, "BR")
+    with pytest.raises(cb._lib.UnsolvableSystemException):
+        cb.from_dict(lp, "BR", lit, handle).solve()
+    ok = cb.from_dict(lp, "BR", None, handle).solve()
+    O.BLOCK_ELIMINATION = "one_trsm"
+    try:
+        s0, _ = O.solveProblem(objF, cnts, eqs, "BR")
+    finally:
+        O.BLOCK_ELIMINATION = "reference"
+    assert abs(ok.objective - objF.valueAt(s0.x)) <= 1e-8 and ok.outer_stages == s0.outer_stages
+
